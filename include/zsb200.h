@@ -1,0 +1,219 @@
+/* zsb200.h -- C ABI of libzsb200.so, the B200 (sm_100a) kernels behind zhusuan's
+ * HMC / SG-MCMC / ELBO-IWAE hot path.
+ *
+ * The reference (thu-ml/zhusuan) has NO native boundary: its arithmetic is TensorFlow-1.x graph
+ * ops.  Each entry point below therefore replaces a *set of TF ops inside one reference function*;
+ * the function it replaces is cited as zhusuan/<file>:<lines>.  INTEGRATION.md shows the ctypes
+ * binding a zhusuan maintainer would add at each of those sites.
+ *
+ * Conventions
+ *   - every function returns int: 0 ok, <0 error (ZSB_ERR_*); zsb_last_error() gives the message
+ *     of the calling thread's last failure.  No exceptions cross the ABI.
+ *   - all data pointers are DEVICE pointers to float32 / int32 unless marked host; the caller
+ *     owns every buffer.  `stream` is a cudaStream_t (NULL = legacy default stream); all work is
+ *     enqueued asynchronously on it, nothing synchronises.
+ *   - latents are row-major [chains, row_len]; per-dimension vectors are [row_len].
+ *   - operands named (ptr, ptr_n) are broadcast by modular indexing: element i reads ptr[i % ptr_n]
+ *     (covers every broadcast where the operand's shape is a suffix of the result's shape).
+ *   - `noise`/`u`/`eps` pointers may be NULL: the kernel then draws Philox4x32-10 numbers keyed by
+ *     (seed; stream id, iter, row0 + local chain, 4-element block), i.e. by GLOBAL chain index, so
+ *     results do not depend on how chains are sharded over GPUs.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with ZSB_ERR_CUDA.
+ */
+#ifndef ZSB200_H_
+#define ZSB200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZSB_OK 0
+#define ZSB_ERR_INVALID (-1)
+#define ZSB_ERR_CUDA (-2)
+#define ZSB_ERR_UNSUPPORTED (-3)
+
+int zsb_version(void);
+int zsb_last_error(char* buf, size_t n);       /* host buffer */
+int zsb_device_count(void);
+int zsb_stream_sync(void* stream);
+
+/* ---- sampler state block: 16 float32 in device memory (tf.Variables of hmc.py:258-264,
+ *      StepsizeTuner hmc.py:82-87, EWMV.t hmc.py:118) ------------------------------------- */
+enum {
+  ZSB_HMC_STATE_T = 0, ZSB_HMC_STATE_STEP_SIZE = 1, ZSB_HMC_STATE_TUNER_STEP = 2,
+  ZSB_HMC_STATE_LOG_EPS_BAR = 3, ZSB_HMC_STATE_H_BAR = 4, ZSB_HMC_STATE_MU = 5,
+  ZSB_HMC_STATE_EWMV_T = 6, ZSB_HMC_STATE_EPS_USED = 7, ZSB_HMC_STATE_ACC_MEAN = 8,
+  ZSB_HMC_STATE_FLAGS = 9 /* uint32 bits; bit0 = non-finite old log-prob, hmc.py:51-53 */,
+  ZSB_HMC_STATE_SEARCH_LAST = 10, ZSB_HMC_STATE_SEARCH_COND = 11, ZSB_HMC_STATE_SIZE = 16
+};
+
+/* ---- K1: Distribution.log_prob (zhusuan/distributions/base.py:290-304) --------------------- */
+/* Normal._log_prob univariate.py:174-181; out[r] = sum over `group` consecutive elements. */
+int zsb_logprob_normal_f32(const float* given, int64_t given_n, const float* mean, int64_t mean_n,
+                           const float* logstd, int64_t logstd_n, float* out, int64_t n_out,
+                           int64_t group, void* stream);
+/* analytic backward (replaces tf.gradients through :174-181); outputs nullable, n_out*group each */
+int zsb_logprob_normal_bwd_f32(const float* given, int64_t given_n, const float* mean,
+                               int64_t mean_n, const float* logstd, int64_t logstd_n,
+                               const float* gout, int64_t n_out, int64_t group, float* dgiven,
+                               float* dmean, float* dlogstd, void* stream);
+/* Bernoulli._log_prob univariate.py:398-403 (given pre-cast to float, :399) */
+int zsb_logprob_bernoulli_f32(const float* given, int64_t given_n, const float* logits,
+                              int64_t logits_n, float* out, int64_t n_out, int64_t group,
+                              void* stream);
+int zsb_logprob_bernoulli_bwd_f32(const float* given, int64_t given_n, const float* logits,
+                                  int64_t logits_n, const float* gout, int64_t n_out,
+                                  int64_t group, float* dlogits, void* stream);
+/* Categorical._log_prob univariate.py:496-548; logits [logits_rows, C], out [rows] */
+int zsb_logprob_categorical_f32(const int32_t* given, int64_t given_n, const float* logits,
+                                int64_t logits_rows, int64_t n_categories, float* out,
+                                int64_t rows, void* stream);
+int zsb_logprob_categorical_bwd_f32(const int32_t* given, int64_t given_n, const float* logits,
+                                    int64_t logits_rows, int64_t n_categories, const float* gout,
+                                    float* dlogits, int64_t rows, void* stream);
+/* Dirichlet._log_prob multivariate.py:665-677 */
+int zsb_logprob_dirichlet_f32(const float* given, int64_t given_rows, const float* alpha,
+                              int64_t alpha_rows, int64_t n_categories, float* out, int64_t rows,
+                              void* stream);
+int zsb_logprob_dirichlet_bwd_given_f32(const float* given, int64_t given_rows,
+                                        const float* alpha, int64_t alpha_rows,
+                                        int64_t n_categories, const float* gout, float* dgiven,
+                                        int64_t rows, void* stream);
+/* UnnormalizedMultinomial._log_prob multivariate.py:435-443 */
+int zsb_logprob_unnorm_multinomial_f32(const float* given, int64_t given_rows,
+                                       const float* logits, int64_t logits_rows,
+                                       int64_t n_categories, int normalize_logits, float* out,
+                                       int64_t rows, void* stream);
+int zsb_logprob_unnorm_multinomial_bwd_f32(const float* given, int64_t given_rows,
+                                           const float* logits, int64_t logits_rows,
+                                           int64_t n_categories, int normalize_logits,
+                                           const float* gout, float* dlogits, int64_t rows,
+                                           void* stream);
+/* MultivariateNormalCholesky._log_prob multivariate.py:169-189; x_out (nullable) = L^-1(x-mean) */
+int zsb_logprob_mvn_chol_f32(const float* given, int64_t given_rows, const float* mean,
+                             int64_t mean_rows, const float* cov_tril, int64_t tril_mats,
+                             int64_t n_dim, float* out, float* x_out, int64_t rows, void* stream);
+int zsb_logprob_mvn_chol_bwd_given_f32(const float* x_in, const float* cov_tril,
+                                       int64_t tril_mats, int64_t n_dim, const float* gout,
+                                       float* dgiven, int64_t rows, void* stream);
+/* reduce_sum over the last group_ndims axes, base.py:303-304 */
+int zsb_group_sum_f32(const float* in, float* out, int64_t n_out, int64_t group, void* stream);
+
+/* ---- K7: Normal._sample (univariate.py:161-172) fused with cond_log_p (bn.py:194-204) ------- */
+int zsb_reparam_normal_f32(const float* mean, int64_t mean_n, const float* logstd,
+                           int64_t logstd_n, const float* eps, uint64_t seed, uint32_t iter,
+                           float* z_out, float* eps_out, float* logq_out, int64_t n_out,
+                           int64_t group, void* stream);
+/* Bernoulli._sample univariate.py:386-396 */
+int zsb_sample_bernoulli_i32(const float* logits, int64_t logits_n, const float* u, uint64_t seed,
+                             uint32_t iter, int32_t* out, int64_t n, void* stream);
+
+/* ---- K6: sample-axis reductions; x viewed as [outer, K, inner], reduced over K --------------
+ * op 0 log_mean_exp (zhusuan/utils.py:177-196; monte_carlo.py:137-141)
+ *    1 mean         (exclusive_kl.py:131-137)   2 log_sum_exp (utils.py:153-174)   3 sum       */
+int zsb_reduce_fwd_f32(int op, const float* x, float* out, int64_t outer, int64_t K, int64_t inner,
+                       void* stream);
+/* backward = what tf.gradients yields for .sgvb(): softmax weights (op 0/2), 1/K (op 1) */
+int zsb_reduce_bwd_f32(int op, const float* x, const float* y, const float* gout, float* dx,
+                       int64_t outer, int64_t K, int64_t inner, void* stream);
+
+/* ---- K2/K3/K4: HMC building blocks (zhusuan/hmc.py) ----------------------------------------- */
+int zsb_hmc_acc_parts(void);   /* capacity (floats) callers must give every acc_part scratch */
+int zsb_hmc_mass_parts(void);  /* mass_stats scratch = zsb_hmc_mass_parts()*2*D floats */
+/* random_momentum hmc.py:21-23 (+ kinetic hmc.py:32-34 into k_out, optional) */
+int zsb_hmc_momentum_f32(float* p, const float* noise, const float* mass, int64_t mass_n,
+                         int64_t chains, int64_t row_len, uint64_t seed, uint32_t iter,
+                         uint32_t stream_id, int64_t row0, float* k_out, int accumulate,
+                         void* stream);
+int zsb_hmc_kinetic_f32(const float* p, const float* mass, int64_t mass_n, int64_t chains,
+                        int64_t row_len, float* k_out, int accumulate, void* stream);
+/* leapfrog_integrator hmc.py:38-43: q += (eps*scale) * (p/mass);  p += (eps*scale) * grad.
+ * eps_dev points at state[ZSB_HMC_STATE_EPS_USED]. */
+int zsb_hmc_leapfrog_q_f32(float* q, const float* p, const float* mass, int64_t mass_n,
+                           int64_t row_len, const float* eps_dev, float scale, int64_t n,
+                           void* stream);
+int zsb_hmc_leapfrog_p_f32(float* p, const float* g, const float* eps_dev, float scale, int64_t n,
+                           void* stream);
+/* get_acceptance_rate + MH decision hmc.py:46-61, 485-486, 498 */
+int zsb_hmc_mh_f32(const float* lp0, const float* lp1, const float* k0, const float* k1,
+                   const float* u, uint64_t seed, uint32_t iter, int64_t row0, int64_t chains,
+                   float* h0, float* h1, float* acc, int32_t* accept, float* lp_sel,
+                   float* acc_part, int* n_part_out /* host */, float* state, void* stream);
+/* where(accept, q_new, q) hmc.py:488-497 */
+int zsb_hmc_select_f32(float* q, const float* q_new, const int32_t* accept, int64_t chains,
+                       int64_t row_len, void* stream);
+/* stats[0] = sum(acc), stats[1] = local chain count; all-reduce(sum) stats across ranks, then tune */
+int zsb_hmc_acc_sum_f32(const float* acc_part, int n_part, int64_t chains, float* stats,
+                        void* stream);
+int zsb_hmc_begin_f32(float* state, int start_search, void* stream);
+/* one pass of _init_step_size's loop bookkeeping hmc.py:326-338 */
+int zsb_hmc_search_update_f32(float* state, const float* stats, float target, void* stream);
+/* StepsizeTuner.tune hmc.py:89-112 + step_size assign hmc.py:379 */
+int zsb_hmc_tune_f32(float* state, const float* stats, int has_tuner, int adapt, float fresh_start,
+                     float gamma, float t0, float kappa, float delta, float t_now, void* stream);
+/* ExponentialWeightedMovingVariance hmc.py:115-159 + _adapt_mass hmc.py:283-305.
+ * stats = [sum_c (q-mean) (D), sum_c (q-mean)^2 (D)]; all-reduce(sum) across ranks between calls */
+int zsb_hmc_mass_stats_f32(const float* q, const float* ewmv_mean, int64_t chains, int64_t D,
+                           float* part, float* stats, void* stream);
+int zsb_hmc_mass_update_f32(float* ewmv_mean, float* ewmv_var, float* mass, const float* stats,
+                            float n_chains_global, int64_t D, float decay, float ewmv_t_new,
+                            int adapt, int use_ones, float* state, void* stream);
+
+/* Fused whole iteration for a diagonal-Gaussian target (Normal node, group_ndims=1;
+ * examples/toy_examples/gaussian.py:15-20): momentum, L+1 gradient passes, Hamiltonians, MH,
+ * in-place select in ONE launch.  search_mode=1: the acceptance probe of hmc.py:314-326. */
+int zsb_hmc_diag_normal_step_f32(float* q, const float* noise, const float* u, const float* mean,
+                                 int64_t mean_n, const float* logstd, int64_t logstd_n,
+                                 const float* mass, int64_t mass_n, float* state, int n_leapfrogs,
+                                 int64_t chains, int64_t D, uint64_t seed, uint32_t iter,
+                                 int64_t row0, int search_mode, float* p0_out, float* h0, float* h1,
+                                 float* lp0, float* lp_sel, float* acc, int32_t* accept,
+                                 float* acc_part, int* n_part_out /* host */, void* stream);
+
+/* Dense-Gaussian target log p = -1/2 (x-mu)^T P (x-mu) + c: one launch per pass of the leapfrog
+ * while-loop body (hmc.py:352-364): g = b - q_cur P; p_out = p_in + p_scale*eps*g;
+ * q_next = q_cur + eps*p_out/mass (skipped if NULL); lp_part/k_part [ntiles, chains] partials.
+ * impl 0 = SIMT fp32, impl 1 = tcgen05 3xTF32 (P = hi part, P_lo = residual). */
+int zsb_hmc_dense_ntiles(int64_t D, int impl);
+int zsb_hmc_dense_leapfrog_f32(const float* q_cur, float* q_next, const float* p_in, float* p_out,
+                               const float* P, const float* P_lo, const float* bvec,
+                               const float* mu, const float* mass, const float* state,
+                               float p_scale, float* lp_part, float* k_part, int64_t chains,
+                               int64_t D, int impl, void* stream);
+int zsb_hmc_dense_finish_f32(const float* lp_part, const float* k_part, int ntiles, int64_t chains,
+                             float const_term, float* lp_out, float* k_out, void* stream);
+
+/* ---- K5: SG-MCMC updates (zhusuan/sgmcmc.py) ------------------------------------------------ */
+int zsb_sgmcmc_parts(void);   /* capacity (floats) of every `part` scratch */
+int zsb_sgmcmc_sgld_f32(float* q, const float* g, const float* noise, float lr, int64_t chains,
+                        int64_t row_len, uint64_t seed, uint32_t iter, int64_t row0,
+                        void* stream);                                   /* sgmcmc.py:195-200 */
+int zsb_sgmcmc_psgld_f32(float* q, float* aux, const float* g, const float* noise, float lr,
+                         float decay, float epsilon, int64_t chains, int64_t row_len,
+                         uint64_t seed, uint32_t iter, int64_t row0, void* stream); /* :225-257 */
+int zsb_sgmcmc_resample_v_f32(float* v, const float* noise, float lr, int64_t chains,
+                              int64_t row_len, uint64_t seed, uint32_t iter, int64_t row0,
+                              void* stream);                             /* :320-336 */
+int zsb_sgmcmc_half_q_f32(float* q, const float* v, int64_t n, void* stream);  /* :351, :493 */
+int zsb_sgmcmc_sghmc_f32(float* q, float* v, const float* g, const float* noise, float lr,
+                         float alpha, float beta, int second_order, int64_t chains,
+                         int64_t row_len, uint64_t seed, uint32_t iter, int64_t row0,
+                         float* part, float* mean_k, void* stream);      /* :338-358 */
+int zsb_sgmcmc_sgnht_vec_f32(float* q, float* v, float* alpha, const float* g, const float* noise,
+                             float lr, float a, float tune_rate, int second_order, int64_t chains,
+                             int64_t row_len, uint64_t seed, uint32_t iter, int64_t row0,
+                             float* mean_k_out, void* stream);           /* :460-523 vector alpha */
+int zsb_sgmcmc_mean_sq_f32(const float* v, int64_t n, float* part, float* out, void* stream);
+int zsb_sgmcmc_sgnht_scalar_f32(float* q, float* v, const float* alpha_eff, const float* g,
+                                const float* noise, float lr, float a, int second_order,
+                                int64_t chains, int64_t row_len, uint64_t seed, uint32_t iter,
+                                int64_t row0, float* part, float* mean_k, void* stream);
+int zsb_sgmcmc_sgnht_alpha_f32(float* out, const float* in, const float* mean_k, float coef,
+                               float lr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZSB200_H_ */

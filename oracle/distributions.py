@@ -1,0 +1,140 @@
+"""NumPy restatement of the hot-path ``log_prob`` formulas (TEST ORACLE ONLY).
+
+Each function follows the reference's ``_log_prob`` followed by
+``Distribution.log_prob``'s reduce_sum over the last ``group_ndims`` axes
+(zhusuan/distributions/base.py:290-304).  Broadcasting is NumPy broadcasting,
+which is what ``maybe_explicit_broadcast`` materialises
+(zhusuan/distributions/utils.py:52-78).
+
+``dtype`` selects the arithmetic type (float32 mirrors TF's default, float64
+is the high-precision twin used to bound fp32 error in the parity tests).
+"""
+import numpy as np
+from scipy import special as _sp
+
+LOG_2PI_HALF = 0.5 * np.log(2.0 * np.pi)
+
+
+def _group_sum(x, group_ndims):
+    # distributions/base.py:303-304: reduce_sum(log_p, range(-group_ndims, 0))
+    if group_ndims == 0:
+        return x
+    return x.sum(axis=tuple(range(-group_ndims, 0)))
+
+
+def normal_log_prob(given, mean, logstd, group_ndims=0, dtype=np.float32):
+    """Normal._log_prob, univariate.py:174-181.
+
+    c - logstd - 0.5 * exp(-2 logstd) * (given - mean)^2, c = -0.5 log(2 pi).
+    """
+    given, mean, logstd = (np.asarray(a, dtype) for a in (given, mean, logstd))
+    c = dtype(-LOG_2PI_HALF)
+    precision = np.exp(dtype(-2.0) * logstd)
+    lp = c - logstd - dtype(0.5) * precision * np.square(given - mean)
+    return _group_sum(lp, group_ndims)
+
+
+def normal_log_prob_grads(given, mean, logstd, dtype=np.float64):
+    """Elementwise d log_prob / d(given, mean, logstd) (for the K1 bwd test)."""
+    given, mean, logstd = (np.asarray(a, dtype) for a in (given, mean, logstd))
+    prec = np.exp(-2.0 * logstd)
+    diff = given - mean
+    dgiven = -prec * diff
+    dmean = prec * diff
+    dlogstd = -1.0 + prec * diff * diff
+    return dgiven, dmean, dlogstd
+
+
+def bernoulli_log_prob(given, logits, group_ndims=0, dtype=np.float32):
+    """Bernoulli._log_prob, univariate.py:398-403.
+
+    -sigmoid_cross_entropy_with_logits(labels=x, logits=l)
+      = -(max(l, 0) - l * x + log(1 + exp(-|l|)))   (TF's stable form).
+    """
+    x = np.asarray(given).astype(dtype)
+    l = np.asarray(logits, dtype)
+    lp = -(np.maximum(l, dtype(0)) - l * x + np.log1p(np.exp(-np.abs(l))))
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def categorical_log_prob(given, logits, group_ndims=0, dtype=np.float32):
+    """Categorical._log_prob, univariate.py:496-548.
+
+    -sparse_softmax_cross_entropy_with_logits = log_softmax(logits)[given].
+    """
+    logits = np.asarray(logits, dtype)
+    given = np.asarray(given).astype(np.int64)
+    bshape = np.broadcast_shapes(given.shape, logits.shape[:-1])
+    given = np.broadcast_to(given, bshape)
+    logits = np.broadcast_to(logits, bshape + logits.shape[-1:])
+    m = logits.max(axis=-1, keepdims=True)
+    lse = np.log(np.exp(logits - m).sum(axis=-1, keepdims=True)) + m
+    logsm = logits - lse
+    lp = np.take_along_axis(logsm, given[..., None], axis=-1)[..., 0]
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def dirichlet_log_prob(given, alpha, group_ndims=0, dtype=np.float32):
+    """Dirichlet._log_prob, multivariate.py:665-677.
+
+    -lbeta(alpha) + sum((alpha - 1) * log(given), -1),
+    lbeta = sum(lgamma(alpha_i)) - lgamma(sum(alpha_i)).
+    """
+    given = np.asarray(given, dtype)
+    alpha = np.asarray(alpha, dtype)
+    given, alpha = np.broadcast_arrays(given, alpha)
+    lbeta = _sp.gammaln(alpha).sum(-1) - _sp.gammaln(alpha.sum(-1))
+    lp = -lbeta + ((alpha - dtype(1)) * np.log(given)).sum(-1)
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def unnormalized_multinomial_log_prob(given, logits, normalize_logits=True,
+                                      group_ndims=0, dtype=np.float32):
+    """UnnormalizedMultinomial._log_prob, multivariate.py:435-443."""
+    given = np.asarray(given).astype(dtype)
+    logits = np.asarray(logits, dtype)
+    given, logits = np.broadcast_arrays(given, logits)
+    if normalize_logits:
+        m = logits.max(axis=-1, keepdims=True)
+        logits = logits - (np.log(np.exp(logits - m).sum(-1, keepdims=True))
+                           + m)
+    lp = (given * logits).sum(-1)
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def mvn_cholesky_log_prob(given, mean, cov_tril, group_ndims=0,
+                          dtype=np.float32):
+    """MultivariateNormalCholesky._log_prob, multivariate.py:169-189.
+
+    log_z = -n/2 log(2 pi) - sum(log diag L);  -0.5 |L^{-1}(given - mean)|^2.
+    """
+    from scipy.linalg import solve_triangular
+    given = np.asarray(given, dtype)
+    mean = np.asarray(mean, dtype)
+    L = np.asarray(cov_tril, dtype)
+    n = mean.shape[-1]
+    log_det = 2 * np.log(np.diagonal(L, axis1=-2, axis2=-1)).sum(-1)
+    log_z = -n / 2 * np.log(2 * np.pi) - log_det / 2
+    y = given - mean
+    bshape = np.broadcast_shapes(y.shape[:-1], L.shape[:-2])
+    y = np.broadcast_to(y, bshape + (n,)).reshape(-1, n)
+    Lb = np.broadcast_to(L, bshape + (n, n)).reshape(-1, n, n)
+    x = np.stack([solve_triangular(Lb[i], y[i], lower=True)
+                  for i in range(y.shape[0])]) if y.shape[0] else \
+        np.zeros((0, n), dtype)
+    stoc = -0.5 * np.square(x).sum(-1).reshape(bshape)
+    lp = (np.broadcast_to(log_z, bshape) + stoc).astype(dtype)
+    return _group_sum(lp, group_ndims)
+
+
+def normal_sample(eps, mean, std, dtype=np.float32):
+    """Normal._sample with injected eps: eps * std + mean (univariate.py:167)."""
+    return (np.asarray(eps, dtype) * np.asarray(std, dtype)
+            + np.asarray(mean, dtype))
+
+
+def bernoulli_sample(u, logits, dtype=np.int32):
+    """Bernoulli._sample with injected uniforms: u < sigmoid(logits)
+    (univariate.py:386-392)."""
+    p = 1.0 / (1.0 + np.exp(-np.asarray(logits, np.float32)))
+    return (np.asarray(u, np.float32) < p.astype(np.float32)).astype(dtype)

@@ -1,0 +1,490 @@
+// K1 / K7: distribution log_prob (+ analytic backward) and sampling kernels.
+//
+// Semantics follow zhusuan/distributions (reference file:line cited per kernel).  Operands are
+// broadcast by "modular" indexing: element i of the broadcast result reads operand[i % operand_n],
+// which covers every case where the operand's shape is a suffix of the broadcast shape (scalars,
+// params shared across the leading sample/chain axes, `given` shared across particles).  Other
+// broadcast patterns are materialised by the host (that is what the reference's
+// maybe_explicit_broadcast does for ALL patterns, distributions/utils.py:52-78).
+//
+// All kernels are HBM-bound elementwise/row-reduce kernels: coalesced loads, grid-stride over rows,
+// warp-shuffle reductions over the event (`group`) axis, deterministic summation order.
+#include "common.cuh"
+
+namespace {
+
+constexpr float kHalfLog2Pi = 0.9189385332046727f;
+
+// rows of `group` consecutive elements; LANES threads cooperate on one row.
+template <int LANES, class F>
+__global__ void __launch_bounds__(256) row_reduce_kernel(float* __restrict__ out, int64_t n_out,
+                                                         int64_t group, F f) {
+  const int rows_per_block = 256 / LANES;
+  const int lane = threadIdx.x % LANES;
+  const int rib = threadIdx.x / LANES;
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_block + rib; row < n_out;
+       row += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t base = row * group;
+    float acc = 0.f;
+    for (int64_t j = lane; j < group; j += LANES) acc += f(base + j);
+    acc = sub_warp_sum<LANES>(acc);
+    if (lane == 0) out[row] = acc;
+  }
+}
+
+template <class F>
+int launch_row_reduce(float* out, int64_t n_out, int64_t group, F f, cudaStream_t st,
+                      const char* what) {
+  if (n_out == 0) return ZSB_OK;
+  int lanes = 1;
+  while (lanes < 32 && lanes < group) lanes <<= 1;
+  const int rows_per_block = 256 / lanes;
+  int64_t blocks = zsb_ceil_div(n_out, rows_per_block);
+  const int64_t cap = (int64_t)ZSB_NUM_SMS * 16;
+  if (blocks > cap) blocks = cap;
+  switch (lanes) {
+    case 1: row_reduce_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(out, n_out, group, f); break;
+    case 2: row_reduce_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(out, n_out, group, f); break;
+    case 4: row_reduce_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(out, n_out, group, f); break;
+    case 8: row_reduce_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(out, n_out, group, f); break;
+    case 16: row_reduce_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(out, n_out, group, f); break;
+    default: row_reduce_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(out, n_out, group, f); break;
+  }
+  return zsb_check_launch(what);
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) elementwise_kernel(int64_t n, F f) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    f(i);
+}
+template <class F>
+int launch_elementwise(int64_t n, F f, cudaStream_t st, const char* what) {
+  if (n == 0) return ZSB_OK;
+  int64_t blocks = zsb_ceil_div(n, 256);
+  const int64_t cap = (int64_t)ZSB_NUM_SMS * 16;
+  if (blocks > cap) blocks = cap;
+  elementwise_kernel<<<(unsigned)blocks, 256, 0, st>>>(n, f);
+  return zsb_check_launch(what);
+}
+
+// TF's numerically stable sigmoid cross entropy: max(l,0) - l*x + log1p(exp(-|l|)).
+__device__ __forceinline__ float bernoulli_lp(float x, float l) {
+  return -(fmaxf(l, 0.f) - l * x + log1pf(expf(-fabsf(l))));
+}
+__device__ __forceinline__ float sigmoidf_(float l) { return 1.f / (1.f + expf(-l)); }
+
+// One warp per row of C categories: returns (max, log-sum-exp) over logits[row*C .. +C).
+__device__ __forceinline__ float warp_row_lse(const float* __restrict__ l, int64_t C, int lane) {
+  float m = -INFINITY;
+  for (int64_t j = lane; j < C; j += 32) m = fmaxf(m, l[j]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int64_t j = lane; j < C; j += 32) s += expf(l[j] - m);
+  s = warp_sum(s);
+  return logf(s) + m;
+}
+
+// Categorical._log_prob, univariate.py:496-548: log_softmax(logits)[given].
+__global__ void __launch_bounds__(256) categorical_lp_kernel(const int32_t* __restrict__ given,
+                                                             int64_t given_n,
+                                                             const float* __restrict__ logits,
+                                                             int64_t logits_rows, int64_t C,
+                                                             float* __restrict__ out, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows;
+       row += (int64_t)gridDim.x * 8) {
+    const float* l = logits + (row % logits_rows) * C;
+    const float lse = warp_row_lse(l, C, lane);
+    if (lane == 0) {
+      const int32_t k = given[row % given_n];
+      out[row] = (k >= 0 && k < C) ? (l[k] - lse) : NAN;
+    }
+  }
+}
+// d lp / d logits = gout * (onehot(given) - softmax(logits)); written at full (row, C) size.
+__global__ void __launch_bounds__(256) categorical_bwd_kernel(
+    const int32_t* __restrict__ given, int64_t given_n, const float* __restrict__ logits,
+    int64_t logits_rows, int64_t C, const float* __restrict__ gout, float* __restrict__ dlogits,
+    int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows;
+       row += (int64_t)gridDim.x * 8) {
+    const float* l = logits + (row % logits_rows) * C;
+    const float lse = warp_row_lse(l, C, lane);
+    const int32_t k = given[row % given_n];
+    const float g = gout[row];
+    for (int64_t j = lane; j < C; j += 32)
+      dlogits[row * C + j] = g * ((j == k ? 1.f : 0.f) - expf(l[j] - lse));
+  }
+}
+
+// Dirichlet._log_prob, multivariate.py:665-677.
+__global__ void __launch_bounds__(256) dirichlet_lp_kernel(const float* __restrict__ given,
+                                                           int64_t given_rows,
+                                                           const float* __restrict__ alpha,
+                                                           int64_t alpha_rows, int64_t C,
+                                                           float* __restrict__ out, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows;
+       row += (int64_t)gridDim.x * 8) {
+    const float* x = given + (row % given_rows) * C;
+    const float* a = alpha + (row % alpha_rows) * C;
+    float sa = 0.f, slg = 0.f, s = 0.f;
+    for (int64_t j = lane; j < C; j += 32) {
+      const float aj = a[j];
+      sa += aj;
+      slg += lgammaf(aj);
+      s += (aj - 1.f) * logf(x[j]);
+    }
+    sa = warp_sum(sa); slg = warp_sum(slg); s = warp_sum(s);
+    if (lane == 0) out[row] = -(slg - lgammaf(sa)) + s;
+  }
+}
+// d lp / d given_j = gout * (alpha_j - 1) / x_j  (the HMC-relevant gradient), full size.
+__global__ void __launch_bounds__(256) dirichlet_bwd_given_kernel(
+    const float* __restrict__ given, int64_t given_rows, const float* __restrict__ alpha,
+    int64_t alpha_rows, int64_t C, const float* __restrict__ gout, float* __restrict__ dgiven,
+    int64_t rows) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * C;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / C, j = i % C;
+    const float x = given[(row % given_rows) * C + j];
+    const float a = alpha[(row % alpha_rows) * C + j];
+    dgiven[i] = gout[row] * (a - 1.f) / x;
+  }
+}
+
+// UnnormalizedMultinomial._log_prob, multivariate.py:435-443: sum x * (logits - [LSE]).
+__global__ void __launch_bounds__(256) unnorm_multinomial_lp_kernel(
+    const float* __restrict__ given, int64_t given_rows, const float* __restrict__ logits,
+    int64_t logits_rows, int64_t C, int normalize, float* __restrict__ out, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows;
+       row += (int64_t)gridDim.x * 8) {
+    const float* x = given + (row % given_rows) * C;
+    const float* l = logits + (row % logits_rows) * C;
+    const float lse = normalize ? warp_row_lse(l, C, lane) : 0.f;
+    float s = 0.f;
+    for (int64_t j = lane; j < C; j += 32) s += x[j] * (l[j] - lse);
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s;
+  }
+}
+// d lp / d logits_j = gout * (x_j - [sum_x * softmax_j]), full size.
+__global__ void __launch_bounds__(256) unnorm_multinomial_bwd_kernel(
+    const float* __restrict__ given, int64_t given_rows, const float* __restrict__ logits,
+    int64_t logits_rows, int64_t C, int normalize, const float* __restrict__ gout,
+    float* __restrict__ dlogits, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows;
+       row += (int64_t)gridDim.x * 8) {
+    const float* x = given + (row % given_rows) * C;
+    const float* l = logits + (row % logits_rows) * C;
+    float lse = 0.f, sx = 0.f;
+    if (normalize) {
+      lse = warp_row_lse(l, C, lane);
+      for (int64_t j = lane; j < C; j += 32) sx += x[j];
+      sx = warp_sum(sx);
+    }
+    const float g = gout[row];
+    for (int64_t j = lane; j < C; j += 32) {
+      const float sm = normalize ? sx * expf(l[j] - lse) : 0.f;
+      dlogits[row * C + j] = g * (x[j] - sm);
+    }
+  }
+}
+
+// MultivariateNormalCholesky._log_prob, multivariate.py:169-189.  One block per row; forward
+// substitution in shared memory (x = L^{-1}(given - mean)), L read through L2.
+__global__ void __launch_bounds__(128) mvn_chol_lp_kernel(const float* __restrict__ given,
+                                                          int64_t given_rows,
+                                                          const float* __restrict__ mean,
+                                                          int64_t mean_rows,
+                                                          const float* __restrict__ L,
+                                                          int64_t L_mats, int64_t D,
+                                                          float* __restrict__ out, int64_t rows,
+                                                          float* __restrict__ x_out) {
+  extern __shared__ float sh[];  // D floats + 32
+  float* y = sh;
+  float* red = sh + D;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float* g = given + (row % given_rows) * D;
+    const float* mu = mean + (row % mean_rows) * D;
+    const float* Lm = L + (row % L_mats) * D * D;
+    for (int64_t j = threadIdx.x; j < D; j += blockDim.x) y[j] = g[j] - mu[j];
+    __syncthreads();
+    float logdet_half = 0.f;
+    for (int64_t j = threadIdx.x; j < D; j += blockDim.x) logdet_half += logf(Lm[j * D + j]);
+    // column-oriented forward substitution
+    for (int64_t k = 0; k < D; ++k) {
+      if (threadIdx.x == 0) y[k] = y[k] / Lm[k * D + k];
+      __syncthreads();
+      const float xk = y[k];
+      for (int64_t j = k + 1 + threadIdx.x; j < D; j += blockDim.x) y[j] -= Lm[j * D + k] * xk;
+      __syncthreads();
+    }
+    float ss = 0.f;
+    for (int64_t j = threadIdx.x; j < D; j += blockDim.x) {
+      ss += y[j] * y[j];
+      if (x_out) x_out[row * D + j] = y[j];
+    }
+    ss = block_sum(ss, red);
+    logdet_half = block_sum(logdet_half, red);
+    if (threadIdx.x == 0)
+      out[row] = -(float)D * kHalfLog2Pi - logdet_half - 0.5f * ss;
+    __syncthreads();
+  }
+}
+// d lp / d given = -L^{-T} x, x = L^{-1}(given - mean): back substitution, one block per row.
+__global__ void __launch_bounds__(128) mvn_chol_bwd_given_kernel(
+    const float* __restrict__ x_in, const float* __restrict__ L, int64_t L_mats, int64_t D,
+    const float* __restrict__ gout, float* __restrict__ dgiven, int64_t rows) {
+  extern __shared__ float sh[];
+  float* y = sh;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float* Lm = L + (row % L_mats) * D * D;
+    for (int64_t j = threadIdx.x; j < D; j += blockDim.x) y[j] = x_in[row * D + j];
+    __syncthreads();
+    for (int64_t k = D - 1; k >= 0; --k) {
+      if (threadIdx.x == 0) y[k] = y[k] / Lm[k * D + k];
+      __syncthreads();
+      const float zk = y[k];
+      // L^T[j][k] = L[k][j], j < k
+      for (int64_t j = threadIdx.x; j < k; j += blockDim.x) y[j] -= Lm[k * D + j] * zk;
+      __syncthreads();
+    }
+    const float g = gout[row];
+    for (int64_t j = threadIdx.x; j < D; j += blockDim.x) dgiven[row * D + j] = -g * y[j];
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Normal._log_prob, univariate.py:174-181 + base.py:303-304 group sum.
+int zsb_logprob_normal_f32(const float* given, int64_t given_n, const float* mean, int64_t mean_n,
+                           const float* logstd, int64_t logstd_n, float* out, int64_t n_out,
+                           int64_t group, void* stream) {
+  ZSB_REQUIRE(given_n > 0 && mean_n > 0 && logstd_n > 0 && group > 0 && n_out >= 0,
+              "zsb_logprob_normal_f32: bad sizes");
+  auto f = [=] __device__(int64_t i) -> float {
+    const float x = given[i % given_n], mu = mean[i % mean_n], ls = logstd[i % logstd_n];
+    const float d = x - mu;
+    return -kHalfLog2Pi - ls - 0.5f * expf(-2.f * ls) * d * d;
+  };
+  return launch_row_reduce(out, n_out, group, f, (cudaStream_t)stream, "logprob_normal");
+}
+
+// Elementwise analytic backward; each output (nullable) has n_out*group elements.
+int zsb_logprob_normal_bwd_f32(const float* given, int64_t given_n, const float* mean,
+                               int64_t mean_n, const float* logstd, int64_t logstd_n,
+                               const float* gout, int64_t n_out, int64_t group, float* dgiven,
+                               float* dmean, float* dlogstd, void* stream) {
+  ZSB_REQUIRE(given_n > 0 && mean_n > 0 && logstd_n > 0 && group > 0 && n_out >= 0,
+              "zsb_logprob_normal_bwd_f32: bad sizes");
+  auto f = [=] __device__(int64_t i) {
+    const float x = given[i % given_n], mu = mean[i % mean_n], ls = logstd[i % logstd_n];
+    const float g = gout[i / group];
+    const float prec = expf(-2.f * ls), d = x - mu;
+    if (dgiven) dgiven[i] = -g * prec * d;
+    if (dmean) dmean[i] = g * prec * d;
+    if (dlogstd) dlogstd[i] = g * (prec * d * d - 1.f);
+  };
+  return launch_elementwise(n_out * group, f, (cudaStream_t)stream, "logprob_normal_bwd");
+}
+
+// Bernoulli._log_prob, univariate.py:398-403 (given already cast to float by the host, :399).
+int zsb_logprob_bernoulli_f32(const float* given, int64_t given_n, const float* logits,
+                              int64_t logits_n, float* out, int64_t n_out, int64_t group,
+                              void* stream) {
+  ZSB_REQUIRE(given_n > 0 && logits_n > 0 && group > 0 && n_out >= 0,
+              "zsb_logprob_bernoulli_f32: bad sizes");
+  auto f = [=] __device__(int64_t i) -> float {
+    return bernoulli_lp(given[i % given_n], logits[i % logits_n]);
+  };
+  return launch_row_reduce(out, n_out, group, f, (cudaStream_t)stream, "logprob_bernoulli");
+}
+int zsb_logprob_bernoulli_bwd_f32(const float* given, int64_t given_n, const float* logits,
+                                  int64_t logits_n, const float* gout, int64_t n_out,
+                                  int64_t group, float* dlogits, void* stream) {
+  ZSB_REQUIRE(given_n > 0 && logits_n > 0 && group > 0 && n_out >= 0 && dlogits,
+              "zsb_logprob_bernoulli_bwd_f32: bad sizes");
+  auto f = [=] __device__(int64_t i) {
+    dlogits[i] = gout[i / group] * (given[i % given_n] - sigmoidf_(logits[i % logits_n]));
+  };
+  return launch_elementwise(n_out * group, f, (cudaStream_t)stream, "logprob_bernoulli_bwd");
+}
+
+int zsb_logprob_categorical_f32(const int32_t* given, int64_t given_n, const float* logits,
+                                int64_t logits_rows, int64_t n_categories, float* out,
+                                int64_t rows, void* stream) {
+  ZSB_REQUIRE(given_n > 0 && logits_rows > 0 && n_categories > 0 && rows >= 0,
+              "zsb_logprob_categorical_f32: bad sizes");
+  if (rows == 0) return ZSB_OK;
+  int64_t blocks = zsb_ceil_div(rows, 8);
+  if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
+  categorical_lp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      given, given_n, logits, logits_rows, n_categories, out, rows);
+  return zsb_check_launch("logprob_categorical");
+}
+int zsb_logprob_categorical_bwd_f32(const int32_t* given, int64_t given_n, const float* logits,
+                                    int64_t logits_rows, int64_t n_categories, const float* gout,
+                                    float* dlogits, int64_t rows, void* stream) {
+  ZSB_REQUIRE(given_n > 0 && logits_rows > 0 && n_categories > 0 && rows >= 0,
+              "zsb_logprob_categorical_bwd_f32: bad sizes");
+  if (rows == 0) return ZSB_OK;
+  int64_t blocks = zsb_ceil_div(rows, 8);
+  if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
+  categorical_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      given, given_n, logits, logits_rows, n_categories, gout, dlogits, rows);
+  return zsb_check_launch("logprob_categorical_bwd");
+}
+
+int zsb_logprob_dirichlet_f32(const float* given, int64_t given_rows, const float* alpha,
+                              int64_t alpha_rows, int64_t n_categories, float* out, int64_t rows,
+                              void* stream) {
+  ZSB_REQUIRE(given_rows > 0 && alpha_rows > 0 && n_categories >= 2 && rows >= 0,
+              "zsb_logprob_dirichlet_f32: bad sizes (n_categories must be >= 2)");
+  if (rows == 0) return ZSB_OK;
+  int64_t blocks = zsb_ceil_div(rows, 8);
+  if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
+  dirichlet_lp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      given, given_rows, alpha, alpha_rows, n_categories, out, rows);
+  return zsb_check_launch("logprob_dirichlet");
+}
+int zsb_logprob_dirichlet_bwd_given_f32(const float* given, int64_t given_rows,
+                                        const float* alpha, int64_t alpha_rows,
+                                        int64_t n_categories, const float* gout, float* dgiven,
+                                        int64_t rows, void* stream) {
+  ZSB_REQUIRE(given_rows > 0 && alpha_rows > 0 && n_categories >= 2 && rows >= 0,
+              "zsb_logprob_dirichlet_bwd_given_f32: bad sizes");
+  if (rows == 0) return ZSB_OK;
+  int64_t blocks = zsb_ceil_div(rows * n_categories, 256);
+  if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
+  dirichlet_bwd_given_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      given, given_rows, alpha, alpha_rows, n_categories, gout, dgiven, rows);
+  return zsb_check_launch("logprob_dirichlet_bwd_given");
+}
+
+int zsb_logprob_unnorm_multinomial_f32(const float* given, int64_t given_rows,
+                                       const float* logits, int64_t logits_rows,
+                                       int64_t n_categories, int normalize_logits, float* out,
+                                       int64_t rows, void* stream) {
+  ZSB_REQUIRE(given_rows > 0 && logits_rows > 0 && n_categories > 0 && rows >= 0,
+              "zsb_logprob_unnorm_multinomial_f32: bad sizes");
+  if (rows == 0) return ZSB_OK;
+  int64_t blocks = zsb_ceil_div(rows, 8);
+  if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
+  unnorm_multinomial_lp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      given, given_rows, logits, logits_rows, n_categories, normalize_logits, out, rows);
+  return zsb_check_launch("logprob_unnorm_multinomial");
+}
+int zsb_logprob_unnorm_multinomial_bwd_f32(const float* given, int64_t given_rows,
+                                           const float* logits, int64_t logits_rows,
+                                           int64_t n_categories, int normalize_logits,
+                                           const float* gout, float* dlogits, int64_t rows,
+                                           void* stream) {
+  ZSB_REQUIRE(given_rows > 0 && logits_rows > 0 && n_categories > 0 && rows >= 0,
+              "zsb_logprob_unnorm_multinomial_bwd_f32: bad sizes");
+  if (rows == 0) return ZSB_OK;
+  int64_t blocks = zsb_ceil_div(rows, 8);
+  if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
+  unnorm_multinomial_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      given, given_rows, logits, logits_rows, n_categories, normalize_logits, gout, dlogits, rows);
+  return zsb_check_launch("logprob_unnorm_multinomial_bwd");
+}
+
+// x_out (nullable, rows*D) receives L^{-1}(given-mean) for the backward.
+int zsb_logprob_mvn_chol_f32(const float* given, int64_t given_rows, const float* mean,
+                             int64_t mean_rows, const float* cov_tril, int64_t tril_mats,
+                             int64_t n_dim, float* out, float* x_out, int64_t rows,
+                             void* stream) {
+  ZSB_REQUIRE(given_rows > 0 && mean_rows > 0 && tril_mats > 0 && n_dim > 0 && rows >= 0,
+              "zsb_logprob_mvn_chol_f32: bad sizes");
+  ZSB_REQUIRE(n_dim <= 12000, "zsb_logprob_mvn_chol_f32: n_dim too large for shared memory");
+  if (rows == 0) return ZSB_OK;
+  int64_t blocks = rows < ZSB_NUM_SMS * 8 ? rows : ZSB_NUM_SMS * 8;
+  const size_t smem = (size_t)(n_dim + 32) * sizeof(float);
+  mvn_chol_lp_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(
+      given, given_rows, mean, mean_rows, cov_tril, tril_mats, n_dim, out, rows, x_out);
+  return zsb_check_launch("logprob_mvn_chol");
+}
+int zsb_logprob_mvn_chol_bwd_given_f32(const float* x_in, const float* cov_tril,
+                                       int64_t tril_mats, int64_t n_dim, const float* gout,
+                                       float* dgiven, int64_t rows, void* stream) {
+  ZSB_REQUIRE(tril_mats > 0 && n_dim > 0 && rows >= 0, "zsb_logprob_mvn_chol_bwd_given_f32: bad sizes");
+  ZSB_REQUIRE(n_dim <= 12000, "zsb_logprob_mvn_chol_bwd_given_f32: n_dim too large");
+  if (rows == 0) return ZSB_OK;
+  int64_t blocks = rows < ZSB_NUM_SMS * 8 ? rows : ZSB_NUM_SMS * 8;
+  const size_t smem = (size_t)(n_dim + 32) * sizeof(float);
+  mvn_chol_bwd_given_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(
+      x_in, cov_tril, tril_mats, n_dim, gout, dgiven, rows);
+  return zsb_check_launch("logprob_mvn_chol_bwd_given");
+}
+
+// out[r] = sum_{j<group} in[r*group + j]   (Distribution.log_prob's reduce_sum, base.py:303-304)
+int zsb_group_sum_f32(const float* in, float* out, int64_t n_out, int64_t group, void* stream) {
+  ZSB_REQUIRE(group > 0 && n_out >= 0, "zsb_group_sum_f32: bad sizes");
+  auto f = [=] __device__(int64_t i) -> float { return in[i]; };
+  return launch_row_reduce(out, n_out, group, f, (cudaStream_t)stream, "group_sum");
+}
+
+// K7: Normal._sample (univariate.py:161-172) fused with log q(z) of the drawn sample
+// (StochasticTensor.cond_log_p, bn.py:194-204).  eps: injected standard normals [n_out*group] or
+// NULL -> in-kernel Philox (stream SAMPLE, counter (i/4, 0, iter, stream)).
+// z = eps * exp(logstd) + mean;   logq[r] = sum_j (-0.5 log 2pi - logstd - 0.5 eps^2)
+// (identical to Normal._log_prob at z because (z - mean) * exp(-logstd) == eps up to rounding;
+// the kernel evaluates the reference expression on z itself for parity).
+int zsb_reparam_normal_f32(const float* mean, int64_t mean_n, const float* logstd,
+                           int64_t logstd_n, const float* eps, uint64_t seed, uint32_t iter,
+                           float* z_out, float* eps_out, float* logq_out, int64_t n_out,
+                           int64_t group, void* stream) {
+  ZSB_REQUIRE(mean_n > 0 && logstd_n > 0 && group > 0 && n_out >= 0 && z_out,
+              "zsb_reparam_normal_f32: bad sizes");
+  auto f = [=] __device__(int64_t i) -> float {
+    float e;
+    if (eps) {
+      e = eps[i];
+    } else {
+      float z4[4];
+      philox_normal4(seed, ZSB_STREAM_SAMPLE, iter, (uint32_t)((uint64_t)i >> 34),
+                     (uint32_t)(i >> 2), z4);
+      e = z4[i & 3];
+    }
+    const float mu = mean[i % mean_n], ls = logstd[i % logstd_n];
+    const float z = e * expf(ls) + mu;
+    z_out[i] = z;
+    if (eps_out) eps_out[i] = e;
+    const float d = z - mu;
+    return -kHalfLog2Pi - ls - 0.5f * expf(-2.f * ls) * d * d;
+  };
+  if (logq_out)
+    return launch_row_reduce(logq_out, n_out, group, f, (cudaStream_t)stream, "reparam_normal");
+  auto g = [=] __device__(int64_t i) { (void)f(i); };
+  return launch_elementwise(n_out * group, g, (cudaStream_t)stream, "reparam_normal");
+}
+
+// Bernoulli._sample, univariate.py:386-396: (u < sigmoid(logits)) as int32; u injected or Philox.
+int zsb_sample_bernoulli_i32(const float* logits, int64_t logits_n, const float* u, uint64_t seed,
+                             uint32_t iter, int32_t* out, int64_t n, void* stream) {
+  ZSB_REQUIRE(logits_n > 0 && n >= 0, "zsb_sample_bernoulli_i32: bad sizes");
+  auto f = [=] __device__(int64_t i) {
+    float uu;
+    if (u) {
+      uu = u[i];
+    } else {
+      const Philox4 r = philox4x32_10((uint32_t)(i >> 2), (uint32_t)((uint64_t)i >> 34), iter,
+                                      ZSB_STREAM_SAMPLE, (uint32_t)seed, (uint32_t)(seed >> 32));
+      const uint32_t w = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
+      uu = u32_to_uniform(w);
+    }
+    out[i] = uu < sigmoidf_(logits[i % logits_n]) ? 1 : 0;
+  };
+  return launch_elementwise(n, f, (cudaStream_t)stream, "sample_bernoulli");
+}
+
+}  // extern "C"

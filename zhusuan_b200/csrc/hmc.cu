@@ -1,0 +1,559 @@
+// K2 / K3 / K4: parallel-chain HMC kernels (reference: zhusuan/hmc.py).
+//
+// Layout: every latent is canonicalised by the host to a row-major [chains, row_len] float32
+// matrix (chain axes flattened to rows, data axes flattened to row_len); per-dimension vectors
+// (mass, EWMV mean/var) are [row_len].  Sampler scalars live in a 16-float device state block
+// (common.cuh: ZSB_ST_*), so an iteration never needs a host read-back.
+//
+// Elementwise arithmetic uses explicit round-to-nearest mul/add (no FMA contraction) in the
+// reference's operation order so that the CPU oracle (NumPy float32) reproduces it bit-for-bit;
+// only reductions (different summation tree) and libm calls (exp/log) can differ in the last ulp.
+// These kernels are HBM-bound, so forgoing FMA costs nothing.
+#include "common.cuh"
+
+namespace {
+
+
+// ---------------------------------------------------------------------------------------------
+// a1  random_momentum (hmc.py:21-23): p = N(0,1) * sqrt(mass);   optional kinetic 0.5*sum p^2/m.
+// LANES threads per chain; each lane walks 4-element Philox blocks.
+template <int LANES>
+__global__ void __launch_bounds__(256) momentum_kernel(float* __restrict__ p,
+                                                       const float* __restrict__ noise,
+                                                       const float* __restrict__ mass,
+                                                       int64_t mass_n, int64_t chains,
+                                                       int64_t row_len, uint64_t seed,
+                                                       uint32_t iter, uint32_t stream_id,
+                                                       int64_t row0, float* __restrict__ k_out,
+                                                       int accumulate) {
+  const int rows_per_block = 256 / LANES;
+  const int lane = threadIdx.x % LANES;
+  const int64_t nblk = (row_len + 3) / 4;
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / LANES; row < chains;
+       row += (int64_t)gridDim.x * rows_per_block) {
+    float kin = 0.f;
+    for (int64_t b = lane; b < nblk; b += LANES) {
+      float z[4];
+      if (!noise) philox_normal4(seed, stream_id, iter, (uint32_t)(row0 + row), (uint32_t)b, z);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t c = b * 4 + e;
+        if (c < row_len) {
+          const float zz = noise ? noise[row * row_len + c] : z[e];
+          const float m = mass[c % mass_n];
+          const float pv = mul(zz, sqrtf(m));
+          p[row * row_len + c] = pv;
+          kin += fdiv(mul(pv, pv), m);
+        }
+      }
+    }
+    kin = sub_warp_sum<LANES>(kin);
+    if (lane == 0 && k_out) {
+      const float v = mul(0.5f, kin);
+      k_out[row] = accumulate ? add(k_out[row], v) : v;
+    }
+  }
+}
+
+// a5 kinetic (hmc.py:32-34): k[c] (+)= 0.5 * sum_d p^2 / mass
+template <int LANES>
+__global__ void __launch_bounds__(256) kinetic_kernel(const float* __restrict__ p,
+                                                      const float* __restrict__ mass,
+                                                      int64_t mass_n, int64_t chains,
+                                                      int64_t row_len, float* __restrict__ k_out,
+                                                      int accumulate) {
+  const int rows_per_block = 256 / LANES;
+  const int lane = threadIdx.x % LANES;
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / LANES; row < chains;
+       row += (int64_t)gridDim.x * rows_per_block) {
+    float kin = 0.f;
+    for (int64_t c = lane; c < row_len; c += LANES) {
+      const float pv = p[row * row_len + c];
+      kin += fdiv(mul(pv, pv), mass[c % mass_n]);
+    }
+    kin = sub_warp_sum<LANES>(kin);
+    if (lane == 0) {
+      const float v = mul(0.5f, kin);
+      k_out[row] = accumulate ? add(k_out[row], v) : v;
+    }
+  }
+}
+
+// a3 leapfrog_integrator, position half (hmc.py:39, 26-27): q += s1 * (p / mass)
+__global__ void __launch_bounds__(256) leapfrog_q_kernel(float* __restrict__ q,
+                                                         const float* __restrict__ p,
+                                                         const float* __restrict__ mass,
+                                                         int64_t mass_n, int64_t row_len,
+                                                         const float* __restrict__ eps_dev,
+                                                         float scale, int64_t n) {
+  const float s1 = mul(*eps_dev, scale);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    q[i] = add(q[i], mul(s1, fdiv(p[i], mass[(i % row_len) % mass_n])));
+}
+// momentum half (hmc.py:42): p += s2 * grad
+__global__ void __launch_bounds__(256) leapfrog_p_kernel(float* __restrict__ p,
+                                                         const float* __restrict__ g,
+                                                         const float* __restrict__ eps_dev,
+                                                         float scale, int64_t n) {
+  const float s2 = mul(*eps_dev, scale);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = add(p[i], mul(s2, g[i]));
+}
+
+// a6 + a7 get_acceptance_rate / MH decision (hmc.py:46-61, 485-486, 498).
+__device__ __forceinline__ void mh_decide(float lp0, float lp1, float k0, float k1, float u,
+                                          float& h0, float& h1, float& acc, int& accept,
+                                          float& lp_sel, bool& bad_old) {
+  h0 = add(-lp0, k0);                                  // hmc.py:31-35 potential + kinetic
+  h1 = add(-lp1, k1);
+  bad_old = !isfinite(lp0);                            // hmc.py:51-53 check_numerics
+  float a = expf(fminf(add(-h1, h0), 0.f));            // hmc.py:54-55
+  if (!(isfinite(a) && isfinite(lp1))) a = 0.f;        // hmc.py:56-59
+  acc = a;
+  accept = (u < a) ? 1 : 0;                            // hmc.py:486
+  lp_sel = accept ? lp1 : lp0;                         // hmc.py:498
+}
+
+__global__ void __launch_bounds__(256) mh_kernel(const float* __restrict__ lp0,
+                                                 const float* __restrict__ lp1,
+                                                 const float* __restrict__ k0,
+                                                 const float* __restrict__ k1,
+                                                 const float* __restrict__ u, uint64_t seed,
+                                                 uint32_t iter, int64_t row0, int64_t chains,
+                                                 float* __restrict__ h0o, float* __restrict__ h1o,
+                                                 float* __restrict__ acco,
+                                                 int32_t* __restrict__ accepto,
+                                                 float* __restrict__ lpselo,
+                                                 float* __restrict__ acc_part,
+                                                 float* __restrict__ state) {
+  __shared__ float red[32];
+  float local = 0.f;
+  bool any_bad = false;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < chains;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const float uu = u ? u[c] : philox_uniform_row(seed, ZSB_STREAM_UNIFORM, iter,
+                                                   (uint32_t)(row0 + c));
+    float h0, h1, acc, lps; int accept; bool bad;
+    mh_decide(lp0[c], lp1[c], k0[c], k1[c], uu, h0, h1, acc, accept, lps, bad);
+    if (h0o) h0o[c] = h0;
+    if (h1o) h1o[c] = h1;
+    acco[c] = acc;
+    if (accepto) accepto[c] = accept;
+    if (lpselo) lpselo[c] = lps;
+    local += acc;
+    any_bad |= bad;
+  }
+  local = block_sum(local, red);
+  if (threadIdx.x == 0 && acc_part) acc_part[blockIdx.x] = local;
+  if (any_bad && state) atomicOr(reinterpret_cast<unsigned int*>(state) + ZSB_ST_FLAGS, 1u);
+}
+
+// q <- accept ? q_new : q   (hmc.py:488-497), broadcasting accept over the data axes.
+__global__ void __launch_bounds__(256) select_kernel(float* __restrict__ q,
+                                                     const float* __restrict__ qn,
+                                                     const int32_t* __restrict__ accept,
+                                                     int64_t row_len, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    if (accept[i / row_len]) q[i] = qn[i];
+}
+
+// fixed-order sum of the per-block partials -> stats[0] = sum(acc), stats[1] = n_chains (local)
+__global__ void acc_sum_kernel(const float* __restrict__ part, int n_part, int64_t chains,
+                               float* __restrict__ stats) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n_part; i += blockDim.x) s += part[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) { stats[0] = s; stats[1] = (float)chains; }
+}
+
+// a8 StepsizeTuner.tune (hmc.py:89-112) + assign step_size (hmc.py:379).  One thread.
+__global__ void tune_kernel(float* __restrict__ st, const float* __restrict__ stats, int has_tuner,
+                            int adapt, float fresh, float gamma, float t0, float kappa,
+                            float delta, float t_now) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float abar = fdiv(stats[0], stats[1]);              // hmc.py:377 reduce_mean (global)
+  st[ZSB_ST_ACC_MEAN] = abar;
+  st[ZSB_ST_T] = t_now;
+  if (!has_tuner) return;                                   // hmc.py:504-505
+  if (adapt) {
+    const float step = add(mul(sub(1.f, fresh), st[ZSB_ST_TUNER_STEP]), 1.f);      // :92
+    const float rate1 = fdiv(1.f, add(step, t0));                                  // :93
+    const float hbar = add(mul(mul(sub(1.f, fresh), sub(1.f, rate1)), st[ZSB_ST_H_BAR]),
+                           mul(rate1, sub(delta, abar)));                          // :94-96
+    const float log_eps = sub(st[ZSB_ST_MU], mul(fdiv(sqrtf(step), gamma), hbar)); // :97
+    const float rate = powf(step, -kappa);                                         // :98
+    const float leb = add(mul(rate, log_eps),
+                          mul(mul(sub(1.f, fresh), sub(1.f, rate)),
+                              st[ZSB_ST_LOG_EPS_BAR]));                            // :99-102
+    st[ZSB_ST_TUNER_STEP] = step;
+    st[ZSB_ST_H_BAR] = hbar;
+    st[ZSB_ST_LOG_EPS_BAR] = leb;
+    st[ZSB_ST_STEP_SIZE] = expf(log_eps);                                          // :106, 379
+  } else {
+    st[ZSB_ST_STEP_SIZE] = expf(st[ZSB_ST_LOG_EPS_BAR]);                           // :110
+  }
+}
+
+// eps_used <- step_size (no search this iteration, hmc.py:472 else-branch / 464)
+__global__ void begin_kernel(float* __restrict__ st, int start_search) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st[ZSB_ST_EPS_USED] = st[ZSB_ST_STEP_SIZE];
+  if (start_search) { st[ZSB_ST_SEARCH_LAST] = 1.0f; st[ZSB_ST_SEARCH_COND] = 1.0f; }  // :343
+}
+// a9 one pass of the _init_step_size loop body's bookkeeping (hmc.py:326-338).
+__global__ void search_update_kernel(float* __restrict__ st, const float* __restrict__ stats,
+                                     float target) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float a = fdiv(stats[0], stats[1]);
+  const float eps = st[ZSB_ST_EPS_USED];
+  const float factor = 1.5f;
+  st[ZSB_ST_EPS_USED] = (a < target) ? mul(eps, fdiv(1.0f, factor)) : mul(eps, factor);
+  const bool last_lt = st[ZSB_ST_SEARCH_LAST] < target, a_lt = a < target;
+  st[ZSB_ST_SEARCH_COND] = (last_lt == a_lt) ? 1.0f : 0.0f;   // not xor
+  st[ZSB_ST_SEARCH_LAST] = a;
+}
+
+// a10 EWMV statistics (hmc.py:130-145), one pass over q:
+//   part[b][0][d] = sum_c (q[c,d] - mean[d]),  part[b][1][d] = sum_c (q[c,d] - mean[d])^2
+// for the rows owned by block-row b.  Coalesced along d; fixed-order final sum in stage 2.
+__global__ void __launch_bounds__(256) mass_stats_kernel(const float* __restrict__ q,
+                                                         const float* __restrict__ mean,
+                                                         int64_t chains, int64_t D,
+                                                         float* __restrict__ part) {
+  const int64_t d = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const float m = mean[d];
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t c = blockIdx.x; c < chains; c += gridDim.x) {
+    const float x = q[c * D + d] - m;
+    s1 += x;
+    s2 += x * x;
+  }
+  part[((int64_t)blockIdx.x * 2 + 0) * D + d] = s1;
+  part[((int64_t)blockIdx.x * 2 + 1) * D + d] = s2;
+}
+__global__ void __launch_bounds__(256) mass_stats_final_kernel(const float* __restrict__ part,
+                                                               int n_part, int64_t D,
+                                                               float* __restrict__ stats) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over 2*D
+  if (j >= 2 * D) return;
+  const int64_t which = j / D, d = j % D;
+  float s = 0.f;
+  for (int b = 0; b < n_part; ++b) s += part[((int64_t)b * 2 + which) * D + d];
+  stats[j] = s;
+}
+// EWMV.update + get_precision + mass gating (hmc.py:130-159, 283-305), per dimension.
+//   w = (1-decay)/(1-decay^tt); delta = S1/C; mean += w*delta;
+//   var = (1-w)*var + w*(S2/C - w*delta^2)   [= reduce_mean(incr*(q-mean_new)), algebraically]
+__global__ void __launch_bounds__(256) mass_update_kernel(float* __restrict__ mean,
+                                                          float* __restrict__ var,
+                                                          float* __restrict__ mass,
+                                                          const float* __restrict__ stats,
+                                                          float n_chains_global, int64_t D,
+                                                          float decay, float tt, int adapt,
+                                                          int use_ones, float* __restrict__ st) {
+  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d == 0 && adapt && st) st[ZSB_ST_EWMV_T] = tt;
+  if (d >= D) return;
+  float v = var[d];
+  if (adapt) {
+    const float w = (1.f - decay) / (1.f - powf(decay, tt));
+    const float delta = stats[d] / n_chains_global;
+    const float s2 = stats[D + d] / n_chains_global;
+    mean[d] = mean[d] + w * delta;
+    v = (1.f - w) * v + w * (s2 - w * delta * delta);
+    var[d] = v;
+  }
+  mass[d] = use_ones ? 1.0f : 1.0f / v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused whole-iteration kernel for a diagonal-Gaussian target (config 1: Normal(mean, std) with
+// group_ndims=1, examples/toy_examples/gaussian.py:15-20).  One warp per chain, E elements per
+// lane held in registers for the entire trajectory: momentum draw, L+1 gradient evaluations,
+// Hamiltonians, MH decision and the in-place select -- q is read once and written once
+// (algorithmic HBM traffic 8*D bytes per chain-ITERATION instead of 16*D per leapfrog step).
+template <int E>
+__global__ void __launch_bounds__(256) diag_normal_traj_kernel(
+    float* __restrict__ q, const float* __restrict__ noise, const float* __restrict__ u,
+    const float* __restrict__ mean, int64_t mean_n, const float* __restrict__ logstd,
+    int64_t logstd_n, const float* __restrict__ mass, int64_t mass_n,
+    const float* __restrict__ state, int n_leapfrogs, int64_t chains, int64_t D, uint64_t seed,
+    uint32_t iter, int64_t row0, int search_mode, float* __restrict__ p0_out,
+    float* __restrict__ h0o, float* __restrict__ h1o, float* __restrict__ lp0o,
+    float* __restrict__ lpselo, float* __restrict__ acco, int32_t* __restrict__ accepto,
+    float* __restrict__ acc_part, float* __restrict__ state_flags) {
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31;
+  const float eps = state[ZSB_ST_EPS_USED];
+  float local_acc = 0.f;
+  bool any_bad = false;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < chains;
+       row += (int64_t)gridDim.x * 8) {
+    float q0[E], qc[E], pc[E], mu[E], prec[E], ls[E], ms[E];
+    // Philox blocks are 4 consecutive columns; lane owns columns c = (j*32 + lane) for j<E
+    // in the noise-injected layout, so draw per element from block c/4, word c%4.
+    float lp0 = 0.f, k0 = 0.f;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int64_t c = (int64_t)j * 32 + lane;
+      if (c < D) {
+        q0[j] = q[row * D + c];
+        mu[j] = mean[c % mean_n];
+        ls[j] = logstd[c % logstd_n];
+        ms[j] = mass[c % mass_n];
+        prec[j] = expf(mul(-2.f, ls[j]));                       // univariate.py:177
+        float z;
+        if (noise) {
+          z = noise[row * D + c];
+        } else {
+          float z4[4];
+          philox_normal4(seed, ZSB_STREAM_MOMENTUM, iter, (uint32_t)(row0 + row),
+                         (uint32_t)(c >> 2), z4);
+          z = z4[c & 3];
+        }
+        pc[j] = mul(z, sqrtf(ms[j]));                           // hmc.py:22
+        if (p0_out) p0_out[row * D + c] = pc[j];
+        qc[j] = q0[j];
+        const float d = sub(q0[j], mu[j]);
+        lp0 += sub(sub(-0.9189385332046727f, ls[j]), mul(mul(0.5f, prec[j]), mul(d, d)));
+        k0 += fdiv(mul(pc[j], pc[j]), ms[j]);
+      }
+    }
+    // trajectory (hmc.py:347-372): i = 0..L ; search_mode: the 1-step probe of hmc.py:316-321
+    const int L = search_mode ? 1 : n_leapfrogs;
+    for (int i = 0; i <= L; ++i) {
+      const float s1 = (i > 0) ? eps : 0.f;
+      const float s2 = (i > 0 && i < L) ? eps : fdiv(eps, 2.f);
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        const int64_t c = (int64_t)j * 32 + lane;
+        if (c < D) {
+          qc[j] = add(qc[j], mul(s1, fdiv(pc[j], ms[j])));
+          const float g = -mul(prec[j], sub(qc[j], mu[j]));     // d/dx Normal log_prob
+          pc[j] = add(pc[j], mul(s2, g));
+        }
+      }
+    }
+    float lp1 = 0.f, k1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int64_t c = (int64_t)j * 32 + lane;
+      if (c < D) {
+        const float d = sub(qc[j], mu[j]);
+        lp1 += sub(sub(-0.9189385332046727f, ls[j]), mul(mul(0.5f, prec[j]), mul(d, d)));
+        k1 += fdiv(mul(pc[j], pc[j]), ms[j]);
+      }
+    }
+    lp0 = warp_sum(lp0); lp1 = warp_sum(lp1);
+    k0 = mul(0.5f, warp_sum(k0)); k1 = mul(0.5f, warp_sum(k1));
+    const float uu = u ? u[row] : philox_uniform_row(seed, ZSB_STREAM_UNIFORM, iter,
+                                                     (uint32_t)(row0 + row));
+    float h0, h1, acc, lps; int accept; bool bad;
+    mh_decide(lp0, lp1, k0, k1, uu, h0, h1, acc, accept, lps, bad);
+    any_bad |= bad;
+    if (lane == 0) {
+      local_acc += acc;
+      acco[row] = acc;
+      if (!search_mode) {
+        if (h0o) h0o[row] = h0;
+        if (h1o) h1o[row] = h1;
+        if (lp0o) lp0o[row] = lp0;
+        if (lpselo) lpselo[row] = lps;
+        if (accepto) accepto[row] = accept;
+      }
+    }
+    if (!search_mode && accept) {
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        const int64_t c = (int64_t)j * 32 + lane;
+        if (c < D) q[row * D + c] = qc[j];
+      }
+    }
+  }
+  local_acc = block_sum(local_acc, red);
+  if (threadIdx.x == 0) acc_part[blockIdx.x] = local_acc;
+  if (any_bad && state_flags)
+    atomicOr(reinterpret_cast<unsigned int*>(state_flags) + ZSB_ST_FLAGS, 1u);
+}
+
+inline int pick_lanes(int64_t work_items) {
+  int lanes = 1;
+  while (lanes < 32 && lanes < work_items) lanes <<= 1;
+  return lanes;
+}
+inline unsigned rows_grid(int64_t chains, int lanes) {
+  int64_t blocks = zsb_ceil_div(chains, 256 / lanes);
+  const int64_t cap = (int64_t)ZSB_NUM_SMS * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+inline unsigned flat_grid(int64_t n) {
+  int64_t blocks = zsb_ceil_div(n, 256);
+  const int64_t cap = (int64_t)ZSB_NUM_SMS * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zsb_hmc_acc_parts(void) { return ZSB_NUM_SMS * 16; }  // capacity the caller must give acc_part
+
+int zsb_hmc_momentum_f32(float* p, const float* noise, const float* mass, int64_t mass_n,
+                         int64_t chains, int64_t row_len, uint64_t seed, uint32_t iter,
+                         uint32_t stream_id, int64_t row0, float* k_out, int accumulate,
+                         void* stream) {
+  ZSB_REQUIRE(chains >= 0 && row_len > 0 && mass_n > 0, "zsb_hmc_momentum_f32: bad sizes");
+  if (chains == 0) return ZSB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int lanes = pick_lanes((row_len + 3) / 4);
+  const unsigned g = rows_grid(chains, lanes);
+#define ZSB_L(LN) momentum_kernel<LN><<<g, 256, 0, st>>>(p, noise, mass, mass_n, chains, row_len, \
+                                                        seed, iter, stream_id, row0, k_out,      \
+                                                        accumulate)
+  switch (lanes) {
+    case 1: ZSB_L(1); break; case 2: ZSB_L(2); break; case 4: ZSB_L(4); break;
+    case 8: ZSB_L(8); break; case 16: ZSB_L(16); break; default: ZSB_L(32); break;
+  }
+#undef ZSB_L
+  return zsb_check_launch("hmc_momentum");
+}
+
+int zsb_hmc_kinetic_f32(const float* p, const float* mass, int64_t mass_n, int64_t chains,
+                        int64_t row_len, float* k_out, int accumulate, void* stream) {
+  ZSB_REQUIRE(chains >= 0 && row_len > 0 && mass_n > 0 && k_out, "zsb_hmc_kinetic_f32: bad sizes");
+  if (chains == 0) return ZSB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int lanes = pick_lanes(row_len);
+  const unsigned g = rows_grid(chains, lanes);
+#define ZSB_L(LN) kinetic_kernel<LN><<<g, 256, 0, st>>>(p, mass, mass_n, chains, row_len, k_out, \
+                                                       accumulate)
+  switch (lanes) {
+    case 1: ZSB_L(1); break; case 2: ZSB_L(2); break; case 4: ZSB_L(4); break;
+    case 8: ZSB_L(8); break; case 16: ZSB_L(16); break; default: ZSB_L(32); break;
+  }
+#undef ZSB_L
+  return zsb_check_launch("hmc_kinetic");
+}
+
+int zsb_hmc_leapfrog_q_f32(float* q, const float* p, const float* mass, int64_t mass_n,
+                           int64_t row_len, const float* eps_dev, float scale, int64_t n,
+                           void* stream) {
+  ZSB_REQUIRE(n >= 0 && row_len > 0 && mass_n > 0 && eps_dev, "zsb_hmc_leapfrog_q_f32: bad args");
+  if (n == 0) return ZSB_OK;
+  leapfrog_q_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(q, p, mass, mass_n, row_len,
+                                                                    eps_dev, scale, n);
+  return zsb_check_launch("hmc_leapfrog_q");
+}
+int zsb_hmc_leapfrog_p_f32(float* p, const float* g, const float* eps_dev, float scale, int64_t n,
+                           void* stream) {
+  ZSB_REQUIRE(n >= 0 && eps_dev, "zsb_hmc_leapfrog_p_f32: bad args");
+  if (n == 0) return ZSB_OK;
+  leapfrog_p_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, eps_dev, scale, n);
+  return zsb_check_launch("hmc_leapfrog_p");
+}
+
+int zsb_hmc_mh_f32(const float* lp0, const float* lp1, const float* k0, const float* k1,
+                   const float* u, uint64_t seed, uint32_t iter, int64_t row0, int64_t chains,
+                   float* h0, float* h1, float* acc, int32_t* accept, float* lp_sel,
+                   float* acc_part, int* n_part_out, float* state, void* stream) {
+  ZSB_REQUIRE(chains > 0 && acc && acc_part && n_part_out, "zsb_hmc_mh_f32: bad args");
+  const unsigned g = flat_grid(chains);
+  *n_part_out = (int)g;
+  mh_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(lp0, lp1, k0, k1, u, seed, iter, row0, chains,
+                                                 h0, h1, acc, accept, lp_sel, acc_part, state);
+  return zsb_check_launch("hmc_mh");
+}
+
+int zsb_hmc_select_f32(float* q, const float* q_new, const int32_t* accept, int64_t chains,
+                       int64_t row_len, void* stream) {
+  ZSB_REQUIRE(chains >= 0 && row_len > 0, "zsb_hmc_select_f32: bad sizes");
+  const int64_t n = chains * row_len;
+  if (n == 0) return ZSB_OK;
+  select_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(q, q_new, accept, row_len, n);
+  return zsb_check_launch("hmc_select");
+}
+
+int zsb_hmc_acc_sum_f32(const float* acc_part, int n_part, int64_t chains, float* stats,
+                        void* stream) {
+  ZSB_REQUIRE(n_part > 0 && stats, "zsb_hmc_acc_sum_f32: bad args");
+  acc_sum_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(acc_part, n_part, chains, stats);
+  return zsb_check_launch("hmc_acc_sum");
+}
+
+int zsb_hmc_begin_f32(float* state, int start_search, void* stream) {
+  begin_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, start_search);
+  return zsb_check_launch("hmc_begin");
+}
+int zsb_hmc_search_update_f32(float* state, const float* stats, float target, void* stream) {
+  search_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, stats, target);
+  return zsb_check_launch("hmc_search_update");
+}
+int zsb_hmc_tune_f32(float* state, const float* stats, int has_tuner, int adapt, float fresh_start,
+                     float gamma, float t0, float kappa, float delta, float t_now, void* stream) {
+  tune_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, stats, has_tuner, adapt, fresh_start,
+                                                  gamma, t0, kappa, delta, t_now);
+  return zsb_check_launch("hmc_tune");
+}
+
+// part: scratch of zsb_hmc_mass_parts()*2*D floats; stats: [2*D] local sums out.
+int zsb_hmc_mass_parts(void) { return 64; }
+int zsb_hmc_mass_stats_f32(const float* q, const float* ewmv_mean, int64_t chains, int64_t D,
+                           float* part, float* stats, void* stream) {
+  ZSB_REQUIRE(chains > 0 && D > 0 && part && stats, "zsb_hmc_mass_stats_f32: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  int nb = (int)(chains < 64 ? chains : 64);
+  dim3 grid(nb, (unsigned)zsb_ceil_div(D, 256));
+  mass_stats_kernel<<<grid, 256, 0, st>>>(q, ewmv_mean, chains, D, part);
+  int rc = zsb_check_launch("hmc_mass_stats");
+  if (rc) return rc;
+  mass_stats_final_kernel<<<(unsigned)zsb_ceil_div(2 * D, 256), 256, 0, st>>>(part, nb, D, stats);
+  return zsb_check_launch("hmc_mass_stats_final");
+}
+int zsb_hmc_mass_update_f32(float* ewmv_mean, float* ewmv_var, float* mass, const float* stats,
+                            float n_chains_global, int64_t D, float decay, float ewmv_t_new,
+                            int adapt, int use_ones, float* state, void* stream) {
+  ZSB_REQUIRE(D > 0 && ewmv_mean && ewmv_var && mass, "zsb_hmc_mass_update_f32: bad args");
+  mass_update_kernel<<<(unsigned)zsb_ceil_div(D, 256), 256, 0, (cudaStream_t)stream>>>(
+      ewmv_mean, ewmv_var, mass, stats, n_chains_global, D, decay, ewmv_t_new, adapt, use_ones,
+      state);
+  return zsb_check_launch("hmc_mass_update");
+}
+
+// Fused diagonal-Gaussian HMC iteration (or, with search_mode=1, the one-step acceptance probe of
+// _init_step_size, hmc.py:314-326, which leaves q untouched and only fills acc / acc_part).
+int zsb_hmc_diag_normal_step_f32(float* q, const float* noise, const float* u, const float* mean,
+                                 int64_t mean_n, const float* logstd, int64_t logstd_n,
+                                 const float* mass, int64_t mass_n, float* state, int n_leapfrogs,
+                                 int64_t chains, int64_t D, uint64_t seed, uint32_t iter,
+                                 int64_t row0, int search_mode, float* p0_out, float* h0, float* h1,
+                                 float* lp0, float* lp_sel, float* acc, int32_t* accept,
+                                 float* acc_part, int* n_part_out, void* stream) {
+  ZSB_REQUIRE(chains > 0 && D > 0 && D <= 1024 && mean_n > 0 && logstd_n > 0 && mass_n > 0 &&
+                  n_leapfrogs >= 0 && state && acc && acc_part && n_part_out,
+              "zsb_hmc_diag_normal_step_f32: bad args (D must be in 1..1024)");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = zsb_ceil_div(chains, 8);
+  if (blocks > ZSB_NUM_SMS * 8) blocks = ZSB_NUM_SMS * 8;
+  *n_part_out = (int)blocks;
+#define ZSB_L(EE)                                                                               \
+  diag_normal_traj_kernel<EE><<<(unsigned)blocks, 256, 0, st>>>(                                 \
+      q, noise, u, mean, mean_n, logstd, logstd_n, mass, mass_n, state, n_leapfrogs, chains, D, \
+      seed, iter, row0, search_mode, p0_out, h0, h1, lp0, lp_sel, acc, accept, acc_part, state)
+  if (D <= 128) ZSB_L(4);
+  else if (D <= 256) ZSB_L(8);
+  else if (D <= 512) ZSB_L(16);
+  else ZSB_L(32);
+#undef ZSB_L
+  return zsb_check_launch("hmc_diag_normal_step");
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+"""Log-joint descriptors that ``HMC.sample`` recognises and runs on fused
+kernels.  Each is also a plain ``log_joint(observed_dict)`` callable built
+from torch ops, so it works on the generic path and as its own cross-check.
+"""
+import math
+
+import numpy as np
+import torch
+
+__all__ = ["GaussianLogJoint"]
+
+
+class GaussianLogJoint(object):
+    """log p(x) = -1/2 (x-mu)^T P (x-mu) - 1/2 log|2 pi Sigma|, P = Sigma^-1
+    shared by all chains (BASELINE config 2; the reference can only express
+    this as a callable ``log_joint`` because MultivariateNormalCholesky
+    broadcasts L to every chain, multivariate.py:183-185).
+
+    precision: [D, D] symmetric (numpy float64 preferred: the b = P mu vector
+    and the hi/lo split are derived in float64 on the host, once).
+    """
+
+    def __init__(self, precision, mean=None, log_det_cov=None, name="x",
+                 device="cuda", impl=0):
+        P64 = np.asarray(precision.detach().cpu().numpy()
+                         if isinstance(precision, torch.Tensor)
+                         else precision, dtype=np.float64)
+        D = P64.shape[0]
+        if P64.shape != (D, D):
+            raise ValueError("precision must be square")
+        if D % 16 != 0:
+            raise ValueError("the fused dense-Gaussian path needs D % 16 == 0")
+        P64 = 0.5 * (P64 + P64.T)
+        self.name = name
+        self.D = D
+        if log_det_cov is None:
+            sign, ld = np.linalg.slogdet(P64)
+            log_det_cov = -ld
+        self.const = float(-0.5 * (D * math.log(2 * math.pi) + log_det_cov))
+        P32 = P64.astype(np.float32)
+        self.P = torch.as_tensor(P32, device=device).contiguous()
+        d = {"kind": "dense_gaussian", "D": D, "P": self.P,
+             "const": self.const, "impl": impl}
+        self.mu = None
+        if mean is not None:
+            mu64 = np.asarray(mean, np.float64).reshape(D)
+            self.mu = torch.as_tensor(mu64.astype(np.float32), device=device)
+            d["mu"] = self.mu
+            d["b"] = torch.as_tensor(
+                (P32.astype(np.float64) @ mu64).astype(np.float32),
+                device=device)
+        # 3xTF32 split for the tensor-core path: hi = fp32 with the low 13
+        # mantissa bits cleared (exactly representable in TF32), lo = P - hi.
+        hi = (P32.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        lo = (P32 - hi).astype(np.float32)
+        d["P_hi"] = torch.as_tensor(hi, device=device).contiguous()
+        d["P_lo"] = torch.as_tensor(lo, device=device).contiguous()
+        self._zsb_fused = d
+
+    def __call__(self, observed):
+        x = observed[self.name]
+        if self.mu is not None:
+            x = x - self.mu
+        return -0.5 * ((x @ self.P) * x).sum(-1) + self.const

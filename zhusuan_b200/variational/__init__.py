@@ -1,0 +1,3 @@
+from .base import *
+from .exclusive_kl import *
+from .monte_carlo import *
