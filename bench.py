@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the HMC hot path (BASELINE.json metric
+"leapfrog-steps*chains/sec").
+
+Workload (configs[1]): 1024-dim dense-covariance Gaussian HMC, 65 536 chains
+PER GPU, 50 leapfrog steps, step-size + mass adaptation ON during the timed
+steps.  A "step" is one HMC iteration = one ``sample_op()`` call: mass
+statistics + update, momentum draw (in-kernel Philox), L+1 fused
+GEMM+leapfrog passes, MH test + select, dual-averaging update.
+
+    python bench.py --gpus N --steps K --warmup W            (N=1)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...     CPU arm (torch-CPU restatement)
+
+Chains shard across ranks with no data-path collective (weak scaling: the
+per-GPU chain count is fixed); the only exchange is the per-iteration
+all-reduce of the acceptance / mass statistics (8 B + 8*D B).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "leapfrog-steps*chains/sec"
+UNIT = "chain-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains-per-gpu", type=int, default=65536)
+    ap.add_argument("--dim", type=int, default=1024)
+    ap.add_argument("--leapfrogs", type=int, default=50)
+    ap.add_argument("--burnin", type=int, default=20,
+                    help="untimed adaptive iterations run as setup, before "
+                         "the W warm-up steps (covers both step-size searches)")
+    ap.add_argument("--dense-impl", type=int, default=None,
+                    help="0 SIMT fp32, 1 tcgen05 3xTF32 (default: best built)")
+    ap.add_argument("--cpu-chains", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf": d.get("bf16_tflops_sustained",
+                                                     d["bf16_tflops"]),
+                "tf_burst": d["bf16_tflops"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf": 1400.0, "tf_burst": 1590.0,
+            "src": "fallback"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clock / throttle-reason sampling DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,"
+         "clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()          # exact PID we started
+            try:
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name)
+                if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[4:8]):
+                if v.strip().lower() == "active":
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [],
+                    "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path.  TensorFlow (and so
+    zhusuan) cannot be installed here, so this arm times the torch-CPU
+    restatement of hmc.py:382-522 (oracle/cpu_baseline.py, kind "port") with
+    all host threads, on a bounded chain sub-sample of the same workload
+    (chains are independent -> the rate is per-chain-step)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle.cpu_baseline import time_dense_hmc
+    chains = min(args.cpu_chains, args.chains_per_gpu)
+    r = time_dense_hmc(args.dim, chains, args.leapfrogs, n_iters=args.steps,
+                       warmup=args.warmup)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": r["value"],
+        "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_iter"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "HMC, %d-dim dense-covariance Gaussian, L=%d; "
+                               "CPU sample of %d chains per step"
+                               % (args.dim, args.leapfrogs, chains)},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT,
+                         "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "host_cpu_count": os.cpu_count(),
+    }
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as td
+    import zhusuan_b200 as zs
+    from zhusuan_b200._lib import lib
+    from oracle.models import make_dense_gaussian_problem   # synthetic target
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        td.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1
+
+    D, C, L = args.dim, args.chains_per_gpu, args.leapfrogs
+    P, const = make_dense_gaussian_problem(D, seed=2)
+    impl = args.dense_impl
+    if impl is None:
+        impl = 1 if os.environ.get("ZSB_DENSE_IMPL", "") == "1" else 0
+    lj = zs.fused.GaussianLogJoint(P, device=dev, impl=impl)
+    g = torch.Generator(device=dev)
+    g.manual_seed(3 + rank)
+    q = torch.randn(C, D, device=dev, generator=g)          # q0 ~ N(0, I)
+    hmc = zs.HMC(step_size=0.05, n_leapfrogs=L, adapt_step_size=True,
+                 adapt_mass=True, mass_collect_iters=10, seed=1234,
+                 dense_impl=impl)
+    sample_op, info = hmc.sample(lj, {}, {"x": q})
+
+    def step():
+        sample_op(adapt_step_size=True, adapt_mass=True)
+
+    for _ in range(args.burnin):        # setup: adaptive burn-in (untimed)
+        step()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+
+    # ---------------- timed region: device-resident inputs -------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    hmc._profile_events = []
+    launches0 = lib.launches
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    launches = lib.launches - launches0
+    kern_ms = [a.elapsed_time(b) for a, b in hmc._profile_events]
+    hmc._profile_events = None
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        td.all_reduce(ms, op=td.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    ms_per_step = total_ms / args.steps
+    value = C * world * L * args.steps / (total_ms * 1e-3)
+    acc_mean = float(info.acceptance_rate.mean())
+    step_size = float(info.updated_step_size)
+
+    # ---------------- e2e: host buffers through the public API ---------------
+    e2e = None
+    if not args.no_e2e:
+        q_host = torch.empty(C, D, dtype=torch.float32).pin_memory()
+        q_host.copy_(q)
+        out_host = torch.empty(C, D, dtype=torch.float32).pin_memory()
+        acc_host = torch.empty(C, dtype=torch.float32).pin_memory()
+        n_e2e = max(2, min(args.steps, 3))
+
+        def e2e_step():
+            q.copy_(q_host, non_blocking=True)               # H2D: chain state
+            step()
+            out_host.copy_(info.samples["x"], non_blocking=True)   # D2H
+            acc_host.copy_(info.acceptance_rate, non_blocking=True)
+        e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        e2e = {"value": C * world * L * n_e2e / (float(t.item()) * 1e-3),
+               "unit": UNIT, "h2d_bytes_per_step": C * D * 4,
+               "d2h_bytes_per_step": C * D * 4 + C * 4, "steps": n_e2e}
+
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ------------------------
+    peaks = load_peaks()
+    kms = float(np.mean(kern_ms)) / (L + 1) if kern_ms else None
+    roof = None
+    if kms:
+        bytes_per_launch = 16.0 * D * C              # 16*D B/chain-step
+        flops_per_launch = 2.0 * D * D * C           # one P.x product
+        hbm = bytes_per_launch / (kms * 1e-3) / 1e9
+        tfl = flops_per_launch / (kms * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic = tj.get("impl%d" % impl, {}).get("dram_bytes_per_launch")
+        f_h, f_t = hbm / peaks["hbm_gbs"], tfl / peaks["tf"]
+        roof = {"bound": "hbm", "achieved": hbm, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": f_h, "traffic": traffic,
+                "peak_source": peaks["src"],
+                "kernel": "dense_leapfrog (impl %d)" % impl,
+                "kernel_ms_per_launch": kms,
+                "kernel_share_of_step": kms * (L + 1) / ms_per_step,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "tensor": {"achieved": tfl, "peak": peaks["tf"],
+                           "unit": "TFLOP/s (fp32-equivalent 2*D^2 per "
+                                   "chain-step vs measured bf16 dense peak)",
+                           "frac": f_t}}
+
+    # ---------------- CPU baseline on this box's host cores ------------------
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle.cpu_baseline import time_dense_hmc
+        r = time_dense_hmc(D, min(args.cpu_chains, C), L, n_iters=1, warmup=1,
+                           P=(P, const))
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"],
+               "kind": "port", "sample": r["sample"],
+               "host_cpu_count": os.cpu_count()}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {
+            "workload": "HMC, %d-dim dense-covariance Gaussian, %d chains/GPU "
+                        "(%d total), L=%d, step-size + mass adaptation on"
+                        % (D, C, C * world, L),
+            "chains_per_gpu": C, "dim": D, "n_leapfrogs": L,
+            "burnin_iters": args.burnin, "dense_impl": impl,
+            "l2": "inputs larger than L2 (q,p = %.0f MB each per GPU vs 126 "
+                  "MB L2)" % (C * D * 4 / 1e6),
+            "rng": "in-kernel Philox4x32-10",
+            "parallelism": "chains sharded x%d, 1 stats all-reduce/iter"
+                           % world},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roof, "cpu_baseline": cpu,
+        "acceptance_mean": acc_mean, "step_size": step_size,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

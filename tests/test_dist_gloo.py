@@ -1,0 +1,70 @@
+"""world_size-2 gloo test (CPU) of the N>1 host logic: contiguous chain
+sharding and the single all-reduce of the per-iteration statistics message
+(section 8e): global mean acceptance and the EWMV mass update computed from
+sharded statistics equal the single-process oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q_all, acc_all, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    from zhusuan_b200 import dist
+    assert dist.world() == (world, rank)
+    C, D = q_all.shape
+    row0, n_local = dist.shard_chains(C)
+    q = torch.tensor(q_all[row0:row0 + n_local])
+    acc = torch.tensor(acc_all[row0:row0 + n_local])
+    mean_old = torch.zeros(D)
+    # what zsb_hmc_acc_sum_f32 / zsb_hmc_mass_stats_f32 write on each rank
+    s1 = (q - mean_old).sum(0)
+    s2 = ((q - mean_old) ** 2).sum(0)
+    msg = dist.pack_stats(acc.sum(), n_local, s1, s2)
+    dist.all_reduce_sum(msg)                     # the ONE collective / iteration
+    abar = msg[0] / msg[1]
+    n = msg[1]
+    S1, S2 = msg[2:2 + D], msg[2 + D:2 + 2 * D]
+    decay, tt = 0.99, 1.0
+    w = (1 - decay) / (1 - decay ** tt)
+    delta = S1 / n
+    mean_new = mean_old + w * delta
+    var_new = w * (S2 / n - w * delta * delta)   # (1-w)*0 + ...
+    out[rank] = (float(abar), mean_new.numpy(), var_new.numpy(), row0, n_local)
+    td.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_statistics_match_single_process_oracle():
+    from oracle.hmc import ExponentialWeightedMovingVariance
+    rng = np.random.RandomState(0)
+    C, D = 37, 6                                  # ragged: 19 + 18 chains
+    q_all = rng.standard_normal((C, D)).astype(np.float32)
+    acc_all = rng.random_sample(C).astype(np.float32)
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, q_all, acc_all, out), nprocs=2, join=True)
+    ew = ExponentialWeightedMovingVariance(0.99, [(1, D)], 1, np.float32)
+    var = ew.update([q_all])[0].reshape(-1)
+    assert out[0][3:] == (0, 19) and out[1][3:] == (19, 18)
+    for r in (0, 1):
+        abar, mean_new, var_new = out[r][:3]
+        np.testing.assert_allclose(abar, acc_all.mean(), rtol=1e-6)
+        np.testing.assert_allclose(mean_new, ew.mean[0].reshape(-1), rtol=1e-5,
+                                   atol=1e-6)
+        np.testing.assert_allclose(var_new, var, rtol=1e-4, atol=1e-6)

@@ -1,0 +1,248 @@
+"""GPU parity: distribution log_prob / backward / sampling kernels vs the
+reference's known answers (tests/cases.py) and vs the CPU oracle.
+Tolerance: float32 path, rtol 1e-5 (north_star: "within 1e-5 relative fp32")."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import distributions as OD
+from oracle import philox
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-5
+
+
+def T(a, dtype=torch.float32):
+    return torch.tensor(np.asarray(a), dtype=dtype, device="cuda")
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def zs():
+    import zhusuan_b200 as zs
+    return zs
+
+
+def test_normal_known_answers(zs):
+    for given, mean, logstd, g, target in cases.normal_cases():
+        d = zs.distributions.Normal(T(mean), logstd=T(logstd), group_ndims=g)
+        np.testing.assert_allclose(N(d.log_prob(T(given))), target,
+                                   rtol=RTOL, atol=ATOL)
+        d2 = zs.distributions.Normal(T(mean), std=T(np.exp(logstd)),
+                                     group_ndims=g)
+        np.testing.assert_allclose(N(d2.log_prob(T(given))), target,
+                                   rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(N(d.prob(T(given))), np.exp(target),
+                                   rtol=1e-4, atol=1e-30)
+
+
+@pytest.mark.parametrize("shape,pshape,g", [
+    ((64, 4096 // 64, 40), (4096 // 64, 40), 1),     # particles x batch x z
+    ((7, 5, 3), (1, 5, 3), 2), ((33, 100), (100,), 1), ((1000,), (), 0),
+    ((4, 6, 5), (6, 1), 1), ((0, 5), (5,), 1)])
+def test_normal_vs_oracle_and_grads(zs, shape, pshape, g):
+    rng = np.random.RandomState(0)
+    x = rng.standard_normal(shape).astype(np.float32)
+    mu = rng.standard_normal(pshape).astype(np.float32)
+    ls = (0.3 * rng.standard_normal(pshape)).astype(np.float32)
+    xt, mt, lt = (T(a).requires_grad_(True) for a in (x, mu, ls))
+    lp = zs.distributions.Normal(mt, logstd=lt, group_ndims=g).log_prob(xt)
+    ref = OD.normal_log_prob(x, mu, ls, g, np.float64)
+    assert tuple(lp.shape) == ref.shape
+    np.testing.assert_allclose(N(lp), ref, rtol=RTOL, atol=1e-4)
+    if x.size == 0:
+        return
+    w = rng.standard_normal(ref.shape).astype(np.float32)
+    (lp * T(w)).sum().backward()
+    dg, dm, dl = OD.normal_log_prob_grads(x, mu, ls)
+    wexp = np.broadcast_to(w.reshape(w.shape + (1,) * g), dg.shape) \
+        if g else np.broadcast_to(w, dg.shape)
+
+    def red(a, s):
+        a = a * wexp
+        while a.ndim > len(s):
+            a = a.sum(0)
+        for ax, n in enumerate(s):
+            if n == 1 and a.shape[ax] != 1:
+                a = a.sum(ax, keepdims=True)
+        return a
+    np.testing.assert_allclose(N(xt.grad), red(dg, x.shape), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(N(mt.grad), red(dm, mu.shape), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(N(lt.grad), red(dl, ls.shape), rtol=1e-4, atol=1e-3)
+
+
+def test_bernoulli_known_answers_and_grad(zs):
+    for logits, given, target in cases.bernoulli_cases():
+        d = zs.distributions.Bernoulli(T(logits))
+        np.testing.assert_allclose(N(d.log_prob(T(given, torch.int32))),
+                                   target, rtol=RTOL, atol=ATOL)
+    # config-3 shaped: logits [K, N, 784] vs x [N, 784], group_ndims=1
+    rng = np.random.RandomState(1)
+    l = (3 * rng.standard_normal((4, 6, 784))).astype(np.float32)
+    x = (rng.random_sample((6, 784)) < 0.13).astype(np.int32)
+    lt = T(l).requires_grad_(True)
+    lp = zs.distributions.Bernoulli(lt, group_ndims=1).log_prob(
+        T(x, torch.int32))
+    np.testing.assert_allclose(N(lp), OD.bernoulli_log_prob(x, l, 1, np.float64),
+                               rtol=RTOL, atol=1e-3)
+    lp.sum().backward()
+    ref = x[None].astype(np.float64) - 1 / (1 + np.exp(-l.astype(np.float64)))
+    np.testing.assert_allclose(N(lt.grad), ref, rtol=1e-4, atol=1e-5)
+
+
+def test_categorical_known_answers_and_grad(zs):
+    for logits, given, target in cases.categorical_cases():
+        d = zs.distributions.Categorical(T(logits))
+        np.testing.assert_allclose(N(d.log_prob(T(given, torch.int32))),
+                                   target, rtol=RTOL, atol=ATOL)
+    rng = np.random.RandomState(2)
+    l = rng.standard_normal((5, 7, 11)).astype(np.float32)
+    k = rng.randint(0, 11, size=(5, 7)).astype(np.int32)
+    lt = T(l).requires_grad_(True)
+    lp = zs.distributions.Categorical(lt, group_ndims=1).log_prob(
+        T(k, torch.int32))
+    np.testing.assert_allclose(N(lp), OD.categorical_log_prob(k, l, 1, np.float64),
+                               rtol=RTOL, atol=1e-5)
+    lp.sum().backward()
+    sm = np.exp(l - l.max(-1, keepdims=True)); sm /= sm.sum(-1, keepdims=True)
+    ref = np.eye(11)[k] - sm
+    np.testing.assert_allclose(N(lt.grad), ref, rtol=1e-4, atol=1e-5)
+
+
+def test_unnormalized_multinomial_known_answers_and_grad(zs):
+    for logits, given, norm, target in cases.unnorm_multinomial_cases():
+        d = zs.distributions.UnnormalizedMultinomial(T(logits),
+                                                     normalize_logits=norm)
+        np.testing.assert_allclose(N(d.log_prob(T(given, torch.int32))),
+                                   target, rtol=1e-5, atol=1e-3)
+    rng = np.random.RandomState(3)
+    l = rng.standard_normal((3, 4, 50)).astype(np.float32)     # [chains, docs, V]
+    x = rng.poisson(2.0, size=(4, 50)).astype(np.int32)        # [docs, V]
+    lt = T(l).requires_grad_(True)
+    lp = zs.distributions.UnnormalizedMultinomial(lt).log_prob(
+        T(x, torch.int32))
+    np.testing.assert_allclose(
+        N(lp), OD.unnormalized_multinomial_log_prob(x, l, True, 0, np.float64),
+        rtol=RTOL, atol=1e-3)
+    lp.sum().backward()
+    sm = np.exp(l - l.max(-1, keepdims=True)); sm /= sm.sum(-1, keepdims=True)
+    ref = x[None] - x.sum(-1, keepdims=True)[None] * sm
+    np.testing.assert_allclose(N(lt.grad), ref, rtol=1e-4, atol=1e-4)
+
+
+def test_dirichlet_known_answers_and_grad(zs):
+    for alpha, given, target in cases.dirichlet_cases():
+        d = zs.distributions.Dirichlet(T(alpha))
+        np.testing.assert_allclose(N(d.log_prob(T(given))), target,
+                                   rtol=1e-5, atol=1e-5)
+    a = np.array([[2., 3., 4.], [1.5, 0.7, 5.]], np.float32)
+    x = np.array([[0.2, 0.3, 0.5], [0.1, 0.6, 0.3]], np.float32)
+    xt = T(x).requires_grad_(True)
+    zs.distributions.Dirichlet(T(a)).log_prob(xt).sum().backward()
+    np.testing.assert_allclose(N(xt.grad), (a - 1) / x, rtol=1e-5)
+    with pytest.raises(ValueError):
+        zs.distributions.Dirichlet(T([1.0]))
+
+
+@pytest.mark.parametrize("seed", [23, 233, 2333])
+def test_mvn_cholesky_vs_scipy(zs, seed):
+    from scipy import stats
+    mean, cov, chol = cases.mvn_params(seed)
+    rng = np.random.RandomState(seed)
+    samples = mean + np.einsum('ijab,nijb->nija', chol,
+                               rng.standard_normal((6,) + mean.shape))
+    d = zs.distributions.MultivariateNormalCholesky(T(mean), T(chol))
+    st = T(samples).requires_grad_(True)
+    lp = d.log_prob(st)
+    assert tuple(lp.shape) == (6,) + mean.shape[:2]
+    for i in range(mean.shape[0]):
+        for j in range(mean.shape[1]):
+            exact = stats.multivariate_normal.logpdf(
+                samples[:, i, j, :], mean[i, j], cov[i, j])
+            np.testing.assert_allclose(N(lp)[:, i, j], exact, rtol=2e-4,
+                                       atol=2e-3)
+    lp.sum().backward()
+    prec = np.linalg.inv(cov)
+    ref = -np.einsum('ijab,nijb->nija', prec, samples - mean)
+    np.testing.assert_allclose(N(st.grad), ref, rtol=2e-3, atol=2e-2)
+
+
+def test_shape_and_dtype_contract(zs):
+    d = zs.distributions.Normal(T(np.zeros((2, 3))), logstd=T(np.zeros(3)),
+                                group_ndims=1)
+    assert tuple(d.get_batch_shape()) == (2, 3)
+    assert tuple(d.get_value_shape()) == ()
+    assert tuple(d.sample(5).shape) == (5, 2, 3)
+    assert tuple(d.sample().shape) == (2, 3)
+    with pytest.raises(ValueError, match="broadcast to match"):
+        d.log_prob(T(np.zeros((4, 5))))
+    with pytest.raises(ValueError, match="Either `std` or `logstd`"):
+        zs.distributions.Normal(0.)
+    with pytest.raises(TypeError, match="must have the same dtype as"):
+        zs.distributions.Normal(T(0.), std=T(1., torch.float64))
+    with pytest.raises(ValueError, match="non-negative"):
+        zs.distributions.Normal(0., std=1., group_ndims=-1)
+    u = zs.distributions.UnnormalizedMultinomial(T(np.zeros((2, 3))))
+    with pytest.raises(NotImplementedError):
+        u.sample(2)
+    b = zs.distributions.Bernoulli(T(np.zeros((2, 3))))
+    s = b.sample(7)
+    assert s.dtype == torch.int32 and tuple(s.shape) == (7, 2, 3)
+    assert set(np.unique(N(s))) <= {0, 1}
+
+
+def test_reparameterised_sample_injected_and_philox(zs):
+    rng = np.random.RandomState(5)
+    mu = rng.standard_normal((4, 40)).astype(np.float32)
+    ls = (0.2 * rng.standard_normal((4, 40))).astype(np.float32)
+    eps = rng.standard_normal((8, 4, 40)).astype(np.float32)
+    mt, lt = T(mu).requires_grad_(True), T(ls).requires_grad_(True)
+    d = zs.distributions.Normal(mt, logstd=lt, group_ndims=1)
+    z = d._sample(8, eps=T(eps))
+    np.testing.assert_allclose(N(z), OD.normal_sample(eps, mu, np.exp(ls)),
+                               rtol=1e-6, atol=1e-6)
+    (z * z).sum().backward()
+    zz = OD.normal_sample(eps, mu, np.exp(ls), np.float64)
+    np.testing.assert_allclose(N(mt.grad), (2 * zz).sum(0), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(N(lt.grad), (2 * zz * eps * np.exp(ls)).sum(0),
+                               rtol=1e-4, atol=1e-3)
+    # in-kernel Philox: standard-normal moments, reproducible per seed
+    zs.set_random_seed(1234)
+    d2 = zs.distributions.Normal(T(np.zeros(4096)), std=T(np.ones(4096)))
+    s1 = N(d2.sample(64))
+    assert abs(s1.mean()) < 0.01 and abs(s1.std() - 1) < 0.01
+    zs.set_random_seed(1234)
+    d3 = zs.distributions.Normal(T(np.zeros(4096)), std=T(np.ones(4096)))
+    np.testing.assert_array_equal(s1, N(d3.sample(64)))
+
+
+def test_kernel_philox_matches_oracle():
+    """momentum kernel with mass = 1 exposes the in-kernel normals; the MH
+    kernel exposes the uniforms (accept <=> u < acc with acc = 1/2...)."""
+    import ctypes
+    from zhusuan_b200._lib import lib, ptr, stream
+    C, D = 37, 22
+    p = torch.empty(C, D, device="cuda")
+    mass = torch.ones(D, device="cuda")
+    seed, it, row0 = 0x1234567887654321, 9, 1000
+    lib.call("zsb_hmc_momentum_f32", ptr(p), None, ptr(mass), D, C, D, seed,
+             it, 1, row0, None, 0, stream())
+    ref = philox.normal_matrix(seed, 1, it, row0, C, D)
+    np.testing.assert_allclose(N(p), ref, rtol=1e-5, atol=2e-6)
+    # uniforms: lp1 - lp0 = log(t) -> acc = t; accept <=> u < t
+    u_ref = philox.uniform_vector(seed, 2, it, row0, C)
+    z = torch.zeros(C, device="cuda")
+    thr = 0.5
+    lp1 = torch.full((C,), float(np.log(thr)), device="cuda")
+    acc = torch.empty(C, device="cuda")
+    accept = torch.empty(C, dtype=torch.int32, device="cuda")
+    part = torch.empty(lib.load().zsb_hmc_acc_parts(), device="cuda")
+    npart = ctypes.c_int(0)
+    lib.call("zsb_hmc_mh_f32", ptr(z), ptr(lp1), ptr(z), ptr(z), None, seed,
+             it, row0, C, None, None, ptr(acc), ptr(accept), None, ptr(part),
+             ctypes.byref(npart), None, stream())
+    np.testing.assert_array_equal(N(accept), (u_ref < N(acc)).astype(np.int32))

@@ -1,0 +1,252 @@
+"""GPU parity: HMC through the drop-in API vs the CPU oracle / committed
+golden vectors (injected noise).  Bar (north_star): accept/reject decisions
+identical given identical uniforms, per-chain log-prob within 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hmc as OH
+from oracle import models as OM
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def T(a, dtype=torch.float32):
+    return torch.tensor(np.asarray(a), dtype=dtype, device="cuda")
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def zs():
+    import zhusuan_b200 as zs
+    return zs
+
+
+def _cfg(g):
+    return dict(step_size=float(g["cfg_step_size"]),
+                n_leapfrogs=int(g["cfg_n_leapfrogs"]), adapt_step_size=True,
+                target_acceptance_rate=float(g["cfg_target_acceptance_rate"]),
+                adapt_mass=True,
+                mass_collect_iters=int(g["cfg_mass_collect_iters"]),
+                mass_decay=float(g["cfg_mass_decay"]))
+
+
+def _replay(zs, g, model, expect_kind, q_tol=2e-5, **hmc_kw):
+    x = T(g["q0"])
+    h = zs.HMC(**_cfg(g), **hmc_kw)
+    op, info = h.sample(model, {}, {"x": x})
+    kind = h._fused["kind"] if h._fused else "generic"
+    assert kind == expect_kind
+    n_mismatch = 0
+    for i in range(g["q"].shape[0]):
+        adapt = i < int(g["n_adapt"])
+        op(adapt_step_size=adapt, adapt_mass=adapt,
+           noise={"p": {"x": T(g["noise_p"][i])}, "u": T(g["noise_u"][i])})
+        acc = N(info.acceptance_rate)
+        accept = (g["noise_u"][i] < acc).astype(np.int32)
+        bad = accept != g["accept"][i]
+        # a flip is only tolerable when u sits within rounding of acc
+        assert np.all(np.abs(g["noise_u"][i] - g["acc"][i])[bad] < 1e-5)
+        n_mismatch += int(bad.sum())
+        np.testing.assert_allclose(acc, g["acc"][i], rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(N(info.orig_log_prob), g["lp0"][i],
+                                   rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(N(info.log_prob), g["lp"][i], rtol=1e-5,
+                                   atol=1e-4)
+        np.testing.assert_allclose(N(info.orig_hamiltonian), g["h0"][i],
+                                   rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(N(info.init_momentum["x"]), g["p0"][i],
+                                   rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(N(x), g["q"][i], rtol=q_tol, atol=q_tol)
+        np.testing.assert_allclose(float(info.updated_step_size),
+                                   g["step_size"][i], rtol=1e-4)
+        np.testing.assert_allclose(float(h._state[7]), g["eps_used"][i],
+                                   rtol=1e-5)
+        np.testing.assert_allclose(N(h._mass[0]), g["mass"][i], rtol=1e-3)
+    op.synchronize()
+    assert n_mismatch == 0
+    assert h.n_search_iters == int(g["n_search_iters"])
+    return h
+
+
+def test_golden_diag_fused_through_bayesian_net(zs):
+    g = np.load(os.path.join(GOLD, "hmc_diag.npz"))
+    D = g["std"].shape[0]
+
+    @zs.meta_bayesian_net()
+    def gaussian(n_x, stdev, n_particles):     # toy_examples/gaussian.py:15-20
+        bn = zs.BayesianNet()
+        bn.normal('x', torch.zeros(n_x, device="cuda"), std=stdev,
+                  n_samples=n_particles, group_ndims=1)
+        return bn
+    _replay(zs, g, gaussian(D, T(g["std"]), g["q0"].shape[0]), "diag_normal")
+
+
+def test_golden_diag_generic_callable(zs):
+    g = np.load(os.path.join(GOLD, "hmc_diag.npz"))
+    std = T(g["std"])
+
+    def log_joint(obs):
+        return zs.distributions.Normal(torch.zeros_like(std), std=std,
+                                       group_ndims=1).log_prob(obs['x'])
+    _replay(zs, g, log_joint, "generic")
+
+
+def test_golden_dense_fused_simt(zs):
+    g = np.load(os.path.join(GOLD, "hmc_dense.npz"))
+    lj = zs.fused.GaussianLogJoint(g["P"], mean=g["mu"],
+                                   log_det_cov=-2 * float(g["const"])
+                                   - g["P"].shape[0] * np.log(2 * np.pi))
+    _replay(zs, g, lj, "dense_gaussian", q_tol=5e-5, dense_impl=0)
+
+
+def test_golden_dense_generic(zs):
+    g = np.load(os.path.join(GOLD, "hmc_dense.npz"))
+    lj = zs.fused.GaussianLogJoint(g["P"], mean=g["mu"],
+                                   log_det_cov=-2 * float(g["const"])
+                                   - g["P"].shape[0] * np.log(2 * np.pi))
+    _replay(zs, g, lambda obs: lj(obs), "generic", q_tol=5e-5)
+
+
+def test_multi_latent_two_chain_axes_generic(zs):
+    """Two latents, chain axes [3, 5], data axes [4] and [2, 3]."""
+    rng = np.random.RandomState(0)
+    s1 = (0.5 + rng.random_sample(4)).astype(np.float32)
+    s2 = (0.5 + rng.random_sample((2, 3))).astype(np.float32)
+    a0 = rng.standard_normal((3, 5, 4)).astype(np.float32)
+    b0 = rng.standard_normal((3, 5, 2, 3)).astype(np.float32)
+
+    class Two(object):
+        def logp(self, q):
+            from oracle import distributions as OD
+            return (OD.normal_log_prob(q[0], 0, np.log(s1), 1)
+                    + OD.normal_log_prob(q[1], 1.0, np.log(s2), 2))
+
+        def grad(self, q):
+            return [(-q[0] / s1 ** 2).astype(np.float32),
+                    (-(q[1] - 1.0) / s2 ** 2).astype(np.float32)]
+
+    @zs.meta_bayesian_net()
+    def model():
+        bn = zs.BayesianNet()
+        bn.normal('a', torch.zeros(4, device="cuda"), std=T(s1), group_ndims=1,
+                  n_samples=None)
+        bn.normal('b', torch.ones(2, 3, device="cuda"), std=T(s2),
+                  group_ndims=2)
+        return bn
+    oh = OH.HMC(step_size=0.05, n_leapfrogs=4, adapt_step_size=True,
+                adapt_mass=True, mass_collect_iters=2)
+    h = zs.HMC(step_size=0.05, n_leapfrogs=4, adapt_step_size=True,
+               adapt_mass=True, mass_collect_iters=2)
+    a, b = T(a0), T(b0)
+    op, info = h.sample(model(), {}, {"a": a, "b": b})
+    assert h._fused is None
+    oq = [a0, b0]
+    m = Two()
+    for i in range(6):
+        na = rng.standard_normal(a0.shape).astype(np.float32)
+        nb = rng.standard_normal(b0.shape).astype(np.float32)
+        u = rng.random_sample((3, 5)).astype(np.float32)
+        oq, oi = oh.step(oq, m.logp, m.grad, [na, nb], u, True, True)
+        op(adapt_step_size=True, adapt_mass=True,
+           noise={"p": {"a": T(na), "b": T(nb)}, "u": T(u)})
+        np.testing.assert_allclose(N(info.acceptance_rate),
+                                   oi.acceptance_rate, rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(N(a), oq[0], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(N(b), oq[1], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(float(info.updated_step_size),
+                                   oi.updated_step_size, rtol=1e-4)
+    assert tuple(info.acceptance_rate.shape) == (3, 5)
+
+
+def test_error_contract(zs):
+    with pytest.raises(ValueError, match="If adapt mass is set"):
+        zs.HMC(adapt_mass=True)
+    h = zs.HMC()
+    with pytest.raises(TypeError, match=r"latent\['x'\] is not a"):
+        h.sample(lambda o: o['x'].sum(-1), {}, {"x": np.zeros((2, 3))})
+    h = zs.HMC()
+    with pytest.raises(ValueError, match="log joint"):
+        h.sample(lambda o: o['x'].sum(), {}, {"x": torch.zeros(2, 3,
+                                                               device="cuda")})
+    # check_numerics (hmc.py:51-53): non-finite old log-prob
+    x = torch.full((4, 3), float("inf"), device="cuda")
+    h = zs.HMC(step_size=0.1, n_leapfrogs=2)
+    op, _ = h.sample(lambda o: -(o['x'] ** 2).sum(-1), {}, {"x": x})
+    op()
+    with pytest.raises(FloatingPointError, match="old_log_prob has numeric"):
+        op.synchronize()
+
+
+def test_non_finite_new_state_is_rejected(zs):
+    """hmc.py:56-59: non-finite acceptance / new log-prob -> acc = 0."""
+    x = T(np.ones((8, 2)))
+    h = zs.HMC(step_size=1e6, n_leapfrogs=3)
+    op, info = h.sample(lambda o: -(o['x'] ** 4).sum(-1), {}, {"x": x})
+    op()
+    op.synchronize()
+    assert float(info.acceptance_rate.max()) == 0.0
+    np.testing.assert_array_equal(N(x), np.ones((8, 2), np.float32))
+
+
+def test_philox_sampling_recovers_target_std(zs):
+    """gaussian.py end-to-end with in-kernel RNG: per-dimension sample std
+    within 5% of the target after adaptation (statistical)."""
+    D, C = 10, 2000
+    std = (1.0 / (1.0 + np.arange(D))).astype(np.float32)
+
+    @zs.meta_bayesian_net()
+    def gaussian():
+        bn = zs.BayesianNet()
+        bn.normal('x', torch.zeros(D, device="cuda"), std=T(std),
+                  n_samples=C, group_ndims=1)
+        return bn
+    x = torch.zeros(C, D, device="cuda")
+    h = zs.HMC(step_size=1e-3, n_leapfrogs=5, adapt_step_size=True,
+               adapt_mass=True, target_acceptance_rate=0.9, seed=42)
+    op, info = h.sample(gaussian(), {}, {"x": x})
+    samples = []
+    for i in range(200):
+        op(adapt_step_size=i < 50, adapt_mass=i < 50)
+        if i >= 100:
+            samples.append(x.clone())
+    s = torch.cat(samples).std(0).cpu().numpy()
+    np.testing.assert_allclose(s, std, rtol=0.05)
+    assert 0.5 < float(info.acceptance_rate.mean()) <= 1.0
+
+
+def test_dense_full_size_energy_conservation(zs):
+    """BASELINE config-2 size (65 536 chains x 1024 dims) property test: with
+    a small step the leapfrog integrator conserves H (|dH| << 1), the chain
+    moves, and two identical runs are bit-identical (determinism)."""
+    D, C = 1024, 65536
+    P, const = OM.make_dense_gaussian_problem(D, seed=2)
+    lj = zs.fused.GaussianLogJoint(P)
+    outs = []
+    for rep in range(2):
+        torch.manual_seed(3)
+        x = torch.randn(C, D, device="cuda")
+        x0 = x.clone()
+        h = zs.HMC(step_size=0.01, n_leapfrogs=3, seed=7, dense_impl=0)
+        op, info = h.sample(lj, {}, {"x": x})
+        op()
+        op.synchronize()
+        dH = (info.hamiltonian - info.orig_hamiltonian).abs()
+        assert float(dH.max()) < 0.05
+        assert float(info.acceptance_rate.min()) > 0.9
+        assert float((x - x0).abs().max()) > 1e-3
+        outs.append((x.clone(), info.acceptance_rate.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    # log-prob of the new state equals a float64 evaluation on a chain subset
+    xs = outs[0][0][:64].double().cpu().numpy()
+    ref = -0.5 * np.einsum('ci,ij,cj->c', xs, P, xs) + const
+    op()   # one more iteration: orig_log_prob now describes outs' state
+    op.synchronize()
+    np.testing.assert_allclose(N(info.orig_log_prob[:64]), ref, rtol=1e-5)

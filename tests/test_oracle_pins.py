@@ -1,0 +1,190 @@
+"""Pins the CPU oracle to the reference's own known-answer tests and golden
+vectors.  CPU only."""
+import numpy as np
+import pytest
+from scipy import stats
+from scipy.special import logsumexp
+
+import cases
+from oracle import distributions as OD
+from oracle import variational as OV
+from oracle import philox
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-6), (np.float64, 1e-12)])
+def test_normal_log_prob(dtype, tol):
+    for given, mean, logstd, g, target in cases.normal_cases():
+        lp = OD.normal_log_prob(given, mean, logstd, g, dtype)
+        np.testing.assert_allclose(lp, target, rtol=max(tol, 1e-6), atol=1e-6)
+
+
+def test_bernoulli_log_prob():
+    for logits, given, target in cases.bernoulli_cases():
+        np.testing.assert_allclose(OD.bernoulli_log_prob(given, logits),
+                                   target, rtol=1e-6, atol=1e-6)
+
+
+def test_categorical_log_prob():
+    for logits, given, target in cases.categorical_cases():
+        np.testing.assert_allclose(OD.categorical_log_prob(given, logits),
+                                   target, rtol=1e-6, atol=1e-6)
+
+
+def test_unnormalized_multinomial_log_prob():
+    for logits, given, norm, target in cases.unnorm_multinomial_cases():
+        lp = OD.unnormalized_multinomial_log_prob(given, logits, norm)
+        np.testing.assert_allclose(lp, target, rtol=1e-5, atol=1e-4)
+
+
+def test_dirichlet_log_prob():
+    for alpha, given, target in cases.dirichlet_cases():
+        np.testing.assert_allclose(OD.dirichlet_log_prob(given, alpha),
+                                   target, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("seed", [23, 233, 2333])
+def test_mvn_cholesky_log_prob(seed):
+    mean, cov, chol = cases.mvn_params(seed)
+    rng = np.random.RandomState(seed)
+    samples = mean + np.einsum('ijab,nijb->nija', chol,
+                               rng.standard_normal((7,) + mean.shape))
+    lp = OD.mvn_cholesky_log_prob(samples, mean, chol, dtype=np.float64)
+    for i in range(mean.shape[0]):
+        for j in range(mean.shape[1]):
+            exact = stats.multivariate_normal.logpdf(
+                samples[:, i, j, :], mean[i, j], cov[i, j])
+            np.testing.assert_allclose(lp[:, i, j], exact, rtol=1e-8,
+                                       atol=1e-8)
+
+
+def test_log_mean_exp_golden():
+    """tests/test_utils.py:270-284."""
+    a = cases.LME_A
+    for keepdims in [True, False]:
+        true = logsumexp(a, (0, 2), keepdims=keepdims) - np.log(
+            a.shape[0] * a.shape[2])
+        np.testing.assert_allclose(
+            OV.log_mean_exp(a, (0, 2), keepdims, np.float64), true,
+            rtol=1e-6)
+        true_s = logsumexp(a, (0, 2), keepdims=keepdims)
+        np.testing.assert_allclose(
+            OV.log_sum_exp(a, (0, 2), keepdims, np.float64), true_s,
+            rtol=1e-6)
+    b = cases.LME_B
+    assert np.abs(OV.log_mean_exp(b, 0, False, np.float64) - b).max() < 1e-6
+
+
+def _kl_normal_normal(m1, s1, m2, s2):
+    return np.log(s2 / s1) + (s1 ** 2 + (m1 - m2) ** 2) / (2 * s2 ** 2) - 0.5
+
+
+def _n01(shape):
+    return np.random.RandomState(1).standard_normal(shape).astype(np.float32)
+
+
+@pytest.mark.parametrize("x_mean,x_std", [(0., 1.), (2., 3.)])
+def test_elbo_value_vs_analytic_kl(x_mean, x_std):
+    """tests/variational/test_exclusive_kl.py:26-47: q-samples are
+    RandomState(1).standard_normal(1e5), p = N(x_mean, x_std);
+    ELBO == -KL(N(0,1) || p) to 1e-3."""
+    z = _n01(100000)
+    log_q = stats.norm.logpdf(z).astype(np.float32)
+    log_p = OD.normal_log_prob(z, x_mean, np.log(x_std))
+    lb = OV.elbo(log_p, [log_q], axis=0)
+    assert abs(lb - (-_kl_normal_normal(0., 1., x_mean, x_std))) < 1e-3
+
+
+def _sgvb_grads(weights, z, eps, x_mean, x_std, sigma):
+    """d(-objective)/d(mu, sigma) through z = mu + sigma*eps with backward
+    weights d objective / d log_w (1/K for ELBO, softmax for IWAE):
+    log_w = log p(z) - log q(z); dlog p/dz = -(z-m)/s^2;
+    log q(z(mu,sigma)) = -log sigma - eps^2/2 + c."""
+    dlogp_dz = -(z - x_mean) / x_std ** 2
+    dmu = -(weights * dlogp_dz).sum()
+    dsigma = -(weights * (dlogp_dz * eps + 1.0 / sigma)).sum()
+    return dmu, dsigma
+
+
+@pytest.mark.parametrize("x_mean,x_std,rtol,atol",
+                         [(0., 1., 1e-2, 1e-6), (2., 3., 1e-6, 1e-2)])
+def test_elbo_sgvb_gradient_vs_kl_grads(x_mean, x_std, rtol, atol):
+    """tests/variational/test_exclusive_kl.py:49-78 (q = N(2, 3))."""
+    mu, sigma = 2., 3.
+    eps = _n01(100000).astype(np.float64)
+    z = eps * sigma + mu
+    w = OV.elbo_grad_logw(z.shape, 0, np.float64)
+    g = _sgvb_grads(w, z, eps, x_mean, x_std, sigma)
+    true = ((mu - x_mean) / x_std ** 2, -1.0 / sigma + sigma / x_std ** 2)
+    np.testing.assert_allclose(g, true, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("x_mean,x_std", [(0., 1.), (2., 3.)])
+def test_iwae_k1_equals_elbo_and_monotone(x_mean, x_std):
+    """tests/variational/test_monte_carlo.py:25-70."""
+    rng = np.random.RandomState(1)
+    n1 = rng.standard_normal(size=(1, 1000)).astype(np.float32)
+    n3 = rng.standard_normal(1000).astype(np.float32)
+    analytic = -_kl_normal_normal(0., 1., x_mean, x_std)
+    log_w = OD.normal_log_prob(n1, x_mean, np.log(x_std)) - \
+        stats.norm.logpdf(n1).astype(np.float32)
+    k1 = OV.iw_objective(log_w, [], axis=0).mean()
+    assert abs(k1 - analytic) < 1e-2
+    log_w3 = OD.normal_log_prob(n3, x_mean, np.log(x_std)) - \
+        stats.norm.logpdf(n3).astype(np.float32)
+    k1000 = OV.iw_objective(log_w3, [], axis=0).mean()
+    assert k1000 > analytic - 1e-6
+    with pytest.raises(ValueError):
+        OV.iw_objective(log_w, [], axis=None)
+
+
+@pytest.mark.parametrize("x_mean,x_std,thr", [(0., 1., 0.04), (2., 3., 0.02)])
+def test_iwae_sgvb_gradient_vs_kl_grads(x_mean, x_std, thr):
+    """tests/variational/test_monte_carlo.py:72-102 (K=1 along axis 0)."""
+    mu, sigma = 2., 3.
+    rng = np.random.RandomState(1)
+    eps = rng.standard_normal(size=(1, 1000)).astype(np.float32).astype(
+        np.float64)
+    z = eps * sigma + mu
+    log_w = stats.norm.logpdf(z, x_mean, x_std) - stats.norm.logpdf(
+        z, mu, sigma)
+    w = OV.iw_grad_logw(log_w, 0, np.float64) / log_w.shape[1]  # reduce_mean
+    g = _sgvb_grads(w, z, eps, x_mean, x_std, sigma)
+    true = ((mu - x_mean) / x_std ** 2, -1.0 / sigma + sigma / x_std ** 2)
+    np.testing.assert_allclose(g, true, rtol=thr, atol=thr)
+
+
+def test_iw_grad_is_softmax():
+    x = np.random.RandomState(0).standard_normal((6, 5))
+    w = OV.iw_grad_logw(x, 0, np.float64)
+    np.testing.assert_allclose(w.sum(0), 1.0, rtol=1e-12)
+    h = 1e-6
+    xp = x.copy()
+    xp[2, 3] += h
+    fd = (OV.log_mean_exp(xp, 0, dtype=np.float64).sum()
+          - OV.log_mean_exp(x, 0, dtype=np.float64).sum()) / h
+    np.testing.assert_allclose(fd, w[2, 3], rtol=1e-4)
+
+
+def test_philox_known_answers():
+    """Random123 philox4x32-10 KAT vectors."""
+    def h(a):
+        return [int(v) for v in a]
+    z4, z2 = np.zeros(4, np.uint32), np.zeros(2, np.uint32)
+    assert h(philox.philox4x32_10(z4, z2)) == [
+        0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f4 = np.full(4, 0xffffffff, np.uint32)
+    f2 = np.full(2, 0xffffffff, np.uint32)
+    assert h(philox.philox4x32_10(f4, f2)) == [
+        0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    c = np.array([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], np.uint32)
+    k = np.array([0xa4093822, 0x299f31d0], np.uint32)
+    assert h(philox.philox4x32_10(c, k)) == [
+        0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_normals_are_standard():
+    z = philox.normal_matrix(seed=7, stream=1, iteration=3, row0=0,
+                             n_rows=2000, n_cols=16)
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
+    u = philox.uniform_vector(7, 2, 3, 0, 20000)
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01

@@ -84,9 +84,15 @@ class _Lib(object):
         self.load().zsb_last_error(buf, 512)
         return buf.value.decode("utf-8", "replace")
 
+    # kernels launched per successful call (entries that launch two kernels)
+    _KERNELS = {"zsb_hmc_mass_stats_f32": 2, "zsb_sgmcmc_sghmc_f32": 2,
+                "zsb_sgmcmc_mean_sq_f32": 2, "zsb_sgmcmc_sgnht_scalar_f32": 2}
+    launches = 0
+
     def call(self, name, *args):
         fn = getattr(self.load(), name)
         rc = fn(*args)
+        self.launches += self._KERNELS.get(name, 1)
         if rc != 0:
             raise ZsbError("%s failed (%d): %s" % (name, rc, self.last_error()))
         return rc

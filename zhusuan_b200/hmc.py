@@ -498,6 +498,10 @@ class HMC(object):
         L = self.n_leapfrogs
         cur, nxt = q0, self._qa
         p_in = self._p0[0]
+        prof = getattr(self, "_profile_events", None)
+        if prof is not None:           # bench.py: device time of the L+1 passes
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
         for i in range(L + 1):
             last = i == L
             self._dense_pass(
@@ -509,6 +513,9 @@ class HMC(object):
             p_in = self._pw
             if not last:
                 cur, nxt = nxt, (self._qb if nxt is self._qa else self._qa)
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1))
         if L == 0:
             self._lp1_part.copy_(self._lp0_part)
         self._dense_finish_mh(noise_u, seed, it, s, full=True)
