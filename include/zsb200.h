@@ -175,13 +175,18 @@ int zsb_hmc_diag_normal_step_f32(float* q, const float* noise, const float* u, c
 /* Dense-Gaussian target log p = -1/2 (x-mu)^T P (x-mu) + c: one launch per pass of the leapfrog
  * while-loop body (hmc.py:352-364): g = b - q_cur P; p_out = p_in + p_scale*eps*g;
  * q_next = q_cur + eps*p_out/mass (skipped if NULL); lp_part/k_part [ntiles, chains] partials.
- * impl 0 = SIMT fp32, impl 1 = tcgen05 3xTF32 (P = hi part, P_lo = residual). */
+ * impl 0 = SIMT fp32 (P full fp32; *_lo ignored).
+ * impl 1 = tcgen05.mma kind::tf32, 3xTF32 split: P = hi part (low 13 mantissa bits cleared),
+ *          P_lo = P - hi; q_cur_lo = residual of q_cur (zsb_hmc_dense_split_lo_f32 for the first
+ *          pass), q_next_lo receives the residual of q_next. */
 int zsb_hmc_dense_ntiles(int64_t D, int impl);
-int zsb_hmc_dense_leapfrog_f32(const float* q_cur, float* q_next, const float* p_in, float* p_out,
+int zsb_hmc_dense_leapfrog_f32(const float* q_cur, const float* q_cur_lo, float* q_next,
+                               float* q_next_lo, const float* p_in, float* p_out,
                                const float* P, const float* P_lo, const float* bvec,
                                const float* mu, const float* mass, const float* state,
                                float p_scale, float* lp_part, float* k_part, int64_t chains,
                                int64_t D, int impl, void* stream);
+int zsb_hmc_dense_split_lo_f32(const float* q, float* lo, int64_t n, void* stream);
 int zsb_hmc_dense_finish_f32(const float* lp_part, const float* k_part, int ntiles, int64_t chains,
                              float const_term, float* lp_out, float* k_out, void* stream);
 

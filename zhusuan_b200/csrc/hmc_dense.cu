@@ -174,11 +174,13 @@ __global__ void __launch_bounds__(256) dense_finish_kernel(const float* __restri
 }  // namespace
 
 // implemented in hmc_dense_tc.cu
-int zsb_dense_leapfrog_tc_launch(const float* q_cur, float* q_next, const float* p_in, float* p_out,
+int zsb_dense_leapfrog_tc_launch(const float* q_cur, const float* q_cur_lo, float* q_next,
+                                 float* q_next_lo, const float* p_in, float* p_out,
                                  const float* P_hi, const float* P_lo, const float* bvec,
                                  const float* mu, const float* mass, const float* state,
                                  float p_scale, float* lp_part, float* k_part, int64_t chains,
                                  int D, cudaStream_t st);
+int zsb_dense_split_lo_launch(const float* q, float* lo, int64_t n, cudaStream_t st);
 int zsb_dense_tc_ntiles(int D);
 
 extern "C" {
@@ -189,8 +191,11 @@ int zsb_hmc_dense_ntiles(int64_t D, int impl) {
   return (int)zsb_ceil_div(D, BN);
 }
 
-// impl 0: SIMT fp32 (P_lo ignored).  impl 1: tcgen05 3xTF32 (needs P_hi/P_lo split, D % 128 == 0).
-int zsb_hmc_dense_leapfrog_f32(const float* q_cur, float* q_next, const float* p_in, float* p_out,
+// impl 0: SIMT fp32 (P = full fp32 matrix; P_lo / q_cur_lo / q_next_lo ignored).
+// impl 1: tcgen05 3xTF32 (P = hi part, P_lo = residual; q_cur_lo = TF32 residual of q_cur on entry,
+//         q_next_lo receives q_next's residual; D % 32 == 0).
+int zsb_hmc_dense_leapfrog_f32(const float* q_cur, const float* q_cur_lo, float* q_next,
+                               float* q_next_lo, const float* p_in, float* p_out,
                                const float* P, const float* P_lo, const float* bvec,
                                const float* mu, const float* mass, const float* state,
                                float p_scale, float* lp_part, float* k_part, int64_t chains,
@@ -201,15 +206,23 @@ int zsb_hmc_dense_leapfrog_f32(const float* q_cur, float* q_next, const float* p
   ZSB_REQUIRE(q_next != q_cur, "zsb_hmc_dense_leapfrog_f32: q_next must not alias q_cur");
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == 1) {
-    ZSB_REQUIRE(P_lo, "zsb_hmc_dense_leapfrog_f32: impl 1 needs the P_lo split");
-    return zsb_dense_leapfrog_tc_launch(q_cur, q_next, p_in, p_out, P, P_lo, bvec, mu, mass, state,
-                                        p_scale, lp_part, k_part, chains, (int)D, st);
+    ZSB_REQUIRE(P_lo && q_cur_lo, "zsb_hmc_dense_leapfrog_f32: impl 1 needs the P_lo / q_lo splits");
+    return zsb_dense_leapfrog_tc_launch(q_cur, q_cur_lo, q_next, q_next_lo, p_in, p_out, P, P_lo,
+                                        bvec, mu, mass, state, p_scale, lp_part, k_part, chains,
+                                        (int)D, st);
   }
   ZSB_REQUIRE(impl == 0, "zsb_hmc_dense_leapfrog_f32: unknown impl %d", impl);
   dim3 grid((unsigned)zsb_ceil_div(D, BN), (unsigned)zsb_ceil_div(chains, BM));
   dense_leapfrog_simt_kernel<<<grid, 256, 0, st>>>(q_cur, q_next, p_in, p_out, P, bvec, mu, mass,
                                                    state, p_scale, lp_part, k_part, chains, (int)D);
   return zsb_check_launch("hmc_dense_leapfrog_simt");
+}
+
+// lo[i] = q[i] - tf32_trunc(q[i])  (the residual operand of the 3xTF32 split), n % 4 == 0
+int zsb_hmc_dense_split_lo_f32(const float* q, float* lo, int64_t n, void* stream) {
+  ZSB_REQUIRE(q && lo && n >= 0, "zsb_hmc_dense_split_lo_f32: bad args");
+  if (n == 0) return ZSB_OK;
+  return zsb_dense_split_lo_launch(q, lo, n, (cudaStream_t)stream);
 }
 
 int zsb_hmc_dense_finish_f32(const float* lp_part, const float* k_part, int ntiles, int64_t chains,

@@ -452,6 +452,10 @@ class HMC(object):
         self._qa, self._qb = torch.empty_like(self._q[0]), \
             torch.empty_like(self._q[0])
         self._pw = torch.empty_like(self._q[0])
+        self._lo = {}
+        if self._impl == 1:            # TF32 residuals of the A operands
+            for t in (self._q[0], self._qa, self._qb):
+                self._lo[t.data_ptr()] = torch.empty_like(t)
         self._lp0_part, self._lp1_part = z(nt * self._chains), \
             z(nt * self._chains)
         self._k_part = z(nt * self._chains)
@@ -460,8 +464,14 @@ class HMC(object):
     def _dense_pass(self, q_cur, q_next, p_in, p_out, scale, lp_part, k_part,
                     s):
         f = self._fused
-        lib.call("zsb_hmc_dense_leapfrog_f32", ptr(q_cur), ptr(q_next),
-                 ptr(p_in), ptr(p_out), ptr(f["P"]), ptr(f.get("P_lo")),
+        tc = self._impl == 1
+        lo_cur = self._lo[q_cur.data_ptr()] if tc else None
+        lo_next = self._lo[q_next.data_ptr()] if tc and q_next is not None \
+            else None
+        lib.call("zsb_hmc_dense_leapfrog_f32", ptr(q_cur), ptr(lo_cur),
+                 ptr(q_next), ptr(lo_next), ptr(p_in), ptr(p_out),
+                 ptr(f["P_hi"] if tc else f["P"]),
+                 ptr(f["P_lo"]) if tc else None,
                  ptr(f.get("b")), ptr(f.get("mu")), ptr(self._mass[0]),
                  ptr(self._state), scale, ptr(lp_part), ptr(k_part),
                  self._chains, f["D"], self._impl, s)
@@ -487,6 +497,9 @@ class HMC(object):
     def _iterate_dense(self, noise_p, noise_u, seed, it, init, s):
         q0 = self._q[0]
         self._momentum(noise_p, seed, it, s)
+        if self._impl == 1:
+            lib.call("zsb_hmc_dense_split_lo_f32", ptr(q0),
+                     ptr(self._lo[q0.data_ptr()]), q0.numel(), s)
         if init:
             def probe():
                 self._dense_pass(q0, self._qa, self._p0[0], self._pw, 0.5,
