@@ -250,3 +250,99 @@ def test_dense_full_size_energy_conservation(zs):
     op()   # one more iteration: orig_log_prob now describes outs' state
     op.synchronize()
     np.testing.assert_allclose(N(info.orig_log_prob[:64]), ref, rtol=1e-5)
+
+
+def _dense_pass_reference(q, p, P, b, mu, mass, eps, scale):
+    """float64 restatement of one pass of the leapfrog loop body for the dense
+    Gaussian (hmc.py:38-43, 352-364): g = b - qP; p' = p + scale*eps*g;
+    q' = q + eps*p'/m; lp = 1/2 (q-mu).g; K = 1/2 sum p'^2/m."""
+    g = b - q @ P
+    pn = p + scale * eps * g
+    qn = q + eps * pn / mass
+    lp = 0.5 * ((q - mu) * g).sum(-1)
+    k = 0.5 * (pn * pn / mass).sum(-1)
+    return pn, qn, lp, k
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("C,D", [(300, 512), (24, 32), (129, 288), (1000, 1024)])
+def test_dense_single_pass_vs_float64(zs, impl, C, D):
+    """One fused GEMM+leapfrog pass through the C ABI vs float64, for the SIMT
+    (impl 0) and tcgen05 3xTF32 (impl 1) kernels, including ragged M / N tiles.
+    Bar: per-evaluation log-prob and gradient-derived p within 1e-5 relative."""
+    from zhusuan_b200._lib import lib, ptr, stream
+    rng = np.random.RandomState(C + D)
+    P64, _ = OM.make_dense_gaussian_problem(D, seed=4)
+    q = rng.standard_normal((C, D)); p = rng.standard_normal((C, D))
+    mu = 0.3 * rng.standard_normal(D)
+    mass = 0.5 + rng.random_sample(D)
+    eps, scale = 0.07, 0.5
+    P32 = P64.astype(np.float32)
+    hi = (P32.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    lo = (P32 - hi).astype(np.float32)
+    b = (P32.astype(np.float64) @ mu).astype(np.float32)
+    qt, pt, mt, mut, bt = T(q), T(p), T(mass), T(mu), T(b)
+    Pt, Pl = (T(hi), T(lo)) if impl == 1 else (T(P32), None)
+    state = torch.zeros(16, device="cuda"); state[7] = eps
+    nt = lib.load().zsb_hmc_dense_ntiles(D, impl)
+    qn = torch.empty_like(qt); pn = torch.empty_like(pt)
+    qlo = torch.empty_like(qt); qnlo = torch.empty_like(qt)
+    lpp = torch.zeros(nt * C, device="cuda"); kp = torch.zeros(nt * C, device="cuda")
+    lp = torch.empty(C, device="cuda"); k = torch.empty(C, device="cuda")
+    s = stream()
+    if impl == 1:
+        lib.call("zsb_hmc_dense_split_lo_f32", ptr(qt), ptr(qlo), qt.numel(), s)
+    lib.call("zsb_hmc_dense_leapfrog_f32", ptr(qt), ptr(qlo), ptr(qn),
+             ptr(qnlo), ptr(pt), ptr(pn), ptr(Pt), ptr(Pl), ptr(bt), ptr(mut),
+             ptr(mt), ptr(state), scale, ptr(lpp), ptr(kp), C, D, impl, s)
+    lib.call("zsb_hmc_dense_finish_f32", ptr(lpp), ptr(kp), nt, C, 0.0,
+             ptr(lp), ptr(k), s)
+    torch.cuda.synchronize()
+    q32 = q.astype(np.float32).astype(np.float64)
+    p32 = p.astype(np.float32).astype(np.float64)
+    rpn, rqn, rlp, rk = _dense_pass_reference(
+        q32, p32, P32.astype(np.float64), b.astype(np.float64),
+        mu.astype(np.float32).astype(np.float64),
+        mass.astype(np.float32).astype(np.float64), np.float32(eps), scale)
+    gscale = np.abs(q32 @ P32.astype(np.float64)).max()
+    np.testing.assert_allclose(N(pn), rpn, rtol=1e-5, atol=1e-5 * gscale)
+    np.testing.assert_allclose(N(qn), rqn, rtol=1e-5, atol=1e-5 * gscale)
+    np.testing.assert_allclose(N(lp), rlp, rtol=1e-5, atol=1e-5 * np.abs(rlp).max())
+    np.testing.assert_allclose(N(k), rk, rtol=1e-5)
+    if impl == 1:   # q_next_lo is exactly the TF32 residual of q_next
+        qn32 = N(qn)
+        res = qn32 - (qn32.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        np.testing.assert_array_equal(N(qnlo), res)
+
+
+def test_golden_dense_fused_tc(zs):
+    g = np.load(os.path.join(GOLD, "hmc_dense.npz"))
+    lj = zs.fused.GaussianLogJoint(g["P"], mean=g["mu"],
+                                   log_det_cov=-2 * float(g["const"])
+                                   - g["P"].shape[0] * np.log(2 * np.pi))
+    _replay(zs, g, lj, "dense_gaussian", q_tol=1e-4, dense_impl=1)
+
+
+def test_dense_tc_vs_simt_full_size(zs):
+    """65 536 x 1024, L=3: the tensor-core and SIMT paths agree on the
+    per-chain Hamiltonians to 1e-5 relative and make identical MH decisions
+    except where u is within rounding of acc."""
+    D, C = 1024, 65536
+    P, const = OM.make_dense_gaussian_problem(D, seed=2)
+    res = []
+    for impl in (0, 1):
+        lj = zs.fused.GaussianLogJoint(P)
+        torch.manual_seed(3)
+        x = torch.randn(C, D, device="cuda")
+        h = zs.HMC(step_size=0.2, n_leapfrogs=3, seed=7, dense_impl=impl)
+        op, info = h.sample(lj, {}, {"x": x})
+        op()
+        op.synchronize()
+        res.append((N(info.hamiltonian), N(info.orig_hamiltonian),
+                    N(info.acceptance_rate), N(x)))
+    np.testing.assert_allclose(res[1][1], res[0][1], rtol=1e-5)
+    np.testing.assert_allclose(res[1][0], res[0][0], rtol=1e-5)
+    np.testing.assert_allclose(res[1][2], res[0][2], rtol=0, atol=2e-3)
+    moved0 = np.abs(res[0][3]).sum(1); moved1 = np.abs(res[1][3]).sum(1)
+    frac_diff = np.mean(np.abs(moved0 - moved1) > 1e-2 * np.abs(moved0))
+    assert frac_diff < 1e-3

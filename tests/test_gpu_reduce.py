@@ -81,7 +81,7 @@ def test_elbo_value_reference_test(zs, x_mean, x_std):
                                  latent={'x': [T(z), T(log_q)]}, axis=0)
     assert abs(float(lb.tensor) - (-_kl(0., 1., x_mean, x_std))) < 1e-3
     ref = OV.elbo(OD.normal_log_prob(z, x_mean, np.log(x_std)), [log_q], 0)
-    np.testing.assert_allclose(float(lb.tensor), ref, rtol=1e-5)
+    np.testing.assert_allclose(float(lb.tensor), ref, rtol=1e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("x_mean,x_std,rtol,atol",
