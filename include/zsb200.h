@@ -186,6 +186,7 @@ int zsb_hmc_dense_leapfrog_f32(const float* q_cur, const float* q_cur_lo, float*
                                const float* mu, const float* mass, const float* state,
                                float p_scale, float* lp_part, float* k_part, int64_t chains,
                                int64_t D, int impl, void* stream);
+int zsb_hmc_dense_tc_config(int bk);   /* impl-1 pipeline shape: 32 (2x96 KB) or 16 (4x48 KB) */
 int zsb_hmc_dense_split_lo_f32(const float* q, float* lo, int64_t n, void* stream);
 int zsb_hmc_dense_finish_f32(const float* lp_part, const float* k_part, int ntiles, int64_t chains,
                              float const_term, float* lp_out, float* k_out, void* stream);

@@ -182,6 +182,7 @@ int zsb_dense_leapfrog_tc_launch(const float* q_cur, const float* q_cur_lo, floa
                                  int D, cudaStream_t st);
 int zsb_dense_split_lo_launch(const float* q, float* lo, int64_t n, cudaStream_t st);
 int zsb_dense_tc_ntiles(int D);
+int zsb_dense_tc_set_bk(int bk);
 
 extern "C" {
 
@@ -216,6 +217,13 @@ int zsb_hmc_dense_leapfrog_f32(const float* q_cur, const float* q_cur_lo, float*
   dense_leapfrog_simt_kernel<<<grid, 256, 0, st>>>(q_cur, q_next, p_in, p_out, P, bvec, mu, mass,
                                                    state, p_scale, lp_part, k_part, chains, (int)D);
   return zsb_check_launch("hmc_dense_leapfrog_simt");
+}
+
+// Pipeline shape of the tensor-core kernel: bk = 32 -> 2 stages x 96 KB (128B swizzle),
+// bk = 16 -> 4 stages x 48 KB (64B swizzle).  Tuning knob; results are identical.
+int zsb_hmc_dense_tc_config(int bk) {
+  ZSB_REQUIRE(zsb_dense_tc_set_bk(bk) == ZSB_OK, "zsb_hmc_dense_tc_config: bk must be 16 or 32");
+  return ZSB_OK;
 }
 
 // lo[i] = q[i] - tf32_trunc(q[i])  (the residual operand of the 3xTF32 split), n % 4 == 0

@@ -1,32 +1,47 @@
 // Dense-Gaussian leapfrog pass on 5th-gen tensor cores (impl 1): tcgen05.mma kind::tf32 with a
-// 3xTF32 split so the fp32 gradient  g = b - q P  keeps ~fp32 accuracy:
+// 3xTF32 split so the fp32 gradient  g = b - P q  keeps ~fp32 accuracy:
 //     q = q_hi + q_lo,  P = P_hi + P_lo   (hi = top 19 bits, exactly what the TF32 datapath reads)
-//     q P ~= q_hi P_hi + q_hi P_lo + q_lo P_hi          (dropped term ~2^-22 relative)
+//     P q ~= P_hi q_hi + P_hi q_lo + P_lo q_hi          (dropped term ~2^-22 relative)
 // accumulated in fp32 in TMEM.  Same fused leapfrog epilogue as the SIMT kernel (hmc_dense.cu).
 //
+// The GEMM is computed TRANSPOSED, G^T[n, c] = sum_k P[n, k] q[c, k]  (A = P rows, B = chain rows,
+// both K-major), so that in TMEM a lane is a dimension n and a column is a chain c: an epilogue
+// warp then touches 32 consecutive dimensions of ONE chain per instruction -- a full 128-byte line
+// of p / q / q_next -- instead of 32 chains 4 KB apart.
+//
 // Structure (one persistent CTA per SM, 192 threads, warp-specialised):
-//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles of q_hi(=q), q_lo, P_hi, P_lo
-//               into a 2-stage shared-memory ring (96 KB / stage), mbarrier complete_tx signalling
-//   warp 1      MMA issuer: one elected lane issues 12 tcgen05.mma (128x256x8, 3 per k-step) per
-//               stage; tcgen05.commit frees the smem slot / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld (32x32b.x32) the fp32 accumulator (thread == chain row),
-//               p += s2*g, q_next = q + eps*p/m, q_next_lo, row partials of lp and K -> HBM
+//   warp 0      TMA producer: cp.async.bulk.tensor swizzled tiles of P_hi, P_lo (128 x BK) and
+//               q (=q_hi), q_lo (256 x BK) into a STAGES-deep shared-memory ring (192 KB total),
+//               mbarrier complete_tx signalling
+//   warp 1      MMA issuer: one elected lane issues 3 tcgen05.mma (128x256x8) per k-step;
+//               tcgen05.commit frees the smem slot / publishes the accumulator
+//   warps 2-5   epilogue: tcgen05.ld (32x32b.x32) the fp32 accumulator, p += s2*g,
+//               q_next = q + eps*p/m, q_next_lo, warp-transpose reductions of lp and K -> HBM
 //   TMEM        2 x 256 columns: accumulator double buffer (epilogue of tile i overlaps MMA of i+1)
-// Tiles (128 chains x 256 dims) are assigned round-robin with the N index fastest, so the CTAs
-// running concurrently share their A rows and the whole (8 MB hi+lo) P through the 126 MB L2.
+// Tiles (128 dims x 256 chains) are assigned round-robin with the dimension block fastest, so the
+// CTAs running concurrently share their chain rows and the whole (8 MB hi+lo) P through the L2.
 #include "common.cuh"
 #include <cuda.h>
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 32, STAGES = 2;
-constexpr int A_TILE_BYTES = BM * BK * 4;            // 16 KB
-constexpr int B_TILE_BYTES = BN * BK * 4;            // 32 KB
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // 96 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int BM = 128;   // dimensions per tile (TMEM lanes)
+constexpr int BN = 256;   // chains per tile (TMEM columns)
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;   // ~2 s: trap instead of hanging the box
+
+template <int BK>
+struct Cfg {
+  static constexpr int A_TILE = BM * BK * 4;
+  static constexpr int B_TILE = BN * BK * 4;
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;      // 96 KB (BK=32) / 48 KB (BK=16)
+  static constexpr int STAGES = (192 * 1024) / STAGE;        // 2 / 4
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+  static constexpr int ROW_BYTES = BK * 4;                   // 128 / 64 -> swizzle width
+  static constexpr int SBO = 8 * ROW_BYTES;                  // 8-row swizzle atom
+  static constexpr uint64_t LAYOUT = (BK == 32) ? 2 : 4;     // SWIZZLE_128B / SWIZZLE_64B
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -71,14 +86,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-// K-major, 128B-swizzled operand tile (rows x 32 fp32 = 128 B per row, 8-row atoms of 1024 B).
+// K-major swizzled operand tile: rows of BK fp32 (128 B or 64 B), 8-row swizzle atoms.
+template <int BK>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address      bits [0,14)
-  d |= (uint64_t)0 << 16;                             // LBO (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                   // SBO = 1024 B       bits [32,46)
+  d |= (uint64_t)(Cfg<BK>::SBO >> 4) << 32;           // stride byte offset bits [32,46)
   d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                             // layout type: SWIZZLE_128B
+  d |= Cfg<BK>::LAYOUT << 61;                         // swizzle mode
   return d;
 }
 // instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N=256
@@ -112,6 +127,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -122,11 +147,31 @@ __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
+// In: every lane holds v[0..15] (value of "column" j at this lane's row).  Out: returns, on lanes
+// l < 16 (and mirrored on l+16), the sum over the 32 lanes of column l & 15 (31 shuffles).
+__device__ __forceinline__ float warp_transpose_sum16(float v[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int o = 8, cnt = 16; o >= 1; o >>= 1, cnt >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt / 2; ++i) {
+      const float keep = upper ? v[i + cnt / 2] : v[i];
+      const float send = upper ? v[i] : v[i + cnt / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// MODE 0: plain pass; 1: + log-prob partials (first pass); 2: + log-prob and kinetic partials.
+template <int BK, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_qhi,
-                         const __grid_constant__ CUtensorMap map_qlo,
-                         const __grid_constant__ CUtensorMap map_phi,
+dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
                          const __grid_constant__ CUtensorMap map_plo,
+                         const __grid_constant__ CUtensorMap map_qhi,
+                         const __grid_constant__ CUtensorMap map_qlo,
                          const float* __restrict__ q_cur, float* __restrict__ q_next,
                          float* __restrict__ q_next_lo, const float* __restrict__ p_in,
                          float* __restrict__ p_out, const float* __restrict__ bvec,
@@ -134,26 +179,27 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_qhi,
                          const float* __restrict__ state, float p_scale,
                          float* __restrict__ lp_part, float* __restrict__ k_part, int64_t chains,
                          int D) {
+  using C = Cfg<BK>;
   extern __shared__ uint8_t smem_raw[];
-  // 1024-B alignment required by the 128B swizzle atoms
+  // 1024-B alignment required by the swizzle atoms
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
-  const uint32_t full_bar = bars;                       // [STAGES]
-  const uint32_t empty_bar = bars + 8 * STAGES;         // [STAGES]
-  const uint32_t tfull_bar = bars + 16 * STAGES;        // [2]
-  const uint32_t tempty_bar = bars + 16 * STAGES + 16;  // [2]
-  const uint32_t tmem_slot = bars + 16 * STAGES + 32;   // u32
+  const uint32_t bars = smem_base + C::STAGES * C::STAGE;
+  const uint32_t full_bar = bars;                          // [STAGES]
+  const uint32_t empty_bar = bars + 8 * C::STAGES;         // [STAGES]
+  const uint32_t tfull_bar = bars + 16 * C::STAGES;        // [2]
+  const uint32_t tempty_bar = bars + 16 * C::STAGES + 16;  // [2]
+  const uint32_t tmem_slot = bars + 16 * C::STAGES + 32;   // u32
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(
       smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles_n = (D + BN - 1) / BN;
-  const int64_t n_tiles_m = (chains + BM - 1) / BM;
-  const int64_t n_tiles = n_tiles_m * n_tiles_n;
+  const int n_blk = (D + BM - 1) / BM;                     // dimension blocks
+  const int64_t c_blk = (chains + BN - 1) / BN;            // chain blocks
+  const int64_t n_tiles = c_blk * n_blk;
   const int n_kb = D / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
     }
@@ -176,25 +222,25 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_qhi,
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qhi) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qlo) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_phi) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_plo) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qhi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qlo) : "memory");
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int m0 = (int)((t / n_tiles_n) * BM);
-        const int n0 = (int)((t % n_tiles_n) * BN);
+        const int n0 = (int)(t % n_blk) * BM;
+        const int c0 = (int)((t / n_blk) * BN);
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb = full_bar + 8 * stage;
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          mbar_expect_tx(fb, STAGE_BYTES);
-          tma_load_2d(sa, &map_qhi, fb, kb * BK, m0);
-          tma_load_2d(sa + A_TILE_BYTES, &map_qlo, fb, kb * BK, m0);
-          tma_load_2d(sa + 2 * A_TILE_BYTES, &map_phi, fb, kb * BK, n0);
-          tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_plo, fb, kb * BK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          const uint32_t sa = smem_base + stage * C::STAGE;
+          mbar_expect_tx(fb, C::STAGE);
+          tma_load_2d(sa, &map_phi, fb, kb * BK, n0);
+          tma_load_2d(sa + C::A_TILE, &map_plo, fb, kb * BK, n0);
+          tma_load_2d(sa + 2 * C::A_TILE, &map_qhi, fb, kb * BK, c0);
+          tma_load_2d(sa + 2 * C::A_TILE + C::B_TILE, &map_qlo, fb, kb * BK, c0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -213,11 +259,11 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_qhi,
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);         // TMA bytes have landed
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint64_t a_hi = make_smem_desc(sa);
-          const uint64_t a_lo = make_smem_desc(sa + A_TILE_BYTES);
-          const uint64_t b_hi = make_smem_desc(sa + 2 * A_TILE_BYTES);
-          const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+          const uint32_t sa = smem_base + stage * C::STAGE;
+          const uint64_t a_hi = make_smem_desc<BK>(sa);
+          const uint64_t a_lo = make_smem_desc<BK>(sa + C::A_TILE);
+          const uint64_t b_hi = make_smem_desc<BK>(sa + 2 * C::A_TILE);
+          const uint64_t b_lo = make_smem_desc<BK>(sa + 2 * C::A_TILE + C::B_TILE);
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);   // +32 B along K per UMMA_K=8
@@ -227,7 +273,7 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_qhi,
             umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
           }
           umma_commit(empty_bar + 8 * stage);             // frees the smem slot when MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull_bar + 8 * acc);                 // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -236,67 +282,68 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_qhi,
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row_in_tile = quarter * 32 + lane;
     const float eps = state[ZSB_ST_EPS_USED];
     const float s2 = mul(eps, p_scale);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int64_t tile_m = t / n_tiles_n;
-      const int tile_n = (int)(t % n_tiles_n);
-      const int64_t m = tile_m * BM + row_in_tile;
-      const int n0 = tile_n * BN;
+      const int nb = (int)(t % n_blk);
+      const int n = nb * BM + quarter * 32 + lane;          // this thread's dimension
+      const int64_t c0 = (t / n_blk) * BN;                  // first chain of the tile
+      const bool n_ok = n < D;
+      const float m_n = n_ok ? mass[n] : 1.f;
+      const float b_n = (n_ok && bvec) ? bvec[n] : 0.f;
+      const float mu_n = (n_ok && mu) ? mu[n] : 0.f;
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
-      float lp_acc = 0.f, k_acc = 0.f;
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(trow + (uint32_t)c, v);      // all 32 lanes participate (sync.aligned)
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + (uint32_t)c, v);      // all 32 lanes participate (sync.aligned)
         tmem_ld_wait();
-        const int n = n0 + c;
-        if (m < chains && n < D) {
-          const float* pin = p_in + m * D + n;
-          const float* qc = q_cur + m * D + n;
-          float* po = p_out + m * D + n;
+        const int64_t cbase = c0 + c;
+        if (cbase < chains) {
+          float pe[16], qe[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 pv = *reinterpret_cast<const float4*>(pin + j);
-            const float4 qv = *reinterpret_cast<const float4*>(qc + j);
-            const float4 ms = *reinterpret_cast<const float4*>(mass + n + j);
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), mv = bv;
-            if (bvec) bv = *reinterpret_cast<const float4*>(bvec + n + j);
-            if (mu) mv = *reinterpret_cast<const float4*>(mu + n + j);
-            const float pe[4] = {pv.x, pv.y, pv.z, pv.w}, qe[4] = {qv.x, qv.y, qv.z, qv.w};
-            const float me[4] = {ms.x, ms.y, ms.z, ms.w}, be[4] = {bv.x, bv.y, bv.z, bv.w};
-            const float ue[4] = {mv.x, mv.y, mv.z, mv.w};
-            float pn[4], qn[4], ql[4];
+          for (int j = 0; j < 16; ++j) {       // issue all loads first (32 in flight / thread)
+            const int64_t ch = cbase + j;
+            const bool ok = n_ok && ch < chains;
+            pe[j] = ok ? p_in[ch * D + n] : 0.f;
+            qe[j] = ok ? q_cur[ch * D + n] : 0.f;
+          }
+          float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float g = sub(be[e], __uint_as_float(v[j + e]));
-              pn[e] = add(pe[e], mul(s2, g));
-              qn[e] = add(qe[e], mul(eps, fdiv(pn[e], me[e])));
-              ql[e] = qn[e] - __uint_as_float(__float_as_uint(qn[e]) & 0xFFFFE000u);
-              lp_acc += (qe[e] - ue[e]) * g;
-              k_acc += fdiv(mul(pn[e], pn[e]), me[e]);
+          for (int j = 0; j < 16; ++j) {
+            const int64_t ch = cbase + j;
+            const bool ok = n_ok && ch < chains;
+            const float g = sub(b_n, __uint_as_float(v[j]));
+            const float pn = add(pe[j], mul(s2, g));
+            if (MODE >= 1) lpv[j] = ok ? (qe[j] - mu_n) * g : 0.f;
+            if (MODE >= 2) kv[j] = ok ? fdiv(mul(pn, pn), m_n) : 0.f;
+            if (ok) {
+              p_out[ch * D + n] = pn;
+              if (q_next) {
+                const float qn = add(qe[j], mul(eps, fdiv(pn, m_n)));
+                q_next[ch * D + n] = qn;
+                q_next_lo[ch * D + n] =
+                    qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
+              }
             }
-            *reinterpret_cast<float4*>(po + j) = make_float4(pn[0], pn[1], pn[2], pn[3]);
-            if (q_next) {
-              *reinterpret_cast<float4*>(q_next + m * D + n + j) =
-                  make_float4(qn[0], qn[1], qn[2], qn[3]);
-              *reinterpret_cast<float4*>(q_next_lo + m * D + n + j) =
-                  make_float4(ql[0], ql[1], ql[2], ql[3]);
-            }
+          }
+          if (MODE >= 1) {
+            const float sum = warp_transpose_sum16(lpv, lane);
+            if (lane < 16 && cbase + lane < chains) lp_part[part_row + cbase + lane] = sum;
+          }
+          if (MODE >= 2) {
+            const float sum = warp_transpose_sum16(kv, lane);
+            if (lane < 16 && cbase + lane < chains) k_part[part_row + cbase + lane] = sum;
           }
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar + 8 * acc);               // 128 arrivals free the accumulator
-      if (m < chains) {
-        if (lp_part) lp_part[(int64_t)tile_n * chains + m] = lp_acc;
-        if (k_part) k_part[(int64_t)tile_n * chains + m] = k_acc;
-      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -344,8 +391,9 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D row-major [rows, cols] fp32 tensor, box = [box_rows, 32 cols], 128B swizzle, zero OOB fill.
-int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2-D row-major [rows, cols] fp32 tensor, box = [box_rows, bk cols], swizzle = row bytes.
+int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+             int bk) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     zsb_set_error("dense_tc: cuTensorMapEncodeTiled unavailable");
@@ -353,10 +401,11 @@ int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, 
   }
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)bk, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     zsb_set_error("dense_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -365,51 +414,89 @@ int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, 
   return ZSB_OK;
 }
 
-}  // namespace
+int g_tc_bk = 32;   // pipeline shape: 32 -> 2 stages x 96 KB (SW128), 16 -> 4 x 48 KB (SW64)
 
-int zsb_dense_tc_ntiles(int D) { return (D + BN - 1) / BN; }
-
-// q_lo scratch: the TC path needs the TF32 residual of every A operand.  `q_cur_lo` must hold the
-// residual of q_cur on entry; the kernel writes q_next's residual to `q_next_lo`.
-int zsb_dense_leapfrog_tc_launch(const float* q_cur, const float* q_cur_lo, float* q_next,
-                                 float* q_next_lo, const float* p_in, float* p_out,
-                                 const float* P_hi, const float* P_lo, const float* bvec,
-                                 const float* mu, const float* mass, const float* state,
-                                 float p_scale, float* lp_part, float* k_part, int64_t chains,
-                                 int D, cudaStream_t st) {
-  if (D % BK != 0 || D < BK) {
-    zsb_set_error("dense_tc: D must be a multiple of %d", BK);
-    return ZSB_ERR_INVALID;
-  }
-  if (chains >= (1LL << 31) || (q_next && !q_next_lo) || !q_cur_lo) {
-    zsb_set_error("dense_tc: bad arguments");
-    return ZSB_ERR_INVALID;
-  }
+template <int BK>
+int launch_tc(const float* q_cur, const float* q_cur_lo, float* q_next, float* q_next_lo,
+              const float* p_in, float* p_out, const float* P_hi, const float* P_lo,
+              const float* bvec, const float* mu, const float* mass, const float* state,
+              float p_scale, float* lp_part, float* k_part, int64_t chains, int D,
+              cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dense_leapfrog_tc_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(dense_leapfrog_tc_kernel<BK, 0>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<BK>::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_leapfrog_tc_kernel<BK, 1>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BK>::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_leapfrog_tc_kernel<BK, 2>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BK>::SMEM);
     if (e != cudaSuccess) {
       zsb_set_error("dense_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return ZSB_ERR_CUDA;
     }
     attr_set = true;
   }
-  CUtensorMap m_qhi, m_qlo, m_phi, m_plo;
+  if (k_part && !lp_part) {
+    zsb_set_error("dense_tc: k_part requires lp_part");
+    return ZSB_ERR_INVALID;
+  }
+  CUtensorMap m_phi, m_plo, m_qhi, m_qlo;
   int rc;
-  if ((rc = make_map(&m_qhi, q_cur, (uint64_t)chains, (uint64_t)D, BM))) return rc;
-  if ((rc = make_map(&m_qlo, q_cur_lo, (uint64_t)chains, (uint64_t)D, BM))) return rc;
-  if ((rc = make_map(&m_phi, P_hi, (uint64_t)D, (uint64_t)D, BN))) return rc;
-  if ((rc = make_map(&m_plo, P_lo, (uint64_t)D, (uint64_t)D, BN))) return rc;
-  const int64_t n_tiles = ((chains + BM - 1) / BM) * ((D + BN - 1) / BN);
+  if ((rc = make_map(&m_phi, P_hi, (uint64_t)D, (uint64_t)D, BM, BK))) return rc;
+  if ((rc = make_map(&m_plo, P_lo, (uint64_t)D, (uint64_t)D, BM, BK))) return rc;
+  if ((rc = make_map(&m_qhi, q_cur, (uint64_t)chains, (uint64_t)D, BN, BK))) return rc;
+  if ((rc = make_map(&m_qlo, q_cur_lo, (uint64_t)chains, (uint64_t)D, BN, BK))) return rc;
+  const int64_t n_tiles = ((chains + BN - 1) / BN) * ((D + BM - 1) / BM);
   int dev = 0, sms = ZSB_NUM_SMS;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-  dense_leapfrog_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(
-      m_qhi, m_qlo, m_phi, m_plo, q_cur, q_next, q_next_lo, p_in, p_out, bvec, mu, mass, state,
-      p_scale, lp_part, k_part, chains, D);
+#define ZSB_TC_LAUNCH(MODE)                                                                  \
+  dense_leapfrog_tc_kernel<BK, MODE><<<grid, NUM_THREADS, Cfg<BK>::SMEM, st>>>(                \
+      m_phi, m_plo, m_qhi, m_qlo, q_cur, q_next, q_next_lo, p_in, p_out, bvec, mu, mass, state, \
+      p_scale, lp_part, k_part, chains, D)
+  if (k_part) ZSB_TC_LAUNCH(2);
+  else if (lp_part) ZSB_TC_LAUNCH(1);
+  else ZSB_TC_LAUNCH(0);
+#undef ZSB_TC_LAUNCH
   return zsb_check_launch("hmc_dense_leapfrog_tc");
+}
+
+}  // namespace
+
+// rows of the [parts, chains] lp/K partial scratch: 4 warp-quarters per 128-dimension block
+int zsb_dense_tc_ntiles(int D) { return 4 * ((D + BM - 1) / BM); }
+
+int zsb_dense_tc_set_bk(int bk) {
+  if (bk != 16 && bk != 32) return ZSB_ERR_INVALID;
+  g_tc_bk = bk;
+  return ZSB_OK;
+}
+
+// `q_cur_lo` must hold the TF32 residual of q_cur on entry; the kernel writes q_next's residual to
+// `q_next_lo`.
+int zsb_dense_leapfrog_tc_launch(const float* q_cur, const float* q_cur_lo, float* q_next,
+                                 float* q_next_lo, const float* p_in, float* p_out,
+                                 const float* P_hi, const float* P_lo, const float* bvec,
+                                 const float* mu, const float* mass, const float* state,
+                                 float p_scale, float* lp_part, float* k_part, int64_t chains,
+                                 int D, cudaStream_t st) {
+  if (D % 32 != 0 || D < 32) {
+    zsb_set_error("dense_tc: D must be a multiple of 32");
+    return ZSB_ERR_INVALID;
+  }
+  if (chains >= (1LL << 31) || (q_next && !q_next_lo) || !q_cur_lo) {
+    zsb_set_error("dense_tc: bad arguments");
+    return ZSB_ERR_INVALID;
+  }
+  if (g_tc_bk == 16)
+    return launch_tc<16>(q_cur, q_cur_lo, q_next, q_next_lo, p_in, p_out, P_hi, P_lo, bvec, mu,
+                         mass, state, p_scale, lp_part, k_part, chains, D, st);
+  return launch_tc<32>(q_cur, q_cur_lo, q_next, q_next_lo, p_in, p_out, P_hi, P_lo, bvec, mu, mass,
+                       state, p_scale, lp_part, k_part, chains, D, st);
 }
 
 int zsb_dense_split_lo_launch(const float* q, float* lo, int64_t n, cudaStream_t st) {

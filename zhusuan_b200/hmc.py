@@ -24,6 +24,7 @@ Three execution paths, all ending in the same MH / adaptation kernels:
                  per gradient evaluation (BASELINE config 2).
 """
 import ctypes
+import os
 
 import torch
 
@@ -447,6 +448,9 @@ class HMC(object):
         if impl is None:
             impl = f.get("impl", 0)
         self._impl = int(impl)
+        if self._impl == 1:            # pipeline-shape tuning knob (same results)
+            lib.call("zsb_hmc_dense_tc_config",
+                     int(os.environ.get("ZSB_TC_BK", "32")))
         nt = lib.load().zsb_hmc_dense_ntiles(D, self._impl)
         z = lambda *s: torch.zeros(*s, dtype=_F32, device=dev)
         self._qa, self._qb = torch.empty_like(self._q[0]), \
