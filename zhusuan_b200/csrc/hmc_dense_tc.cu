@@ -178,7 +178,9 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
                          const float* __restrict__ mu, const float* __restrict__ mass,
                          const float* __restrict__ state, float p_scale,
                          float* __restrict__ lp_part, float* __restrict__ k_part, int64_t chains,
-                         int D) {
+                         int D, int dbg) {
+  // dbg (timing experiments only, results are then WRONG): bit0 skip epilogue global traffic,
+  // bit1 issue only the hi*hi MMA, bit2 skip the TMA loads of the lo tiles.
   using C = Cfg<BK>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-B alignment required by the swizzle atoms
@@ -235,11 +237,11 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb = full_bar + 8 * stage;
           const uint32_t sa = smem_base + stage * C::STAGE;
-          mbar_expect_tx(fb, C::STAGE);
+          mbar_expect_tx(fb, (dbg & 4) ? C::STAGE / 2 : C::STAGE);
           tma_load_2d(sa, &map_phi, fb, kb * BK, n0);
-          tma_load_2d(sa + C::A_TILE, &map_plo, fb, kb * BK, n0);
+          if (!(dbg & 4)) tma_load_2d(sa + C::A_TILE, &map_plo, fb, kb * BK, n0);
           tma_load_2d(sa + 2 * C::A_TILE, &map_qhi, fb, kb * BK, c0);
-          tma_load_2d(sa + 2 * C::A_TILE + C::B_TILE, &map_qlo, fb, kb * BK, c0);
+          if (!(dbg & 4)) tma_load_2d(sa + 2 * C::A_TILE + C::B_TILE, &map_qlo, fb, kb * BK, c0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -268,9 +270,13 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);   // +32 B along K per UMMA_K=8
             // small cross terms first, hi*hi last
-            umma_tf32(d_tmem, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_tf32(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-            umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            if (dbg & 2) {
+              umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+            } else {
+              umma_tf32(d_tmem, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_tf32(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma_tf32(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            }
           }
           umma_commit(empty_bar + 8 * stage);             // frees the smem slot when MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -304,7 +310,7 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
         tmem_ld16(trow + (uint32_t)c, v);      // all 32 lanes participate (sync.aligned)
         tmem_ld_wait();
         const int64_t cbase = c0 + c;
-        if (cbase < chains) {
+        if (cbase < chains && !(dbg & 1)) {
           float pe[16], qe[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {       // issue all loads first (32 in flight / thread)
@@ -414,7 +420,8 @@ int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, 
   return ZSB_OK;
 }
 
-int g_tc_bk = 32;   // pipeline shape: 32 -> 2 stages x 96 KB (SW128), 16 -> 4 x 48 KB (SW64)
+int g_tc_bk = 32;
+int g_tc_dbg = 0;  // timing experiments only (see kernel)   // pipeline shape: 32 -> 2 stages x 96 KB (SW128), 16 -> 4 x 48 KB (SW64)
 
 template <int BK>
 int launch_tc(const float* q_cur, const float* q_cur_lo, float* q_next, float* q_next_lo,
@@ -457,7 +464,7 @@ int launch_tc(const float* q_cur, const float* q_cur_lo, float* q_next, float* q
 #define ZSB_TC_LAUNCH(MODE)                                                                  \
   dense_leapfrog_tc_kernel<BK, MODE><<<grid, NUM_THREADS, Cfg<BK>::SMEM, st>>>(                \
       m_phi, m_plo, m_qhi, m_qlo, q_cur, q_next, q_next_lo, p_in, p_out, bvec, mu, mass, state, \
-      p_scale, lp_part, k_part, chains, D)
+      p_scale, lp_part, k_part, chains, D, g_tc_dbg)
   if (k_part) ZSB_TC_LAUNCH(2);
   else if (lp_part) ZSB_TC_LAUNCH(1);
   else ZSB_TC_LAUNCH(0);
@@ -470,9 +477,11 @@ int launch_tc(const float* q_cur, const float* q_cur_lo, float* q_next, float* q
 // rows of the [parts, chains] lp/K partial scratch: 4 warp-quarters per 128-dimension block
 int zsb_dense_tc_ntiles(int D) { return 4 * ((D + BM - 1) / BM); }
 
-int zsb_dense_tc_set_bk(int bk) {
+int zsb_dense_tc_set_bk(int cfg) {
+  const int bk = cfg & 0xFF;
   if (bk != 16 && bk != 32) return ZSB_ERR_INVALID;
   g_tc_bk = bk;
+  g_tc_dbg = (cfg >> 8) & 0xFF;   // undocumented timing-experiment flags
   return ZSB_OK;
 }
 
