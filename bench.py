@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--cpu-chains", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-adapt", action="store_true",
+                    help="kernel-timing experiments only: fixed step size, no "
+                         "adaptation (not the benchmark configuration)")
     return ap.parse_args()
 
 
@@ -180,13 +183,19 @@ def main():
     g = torch.Generator(device=dev)
     g.manual_seed(3 + rank)
     q = torch.randn(C, D, device=dev, generator=g)          # q0 ~ N(0, I)
-    hmc = zs.HMC(step_size=0.05, n_leapfrogs=L, adapt_step_size=True,
-                 adapt_mass=True, mass_collect_iters=10, seed=1234,
-                 dense_impl=impl)
+    if args.no_adapt:
+        hmc = zs.HMC(step_size=0.2, n_leapfrogs=L, seed=1234, dense_impl=impl)
+    else:
+        hmc = zs.HMC(step_size=0.05, n_leapfrogs=L, adapt_step_size=True,
+                     adapt_mass=True, mass_collect_iters=10, seed=1234,
+                     dense_impl=impl)
     sample_op, info = hmc.sample(lj, {}, {"x": q})
 
     def step():
-        sample_op(adapt_step_size=True, adapt_mass=True)
+        if args.no_adapt:
+            sample_op()
+        else:
+            sample_op(adapt_step_size=True, adapt_mass=True)
 
     for _ in range(args.burnin):        # setup: adaptive burn-in (untimed)
         step()

@@ -9,13 +9,13 @@
 // warp then touches 32 consecutive dimensions of ONE chain per instruction -- a full 128-byte line
 // of p / q / q_next -- instead of 32 chains 4 KB apart.
 //
-// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
 //   warp 0      TMA producer: cp.async.bulk.tensor swizzled tiles of P_hi, P_lo (128 x BK) and
 //               q (=q_hi), q_lo (256 x BK) into a STAGES-deep shared-memory ring (192 KB total),
 //               mbarrier complete_tx signalling
 //   warp 1      MMA issuer: one elected lane issues 3 tcgen05.mma (128x256x8) per k-step;
 //               tcgen05.commit frees the smem slot / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld (32x32b.x32) the fp32 accumulator, p += s2*g,
+//   warps 2-9   epilogue: tcgen05.ld (32x32b.x16) the fp32 accumulator, p += s2*g,
 //               q_next = q + eps*p/m, q_next_lo, warp-transpose reductions of lp and K -> HBM
 //   TMEM        2 x 256 columns: accumulator double buffer (epilogue of tile i overlaps MMA of i+1)
 // Tiles (128 dims x 256 chains) are assigned round-robin with the dimension block fastest, so the
@@ -27,7 +27,8 @@ namespace {
 
 constexpr int BM = 128;   // dimensions per tile (TMEM lanes)
 constexpr int BN = 256;   // chains per tile (TMEM columns)
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;                         // 2 per TMEM lane quarter
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;      // TMA warp + MMA warp + epilogue
 constexpr int TMEM_COLS = 512;
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;   // ~2 s: trap instead of hanging the box
 
@@ -207,7 +208,7 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
-      mbar_init(tempty_bar + 8 * a, 128);
+      mbar_init(tempty_bar + 8 * a, 32 * NUM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -286,8 +287,12 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // Warp w may read TMEM lanes [32*(w%4), +32).  Two warps share each lane quarter and split
+    // the tile's 256 chain columns in halves, so every scheduler has two epilogue warps to
+    // overlap the global-load latency of one with the arithmetic of the other.
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const float eps = state[ZSB_ST_EPS_USED];
     const float s2 = mul(eps, p_scale);
     int acc = 0;
@@ -295,46 +300,75 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int nb = (int)(t % n_blk);
       const int n = nb * BM + quarter * 32 + lane;          // this thread's dimension
-      const int64_t c0 = (t / n_blk) * BN;                  // first chain of the tile
+      const int64_t c0 = (t / n_blk) * BN + half * (BN / 2);  // first chain of this warp's half
       const bool n_ok = n < D;
       const float m_n = n_ok ? mass[n] : 1.f;
+      const float eps_over_m = fdiv(eps, m_n);              // q += eps * (p / m) as p * (eps / m)
+      const float inv_m = fdiv(1.f, m_n);
       const float b_n = (n_ok && bvec) ? bvec[n] : 0.f;
       const float mu_n = (n_ok && mu) ? mu[n] : 0.f;
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                            (uint32_t)(acc * BN + half * (BN / 2));
       const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
+      const bool warp_n_ok = __all_sync(0xffffffffu, n_ok);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
+      for (int c = 0; c < BN / 2; c += 16) {
         uint32_t v[16];
         tmem_ld16(trow + (uint32_t)c, v);      // all 32 lanes participate (sync.aligned)
         tmem_ld_wait();
         const int64_t cbase = c0 + c;
         if (cbase < chains && !(dbg & 1)) {
+          const int64_t off0 = cbase * D + n;
+          const float* __restrict__ pin = p_in + off0;
+          const float* __restrict__ qc = q_cur + off0;
+          float* __restrict__ po = p_out + off0;
           float pe[16], qe[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {       // issue all loads first (32 in flight / thread)
-            const int64_t ch = cbase + j;
-            const bool ok = n_ok && ch < chains;
-            pe[j] = ok ? p_in[ch * D + n] : 0.f;
-            qe[j] = ok ? q_cur[ch * D + n] : 0.f;
-          }
           float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
+          if (warp_n_ok && cbase + 16 <= chains) {
+            // fast path: whole 16-chain x 32-dim block in range, no predicates
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int64_t ch = cbase + j;
-            const bool ok = n_ok && ch < chains;
-            const float g = sub(b_n, __uint_as_float(v[j]));
-            const float pn = add(pe[j], mul(s2, g));
-            if (MODE >= 1) lpv[j] = ok ? (qe[j] - mu_n) * g : 0.f;
-            if (MODE >= 2) kv[j] = ok ? fdiv(mul(pn, pn), m_n) : 0.f;
-            if (ok) {
-              p_out[ch * D + n] = pn;
+            for (int j = 0; j < 16; ++j) {     // all loads first (32 in flight per thread)
+              pe[j] = pin[(uint32_t)(j * D)];
+              qe[j] = qc[(uint32_t)(j * D)];
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float g = b_n - __uint_as_float(v[j]);
+              const float pn = fmaf(s2, g, pe[j]);
+              po[(uint32_t)(j * D)] = pn;
+              if (MODE >= 1) lpv[j] = (qe[j] - mu_n) * g;
+              if (MODE >= 2) kv[j] = pn * pn * inv_m;
               if (q_next) {
-                const float qn = add(qe[j], mul(eps, fdiv(pn, m_n)));
-                q_next[ch * D + n] = qn;
-                q_next_lo[ch * D + n] =
+                const float qn = fmaf(eps_over_m, pn, qe[j]);
+                q_next[off0 + (uint32_t)(j * D)] = qn;
+                q_next_lo[off0 + (uint32_t)(j * D)] =
                     qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const bool ok = n_ok && cbase + j < chains;
+              pe[j] = ok ? pin[(uint32_t)(j * D)] : 0.f;
+              qe[j] = ok ? qc[(uint32_t)(j * D)] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const bool ok = n_ok && cbase + j < chains;
+              const float g = b_n - __uint_as_float(v[j]);
+              const float pn = fmaf(s2, g, pe[j]);
+              if (MODE >= 1) lpv[j] = ok ? (qe[j] - mu_n) * g : 0.f;
+              if (MODE >= 2) kv[j] = ok ? pn * pn * inv_m : 0.f;
+              if (ok) {
+                po[(uint32_t)(j * D)] = pn;
+                if (q_next) {
+                  const float qn = fmaf(eps_over_m, pn, qe[j]);
+                  q_next[off0 + (uint32_t)(j * D)] = qn;
+                  q_next_lo[off0 + (uint32_t)(j * D)] =
+                      qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
+                }
               }
             }
           }
@@ -349,7 +383,7 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar + 8 * acc);               // 128 arrivals free the accumulator
+      mbar_arrive(tempty_bar + 8 * acc);               // all epilogue threads free the accumulator
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
