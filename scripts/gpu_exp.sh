@@ -1,5 +1,4 @@
 #!/bin/bash
-# Timing experiments of the TC kernel (fixed step size, no adaptation -> no data-dependent host loop).
 mkdir -p gpurun_out
 run() { # name env...
   name=$1; shift
@@ -13,9 +12,4 @@ echo "== parity first"
 timeout 300 python -m pytest tests/test_gpu_hmc.py -q -x -k "single_pass or dense_fused_tc or tc_vs_simt" --no-header -p no:cacheprovider 2>&1 | tail -15
 run base32 ZSB_TC_BK=32
 run base16 ZSB_TC_BK=16
-run noepi32 ZSB_TC_BK=32 ZSB_TC_DBG=1
-run onemma32 ZSB_TC_BK=32 ZSB_TC_DBG=2
-run noepi_onemma32 ZSB_TC_BK=32 ZSB_TC_DBG=3
-run noepi_onemma_nolo32 ZSB_TC_BK=32 ZSB_TC_DBG=7
 run noepi16 ZSB_TC_BK=16 ZSB_TC_DBG=1
-run noepi_onemma_nolo16 ZSB_TC_BK=16 ZSB_TC_DBG=7

@@ -313,41 +313,78 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
                             (uint32_t)(acc * BN + half * (BN / 2));
       const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
       const bool warp_n_ok = __all_sync(0xffffffffu, n_ok);
-#pragma unroll 1
-      for (int c = 0; c < BN / 2; c += 16) {
+      const bool fast_tile = warp_n_ok && (c0 + BN / 2 <= chains) && !(dbg & 1);
+
+      // one 16-chain x 32-dim block: fused leapfrog update on accumulator values v[]
+      auto compute = [&](const uint32_t* v, const float* pe, const float* qe, int64_t cbase) {
+        const int64_t off0 = cbase * D + n;
+        float* __restrict__ po = p_out + off0;
+        float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float g = b_n - __uint_as_float(v[j]);
+          const float pn = fmaf(s2, g, pe[j]);
+          po[(uint32_t)(j * D)] = pn;
+          if (MODE >= 1) lpv[j] = (qe[j] - mu_n) * g;
+          if (MODE >= 2) kv[j] = pn * pn * inv_m;
+          if (q_next) {
+            const float qn = fmaf(eps_over_m, pn, qe[j]);
+            q_next[off0 + (uint32_t)(j * D)] = qn;
+            q_next_lo[off0 + (uint32_t)(j * D)] =
+                qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
+          }
+        }
+        if (MODE >= 1) {
+          const float sum = warp_transpose_sum16(lpv, lane);
+          if (lane < 16) lp_part[part_row + cbase + lane] = sum;
+        }
+        if (MODE >= 2) {
+          const float sum = warp_transpose_sum16(kv, lane);
+          if (lane < 16) k_part[part_row + cbase + lane] = sum;
+        }
+      };
+      auto load = [&](float* pe, float* qe, int64_t cbase) {
+        const int64_t off0 = cbase * D + n;
+        const float* __restrict__ pin = p_in + off0;
+        const float* __restrict__ qc = q_cur + off0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          pe[j] = __ldcs(pin + (uint32_t)(j * D));     // p is streamed: evict-first
+          qe[j] = __ldg(qc + (uint32_t)(j * D));
+        }
+      };
+
+      if (fast_tile) {
+        // software-pipelined: the global loads of block i+1 are in flight while block i is
+        // computed and stored (two register sets A/B, loop unrolled by two blocks)
+        float pa[16], qa[16], pb[16], qb[16];
         uint32_t v[16];
-        tmem_ld16(trow + (uint32_t)c, v);      // all 32 lanes participate (sync.aligned)
-        tmem_ld_wait();
-        const int64_t cbase = c0 + c;
-        if (cbase < chains && !(dbg & 1)) {
-          const int64_t off0 = cbase * D + n;
-          const float* __restrict__ pin = p_in + off0;
-          const float* __restrict__ qc = q_cur + off0;
-          float* __restrict__ po = p_out + off0;
-          float pe[16], qe[16];
-          float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
-          if (warp_n_ok && cbase + 16 <= chains) {
-            // fast path: whole 16-chain x 32-dim block in range, no predicates
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {     // all loads first (32 in flight per thread)
-              pe[j] = pin[(uint32_t)(j * D)];
-              qe[j] = qc[(uint32_t)(j * D)];
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float g = b_n - __uint_as_float(v[j]);
-              const float pn = fmaf(s2, g, pe[j]);
-              po[(uint32_t)(j * D)] = pn;
-              if (MODE >= 1) lpv[j] = (qe[j] - mu_n) * g;
-              if (MODE >= 2) kv[j] = pn * pn * inv_m;
-              if (q_next) {
-                const float qn = fmaf(eps_over_m, pn, qe[j]);
-                q_next[off0 + (uint32_t)(j * D)] = qn;
-                q_next_lo[off0 + (uint32_t)(j * D)] =
-                    qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
-              }
-            }
-          } else {
+        load(pa, qa, c0);
+#pragma unroll 1
+        for (int c = 0; c < BN / 2; c += 32) {
+          load(pb, qb, c0 + c + 16);
+          tmem_ld16(trow + (uint32_t)c, v);
+          tmem_ld_wait();
+          compute(v, pa, qa, c0 + c);
+          if (c + 32 < BN / 2) load(pa, qa, c0 + c + 32);
+          tmem_ld16(trow + (uint32_t)(c + 16), v);
+          tmem_ld_wait();
+          compute(v, pb, qb, c0 + c + 16);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 2; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(trow + (uint32_t)c, v);      // all 32 lanes participate (sync.aligned)
+          tmem_ld_wait();
+          const int64_t cbase = c0 + c;
+          if (cbase < chains && !(dbg & 1)) {
+            const int64_t off0 = cbase * D + n;
+            const float* __restrict__ pin = p_in + off0;
+            const float* __restrict__ qc = q_cur + off0;
+            float* __restrict__ po = p_out + off0;
+            float pe[16], qe[16];
+            float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const bool ok = n_ok && cbase + j < chains;
@@ -371,14 +408,14 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
                 }
               }
             }
-          }
-          if (MODE >= 1) {
-            const float sum = warp_transpose_sum16(lpv, lane);
-            if (lane < 16 && cbase + lane < chains) lp_part[part_row + cbase + lane] = sum;
-          }
-          if (MODE >= 2) {
-            const float sum = warp_transpose_sum16(kv, lane);
-            if (lane < 16 && cbase + lane < chains) k_part[part_row + cbase + lane] = sum;
+            if (MODE >= 1) {
+              const float sum = warp_transpose_sum16(lpv, lane);
+              if (lane < 16 && cbase + lane < chains) lp_part[part_row + cbase + lane] = sum;
+            }
+            if (MODE >= 2) {
+              const float sum = warp_transpose_sum16(kv, lane);
+              if (lane < 16 && cbase + lane < chains) k_part[part_row + cbase + lane] = sum;
+            }
           }
         }
       }
