@@ -87,6 +87,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 // K-major swizzled operand tile: rows of BK fp32 (128 B or 64 B), 8-row swizzle atoms.
 template <int BK>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -181,7 +185,7 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
                          float* __restrict__ lp_part, float* __restrict__ k_part, int64_t chains,
                          int D, int dbg) {
   // dbg (timing experiments only, results are then WRONG): bit0 skip epilogue global traffic,
-  // bit1 issue only the hi*hi MMA, bit2 skip the TMA loads of the lo tiles.
+  // bit1 issue only the hi*hi MMA, bit2 skip the TMA loads of the lo tiles, bit3 no L2 prefetch.
   using C = Cfg<BK>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-B alignment required by the swizzle atoms
@@ -234,7 +238,16 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
       for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int n0 = (int)(t % n_blk) * BM;
         const int c0 = (int)((t / n_blk) * BN);
+        // L2 prefetch of the chain block this CTA needs NEXT (one CTA of the n_blk that share
+        // the block issues it), so those first-touch DRAM misses are off the TMA critical path.
+        const int64_t tn = t + gridDim.x;
+        const bool do_pf = !(dbg & 8) && tn < n_tiles && (tn % n_blk) == 0;
+        const int c0n = (int)((tn / n_blk) * BN);
         for (int kb = 0; kb < n_kb; ++kb) {
+          if (do_pf) {
+            tma_prefetch_l2_2d(&map_qhi, kb * BK, c0n);
+            tma_prefetch_l2_2d(&map_qlo, kb * BK, c0n);
+          }
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb = full_bar + 8 * stage;
           const uint32_t sa = smem_base + stage * C::STAGE;
