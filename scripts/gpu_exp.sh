@@ -8,10 +8,10 @@ import json
 d=json.loads(open('gpurun_out/exp_$name.json').read().strip().splitlines()[-1]); r=d['roofline']
 print('%-28s kernel_ms %.4f  ms/step %.2f' % ('$name', r['kernel_ms_per_launch'], d['ms_per_step']))" 2>/dev/null || { echo "$name FAILED"; tail -3 gpurun_out/exp_$name.err; }
 }
-echo "== parity first"
-timeout 300 python -m pytest tests/test_gpu_hmc.py -q -x -k "single_pass or dense_fused_tc" --no-header -p no:cacheprovider 2>&1 | tail -5
-run pf32 ZSB_TC_BK=32
-run pf16 ZSB_TC_BK=16
-run nopf16 ZSB_TC_BK=16 ZSB_TC_DBG=8
-run pf_noepi16 ZSB_TC_BK=16 ZSB_TC_DBG=1
-run nopf_noepi16 ZSB_TC_BK=16 ZSB_TC_DBG=9
+for BK in 32 16; do
+echo "== pair kernel parity BK=$BK"
+ZSB_TC_PAIR=1 ZSB_TC_BK=$BK timeout 200 python -m pytest tests/test_gpu_hmc.py -q -x -k "single_pass or dense_fused_tc or tc_vs_simt" --no-header -p no:cacheprovider 2>&1 | tail -12
+done
+run pair32 ZSB_TC_PAIR=1 ZSB_TC_BK=32
+run pair16 ZSB_TC_PAIR=1 ZSB_TC_BK=16
+run single32 ZSB_TC_BK=32

@@ -185,7 +185,7 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
                          float* __restrict__ lp_part, float* __restrict__ k_part, int64_t chains,
                          int D, int dbg) {
   // dbg (timing experiments only, results are then WRONG): bit0 skip epilogue global traffic,
-  // bit1 issue only the hi*hi MMA, bit2 skip the TMA loads of the lo tiles, bit3 no L2 prefetch.
+  // bit1 issue only the hi*hi MMA, bit2 skip the TMA loads of the lo tiles, bit3 enable L2 prefetch (measured slower: the kernel is L2-bandwidth bound).
   using C = Cfg<BK>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-B alignment required by the swizzle atoms
@@ -241,7 +241,7 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
         // L2 prefetch of the chain block this CTA needs NEXT (one CTA of the n_blk that share
         // the block issues it), so those first-touch DRAM misses are off the TMA critical path.
         const int64_t tn = t + gridDim.x;
-        const bool do_pf = !(dbg & 8) && tn < n_tiles && (tn % n_blk) == 0;
+        const bool do_pf = (dbg & 8) && tn < n_tiles && (tn % n_blk) == 0;   // opt-in: measured slower
         const int c0n = (int)((tn / n_blk) * BN);
         for (int kb = 0; kb < n_kb; ++kb) {
           if (do_pf) {
@@ -448,6 +448,279 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
   }
 }
 
+__device__ __forceinline__ bool n_ok_warp_any(bool n_ok) {
+  return __any_sync(0xffffffffu, n_ok);
+}
+
+// =================================================================================================
+// cta_group::2 variant: a CTA PAIR (cluster of 2) computes a 256-dim x 256-chain tile with ONE
+// tcgen05.mma.cta_group::2 (M=256) per k-step, issued by the leader CTA.  Each CTA stages only
+// its own 128 dimension rows of P and HALF (128) of the tile's chain rows, so the operand bytes
+// per MAC pulled through the L2 drop by a third (the measured limiter of the 1-CTA kernel), and
+// the tensor core reads the shared chain operand from both CTAs' shared memory.
+//   full[s]   (leader only)  1 arrival (leader's expect_tx) + bytes of BOTH CTAs' TMA loads
+//   empty[s]  (each CTA)     1 arrival: leader's tcgen05.commit multicast to both CTAs
+//   tfull[a]  (each CTA)     1 arrival: leader's commit multicast (accumulator ready)
+//   tempty[a] (leader only)  2 x 256 arrivals: both CTAs' epilogue threads (peer arrives remotely)
+// Accumulator rows 0-127 (dimension block 2i) live in the leader's TMEM, rows 128-255 (block
+// 2i+1) in the peer's; the epilogue is the same as the 1-CTA kernel's.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of CTA 0's copy
+
+template <int BK>
+struct Cfg2 {
+  static constexpr int A_TILE = BM * BK * 4;                 // own 128 dimension rows
+  static constexpr int B_TILE = (BN / 2) * BK * 4;           // own half of the chain rows
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;      // 64 KB (BK=32) / 32 KB (BK=16)
+  static constexpr int STAGES = (192 * 1024) / STAGE;        // 3 / 6
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;"
+               ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map,
+                                                uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives in BOTH CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+      " [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_2sm() {   // M=256 (pair), N=256
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+         ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BK, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
+                          const __grid_constant__ CUtensorMap map_plo,
+                          const __grid_constant__ CUtensorMap map_qhi,
+                          const __grid_constant__ CUtensorMap map_qlo,
+                          const float* __restrict__ q_cur, float* __restrict__ q_next,
+                          float* __restrict__ q_next_lo, const float* __restrict__ p_in,
+                          float* __restrict__ p_out, const float* __restrict__ bvec,
+                          const float* __restrict__ mu, const float* __restrict__ mass,
+                          const float* __restrict__ state, float p_scale,
+                          float* __restrict__ lp_part, float* __restrict__ k_part, int64_t chains,
+                          int D) {
+  using C = Cfg2<BK>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + C::STAGES * C::STAGE;
+  const uint32_t full_bar = bars;                          // [STAGES]
+  const uint32_t empty_bar = bars + 8 * C::STAGES;         // [STAGES]
+  const uint32_t tfull_bar = bars + 16 * C::STAGES;        // [2]
+  const uint32_t tempty_bar = bars + 16 * C::STAGES + 16;  // [2]
+  const uint32_t tmem_slot = bars + 16 * C::STAGES + 32;   // u32
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(
+      smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                 // 0 = leader
+  const bool leader = rank == 0;
+  const int n_blk = (D + BM - 1) / BM;
+  const int n_pair = (n_blk + 1) / 2;                      // dimension-block pairs
+  const int64_t c_blk = (chains + BN - 1) / BN;
+  const int64_t n_units = c_blk * n_pair;                  // work units of the cluster
+  const int64_t unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
+  const int n_kb = D / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, 2 * 32 * NUM_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();            // barrier inits + TMEM allocation visible to both CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_phi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_plo) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qhi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qlo) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t u = unit0; u < n_units; u += unit_step) {
+        const int n0 = ((int)(u % n_pair) * 2 + (int)rank) * BM;     // own dimension block
+        const int c0 = (int)((u / n_pair) * BN) + (int)rank * (BN / 2);  // own chain half
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);    // own slot free (leader's commit)
+          const uint32_t fb = full_bar + 8 * stage;
+          const uint32_t sa = smem_base + stage * C::STAGE;
+          if (leader) mbar_expect_tx(fb, 2 * C::STAGE);   // bytes of both CTAs
+          tma_load_2d_2sm(sa, &map_phi, fb, kb * BK, n0);
+          tma_load_2d_2sm(sa + C::A_TILE, &map_plo, fb, kb * BK, n0);
+          tma_load_2d_2sm(sa + 2 * C::A_TILE, &map_qhi, fb, kb * BK, c0);
+          tma_load_2d_2sm(sa + 2 * C::A_TILE + C::B_TILE, &map_qlo, fb, kb * BK, c0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_2sm();
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t u = unit0; u < n_units; u += unit_step) {
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);   // both epilogues drained this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);         // both CTAs' TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE;
+          const uint64_t a_hi = make_smem_desc<BK>(sa);
+          const uint64_t a_lo = make_smem_desc<BK>(sa + C::A_TILE);
+          const uint64_t b_hi = make_smem_desc<BK>(sa + 2 * C::A_TILE);
+          const uint64_t b_lo = make_smem_desc<BK>(sa + 2 * C::A_TILE + C::B_TILE);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);
+            umma_tf32_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_tf32_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+            umma_tf32_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+          }
+          umma_commit_2sm(empty_bar + 8 * stage);         // frees the slot in both CTAs
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(tfull_bar + 8 * acc);             // accumulators ready in both CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9, both CTAs) =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const float eps = state[ZSB_ST_EPS_USED];
+    const float s2 = mul(eps, p_scale);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t u = unit0; u < n_units; u += unit_step) {
+      const int nb = (int)(u % n_pair) * 2 + (int)rank;
+      const int n = nb * BM + quarter * 32 + lane;
+      const int64_t c0 = (u / n_pair) * BN + half * (BN / 2);
+      const bool n_ok = n < D;
+      const float m_n = n_ok ? mass[n] : 1.f;
+      const float eps_over_m = fdiv(eps, m_n);
+      const float inv_m = fdiv(1.f, m_n);
+      const float b_n = (n_ok && bvec) ? bvec[n] : 0.f;
+      const float mu_n = (n_ok && mu) ? mu[n] : 0.f;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                            (uint32_t)(acc * BN + half * (BN / 2));
+      const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
+#pragma unroll 1
+      for (int c = 0; c < BN / 2; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + (uint32_t)c, v);
+        tmem_ld_wait();
+        const int64_t cbase = c0 + c;
+        if (cbase < chains) {
+          const int64_t off0 = cbase * D + n;
+          const float* __restrict__ pin = p_in + off0;
+          const float* __restrict__ qc = q_cur + off0;
+          float* __restrict__ po = p_out + off0;
+          float pe[16], qe[16];
+          float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const bool ok = n_ok && cbase + j < chains;
+            pe[j] = ok ? __ldcs(pin + (uint32_t)(j * D)) : 0.f;
+            qe[j] = ok ? __ldg(qc + (uint32_t)(j * D)) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const bool ok = n_ok && cbase + j < chains;
+            const float g = b_n - __uint_as_float(v[j]);
+            const float pn = fmaf(s2, g, pe[j]);
+            if (MODE >= 1) lpv[j] = ok ? (qe[j] - mu_n) * g : 0.f;
+            if (MODE >= 2) kv[j] = ok ? pn * pn * inv_m : 0.f;
+            if (ok) {
+              po[(uint32_t)(j * D)] = pn;
+              if (q_next) {
+                const float qn = fmaf(eps_over_m, pn, qe[j]);
+                q_next[off0 + (uint32_t)(j * D)] = qn;
+                q_next_lo[off0 + (uint32_t)(j * D)] =
+                    qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
+              }
+            }
+          }
+          if (MODE >= 1 && n_ok_warp_any(n_ok)) {
+            const float sum = warp_transpose_sum16(lpv, lane);
+            if (lane < 16 && cbase + lane < chains && nb < n_blk)
+              lp_part[part_row + cbase + lane] = sum;
+          }
+          if (MODE >= 2 && n_ok_warp_any(n_ok)) {
+            const float sum = warp_transpose_sum16(kv, lane);
+            if (lane < 16 && cbase + lane < chains && nb < n_blk)
+              k_part[part_row + cbase + lane] = sum;
+          }
+        }
+      }
+      tc_fence_before();
+      if (leader) mbar_arrive(tempty_bar + 8 * acc);
+      else mbar_arrive_remote(tempty_bar + 8 * acc, 0);   // leader's barrier counts both CTAs
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();            // nobody exits / frees TMEM while the peer may still use it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
+                 ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
 // q_lo = q - (q with the low 13 mantissa bits cleared): the residual the TF32 datapath drops.
 __global__ void __launch_bounds__(256) split_lo_kernel(const float* __restrict__ q,
                                                        float* __restrict__ lo, int64_t n4) {
@@ -504,6 +777,7 @@ int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, 
   return ZSB_OK;
 }
 
+int g_tc_pair = 0;  // 1: cta_group::2 CTA-pair kernel
 int g_tc_bk = 32;
 int g_tc_dbg = 0;  // timing experiments only (see kernel)   // pipeline shape: 32 -> 2 stages x 96 KB (SW128), 16 -> 4 x 48 KB (SW64)
 
@@ -556,16 +830,69 @@ int launch_tc(const float* q_cur, const float* q_cur_lo, float* q_next, float* q
   return zsb_check_launch("hmc_dense_leapfrog_tc");
 }
 
+template <int BK>
+int launch_tc2(const float* q_cur, const float* q_cur_lo, float* q_next, float* q_next_lo,
+               const float* p_in, float* p_out, const float* P_hi, const float* P_lo,
+               const float* bvec, const float* mu, const float* mass, const float* state,
+               float p_scale, float* lp_part, float* k_part, int64_t chains, int D,
+               cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(dense_leapfrog_tc2_kernel<BK, 0>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg2<BK>::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_leapfrog_tc2_kernel<BK, 1>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BK>::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dense_leapfrog_tc2_kernel<BK, 2>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BK>::SMEM);
+    if (e != cudaSuccess) {
+      zsb_set_error("dense_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return ZSB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  if (k_part && !lp_part) {
+    zsb_set_error("dense_tc2: k_part requires lp_part");
+    return ZSB_ERR_INVALID;
+  }
+  CUtensorMap m_phi, m_plo, m_qhi, m_qlo;
+  int rc;
+  if ((rc = make_map(&m_phi, P_hi, (uint64_t)D, (uint64_t)D, BM, BK))) return rc;
+  if ((rc = make_map(&m_plo, P_lo, (uint64_t)D, (uint64_t)D, BM, BK))) return rc;
+  if ((rc = make_map(&m_qhi, q_cur, (uint64_t)chains, (uint64_t)D, BN / 2, BK))) return rc;
+  if ((rc = make_map(&m_qlo, q_cur_lo, (uint64_t)chains, (uint64_t)D, BN / 2, BK))) return rc;
+  const int n_blk = (D + BM - 1) / BM;
+  const int64_t n_units = ((chains + BN - 1) / BN) * ((n_blk + 1) / 2);
+  int dev = 0, sms = ZSB_NUM_SMS;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t pairs = sms / 2;
+  if (n_units < pairs) pairs = n_units;
+  const unsigned grid = (unsigned)(2 * pairs);
+#define ZSB_TC2_LAUNCH(MODE)                                                                  \
+  dense_leapfrog_tc2_kernel<BK, MODE><<<grid, NUM_THREADS, Cfg2<BK>::SMEM, st>>>(              \
+      m_phi, m_plo, m_qhi, m_qlo, q_cur, q_next, q_next_lo, p_in, p_out, bvec, mu, mass, state, \
+      p_scale, lp_part, k_part, chains, D)
+  if (k_part) ZSB_TC2_LAUNCH(2);
+  else if (lp_part) ZSB_TC2_LAUNCH(1);
+  else ZSB_TC2_LAUNCH(0);
+#undef ZSB_TC2_LAUNCH
+  return zsb_check_launch("hmc_dense_leapfrog_tc2");
+}
+
 }  // namespace
 
 // rows of the [parts, chains] lp/K partial scratch: 4 warp-quarters per 128-dimension block
-int zsb_dense_tc_ntiles(int D) { return 4 * ((D + BM - 1) / BM); }
+int zsb_dense_tc_ntiles(int D) { return 4 * (2 * (((D + BM - 1) / BM + 1) / 2)); }
 
 int zsb_dense_tc_set_bk(int cfg) {
   const int bk = cfg & 0xFF;
   if (bk != 16 && bk != 32) return ZSB_ERR_INVALID;
   g_tc_bk = bk;
   g_tc_dbg = (cfg >> 8) & 0xFF;   // undocumented timing-experiment flags
+  g_tc_pair = (cfg >> 16) & 1;    // 1: cta_group::2 CTA-pair kernel
   return ZSB_OK;
 }
 
@@ -584,6 +911,13 @@ int zsb_dense_leapfrog_tc_launch(const float* q_cur, const float* q_cur_lo, floa
   if (chains >= (1LL << 31) || (q_next && !q_next_lo) || !q_cur_lo) {
     zsb_set_error("dense_tc: bad arguments");
     return ZSB_ERR_INVALID;
+  }
+  if (g_tc_pair) {
+    if (g_tc_bk == 16)
+      return launch_tc2<16>(q_cur, q_cur_lo, q_next, q_next_lo, p_in, p_out, P_hi, P_lo, bvec, mu,
+                            mass, state, p_scale, lp_part, k_part, chains, D, st);
+    return launch_tc2<32>(q_cur, q_cur_lo, q_next, q_next_lo, p_in, p_out, P_hi, P_lo, bvec, mu,
+                          mass, state, p_scale, lp_part, k_part, chains, D, st);
   }
   if (g_tc_bk == 16)
     return launch_tc<16>(q_cur, q_cur_lo, q_next, q_next_lo, p_in, p_out, P_hi, P_lo, bvec, mu,
