@@ -171,6 +171,133 @@ __device__ __forceinline__ float warp_transpose_sum16(float v[16], int lane) {
 }
 
 // MODE 0: plain pass; 1: + log-prob partials (first pass); 2: + log-prob and kinetic partials.
+// Fused leapfrog epilogue for one warp's share of a tile: this thread's dimension `n` (TMEM lane)
+// against 128 chains starting at c0 (TMEM columns trow .. trow+127).  MODE 0: plain pass;
+// 1: + log-prob partials (first pass); 2: + log-prob and kinetic partials (last pass).
+struct EpiArgs {
+  const float* __restrict__ q_cur; float* __restrict__ q_next; float* __restrict__ q_next_lo;
+  const float* __restrict__ p_in; float* __restrict__ p_out;
+  float* __restrict__ lp_part; float* __restrict__ k_part;
+  int64_t chains; int D;
+};
+template <int MODE>
+__device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t trow, int n,
+                                                   bool n_ok, bool parts_ok, int64_t c0,
+                                                   int64_t part_row, int lane, float s2,
+                                                   float eps_over_m, float inv_m, float b_n,
+                                                   float mu_n, bool skip) {
+  const int D = a.D;
+  const int64_t chains = a.chains;
+  const bool warp_n_ok = __all_sync(0xffffffffu, n_ok);
+  const bool fast_tile = warp_n_ok && (c0 + BN / 2 <= chains) && !skip;
+
+  auto compute = [&](const uint32_t* v, const float* pe, const float* qe, int64_t cbase) {
+    const int64_t off0 = cbase * D + n;
+    float* __restrict__ po = a.p_out + off0;
+    float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float g = b_n - __uint_as_float(v[j]);
+      const float pn = fmaf(s2, g, pe[j]);
+      po[(uint32_t)(j * D)] = pn;
+      if (MODE >= 1) lpv[j] = (qe[j] - mu_n) * g;
+      if (MODE >= 2) kv[j] = pn * pn * inv_m;
+      if (a.q_next) {
+        const float qn = fmaf(eps_over_m, pn, qe[j]);
+        a.q_next[off0 + (uint32_t)(j * D)] = qn;
+        a.q_next_lo[off0 + (uint32_t)(j * D)] =
+            qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
+      }
+    }
+    if (MODE >= 1) {
+      const float sum = warp_transpose_sum16(lpv, lane);
+      if (lane < 16) a.lp_part[part_row + cbase + lane] = sum;
+    }
+    if (MODE >= 2) {
+      const float sum = warp_transpose_sum16(kv, lane);
+      if (lane < 16) a.k_part[part_row + cbase + lane] = sum;
+    }
+  };
+  auto load = [&](float* pe, float* qe, int64_t cbase) {
+    const int64_t off0 = cbase * D + n;
+    const float* __restrict__ pin = a.p_in + off0;
+    const float* __restrict__ qc = a.q_cur + off0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      pe[j] = __ldcs(pin + (uint32_t)(j * D));     // p is streamed: evict-first
+      qe[j] = __ldg(qc + (uint32_t)(j * D));
+    }
+  };
+
+  if (fast_tile) {
+    // software-pipelined: the global loads of block i+1 are in flight while block i is computed
+    // and stored (two register sets A/B, loop unrolled by two blocks)
+    float pa[16], qa[16], pb[16], qb[16];
+    uint32_t v[16];
+    load(pa, qa, c0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 2; c += 32) {
+      load(pb, qb, c0 + c + 16);
+      tmem_ld16(trow + (uint32_t)c, v);
+      tmem_ld_wait();
+      compute(v, pa, qa, c0 + c);
+      if (c + 32 < BN / 2) load(pa, qa, c0 + c + 32);
+      tmem_ld16(trow + (uint32_t)(c + 16), v);
+      tmem_ld_wait();
+      compute(v, pb, qb, c0 + c + 16);
+    }
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < BN / 2; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)c, v);      // all 32 lanes participate (sync.aligned)
+      tmem_ld_wait();
+      const int64_t cbase = c0 + c;
+      if (cbase < chains && !skip) {
+        const int64_t off0 = cbase * D + n;
+        const float* __restrict__ pin = a.p_in + off0;
+        const float* __restrict__ qc = a.q_cur + off0;
+        float* __restrict__ po = a.p_out + off0;
+        float pe[16], qe[16];
+        float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const bool ok = n_ok && cbase + j < chains;
+          pe[j] = ok ? pin[(uint32_t)(j * D)] : 0.f;
+          qe[j] = ok ? qc[(uint32_t)(j * D)] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const bool ok = n_ok && cbase + j < chains;
+          const float g = b_n - __uint_as_float(v[j]);
+          const float pn = fmaf(s2, g, pe[j]);
+          if (MODE >= 1) lpv[j] = ok ? (qe[j] - mu_n) * g : 0.f;
+          if (MODE >= 2) kv[j] = ok ? pn * pn * inv_m : 0.f;
+          if (ok) {
+            po[(uint32_t)(j * D)] = pn;
+            if (a.q_next) {
+              const float qn = fmaf(eps_over_m, pn, qe[j]);
+              a.q_next[off0 + (uint32_t)(j * D)] = qn;
+              a.q_next_lo[off0 + (uint32_t)(j * D)] =
+                  qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
+            }
+          }
+        }
+        if (MODE >= 1) {
+          const float sum = warp_transpose_sum16(lpv, lane);
+          if (parts_ok && lane < 16 && cbase + lane < chains)
+            a.lp_part[part_row + cbase + lane] = sum;
+        }
+        if (MODE >= 2) {
+          const float sum = warp_transpose_sum16(kv, lane);
+          if (parts_ok && lane < 16 && cbase + lane < chains)
+            a.k_part[part_row + cbase + lane] = sum;
+        }
+      }
+    }
+  }
+}
+
 template <int BK, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
@@ -325,113 +452,9 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)(acc * BN + half * (BN / 2));
       const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
-      const bool warp_n_ok = __all_sync(0xffffffffu, n_ok);
-      const bool fast_tile = warp_n_ok && (c0 + BN / 2 <= chains) && !(dbg & 1);
-
-      // one 16-chain x 32-dim block: fused leapfrog update on accumulator values v[]
-      auto compute = [&](const uint32_t* v, const float* pe, const float* qe, int64_t cbase) {
-        const int64_t off0 = cbase * D + n;
-        float* __restrict__ po = p_out + off0;
-        float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float g = b_n - __uint_as_float(v[j]);
-          const float pn = fmaf(s2, g, pe[j]);
-          po[(uint32_t)(j * D)] = pn;
-          if (MODE >= 1) lpv[j] = (qe[j] - mu_n) * g;
-          if (MODE >= 2) kv[j] = pn * pn * inv_m;
-          if (q_next) {
-            const float qn = fmaf(eps_over_m, pn, qe[j]);
-            q_next[off0 + (uint32_t)(j * D)] = qn;
-            q_next_lo[off0 + (uint32_t)(j * D)] =
-                qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
-          }
-        }
-        if (MODE >= 1) {
-          const float sum = warp_transpose_sum16(lpv, lane);
-          if (lane < 16) lp_part[part_row + cbase + lane] = sum;
-        }
-        if (MODE >= 2) {
-          const float sum = warp_transpose_sum16(kv, lane);
-          if (lane < 16) k_part[part_row + cbase + lane] = sum;
-        }
-      };
-      auto load = [&](float* pe, float* qe, int64_t cbase) {
-        const int64_t off0 = cbase * D + n;
-        const float* __restrict__ pin = p_in + off0;
-        const float* __restrict__ qc = q_cur + off0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          pe[j] = __ldcs(pin + (uint32_t)(j * D));     // p is streamed: evict-first
-          qe[j] = __ldg(qc + (uint32_t)(j * D));
-        }
-      };
-
-      if (fast_tile) {
-        // software-pipelined: the global loads of block i+1 are in flight while block i is
-        // computed and stored (two register sets A/B, loop unrolled by two blocks)
-        float pa[16], qa[16], pb[16], qb[16];
-        uint32_t v[16];
-        load(pa, qa, c0);
-#pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 32) {
-          load(pb, qb, c0 + c + 16);
-          tmem_ld16(trow + (uint32_t)c, v);
-          tmem_ld_wait();
-          compute(v, pa, qa, c0 + c);
-          if (c + 32 < BN / 2) load(pa, qa, c0 + c + 32);
-          tmem_ld16(trow + (uint32_t)(c + 16), v);
-          tmem_ld_wait();
-          compute(v, pb, qb, c0 + c + 16);
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 16) {
-          uint32_t v[16];
-          tmem_ld16(trow + (uint32_t)c, v);      // all 32 lanes participate (sync.aligned)
-          tmem_ld_wait();
-          const int64_t cbase = c0 + c;
-          if (cbase < chains && !(dbg & 1)) {
-            const int64_t off0 = cbase * D + n;
-            const float* __restrict__ pin = p_in + off0;
-            const float* __restrict__ qc = q_cur + off0;
-            float* __restrict__ po = p_out + off0;
-            float pe[16], qe[16];
-            float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const bool ok = n_ok && cbase + j < chains;
-              pe[j] = ok ? pin[(uint32_t)(j * D)] : 0.f;
-              qe[j] = ok ? qc[(uint32_t)(j * D)] : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const bool ok = n_ok && cbase + j < chains;
-              const float g = b_n - __uint_as_float(v[j]);
-              const float pn = fmaf(s2, g, pe[j]);
-              if (MODE >= 1) lpv[j] = ok ? (qe[j] - mu_n) * g : 0.f;
-              if (MODE >= 2) kv[j] = ok ? pn * pn * inv_m : 0.f;
-              if (ok) {
-                po[(uint32_t)(j * D)] = pn;
-                if (q_next) {
-                  const float qn = fmaf(eps_over_m, pn, qe[j]);
-                  q_next[off0 + (uint32_t)(j * D)] = qn;
-                  q_next_lo[off0 + (uint32_t)(j * D)] =
-                      qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
-                }
-              }
-            }
-            if (MODE >= 1) {
-              const float sum = warp_transpose_sum16(lpv, lane);
-              if (lane < 16 && cbase + lane < chains) lp_part[part_row + cbase + lane] = sum;
-            }
-            if (MODE >= 2) {
-              const float sum = warp_transpose_sum16(kv, lane);
-              if (lane < 16 && cbase + lane < chains) k_part[part_row + cbase + lane] = sum;
-            }
-          }
-        }
-      }
+      const EpiArgs ea{q_cur, q_next, q_next_lo, p_in, p_out, lp_part, k_part, chains, D};
+      epilogue_half_tile<MODE>(ea, trow, n, n_ok, true, c0, part_row, lane, s2, eps_over_m, inv_m,
+                               b_n, mu_n, (dbg & 1) != 0);
       tc_fence_before();
       mbar_arrive(tempty_bar + 8 * acc);               // all epilogue threads free the accumulator
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -446,10 +469,6 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
                  ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
-}
-
-__device__ __forceinline__ bool n_ok_warp_any(bool n_ok) {
-  return __any_sync(0xffffffffu, n_ok);
 }
 
 // =================================================================================================
@@ -657,54 +676,9 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)(acc * BN + half * (BN / 2));
       const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
-#pragma unroll 1
-      for (int c = 0; c < BN / 2; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(trow + (uint32_t)c, v);
-        tmem_ld_wait();
-        const int64_t cbase = c0 + c;
-        if (cbase < chains) {
-          const int64_t off0 = cbase * D + n;
-          const float* __restrict__ pin = p_in + off0;
-          const float* __restrict__ qc = q_cur + off0;
-          float* __restrict__ po = p_out + off0;
-          float pe[16], qe[16];
-          float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const bool ok = n_ok && cbase + j < chains;
-            pe[j] = ok ? __ldcs(pin + (uint32_t)(j * D)) : 0.f;
-            qe[j] = ok ? __ldg(qc + (uint32_t)(j * D)) : 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const bool ok = n_ok && cbase + j < chains;
-            const float g = b_n - __uint_as_float(v[j]);
-            const float pn = fmaf(s2, g, pe[j]);
-            if (MODE >= 1) lpv[j] = ok ? (qe[j] - mu_n) * g : 0.f;
-            if (MODE >= 2) kv[j] = ok ? pn * pn * inv_m : 0.f;
-            if (ok) {
-              po[(uint32_t)(j * D)] = pn;
-              if (q_next) {
-                const float qn = fmaf(eps_over_m, pn, qe[j]);
-                q_next[off0 + (uint32_t)(j * D)] = qn;
-                q_next_lo[off0 + (uint32_t)(j * D)] =
-                    qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
-              }
-            }
-          }
-          if (MODE >= 1 && n_ok_warp_any(n_ok)) {
-            const float sum = warp_transpose_sum16(lpv, lane);
-            if (lane < 16 && cbase + lane < chains && nb < n_blk)
-              lp_part[part_row + cbase + lane] = sum;
-          }
-          if (MODE >= 2 && n_ok_warp_any(n_ok)) {
-            const float sum = warp_transpose_sum16(kv, lane);
-            if (lane < 16 && cbase + lane < chains && nb < n_blk)
-              k_part[part_row + cbase + lane] = sum;
-          }
-        }
-      }
+      const EpiArgs ea{q_cur, q_next, q_next_lo, p_in, p_out, lp_part, k_part, chains, D};
+      epilogue_half_tile<MODE>(ea, trow, n, n_ok, nb < n_blk, c0, part_row, lane, s2, eps_over_m,
+                               inv_m, b_n, mu_n, false);
       tc_fence_before();
       if (leader) mbar_arrive(tempty_bar + 8 * acc);
       else mbar_arrive_remote(tempty_bar + 8 * acc, 0);   // leader's barrier counts both CTAs
