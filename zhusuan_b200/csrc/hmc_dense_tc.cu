@@ -550,7 +550,7 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
                           const float* __restrict__ mu, const float* __restrict__ mass,
                           const float* __restrict__ state, float p_scale,
                           float* __restrict__ lp_part, float* __restrict__ k_part, int64_t chains,
-                          int D) {
+                          int D, int dbg) {
   using C = Cfg2<BK>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -642,9 +642,13 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);
-            umma_tf32_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_tf32_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-            umma_tf32_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            if (dbg & 2) {
+              umma_tf32_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+            } else {
+              umma_tf32_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_tf32_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma_tf32_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            }
           }
           umma_commit_2sm(empty_bar + 8 * stage);         // frees the slot in both CTAs
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -678,7 +682,7 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
       const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
       const EpiArgs ea{q_cur, q_next, q_next_lo, p_in, p_out, lp_part, k_part, chains, D};
       epilogue_half_tile<MODE>(ea, trow, n, n_ok, nb < n_blk, c0, part_row, lane, s2, eps_over_m,
-                               inv_m, b_n, mu_n, false);
+                               inv_m, b_n, mu_n, (dbg & 1) != 0);
       tc_fence_before();
       if (leader) mbar_arrive(tempty_bar + 8 * acc);
       else mbar_arrive_remote(tempty_bar + 8 * acc, 0);   // leader's barrier counts both CTAs
@@ -848,7 +852,7 @@ int launch_tc2(const float* q_cur, const float* q_cur_lo, float* q_next, float* 
 #define ZSB_TC2_LAUNCH(MODE)                                                                  \
   dense_leapfrog_tc2_kernel<BK, MODE><<<grid, NUM_THREADS, Cfg2<BK>::SMEM, st>>>(              \
       m_phi, m_plo, m_qhi, m_qlo, q_cur, q_next, q_next_lo, p_in, p_out, bvec, mu, mass, state, \
-      p_scale, lp_part, k_part, chains, D)
+      p_scale, lp_part, k_part, chains, D, g_tc_dbg)
   if (k_part) ZSB_TC2_LAUNCH(2);
   else if (lp_part) ZSB_TC2_LAUNCH(1);
   else ZSB_TC2_LAUNCH(0);
