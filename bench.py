@@ -178,7 +178,7 @@ def main():
     P, const = make_dense_gaussian_problem(D, seed=2)
     impl = args.dense_impl
     if impl is None:
-        impl = 1 if os.environ.get("ZSB_DENSE_IMPL", "") == "1" else 0
+        impl = 1 if D % 32 == 0 else 0
     lj = zs.fused.GaussianLogJoint(P, device=dev, impl=impl)
     g = torch.Generator(device=dev)
     g.manual_seed(3 + rank)

@@ -21,7 +21,7 @@ class GaussianLogJoint(object):
     """
 
     def __init__(self, precision, mean=None, log_det_cov=None, name="x",
-                 device="cuda", impl=0):
+                 device="cuda", impl=None):
         P64 = np.asarray(precision.detach().cpu().numpy()
                          if isinstance(precision, torch.Tensor)
                          else precision, dtype=np.float64)

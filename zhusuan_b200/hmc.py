@@ -446,13 +446,15 @@ class HMC(object):
         D = f["D"]
         impl = self._dense_impl
         if impl is None:
-            impl = f.get("impl", 0)
+            impl = f.get("impl")
+        if impl is None:               # default: tensor cores whenever legal
+            impl = 1 if D % 32 == 0 else 0
         self._impl = int(impl)
         if self._impl == 1:            # pipeline-shape tuning knob (same results)
             lib.call("zsb_hmc_dense_tc_config",
                      int(os.environ.get("ZSB_TC_BK", "32"))
                      | (int(os.environ.get("ZSB_TC_DBG", "0")) << 8)
-                     | (int(os.environ.get("ZSB_TC_PAIR", "0")) << 16))
+                     | (int(os.environ.get("ZSB_TC_PAIR", "1")) << 16))
         nt = lib.load().zsb_hmc_dense_ntiles(D, self._impl)
         z = lambda *s: torch.zeros(*s, dtype=_F32, device=dev)
         self._qa, self._qb = torch.empty_like(self._q[0]), \
