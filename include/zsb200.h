@@ -188,6 +188,17 @@ int zsb_hmc_dense_leapfrog_f32(const float* q_cur, const float* q_cur_lo, float*
                                int64_t D, int impl, void* stream);
 int zsb_hmc_dense_tc_config(int bk);   /* impl-1 pipeline shape: 32 (2x96 KB) or 16 (4x48 KB) */
 int zsb_hmc_dense_split_lo_f32(const float* q, float* lo, int64_t n, void* stream);
+/* impl 2: fp16-split tensor-core path (3 kind::f16 MMAs per k-step at twice the TF32 rate).
+ * P_h16/P_l16: [D,D] __half hi/lo of P*sP; q_*_planes: [2][chains][D] __half hi/lo of q*sq;
+ * scales: device float[4] = {sq, 1/(sP*sq), scratch, sP}.  D % 64 == 0. */
+int zsb_hmc_dense_h16_prepare_f32(const float* q, void* planes, float* scales, int64_t n,
+                                  void* stream);
+int zsb_hmc_dense_leapfrog_h16_f32(const float* q_cur, const void* q_cur_planes, float* q_next,
+                                   void* q_next_planes, const float* p_in, float* p_out,
+                                   const void* P_h16, const void* P_l16, const float* scales,
+                                   const float* bvec, const float* mu, const float* mass,
+                                   const float* state, float p_scale, float* lp_part,
+                                   float* k_part, int64_t chains, int64_t D, void* stream);
 int zsb_hmc_dense_finish_f32(const float* lp_part, const float* k_part, int ntiles, int64_t chains,
                              float const_term, float* lp_out, float* k_out, void* stream);
 

@@ -264,13 +264,16 @@ def _dense_pass_reference(q, p, P, b, mu, mass, eps, scale):
     return pn, qn, lp, k
 
 
-@pytest.mark.parametrize("impl", [0, 1])
-@pytest.mark.parametrize("C,D", [(300, 512), (24, 32), (129, 288), (1000, 1024)])
+@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("C,D", [(300, 512), (24, 32), (129, 288), (1000, 1024),
+                                 (130, 64), (515, 192)])
 def test_dense_single_pass_vs_float64(zs, impl, C, D):
     """One fused GEMM+leapfrog pass through the C ABI vs float64, for the SIMT
     (impl 0) and tcgen05 3xTF32 (impl 1) kernels, including ragged M / N tiles.
     Bar: per-evaluation log-prob and gradient-derived p within 1e-5 relative."""
     from zhusuan_b200._lib import lib, ptr, stream
+    if impl == 2 and D % 64:
+        pytest.skip("fp16-split path needs D % 64 == 0")
     rng = np.random.RandomState(C + D)
     P64, _ = OM.make_dense_gaussian_problem(D, seed=4)
     q = rng.standard_normal((C, D)); p = rng.standard_normal((C, D))
@@ -284,17 +287,31 @@ def test_dense_single_pass_vs_float64(zs, impl, C, D):
     qt, pt, mt, mut, bt = T(q), T(p), T(mass), T(mu), T(b)
     Pt, Pl = (T(hi), T(lo)) if impl == 1 else (T(P32), None)
     state = torch.zeros(16, device="cuda"); state[7] = eps
-    nt = lib.load().zsb_hmc_dense_ntiles(D, impl)
+    nt = lib.load().zsb_hmc_dense_ntiles(D, min(impl, 1))
     qn = torch.empty_like(qt); pn = torch.empty_like(pt)
     qlo = torch.empty_like(qt); qnlo = torch.empty_like(qt)
     lpp = torch.zeros(nt * C, device="cuda"); kp = torch.zeros(nt * C, device="cuda")
     lp = torch.empty(C, device="cuda"); k = torch.empty(C, device="cuda")
     s = stream()
-    if impl == 1:
-        lib.call("zsb_hmc_dense_split_lo_f32", ptr(qt), ptr(qlo), qt.numel(), s)
-    lib.call("zsb_hmc_dense_leapfrog_f32", ptr(qt), ptr(qlo), ptr(qn),
-             ptr(qnlo), ptr(pt), ptr(pn), ptr(Pt), ptr(Pl), ptr(bt), ptr(mut),
-             ptr(mt), ptr(state), scale, ptr(lpp), ptr(kp), C, D, impl, s)
+    if impl == 2:
+        lj = zs.fused.GaussianLogJoint(P64, device="cuda")._zsb_fused
+        planes = torch.empty(2, C, D, dtype=torch.float16, device="cuda")
+        nplanes = torch.empty_like(planes)
+        scales = torch.zeros(4, device="cuda"); scales[3] = lj["sP"]
+        lib.call("zsb_hmc_dense_h16_prepare_f32", ptr(qt), ptr(planes),
+                 ptr(scales), qt.numel(), s)
+        lib.call("zsb_hmc_dense_leapfrog_h16_f32", ptr(qt), ptr(planes), ptr(qn),
+                 ptr(nplanes), ptr(pt), ptr(pn), ptr(lj["P_h16"]),
+                 ptr(lj["P_l16"]), ptr(scales), ptr(bt), ptr(mut), ptr(mt),
+                 ptr(state), scale, ptr(lpp), ptr(kp), C, D, s)
+    else:
+        if impl == 1:
+            lib.call("zsb_hmc_dense_split_lo_f32", ptr(qt), ptr(qlo),
+                     qt.numel(), s)
+        lib.call("zsb_hmc_dense_leapfrog_f32", ptr(qt), ptr(qlo), ptr(qn),
+                 ptr(qnlo), ptr(pt), ptr(pn), ptr(Pt), ptr(Pl), ptr(bt),
+                 ptr(mut), ptr(mt), ptr(state), scale, ptr(lpp), ptr(kp), C, D,
+                 impl, s)
     lib.call("zsb_hmc_dense_finish_f32", ptr(lpp), ptr(kp), nt, C, 0.0,
              ptr(lp), ptr(k), s)
     torch.cuda.synchronize()
@@ -313,6 +330,12 @@ def test_dense_single_pass_vs_float64(zs, impl, C, D):
         qn32 = N(qn)
         res = qn32 - (qn32.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
         np.testing.assert_array_equal(N(qnlo), res)
+    if impl == 2:   # the planes reconstruct q_next * sq to ~2^-22 relative
+        sq = float(scales[0])
+        rec = (N(nplanes[0]).astype(np.float64) + N(nplanes[1]).astype(np.float64)) / sq
+        np.testing.assert_allclose(rec, N(qn).astype(np.float64), rtol=1e-6,
+                                   atol=1e-6 * np.abs(N(qn)).max())
+        assert 2 ** 11 <= np.abs(q).max() * sq < 2 ** 12
 
 
 def test_golden_dense_fused_tc(zs):
@@ -330,7 +353,7 @@ def test_dense_tc_vs_simt_full_size(zs):
     D, C = 1024, 65536
     P, const = OM.make_dense_gaussian_problem(D, seed=2)
     res = []
-    for impl in (0, 1):
+    for impl in (0, 1, 2):
         lj = zs.fused.GaussianLogJoint(P)
         torch.manual_seed(3)
         x = torch.randn(C, D, device="cuda")
@@ -340,9 +363,10 @@ def test_dense_tc_vs_simt_full_size(zs):
         op.synchronize()
         res.append((N(info.hamiltonian), N(info.orig_hamiltonian),
                     N(info.acceptance_rate), N(x)))
-    np.testing.assert_allclose(res[1][1], res[0][1], rtol=1e-5)
-    np.testing.assert_allclose(res[1][0], res[0][0], rtol=1e-5)
-    np.testing.assert_allclose(res[1][2], res[0][2], rtol=0, atol=2e-3)
-    moved0 = np.abs(res[0][3]).sum(1); moved1 = np.abs(res[1][3]).sum(1)
-    frac_diff = np.mean(np.abs(moved0 - moved1) > 1e-2 * np.abs(moved0))
-    assert frac_diff < 1e-3
+    for k in (1, 2):
+        np.testing.assert_allclose(res[k][1], res[0][1], rtol=1e-5)
+        np.testing.assert_allclose(res[k][0], res[0][0], rtol=1e-5)
+        np.testing.assert_allclose(res[k][2], res[0][2], rtol=0, atol=2e-3)
+        moved0 = np.abs(res[0][3]).sum(1); moved1 = np.abs(res[k][3]).sum(1)
+        frac_diff = np.mean(np.abs(moved0 - moved1) > 1e-2 * np.abs(moved0))
+        assert frac_diff < 1e-3

@@ -85,7 +85,7 @@ class _Lib(object):
         return buf.value.decode("utf-8", "replace")
 
     # kernels launched per successful call (entries that launch two kernels)
-    _KERNELS = {"zsb_hmc_mass_stats_f32": 2, "zsb_sgmcmc_sghmc_f32": 2,
+    _KERNELS = {"zsb_hmc_mass_stats_f32": 2, "zsb_hmc_dense_h16_prepare_f32": 3, "zsb_sgmcmc_sghmc_f32": 2,
                 "zsb_sgmcmc_mean_sq_f32": 2, "zsb_sgmcmc_sgnht_scalar_f32": 2}
     launches = 0
 

@@ -183,6 +183,14 @@ int zsb_dense_leapfrog_tc_launch(const float* q_cur, const float* q_cur_lo, floa
 int zsb_dense_split_lo_launch(const float* q, float* lo, int64_t n, cudaStream_t st);
 int zsb_dense_tc_ntiles(int D);
 int zsb_dense_tc_set_bk(int bk);
+int zsb_dense_leapfrog_h16_launch(const float* q_cur, const void* q_cur_planes, float* q_next,
+                                  void* q_next_planes, const float* p_in, float* p_out,
+                                  const void* P_h16, const void* P_l16, const float* scales,
+                                  const float* bvec, const float* mu, const float* mass,
+                                  const float* state, float p_scale, float* lp_part, float* k_part,
+                                  int64_t chains, int D, cudaStream_t st);
+int zsb_dense_h16_prepare_launch(const float* q, void* planes, float* scales, int64_t n,
+                                 cudaStream_t st);
 
 extern "C" {
 
@@ -231,6 +239,30 @@ int zsb_hmc_dense_split_lo_f32(const float* q, float* lo, int64_t n, void* strea
   ZSB_REQUIRE(q && lo && n >= 0, "zsb_hmc_dense_split_lo_f32: bad args");
   if (n == 0) return ZSB_OK;
   return zsb_dense_split_lo_launch(q, lo, n, (cudaStream_t)stream);
+}
+
+// impl 2 (fp16-split tensor-core path).  Operands are fp16 hi/lo planes of P*sP and q*sq:
+//   P_h16, P_l16: [D, D] __half;  q_*_planes: [2][chains][D] __half (hi plane, lo plane);
+//   scales (device float[4]): [0] sq, [1] 1/(sP*sq), [2] scratch, [3] sP (set by the caller once).
+// zsb_hmc_dense_h16_prepare_f32 derives sq from max|q| (power of two, 3 bits of head-room) and
+// writes q's planes; the leapfrog pass writes q_next's planes with the same sq.  D % 64 == 0.
+int zsb_hmc_dense_h16_prepare_f32(const float* q, void* planes, float* scales, int64_t n,
+                                  void* stream) {
+  ZSB_REQUIRE(q && planes && scales && n > 0, "zsb_hmc_dense_h16_prepare_f32: bad args");
+  return zsb_dense_h16_prepare_launch(q, planes, scales, n, (cudaStream_t)stream);
+}
+int zsb_hmc_dense_leapfrog_h16_f32(const float* q_cur, const void* q_cur_planes, float* q_next,
+                                   void* q_next_planes, const float* p_in, float* p_out,
+                                   const void* P_h16, const void* P_l16, const float* scales,
+                                   const float* bvec, const float* mu, const float* mass,
+                                   const float* state, float p_scale, float* lp_part,
+                                   float* k_part, int64_t chains, int64_t D, void* stream) {
+  ZSB_REQUIRE(q_cur && p_in && p_out && P_h16 && P_l16 && mass && state,
+              "zsb_hmc_dense_leapfrog_h16_f32: null arg");
+  ZSB_REQUIRE(q_next != q_cur, "zsb_hmc_dense_leapfrog_h16_f32: q_next must not alias q_cur");
+  return zsb_dense_leapfrog_h16_launch(q_cur, q_cur_planes, q_next, q_next_planes, p_in, p_out,
+                                       P_h16, P_l16, scales, bvec, mu, mass, state, p_scale,
+                                       lp_part, k_part, chains, (int)D, (cudaStream_t)stream);
 }
 
 int zsb_hmc_dense_finish_f32(const float* lp_part, const float* k_part, int ntiles, int64_t chains,

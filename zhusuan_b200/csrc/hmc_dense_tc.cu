@@ -22,6 +22,7 @@
 // CTAs running concurrently share their chain rows and the whole (8 MB hi+lo) P through the L2.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -179,7 +180,22 @@ struct EpiArgs {
   const float* __restrict__ p_in; float* __restrict__ p_out;
   float* __restrict__ lp_part; float* __restrict__ k_part;
   int64_t chains; int D;
+  // fp16-split operands (impl 2): q_next_lo is then a [2][chains][D] __half buffer (hi plane, lo
+  // plane) of q_next * q_scale, and the accumulator holds (P*sP)(q*sq): g = b - acc * acc_scale.
+  int h16; float q_scale; float acc_scale;
 };
+// residual operand(s) of q_next for the next pass's MMA
+__device__ __forceinline__ void store_split(const EpiArgs& a, int64_t idx, float qn) {
+  if (a.h16) {
+    __half* planes = reinterpret_cast<__half*>(a.q_next_lo);
+    const float x = qn * a.q_scale;
+    const __half h = __float2half_rn(x);
+    planes[idx] = h;
+    planes[(int64_t)a.chains * a.D + idx] = __float2half_rn(x - __half2float(h));
+  } else {
+    a.q_next_lo[idx] = qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
+  }
+}
 template <int MODE>
 __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t trow, int n,
                                                    bool n_ok, bool parts_ok, int64_t c0,
@@ -197,7 +213,7 @@ __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t tr
     float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float g = b_n - __uint_as_float(v[j]);
+      const float g = b_n - a.acc_scale * __uint_as_float(v[j]);
       const float pn = fmaf(s2, g, pe[j]);
       po[(uint32_t)(j * D)] = pn;
       if (MODE >= 1) lpv[j] = (qe[j] - mu_n) * g;
@@ -205,8 +221,7 @@ __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t tr
       if (a.q_next) {
         const float qn = fmaf(eps_over_m, pn, qe[j]);
         a.q_next[off0 + (uint32_t)(j * D)] = qn;
-        a.q_next_lo[off0 + (uint32_t)(j * D)] =
-            qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
+        store_split(a, off0 + (uint32_t)(j * D), qn);
       }
     }
     if (MODE >= 1) {
@@ -269,7 +284,7 @@ __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t tr
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const bool ok = n_ok && cbase + j < chains;
-          const float g = b_n - __uint_as_float(v[j]);
+          const float g = b_n - a.acc_scale * __uint_as_float(v[j]);
           const float pn = fmaf(s2, g, pe[j]);
           if (MODE >= 1) lpv[j] = ok ? (qe[j] - mu_n) * g : 0.f;
           if (MODE >= 2) kv[j] = ok ? pn * pn * inv_m : 0.f;
@@ -278,8 +293,7 @@ __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t tr
             if (a.q_next) {
               const float qn = fmaf(eps_over_m, pn, qe[j]);
               a.q_next[off0 + (uint32_t)(j * D)] = qn;
-              a.q_next_lo[off0 + (uint32_t)(j * D)] =
-                  qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
+              store_split(a, off0 + (uint32_t)(j * D), qn);
             }
           }
         }
@@ -452,7 +466,8 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)(acc * BN + half * (BN / 2));
       const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
-      const EpiArgs ea{q_cur, q_next, q_next_lo, p_in, p_out, lp_part, k_part, chains, D};
+      const EpiArgs ea{q_cur, q_next, q_next_lo, p_in, p_out, lp_part, k_part, chains, D,
+                       0, 1.f, 1.f};
       epilogue_half_tile<MODE>(ea, trow, n, n_ok, true, c0, part_row, lane, s2, eps_over_m, inv_m,
                                b_n, mu_n, (dbg & 1) != 0);
       tc_fence_before();
@@ -520,6 +535,15 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, u
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives in BOTH CTAs
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
@@ -533,12 +557,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
       "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(cta) : "memory");
 }
-__device__ __forceinline__ uint32_t make_idesc_2sm() {   // M=256 (pair), N=256
+__device__ __forceinline__ uint32_t make_idesc_2sm() {   // TF32 x TF32 -> F32, M=256 (pair), N=256
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
          ((uint32_t)(256 >> 4) << 24);
 }
+__device__ __forceinline__ uint32_t make_idesc_2sm_f16() {   // F16 x F16 -> F32 (formats 0)
+  return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
 
-template <int BK, int MODE>
+// OP 0: TF32 operands (fp32 words, 3xTF32 split).  OP 1: fp16 operands (impl 2): the operand
+// tiles hold (P*sP) and (q*sq) split as hi + lo halves, 2*BK elements per 128/64-byte row, three
+// kind::f16 MMAs per 16-element k-step; `scales` = {sq, 1/(sP*sq)} in device memory.
+template <int BK, int MODE, int OP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
                           const __grid_constant__ CUtensorMap map_plo,
@@ -550,8 +580,9 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
                           const float* __restrict__ mu, const float* __restrict__ mass,
                           const float* __restrict__ state, float p_scale,
                           float* __restrict__ lp_part, float* __restrict__ k_part, int64_t chains,
-                          int D, int dbg) {
+                          int D, int dbg, const float* __restrict__ scales) {
   using C = Cfg2<BK>;
+  constexpr int KELEMS = OP ? 2 * BK : BK;                 // operand elements per smem row
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + C::STAGES * C::STAGE;
@@ -571,7 +602,7 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
   const int64_t c_blk = (chains + BN - 1) / BN;
   const int64_t n_units = c_blk * n_pair;                  // work units of the cluster
   const int64_t unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
-  const int n_kb = D / BK;
+  const int n_kb = D / KELEMS;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -611,10 +642,10 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
           const uint32_t fb = full_bar + 8 * stage;
           const uint32_t sa = smem_base + stage * C::STAGE;
           if (leader) mbar_expect_tx(fb, 2 * C::STAGE);   // bytes of both CTAs
-          tma_load_2d_2sm(sa, &map_phi, fb, kb * BK, n0);
-          tma_load_2d_2sm(sa + C::A_TILE, &map_plo, fb, kb * BK, n0);
-          tma_load_2d_2sm(sa + 2 * C::A_TILE, &map_qhi, fb, kb * BK, c0);
-          tma_load_2d_2sm(sa + 2 * C::A_TILE + C::B_TILE, &map_qlo, fb, kb * BK, c0);
+          tma_load_2d_2sm(sa, &map_phi, fb, kb * KELEMS, n0);
+          tma_load_2d_2sm(sa + C::A_TILE, &map_plo, fb, kb * KELEMS, n0);
+          tma_load_2d_2sm(sa + 2 * C::A_TILE, &map_qhi, fb, kb * KELEMS, c0);
+          tma_load_2d_2sm(sa + 2 * C::A_TILE + C::B_TILE, &map_qlo, fb, kb * KELEMS, c0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -622,7 +653,7 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      const uint32_t idesc = make_idesc_2sm();
+      const uint32_t idesc = OP ? make_idesc_2sm_f16() : make_idesc_2sm();
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -642,10 +673,15 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);
-            if (dbg & 2) {
-              umma_tf32_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+            if (OP) {               // 32 B per k-step either way: 16 halves or 8 TF32 words
+              umma_f16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+              umma_f16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma_f16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            } else if (dbg & 2) {
+              umma_tf32_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, first);
             } else {
-              umma_tf32_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_tf32_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
               umma_tf32_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
               umma_tf32_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
             }
@@ -663,6 +699,8 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
     const int half = (warp - 2) >> 2;
     const float eps = state[ZSB_ST_EPS_USED];
     const float s2 = mul(eps, p_scale);
+    const float q_scale = OP ? scales[0] : 1.f;
+    const float acc_scale = OP ? scales[1] : 1.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t u = unit0; u < n_units; u += unit_step) {
@@ -680,7 +718,8 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)(acc * BN + half * (BN / 2));
       const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
-      const EpiArgs ea{q_cur, q_next, q_next_lo, p_in, p_out, lp_part, k_part, chains, D};
+      const EpiArgs ea{q_cur, q_next, q_next_lo, p_in, p_out, lp_part, k_part, chains, D,
+                       OP, q_scale, acc_scale};
       epilogue_half_tile<MODE>(ea, trow, n, n_ok, nb < n_blk, c0, part_row, lane, s2, eps_over_m,
                                inv_m, b_n, mu_n, (dbg & 1) != 0);
       tc_fence_before();
@@ -714,6 +753,44 @@ __global__ void __launch_bounds__(256) split_lo_kernel(const float* __restrict__
   }
 }
 
+// fp16-split support (impl 2).  scales[0] = sq (power of two putting max|q| near 2^12: three bits of
+// head-room below fp16's 2^15 so q may grow 8x inside a trajectory), scales[1] = 1/(sP*sq),
+// scales[2] = running max|q| bits (uint), scales[3] = sP.
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ q, int64_t n,
+                                                     float* __restrict__ scales) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = fabsf(q[i]);
+    m = (a == a && a <= 3.0e38f) ? fmaxf(m, a) : m;       // ignore NaN / inf
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0)
+    atomicMax(reinterpret_cast<unsigned int*>(scales) + 2, __float_as_uint(m));
+}
+__global__ void scale_kernel(float* __restrict__ scales) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float m = __uint_as_float(reinterpret_cast<unsigned int*>(scales)[2]);
+  int e = 0;
+  if (m > 0.f) frexpf(m, &e);              // m = f * 2^e, f in [0.5, 1)  ->  m < 2^e
+  const float sq = ldexpf(1.f, 12 - e);    // max|q| * sq in [2^11, 2^12)
+  scales[0] = sq;
+  scales[1] = 1.f / (scales[3] * sq);
+  reinterpret_cast<unsigned int*>(scales)[2] = 0u;   // reset the running max for the next call
+}
+__global__ void __launch_bounds__(256) split16_kernel(const float* __restrict__ q,
+                                                      __half* __restrict__ planes, int64_t n,
+                                                      const float* __restrict__ scales) {
+  const float sq = scales[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = q[i] * sq;
+    const __half h = __float2half_rn(x);
+    planes[i] = h;
+    planes[n + i] = __float2half_rn(x - __half2float(h));
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -733,18 +810,19 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D row-major [rows, cols] fp32 tensor, box = [box_rows, bk cols], swizzle = row bytes.
-int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-             int bk) {
+int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+             int bk, int half_elems = 0) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     zsb_set_error("dense_tc: cuTensorMapEncodeTiled unavailable");
     return ZSB_ERR_CUDA;
   }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)bk, box_rows};
+  cuuint64_t strides[1] = {cols * (half_elems ? 2 : 4)};
+  cuuint32_t box[2] = {(cuuint32_t)(half_elems ? 2 * bk : bk), box_rows};   // same bytes per row
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+  CUresult r = enc(map, half_elems ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                   2, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
                    bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -808,22 +886,22 @@ int launch_tc(const float* q_cur, const float* q_cur_lo, float* q_next, float* q
   return zsb_check_launch("hmc_dense_leapfrog_tc");
 }
 
-template <int BK>
+template <int BK, int OP>
 int launch_tc2(const float* q_cur, const float* q_cur_lo, float* q_next, float* q_next_lo,
                const float* p_in, float* p_out, const float* P_hi, const float* P_lo,
                const float* bvec, const float* mu, const float* mass, const float* state,
                float p_scale, float* lp_part, float* k_part, int64_t chains, int D,
-               cudaStream_t st) {
+               const float* scales, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dense_leapfrog_tc2_kernel<BK, 0>,
+    cudaError_t e = cudaFuncSetAttribute(dense_leapfrog_tc2_kernel<BK, 0, OP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg2<BK>::SMEM);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(dense_leapfrog_tc2_kernel<BK, 1>,
+      e = cudaFuncSetAttribute(dense_leapfrog_tc2_kernel<BK, 1, OP>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BK>::SMEM);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(dense_leapfrog_tc2_kernel<BK, 2>,
+      e = cudaFuncSetAttribute(dense_leapfrog_tc2_kernel<BK, 2, OP>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BK>::SMEM);
     if (e != cudaSuccess) {
       zsb_set_error("dense_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -837,10 +915,21 @@ int launch_tc2(const float* q_cur, const float* q_cur_lo, float* q_next, float* 
   }
   CUtensorMap m_phi, m_plo, m_qhi, m_qlo;
   int rc;
+  if (OP) {
+    // fp16 planes: P_hi / P_lo are [D, D] __half matrices; q_cur_lo is a [2][chains][D] __half
+    // buffer holding the hi plane then the lo plane of q_cur * sq.
+    const __half* qp = reinterpret_cast<const __half*>(q_cur_lo);
+    if ((rc = make_map(&m_phi, P_hi, (uint64_t)D, (uint64_t)D, BM, BK, 1))) return rc;
+    if ((rc = make_map(&m_plo, P_lo, (uint64_t)D, (uint64_t)D, BM, BK, 1))) return rc;
+    if ((rc = make_map(&m_qhi, qp, (uint64_t)chains, (uint64_t)D, BN / 2, BK, 1))) return rc;
+    if ((rc = make_map(&m_qlo, qp + chains * D, (uint64_t)chains, (uint64_t)D, BN / 2, BK, 1)))
+      return rc;
+  } else {
   if ((rc = make_map(&m_phi, P_hi, (uint64_t)D, (uint64_t)D, BM, BK))) return rc;
   if ((rc = make_map(&m_plo, P_lo, (uint64_t)D, (uint64_t)D, BM, BK))) return rc;
   if ((rc = make_map(&m_qhi, q_cur, (uint64_t)chains, (uint64_t)D, BN / 2, BK))) return rc;
   if ((rc = make_map(&m_qlo, q_cur_lo, (uint64_t)chains, (uint64_t)D, BN / 2, BK))) return rc;
+  }
   const int n_blk = (D + BM - 1) / BM;
   const int64_t n_units = ((chains + BN - 1) / BN) * ((n_blk + 1) / 2);
   int dev = 0, sms = ZSB_NUM_SMS;
@@ -850,9 +939,9 @@ int launch_tc2(const float* q_cur, const float* q_cur_lo, float* q_next, float* 
   if (n_units < pairs) pairs = n_units;
   const unsigned grid = (unsigned)(2 * pairs);
 #define ZSB_TC2_LAUNCH(MODE)                                                                  \
-  dense_leapfrog_tc2_kernel<BK, MODE><<<grid, NUM_THREADS, Cfg2<BK>::SMEM, st>>>(              \
+  dense_leapfrog_tc2_kernel<BK, MODE, OP><<<grid, NUM_THREADS, Cfg2<BK>::SMEM, st>>>(          \
       m_phi, m_plo, m_qhi, m_qlo, q_cur, q_next, q_next_lo, p_in, p_out, bvec, mu, mass, state, \
-      p_scale, lp_part, k_part, chains, D, g_tc_dbg)
+      p_scale, lp_part, k_part, chains, D, g_tc_dbg, scales)
   if (k_part) ZSB_TC2_LAUNCH(2);
   else if (lp_part) ZSB_TC2_LAUNCH(1);
   else ZSB_TC2_LAUNCH(0);
@@ -892,10 +981,10 @@ int zsb_dense_leapfrog_tc_launch(const float* q_cur, const float* q_cur_lo, floa
   }
   if (g_tc_pair) {
     if (g_tc_bk == 16)
-      return launch_tc2<16>(q_cur, q_cur_lo, q_next, q_next_lo, p_in, p_out, P_hi, P_lo, bvec, mu,
-                            mass, state, p_scale, lp_part, k_part, chains, D, st);
-    return launch_tc2<32>(q_cur, q_cur_lo, q_next, q_next_lo, p_in, p_out, P_hi, P_lo, bvec, mu,
-                          mass, state, p_scale, lp_part, k_part, chains, D, st);
+      return launch_tc2<16, 0>(q_cur, q_cur_lo, q_next, q_next_lo, p_in, p_out, P_hi, P_lo, bvec,
+                               mu, mass, state, p_scale, lp_part, k_part, chains, D, nullptr, st);
+    return launch_tc2<32, 0>(q_cur, q_cur_lo, q_next, q_next_lo, p_in, p_out, P_hi, P_lo, bvec, mu,
+                             mass, state, p_scale, lp_part, k_part, chains, D, nullptr, st);
   }
   if (g_tc_bk == 16)
     return launch_tc<16>(q_cur, q_cur_lo, q_next, q_next_lo, p_in, p_out, P_hi, P_lo, bvec, mu,
@@ -915,4 +1004,38 @@ int zsb_dense_split_lo_launch(const float* q, float* lo, int64_t n, cudaStream_t
   if (blocks < 1) blocks = 1;
   split_lo_kernel<<<(unsigned)blocks, 256, 0, st>>>(q, lo, n4);
   return zsb_check_launch("hmc_dense_split_lo");
+}
+
+// ---- impl 2: fp16-split operands (see dense_leapfrog_tc2_kernel OP=1) ----
+int zsb_dense_leapfrog_h16_launch(const float* q_cur, const void* q_cur_planes, float* q_next,
+                                  void* q_next_planes, const float* p_in, float* p_out,
+                                  const void* P_h16, const void* P_l16, const float* scales,
+                                  const float* bvec, const float* mu, const float* mass,
+                                  const float* state, float p_scale, float* lp_part, float* k_part,
+                                  int64_t chains, int D, cudaStream_t st) {
+  if (D % 64 != 0 || D < 64) {
+    zsb_set_error("dense_h16: D must be a multiple of 64");
+    return ZSB_ERR_INVALID;
+  }
+  if (chains >= (1LL << 31) || (q_next && !q_next_planes) || !q_cur_planes || !scales) {
+    zsb_set_error("dense_h16: bad arguments");
+    return ZSB_ERR_INVALID;
+  }
+  return launch_tc2<32, 1>(q_cur, reinterpret_cast<const float*>(q_cur_planes), q_next,
+                           reinterpret_cast<float*>(q_next_planes), p_in, p_out,
+                           reinterpret_cast<const float*>(P_h16),
+                           reinterpret_cast<const float*>(P_l16), bvec, mu, mass, state, p_scale,
+                           lp_part, k_part, chains, D, scales, st);
+}
+
+// scales[3] must hold sP on entry; computes sq from max|q| and writes the fp16 hi/lo planes.
+int zsb_dense_h16_prepare_launch(const float* q, void* planes, float* scales, int64_t n,
+                                 cudaStream_t st) {
+  int64_t blocks = zsb_ceil_div(n, 256 * 8);
+  if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
+  if (blocks < 1) blocks = 1;
+  absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(q, n, scales);
+  scale_kernel<<<1, 32, 0, st>>>(scales);
+  split16_kernel<<<(unsigned)blocks, 256, 0, st>>>(q, reinterpret_cast<__half*>(planes), n, scales);
+  return zsb_check_launch("hmc_dense_h16_prepare");
 }

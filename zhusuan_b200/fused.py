@@ -55,6 +55,16 @@ class GaussianLogJoint(object):
         lo = (P32 - hi).astype(np.float32)
         d["P_hi"] = torch.as_tensor(hi, device=device).contiguous()
         d["P_lo"] = torch.as_tensor(lo, device=device).contiguous()
+        # fp16 split for impl 2: P*sP = h + l with sP a power of two that puts
+        # max|P| in [2^11, 2^12); products then fit fp32 accumulation exactly.
+        pmax = float(np.abs(P32).max())
+        sP = float(2.0 ** (12 - np.frexp(pmax)[1])) if pmax > 0 else 1.0
+        x = P32.astype(np.float64) * sP
+        h16 = x.astype(np.float16)
+        l16 = (x - h16.astype(np.float64)).astype(np.float16)
+        d["sP"] = sP
+        d["P_h16"] = torch.as_tensor(h16, device=device).contiguous()
+        d["P_l16"] = torch.as_tensor(l16, device=device).contiguous()
         self._zsb_fused = d
 
     def __call__(self, observed):

@@ -449,13 +449,15 @@ class HMC(object):
             impl = f.get("impl")
         if impl is None:               # default: tensor cores whenever legal
             impl = 1 if D % 32 == 0 else 0
+        if int(impl) == 2 and D % 64 != 0:
+            raise ValueError("dense_impl=2 (fp16 split) needs D % 64 == 0")
         self._impl = int(impl)
         if self._impl == 1:            # pipeline-shape tuning knob (same results)
             lib.call("zsb_hmc_dense_tc_config",
                      int(os.environ.get("ZSB_TC_BK", "32"))
                      | (int(os.environ.get("ZSB_TC_DBG", "0")) << 8)
                      | (int(os.environ.get("ZSB_TC_PAIR", "1")) << 16))
-        nt = lib.load().zsb_hmc_dense_ntiles(D, self._impl)
+        nt = lib.load().zsb_hmc_dense_ntiles(D, min(self._impl, 1))
         z = lambda *s: torch.zeros(*s, dtype=_F32, device=dev)
         self._qa, self._qb = torch.empty_like(self._q[0]), \
             torch.empty_like(self._q[0])
@@ -464,6 +466,12 @@ class HMC(object):
         if self._impl == 1:            # TF32 residuals of the A operands
             for t in (self._q[0], self._qa, self._qb):
                 self._lo[t.data_ptr()] = torch.empty_like(t)
+        if self._impl == 2:            # fp16 hi/lo planes of q * sq
+            for t in (self._q[0], self._qa, self._qb):
+                self._lo[t.data_ptr()] = torch.empty(
+                    (2,) + tuple(t.shape), dtype=torch.float16, device=dev)
+            self._scales = z(4)
+            self._scales[3] = f["sP"]
         self._lp0_part, self._lp1_part = z(nt * self._chains), \
             z(nt * self._chains)
         self._k_part = z(nt * self._chains)
@@ -472,6 +480,16 @@ class HMC(object):
     def _dense_pass(self, q_cur, q_next, p_in, p_out, scale, lp_part, k_part,
                     s):
         f = self._fused
+        if self._impl == 2:
+            lib.call("zsb_hmc_dense_leapfrog_h16_f32", ptr(q_cur),
+                     ptr(self._lo[q_cur.data_ptr()]), ptr(q_next),
+                     ptr(self._lo[q_next.data_ptr()])
+                     if q_next is not None else None, ptr(p_in), ptr(p_out),
+                     ptr(f["P_h16"]), ptr(f["P_l16"]), ptr(self._scales),
+                     ptr(f.get("b")), ptr(f.get("mu")), ptr(self._mass[0]),
+                     ptr(self._state), scale, ptr(lp_part), ptr(k_part),
+                     self._chains, f["D"], s)
+            return
         tc = self._impl == 1
         lo_cur = self._lo[q_cur.data_ptr()] if tc else None
         lo_next = self._lo[q_next.data_ptr()] if tc and q_next is not None \
@@ -508,6 +526,10 @@ class HMC(object):
         if self._impl == 1:
             lib.call("zsb_hmc_dense_split_lo_f32", ptr(q0),
                      ptr(self._lo[q0.data_ptr()]), q0.numel(), s)
+        elif self._impl == 2:
+            lib.call("zsb_hmc_dense_h16_prepare_f32", ptr(q0),
+                     ptr(self._lo[q0.data_ptr()]), ptr(self._scales),
+                     q0.numel(), s)
         if init:
             def probe():
                 self._dense_pass(q0, self._qa, self._p0[0], self._pw, 0.5,
