@@ -47,7 +47,8 @@ def parse():
                     help="untimed adaptive iterations run as setup, before "
                          "the W warm-up steps (covers both step-size searches)")
     ap.add_argument("--dense-impl", type=int, default=None,
-                    help="0 SIMT fp32, 1 tcgen05 3xTF32 (default: best built)")
+                    help="0 SIMT fp32, 1 tcgen05 3xTF32, 2 tcgen05 fp16-split "
+                         "(default: fastest legal)")
     ap.add_argument("--cpu-chains", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -178,7 +179,7 @@ def main():
     P, const = make_dense_gaussian_problem(D, seed=2)
     impl = args.dense_impl
     if impl is None:
-        impl = 1 if D % 32 == 0 else 0
+        impl = 2 if D % 64 == 0 else (1 if D % 32 == 0 else 0)
     lj = zs.fused.GaussianLogJoint(P, device=dev, impl=impl)
     g = torch.Generator(device=dev)
     g.manual_seed(3 + rank)
@@ -284,7 +285,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            traffic = tj.get("impl%d" % impl, {}).get("dram_bytes_per_launch")
+            traffic = (tj.get("impl%d" % impl) or {}).get("dram_bytes_per_launch")
         f_h, f_t = hbm / peaks["hbm_gbs"], tfl / peaks["tf"]
         roof = {"bound": "hbm", "achieved": hbm, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": f_h, "traffic": traffic,

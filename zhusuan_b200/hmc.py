@@ -447,8 +447,8 @@ class HMC(object):
         impl = self._dense_impl
         if impl is None:
             impl = f.get("impl")
-        if impl is None:               # default: tensor cores whenever legal
-            impl = 1 if D % 32 == 0 else 0
+        if impl is None:               # default: fastest legal tensor-core path
+            impl = 2 if D % 64 == 0 else (1 if D % 32 == 0 else 0)
         if int(impl) == 2 and D % 64 != 0:
             raise ValueError("dense_impl=2 (fp16 split) needs D % 64 == 0")
         self._impl = int(impl)
