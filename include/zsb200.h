@@ -230,6 +230,20 @@ int zsb_sgmcmc_sgnht_scalar_f32(float* q, float* v, const float* alpha_eff, cons
 int zsb_sgmcmc_sgnht_alpha_f32(float* out, const float* in, const float* mean_k, float coef,
                                float lr, void* stream);
 
+/* Fused SGHMC step for the two-layer BNN regression log-joint of
+ * examples/bayesian_neural_nets/bnn_sgmcmc.py:19-35, 74-91 (layer sizes [n_in, H, 1]; per-chain
+ * weights w0 [chains,H,n_in+1], w1 [chains,1,H+1]): momentum resample, half step, hand-derived
+ * forward/backward over the minibatch, prior gradient and the sgmcmc.py:338-358 update in ONE
+ * launch.  part: 2*zsb_sgmcmc_parts() floats; mean_k: 2 floats (one per latent). */
+int zsb_sgmcmc_sghmc_bnn_f32(float* w0, float* w1, float* v0, float* v1, const float* x,
+                             const float* y, int B, int n_in, int H, const float* logstd0,
+                             int64_t logstd0_n, const float* logstd1, int64_t logstd1_n,
+                             float y_logstd, float n_train, float lr, float alpha, float beta,
+                             int second_order, int resample, const float* noise0,
+                             const float* noise1, const float* resample0, const float* resample1,
+                             uint64_t seed, uint32_t iter, int64_t row0, float* part,
+                             float* mean_k, int64_t chains, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,3 +114,74 @@ def test_type_error_contract(zs):
     s = zs.SGLD(learning_rate=0.1)
     with pytest.raises(TypeError, match=r"latent\['x'\] is not a"):
         s.sample(lambda o: o['x'].sum(-1), {}, {"x": [1.0, 2.0]})
+
+
+@pytest.mark.parametrize("second_order", [True, False])
+def test_bnn_fused_step_vs_oracle(zs, second_order):
+    """config-4 shape at a small size: fused SGHMC+BNN kernel vs the float64
+    oracle (oracle/models.py::BNN analytic gradient + oracle/sgmcmc.py::SGHMC)
+    with injected noise, including the resample steps (t = 0, 3)."""
+    from oracle import models as OM, sgmcmc as OS
+    rng = np.random.RandomState(7)
+    C, n_in, H, B, n_train = 9, 4, 37, 23, 500
+    x = rng.standard_normal((B, n_in)); y = rng.standard_normal(B)
+    ls0 = 0.1 * rng.standard_normal((H, n_in + 1)); ls1 = 0.1 * rng.standard_normal((1, H + 1))
+    w0 = rng.uniform(-2, 2, (C, H, n_in + 1)); w1 = rng.uniform(-2, 2, (C, 1, H + 1))
+
+    class M(OM.BNN):
+        def grad(self, qs):
+            g0, g1 = OM.BNN.grad(self, qs)
+            # per-weight prior log-stddevs (bnn_sgmcmc.py:71)
+            g0 = g0 + np.exp(-2 * self.ls0) * qs[0] - np.exp(-2 * ls0) * qs[0]
+            g1 = g1 + np.exp(-2 * self.ls1) * qs[1] - np.exp(-2 * ls1) * qs[1]
+            return [g0, g1]
+    om = M(x, y, n_train, dtype=np.float64)
+    kw = dict(learning_rate=1e-4, friction=0.2, variance_estimate=0.01,
+              n_iter_resample_v=3, second_order=second_order)
+    osg = OS.SGHMC(dtype=np.float64, **kw)
+    v0n = [rng.standard_normal(w0.shape), rng.standard_normal(w1.shape)]
+    osg.init_v(v0n)
+    lj = zs.fused.BNNRegressionLogJoint(T(x), T(y), [T(ls0), T(ls1)], n_train)
+    tw0, tw1 = T(w0), T(w1)
+    sg = zs.SGHMC(**kw)
+    op, info = sg.sample(lj, {}, {"w0": tw0, "w1": tw1})
+    assert sg._fused_bnn() is lj
+    sg.init_momentum({"w0": T(v0n[0]), "w1": T(v0n[1])})
+    oq = [w0, w1]
+    for t in range(5):
+        nz = [rng.standard_normal(w0.shape), rng.standard_normal(w1.shape)]
+        rs = [rng.standard_normal(w0.shape), rng.standard_normal(w1.shape)]
+        oq, oinfo = osg.step(oq, om.grad, rs, nz)
+        op(noise={"noise": {"w0": T(nz[0]), "w1": T(nz[1])},
+                  "resample": {"w0": T(rs[0]), "w1": T(rs[1])}})
+        np.testing.assert_allclose(N(tw0), oq[0], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(N(tw1), oq[1], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(N(info.mean_k["w0"]), oinfo["mean_k"][0], rtol=1e-3)
+        np.testing.assert_allclose(N(info.mean_k["w1"]), oinfo["mean_k"][1], rtol=1e-3)
+
+
+def test_bnn_fused_matches_generic_path_with_philox(zs):
+    """[10, 50, 1] (bnn_sgmcmc.py) with in-kernel noise: the fused kernel and
+    the generic path (registry kernels + autograd) draw the same Philox numbers
+    and must agree step for step."""
+    torch.manual_seed(0)
+    C, n_in, H, B = 64, 10, 50, 100
+    x = torch.randn(B, n_in, device="cuda"); y = torch.sin(x.sum(1))
+    ls = [torch.zeros(H, n_in + 1, device="cuda"), torch.zeros(1, H + 1, device="cuda")]
+    w0i = torch.rand(C, H, n_in + 1, device="cuda") * 4 - 2
+    w1i = torch.rand(C, 1, H + 1, device="cuda") * 4 - 2
+    outs = []
+    for fused in (True, False):
+        lj = zs.fused.BNNRegressionLogJoint(x, y, ls, n_train=10000)
+        w0, w1 = w0i.clone(), w1i.clone()
+        sg = zs.SGHMC(learning_rate=2e-6, friction=0.2, n_iter_resample_v=1000,
+                      second_order=True, seed=11, use_fused=fused)
+        op, info = sg.sample(lj, {}, {"w0": w0, "w1": w1})
+        # identical initial momentum
+        sg.vs[0].copy_(torch.full_like(w0, 1e-3)); sg.vs[1].copy_(torch.full_like(w1, -1e-3))
+        for t in range(4):
+            op()
+        outs.append((N(w0), N(w1), float(info.mean_k["w0"])))
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-3)

@@ -7,7 +7,7 @@ import math
 import numpy as np
 import torch
 
-__all__ = ["GaussianLogJoint"]
+__all__ = ["GaussianLogJoint", "BNNRegressionLogJoint"]
 
 
 class GaussianLogJoint(object):
@@ -72,3 +72,57 @@ class GaussianLogJoint(object):
         if self.mu is not None:
             x = x - self.mu
         return -0.5 * ((x @ self.P) * x).sum(-1) + self.const
+
+
+class BNNRegressionLogJoint(object):
+    """The log-joint of examples/bayesian_neural_nets/bnn_sgmcmc.py:19-35, 74-77
+    for layer sizes [n_in, H, 1] and per-chain weights:
+
+        w0 [chains, H, n_in+1] ~ N(0, exp(logstds[0])),
+        w1 [chains, 1, H+1]    ~ N(0, exp(logstds[1])),
+        y ~ N(net(x; w), exp(y_logstd)),
+        log_joint = sum log p(w) + mean_batch(log p(y|x,w)) * n_train.
+
+    As a callable it is the generic-path log-joint (registry Normal kernels +
+    torch einsum under the tape); ``zs.SGHMC.sample`` recognises it and runs
+    the whole step in one fused kernel (zsb_sgmcmc_sghmc_bnn_f32).  Feed
+    minibatches with ``sample_op(observed={'x': xb, 'y': yb})``.
+    """
+
+    def __init__(self, x, y, logstds, n_train, y_logstd=-0.95,
+                 names=("w0", "w1")):
+        from .distributions import Normal
+        self._Normal = Normal
+        self.x, self.y = x, y
+        self.logstds = [l.contiguous() for l in logstds]
+        self.n_train = float(n_train)
+        self.y_logstd = float(y_logstd)
+        self.names = tuple(names)
+        self._zsb_fused = {"kind": "bnn_regression", "obj": self}
+
+    def set_batch(self, observed):
+        if "x" in observed:
+            self.x = observed["x"]
+        if "y" in observed:
+            self.y = observed["y"]
+
+    def __call__(self, observed):
+        x = observed.get("x", self.x)
+        y = observed.get("y", self.y)
+        w0, w1 = observed[self.names[0]], observed[self.names[1]]
+        C = w0.shape[0]
+        h = x.unsqueeze(0).expand(C, -1, -1)
+        lp = 0.0
+        for w, ls in zip((w0, w1), self.logstds):
+            ones = torch.ones(h.shape[:-1] + (1,), device=h.device)
+            h = torch.cat([h, ones], -1)
+            h = torch.einsum("imk,ijk->ijm", w, h) / math.sqrt(h.shape[2])
+            if w is w0:
+                h = torch.relu(h)
+            lp = lp + self._Normal(torch.zeros_like(ls), logstd=ls,
+                                   group_ndims=2).log_prob(w)
+        y_mean = h.squeeze(2)
+        lpy = self._Normal(y_mean, logstd=torch.full_like(y_mean,
+                                                         self.y_logstd)
+                           ).log_prob(y.unsqueeze(0))
+        return lp + lpy.mean(1) * self.n_train

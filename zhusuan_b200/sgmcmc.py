@@ -107,6 +107,9 @@ class SGMCMC(object):
     def _iterate(self, observed, noise, learning_rate):
         if observed is not None:
             self._observed.update(observed)
+            f = getattr(self._log_joint, "_zsb_fused", None)
+            if f is not None and "obj" in f and hasattr(f["obj"], "set_batch"):
+                f["obj"].set_batch(observed)
         if learning_rate is not None:
             self.lr = float(learning_rate)
         self._update(self._var_list, self._grad_func, noise or {})
@@ -170,7 +173,9 @@ class SGHMC(SGMCMC):
     """sgmcmc.py:260-371."""
 
     def __init__(self, learning_rate, friction=0.25, variance_estimate=0.,
-                 n_iter_resample_v=20, second_order=True, **kw):
+                 n_iter_resample_v=20, second_order=True, use_fused=True,
+                 **kw):
+        self._use_fused = bool(use_fused)
         self.lr = float(learning_rate)
         self.alpha = float(friction)
         self.beta = float(variance_estimate)
@@ -205,7 +210,48 @@ class SGHMC(SGMCMC):
             for k, v in enumerate(self.vs):
                 self._resample(k, v, noise, "resample", self.t & 0xFFFFFFFF)
 
+    def _fused_bnn(self):
+        f = getattr(self._log_joint, "_zsb_fused", None)
+        if f is None or f.get("kind") != "bnn_regression":
+            return None
+        obj = f["obj"]
+        if list(self._latent_k) != list(obj.names):
+            return None
+        w0, w1 = self._var_list
+        if w0.dim() != 3 or w1.dim() != 3 or w1.shape[1] != 1 or \
+                w1.shape[2] != w0.shape[1] + 1 or w0.shape[2] > 16 or \
+                w0.shape[1] > 64 or obj.x.shape[0] > 512:
+            return None
+        return obj
+
+    def _update_fused_bnn(self, obj, noise):
+        """Whole step in one kernel (csrc/sgmcmc_bnn.cu)."""
+        w0, w1 = self._var_list
+        x, y = obj.x.contiguous(), obj.y.contiguous()
+        resample = int(self.n_iter_resample_v != 0 and
+                       self.t % self.n_iter_resample_v == 0)
+        if not hasattr(self, "_bnn_part"):
+            self._bnn_part = torch.zeros(2 * lib.load().zsb_sgmcmc_parts(),
+                                         dtype=_F32, device=w0.device)
+            self._bnn_mean_k = torch.zeros(2, dtype=_F32, device=w0.device)
+            self._info.mean_k[self._latent_k[0]] = self._bnn_mean_k[0]
+            self._info.mean_k[self._latent_k[1]] = self._bnn_mean_k[1]
+        lib.call("zsb_sgmcmc_sghmc_bnn_f32", ptr(w0), ptr(w1), ptr(self.vs[0]),
+                 ptr(self.vs[1]), ptr(x), ptr(y), int(x.shape[0]),
+                 int(x.shape[1]), int(w0.shape[1]), ptr(obj.logstds[0]),
+                 obj.logstds[0].numel(), ptr(obj.logstds[1]),
+                 obj.logstds[1].numel(), obj.y_logstd, obj.n_train, self.lr,
+                 self.alpha, self.beta, int(self.second_order), resample,
+                 self._noise(noise, "noise", 0), self._noise(noise, "noise", 1),
+                 self._noise(noise, "resample", 0),
+                 self._noise(noise, "resample", 1), self._seed_now(),
+                 self.t & 0xFFFFFFFF, self._row0, ptr(self._bnn_part),
+                 ptr(self._bnn_mean_k), self._chains, stream())
+
     def _update(self, qs, grad_func, noise):
+        obj = self._fused_bnn() if self._use_fused else None
+        if obj is not None:
+            return self._update_fused_bnn(obj, noise)
         s = stream()
         self._maybe_resample(noise)
         if self.second_order:                              # sgmcmc.py:351
