@@ -44,17 +44,26 @@ __device__ __forceinline__ float noise_at(const float* injected, int64_t idx, ui
   return z[col & 3];
 }
 
-__global__ void __launch_bounds__(256) sghmc_bnn_kernel(BnnArgs a) {
+constexpr int PB = 4;   // data points processed together (independent FMA / shuffle chains)
+
+template <int IN1>
+__global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
   extern __shared__ float sh[];
-  const int in1 = a.n_in + 1, H1 = a.H + 1;
-  float* xs = sh;                       // [B][in1]  (bias column appended)
-  float* ys = sh + a.B * in1;           // [B]
+  constexpr int in1 = IN1;
+  const int H1 = a.H + 1;
+  const int Bp = (a.B + PB - 1) / PB * PB;   // padded with zero-weight rows
+  float* xs = sh;                       // [Bp][in1]  (bias column appended)
+  float* ys = sh + Bp * in1;            // [Bp]
+  float* wt = ys + Bp;                  // [Bp] 1 for real rows, 0 for padding
   __shared__ float red[32];
-  for (int i = threadIdx.x; i < a.B * in1; i += blockDim.x) {
+  for (int i = threadIdx.x; i < Bp * in1; i += blockDim.x) {
     const int b = i / in1, k = i % in1;
-    xs[i] = (k < a.n_in) ? a.x[b * a.n_in + k] : 1.f;
+    xs[i] = (b < a.B) ? ((k < a.n_in) ? a.x[b * a.n_in + k] : 1.f) : 0.f;
   }
-  for (int i = threadIdx.x; i < a.B; i += blockDim.x) ys[i] = a.y[i];
+  for (int i = threadIdx.x; i < Bp; i += blockDim.x) {
+    ys[i] = (i < a.B) ? a.y[i] : 0.f;
+    wt[i] = (i < a.B) ? 1.f : 0.f;
+  }
   __syncthreads();
 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -72,70 +81,88 @@ __global__ void __launch_bounds__(256) sghmc_bnn_kernel(BnnArgs a) {
     float* w1c = a.w1 + c * H1;
     float* v1c = a.v1 + c * H1;
     const int64_t grow = a.row0 + c;
-    // ---- load this lane's parameters (hidden units m = lane, lane + 32; lane 0 also the bias)
-    float W[2][MAX_IN1], V[2][MAX_IN1], G[2][MAX_IN1];
-    float w1r[2], v1r[2], g1r[2];
-    float w1b = 0.f, v1b = 0.f, g1b = 0.f;
+    // ---- momentum resample (sgmcmc.py:327-336): written back so phase 3 can re-read it
+    if (a.resample) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int m = lane + 32 * u;
+        if (m < a.H) {
+#pragma unroll
+          for (int k = 0; k < in1; ++k) {
+            const int64_t idx = (int64_t)m * in1 + k;
+            v0c[idx] = mul(noise_at(a.rs0, c * a.H * in1 + idx, a.seed,
+                                    ZSB_STREAM_SGMCMC_RESAMPLE, a.iter, grow, idx), sd_v);
+          }
+          v1c[m] = mul(noise_at(a.rs1, c * H1 + m, a.seed + 1, ZSB_STREAM_SGMCMC_RESAMPLE,
+                                a.iter, grow, m), sd_v);
+        }
+      }
+      if (lane == 0)
+        v1c[a.H] = mul(noise_at(a.rs1, c * H1 + a.H, a.seed + 1, ZSB_STREAM_SGMCMC_RESAMPLE,
+                                a.iter, grow, a.H), sd_v);
+      __syncwarp();
+    }
+    // ---- this lane's parameters (hidden units m = lane, lane + 32; lane 0 also the h1 bias)
+    float W[2][IN1], G[2][IN1];
+    float w1r[2], g1r[2];
+    float w1b = 0.f, g1b = 0.f;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int m = lane + 32 * u;
       const bool mv = m < a.H;
 #pragma unroll
-      for (int k = 0; k < MAX_IN1; ++k) {
-        const bool ok = mv && k < in1;
+      for (int k = 0; k < in1; ++k) {
         const int64_t idx = (int64_t)m * in1 + k;
-        float v = ok ? v0c[idx] : 0.f;
-        if (ok && a.resample)
-          v = mul(noise_at(a.rs0, c * a.H * in1 + idx, a.seed, ZSB_STREAM_SGMCMC_RESAMPLE, a.iter,
-                           grow, idx), sd_v);
-        float w = ok ? w0c[idx] : 0.f;
-        if (a.second_order) w = add(w, mul(0.5f, v));             // q1 = q + v/2
-        W[u][k] = w; V[u][k] = v; G[u][k] = 0.f;
+        float w = mv ? w0c[idx] : 0.f;
+        if (a.second_order && mv) w = add(w, mul(0.5f, v0c[idx]));   // q1 = q + v/2
+        W[u][k] = w; G[u][k] = 0.f;
       }
-      float v = mv ? v1c[m] : 0.f;
-      if (mv && a.resample)
-        v = mul(noise_at(a.rs1, c * H1 + m, a.seed + 1, ZSB_STREAM_SGMCMC_RESAMPLE, a.iter, grow,
-                         m), sd_v);
       float w = mv ? w1c[m] : 0.f;
-      if (a.second_order) w = add(w, mul(0.5f, v));
-      w1r[u] = w; v1r[u] = v; g1r[u] = 0.f;
+      if (a.second_order && mv) w = add(w, mul(0.5f, v1c[m]));
+      w1r[u] = w; g1r[u] = 0.f;
     }
     if (lane == 0) {
-      v1b = v1c[a.H];
-      if (a.resample)
-        v1b = mul(noise_at(a.rs1, c * H1 + a.H, a.seed + 1, ZSB_STREAM_SGMCMC_RESAMPLE, a.iter,
-                           grow, a.H), sd_v);
       w1b = w1c[a.H];
-      if (a.second_order) w1b = add(w1b, mul(0.5f, v1b));
+      if (a.second_order) w1b = add(w1b, mul(0.5f, v1c[a.H]));
     }
-    // ---- forward + backward over the minibatch (likelihood part of the gradient)
-    for (int b = 0; b < a.B; ++b) {
-      const float* xb = xs + b * in1;
-      float a1[2], r1[2];
-      float part = 0.f;
+    // ---- forward + backward over the minibatch, PB points at a time
+    for (int b0 = 0; b0 < Bp; b0 += PB) {
+      float a1[2][PB], part[PB];
+#pragma unroll
+      for (int p = 0; p < PB; ++p) part[p] = (lane == 0) ? w1b : 0.f;   // bias unit of h1
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < MAX_IN1; ++k)
-          if (k < in1) s = fmaf(W[u][k], xb[k], s);
-        a1[u] = s * inv_s0;
-        r1[u] = fmaxf(a1[u], 0.f);
-        part = fmaf(w1r[u], r1[u], part);
+        for (int p = 0; p < PB; ++p) {
+          const float* xb = xs + (b0 + p) * in1;
+          float sacc = 0.f;
+#pragma unroll
+          for (int k = 0; k < in1; ++k) sacc = fmaf(W[u][k], xb[k], sacc);
+          a1[u][p] = sacc * inv_s0;
+          part[p] = fmaf(w1r[u], fmaxf(a1[u][p], 0.f), part[p]);
+        }
       }
-      if (lane == 0) part += w1b;                       // bias unit of h1
-      const float ym = warp_sum(part) * inv_s1;
-      const float dym = prec_y * (ys[b] - ym) * lik_scale;   // d log_joint / d y_mean
-      const float dout = dym * inv_s1;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        g1r[u] = fmaf(dout, r1[u], g1r[u]);
-        const float da1 = (a1[u] > 0.f) ? dout * w1r[u] * inv_s0 : 0.f;
+      for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int k = 0; k < MAX_IN1; ++k)
-          if (k < in1) G[u][k] = fmaf(da1, xb[k], G[u][k]);
+        for (int p = 0; p < PB; ++p) part[p] += __shfl_xor_sync(0xffffffffu, part[p], o);
       }
-      if (lane == 0) g1b += dout;
+#pragma unroll
+      for (int p = 0; p < PB; ++p) {
+        const float* xb = xs + (b0 + p) * in1;
+        const float ym = part[p] * inv_s1;
+        // d log_joint / d y_mean (zero for padding rows), then back through the output layer
+        const float dout = prec_y * (ys[b0 + p] - ym) * lik_scale * wt[b0 + p] * inv_s1;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float r1 = fmaxf(a1[u][p], 0.f);
+          g1r[u] = fmaf(dout, r1, g1r[u]);
+          const float da1 = (a1[u][p] > 0.f) ? dout * w1r[u] * inv_s0 : 0.f;
+#pragma unroll
+          for (int k = 0; k < in1; ++k) G[u][k] = fmaf(da1, xb[k], G[u][k]);
+        }
+        if (lane == 0) g1b += dout;
+      }
     }
     // ---- prior gradient, SGHMC update, write back
 #pragma unroll
@@ -143,35 +170,35 @@ __global__ void __launch_bounds__(256) sghmc_bnn_kernel(BnnArgs a) {
       const int m = lane + 32 * u;
       if (m < a.H) {
 #pragma unroll
-        for (int k = 0; k < MAX_IN1; ++k) {
-          if (k < in1) {
-            const int64_t idx = (int64_t)m * in1 + k;
-            const float ls = a.logstd0[idx % a.logstd0_n];
-            const float g = G[u][k] - expf(-2.f * ls) * W[u][k];
-            const float xi = mul(noise_at(a.noise0, c * a.H * in1 + idx, a.seed,
-                                          ZSB_STREAM_SGMCMC_NOISE, a.iter, grow, idx), sd_xi);
-            float nv, nq;
-            if (a.second_order) {
-              nv = mul(dh, add(add(mul(dh, V[u][k]), mul(a.lr, g)), xi));
-              nq = add(W[u][k], mul(0.5f, nv));
-            } else {
-              nv = add(add(mul(oma, V[u][k]), mul(a.lr, g)), xi);
-              nq = add(W[u][k], nv);
-            }
-            w0c[idx] = nq; v0c[idx] = nv;
-            ksum0 += nv * nv;
+        for (int k = 0; k < in1; ++k) {
+          const int64_t idx = (int64_t)m * in1 + k;
+          const float ls = a.logstd0[idx % a.logstd0_n];
+          const float g = G[u][k] - expf(-2.f * ls) * W[u][k];
+          const float xi = mul(noise_at(a.noise0, c * a.H * in1 + idx, a.seed,
+                                        ZSB_STREAM_SGMCMC_NOISE, a.iter, grow, idx), sd_xi);
+          const float vold = v0c[idx];
+          float nv, nq;
+          if (a.second_order) {
+            nv = mul(dh, add(add(mul(dh, vold), mul(a.lr, g)), xi));
+            nq = add(W[u][k], mul(0.5f, nv));
+          } else {
+            nv = add(add(mul(oma, vold), mul(a.lr, g)), xi);
+            nq = add(W[u][k], nv);
           }
+          w0c[idx] = nq; v0c[idx] = nv;
+          ksum0 += nv * nv;
         }
         const float ls = a.logstd1[m % a.logstd1_n];
         const float g = g1r[u] - expf(-2.f * ls) * w1r[u];
         const float xi = mul(noise_at(a.noise1, c * H1 + m, a.seed + 1, ZSB_STREAM_SGMCMC_NOISE,
                                       a.iter, grow, m), sd_xi);
+        const float vold = v1c[m];
         float nv, nq;
         if (a.second_order) {
-          nv = mul(dh, add(add(mul(dh, v1r[u]), mul(a.lr, g)), xi));
+          nv = mul(dh, add(add(mul(dh, vold), mul(a.lr, g)), xi));
           nq = add(w1r[u], mul(0.5f, nv));
         } else {
-          nv = add(add(mul(oma, v1r[u]), mul(a.lr, g)), xi);
+          nv = add(add(mul(oma, vold), mul(a.lr, g)), xi);
           nq = add(w1r[u], nv);
         }
         w1c[m] = nq; v1c[m] = nv;
@@ -183,12 +210,13 @@ __global__ void __launch_bounds__(256) sghmc_bnn_kernel(BnnArgs a) {
       const float g = g1b - expf(-2.f * ls) * w1b;
       const float xi = mul(noise_at(a.noise1, c * H1 + a.H, a.seed + 1, ZSB_STREAM_SGMCMC_NOISE,
                                     a.iter, grow, a.H), sd_xi);
+      const float vold = v1c[a.H];
       float nv, nq;
       if (a.second_order) {
-        nv = mul(dh, add(add(mul(dh, v1b), mul(a.lr, g)), xi));
+        nv = mul(dh, add(add(mul(dh, vold), mul(a.lr, g)), xi));
         nq = add(w1b, mul(0.5f, nv));
       } else {
-        nv = add(add(mul(oma, v1b), mul(a.lr, g)), xi);
+        nv = add(add(mul(oma, vold), mul(a.lr, g)), xi);
         nq = add(w1b, nv);
       }
       w1c[a.H] = nq; v1c[a.H] = nv;
@@ -245,8 +273,16 @@ int zsb_sgmcmc_sghmc_bnn_f32(float* w0, float* w1, float* v0, float* v1, const f
   a.seed = seed; a.iter = iter; a.row0 = row0;
   int64_t blocks = zsb_ceil_div(chains, 8);
   if (blocks > cap) blocks = cap;
-  const size_t smem = (size_t)(B * (n_in + 1) + B) * sizeof(float);
-  sghmc_bnn_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(a);
+  const int Bp = (B + PB - 1) / PB * PB;
+  const size_t smem = (size_t)(Bp * (n_in + 1) + 2 * Bp) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (n_in + 1) {
+#define ZSB_BNN_CASE(N) case N: sghmc_bnn_kernel<N><<<(unsigned)blocks, 256, smem, st>>>(a); break;
+    ZSB_BNN_CASE(2) ZSB_BNN_CASE(3) ZSB_BNN_CASE(4) ZSB_BNN_CASE(5) ZSB_BNN_CASE(6)
+    ZSB_BNN_CASE(7) ZSB_BNN_CASE(8) ZSB_BNN_CASE(9) ZSB_BNN_CASE(10) ZSB_BNN_CASE(11)
+    ZSB_BNN_CASE(12) ZSB_BNN_CASE(13) ZSB_BNN_CASE(14) ZSB_BNN_CASE(15) ZSB_BNN_CASE(16)
+#undef ZSB_BNN_CASE
+  }
   int rc = zsb_check_launch("sgmcmc_sghmc_bnn");
   if (rc) return rc;
   bnn_mean_k_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(
