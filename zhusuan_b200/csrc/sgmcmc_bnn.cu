@@ -46,6 +46,25 @@ __device__ __forceinline__ float noise_at(const float* injected, int64_t idx, ui
 
 constexpr int PB = 4;   // data points processed together (independent FMA / shuffle chains)
 
+// Same numbers as noise_at(), but one Philox block (4 normals) is generated once and reused for
+// the up-to-4 consecutive columns that share it.
+struct NoiseCache {
+  const float* injected; uint64_t seed; uint32_t stream_id, iter; int64_t row;
+  int64_t blk; float z[4];
+  __device__ __forceinline__ NoiseCache(const float* inj, uint64_t s, uint32_t st, uint32_t it,
+                                        int64_t r)
+      : injected(inj), seed(s), stream_id(st), iter(it), row(r), blk(-1) {}
+  __device__ __forceinline__ float at(int64_t flat_idx, int64_t col) {
+    if (injected) return injected[flat_idx];
+    if ((col >> 2) != blk) {
+      blk = col >> 2;
+      philox_normal4(seed, stream_id, iter, (uint32_t)row, (uint32_t)blk, z);
+    }
+    const int w = (int)(col & 3);
+    return w == 0 ? z[0] : w == 1 ? z[1] : w == 2 ? z[2] : z[3];
+  }
+};
+
 template <int IN1>
 __global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
   extern __shared__ float sh[];
@@ -83,6 +102,7 @@ __global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
     const int64_t grow = a.row0 + c;
     // ---- momentum resample (sgmcmc.py:327-336): written back so phase 3 can re-read it
     if (a.resample) {
+      NoiseCache rc0(a.rs0, a.seed, ZSB_STREAM_SGMCMC_RESAMPLE, a.iter, grow);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int m = lane + 32 * u;
@@ -90,8 +110,7 @@ __global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
 #pragma unroll
           for (int k = 0; k < in1; ++k) {
             const int64_t idx = (int64_t)m * in1 + k;
-            v0c[idx] = mul(noise_at(a.rs0, c * a.H * in1 + idx, a.seed,
-                                    ZSB_STREAM_SGMCMC_RESAMPLE, a.iter, grow, idx), sd_v);
+            v0c[idx] = mul(rc0.at(c * a.H * in1 + idx, idx), sd_v);
           }
           v1c[m] = mul(noise_at(a.rs1, c * H1 + m, a.seed + 1, ZSB_STREAM_SGMCMC_RESAMPLE,
                                 a.iter, grow, m), sd_v);
@@ -165,6 +184,7 @@ __global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
       }
     }
     // ---- prior gradient, SGHMC update, write back
+    NoiseCache nc0(a.noise0, a.seed, ZSB_STREAM_SGMCMC_NOISE, a.iter, grow);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int m = lane + 32 * u;
@@ -174,8 +194,7 @@ __global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
           const int64_t idx = (int64_t)m * in1 + k;
           const float ls = a.logstd0[idx % a.logstd0_n];
           const float g = G[u][k] - expf(-2.f * ls) * W[u][k];
-          const float xi = mul(noise_at(a.noise0, c * a.H * in1 + idx, a.seed,
-                                        ZSB_STREAM_SGMCMC_NOISE, a.iter, grow, idx), sd_xi);
+          const float xi = mul(nc0.at(c * a.H * in1 + idx, idx), sd_xi);
           const float vold = v0c[idx];
           float nv, nq;
           if (a.second_order) {
