@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
   const float sd_v = sqrtf(a.lr);
   const float dh = expf(mul(-0.5f, a.alpha)), oma = sub(1.f, a.alpha);
   float ksum0 = 0.f, ksum1 = 0.f;
+  const int ls0_n = (int)a.logstd0_n, ls1_n = (int)a.logstd1_n;     // 32-bit index math only
+  const bool ls0_full = ls0_n == a.H * in1, ls1_full = ls1_n == H1;
 
   for (int64_t c = (int64_t)blockIdx.x * 8 + wib; c < a.chains; c += (int64_t)gridDim.x * 8) {
     float* w0c = a.w0 + c * a.H * in1;
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
     float* w1c = a.w1 + c * H1;
     float* v1c = a.v1 + c * H1;
     const int64_t grow = a.row0 + c;
+    const int64_t c0off = c * a.H * in1;
     // ---- momentum resample (sgmcmc.py:327-336): written back so phase 3 can re-read it
     if (a.resample) {
       NoiseCache rc0(a.rs0, a.seed, ZSB_STREAM_SGMCMC_RESAMPLE, a.iter, grow);
@@ -109,8 +112,8 @@ __global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
         if (m < a.H) {
 #pragma unroll
           for (int k = 0; k < in1; ++k) {
-            const int64_t idx = (int64_t)m * in1 + k;
-            v0c[idx] = mul(rc0.at(c * a.H * in1 + idx, idx), sd_v);
+            const int idx = m * in1 + k;
+            v0c[idx] = mul(rc0.at(c0off + idx, idx), sd_v);
           }
           v1c[m] = mul(noise_at(a.rs1, c * H1 + m, a.seed + 1, ZSB_STREAM_SGMCMC_RESAMPLE,
                                 a.iter, grow, m), sd_v);
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
       const bool mv = m < a.H;
 #pragma unroll
       for (int k = 0; k < in1; ++k) {
-        const int64_t idx = (int64_t)m * in1 + k;
+        const int idx = m * in1 + k;
         float w = mv ? w0c[idx] : 0.f;
         if (a.second_order && mv) w = add(w, mul(0.5f, v0c[idx]));   // q1 = q + v/2
         W[u][k] = w; G[u][k] = 0.f;
@@ -191,10 +194,10 @@ __global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
       if (m < a.H) {
 #pragma unroll
         for (int k = 0; k < in1; ++k) {
-          const int64_t idx = (int64_t)m * in1 + k;
-          const float ls = a.logstd0[idx % a.logstd0_n];
+          const int idx = m * in1 + k;
+          const float ls = a.logstd0[ls0_full ? (int)idx : ((int)idx % ls0_n)];
           const float g = G[u][k] - expf(-2.f * ls) * W[u][k];
-          const float xi = mul(nc0.at(c * a.H * in1 + idx, idx), sd_xi);
+          const float xi = mul(nc0.at(c0off + idx, idx), sd_xi);
           const float vold = v0c[idx];
           float nv, nq;
           if (a.second_order) {
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
           w0c[idx] = nq; v0c[idx] = nv;
           ksum0 += nv * nv;
         }
-        const float ls = a.logstd1[m % a.logstd1_n];
+        const float ls = a.logstd1[ls1_full ? m : (m % ls1_n)];
         const float g = g1r[u] - expf(-2.f * ls) * w1r[u];
         const float xi = mul(noise_at(a.noise1, c * H1 + m, a.seed + 1, ZSB_STREAM_SGMCMC_NOISE,
                                       a.iter, grow, m), sd_xi);
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
       }
     }
     if (lane == 0) {
-      const float ls = a.logstd1[a.H % a.logstd1_n];
+      const float ls = a.logstd1[ls1_full ? a.H : (a.H % ls1_n)];
       const float g = g1b - expf(-2.f * ls) * w1b;
       const float xi = mul(noise_at(a.noise1, c * H1 + a.H, a.seed + 1, ZSB_STREAM_SGMCMC_NOISE,
                                     a.iter, grow, a.H), sd_xi);
