@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""Config 3 (BASELINE.json): VAE 784-(500,500)-40, IWAE K=64 particles, batch
+4096, SGVB reparameterised gradient (examples/variational_autoencoders/
+iwae.py:23-78).  Unit: particle-ELBOs/s = K*N per step, forward + backward.
+
+Generic path of this repo: BayesianNet / StochasticTensor wiring, the Normal
+and Bernoulli log-prob kernels (+ analytic backward), the reparameterised
+sampler and the log_mean_exp kernel are libzsb200; the dense layers are
+torch.nn.functional.linear (cuBLAS = library code).  A fused decoder GEMM with
+a Bernoulli epilogue is round-2 work.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import zhusuan_b200 as zs  # noqa: E402
+
+
+def glorot(rng, n_in, n_out, dev):
+    lim = np.sqrt(6.0 / (n_in + n_out))          # tf.layers.dense default init
+    return torch.tensor(rng.uniform(-lim, lim, (n_out, n_in)), dtype=torch.float32,
+                        device=dev).requires_grad_(True)
+
+
+def build(dev, seed=5, x_dim=784, z_dim=40, h=500):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    W = {}
+    for name, (i, o) in dict(e1=(x_dim, h), e2=(h, h), em=(h, z_dim), es=(h, z_dim),
+                             d1=(z_dim, h), d2=(h, h), d3=(h, x_dim)).items():
+        W[name] = glorot(rng, i, o, dev)
+        W[name + "_b"] = torch.zeros(o, device=dev, requires_grad=True)
+    return W
+
+
+def step_fn(W, x, K, dev):
+    n, x_dim = x.shape
+    z_dim = W["em"].shape[0]
+
+    @zs.meta_bayesian_net(scope="gen", reuse_variables=True)
+    def build_gen(n, n_particles):                                   # iwae.py:23-32
+        bn = zs.BayesianNet()
+        z = bn.normal("z", torch.zeros(n, z_dim, device=dev), std=1., group_ndims=1,
+                      n_samples=n_particles)
+        hh = F.relu(F.linear(z.tensor, W["d1"], W["d1_b"]))
+        hh = F.relu(F.linear(hh, W["d2"], W["d2_b"]))
+        bn.bernoulli("x", F.linear(hh, W["d3"], W["d3_b"]), group_ndims=1)
+        return bn
+
+    def build_q_net(x, n_particles):                                 # iwae.py:35-44
+        bn = zs.BayesianNet()
+        hh = F.relu(F.linear(x.float(), W["e1"], W["e1_b"]))
+        hh = F.relu(F.linear(hh, W["e2"], W["e2_b"]))
+        bn.normal("z", F.linear(hh, W["em"], W["em_b"]), logstd=F.linear(hh, W["es"], W["es_b"]),
+                  group_ndims=1, n_samples=n_particles)
+        return bn
+
+    def step():
+        model = build_gen(n, K)
+        variational = build_q_net(x, K)
+        lb = zs.variational.iw_objective(model, {'x': x}, variational=variational, axis=0)
+        cost = torch.mean(lb.sgvb())                                 # iwae.py:72-75
+        grads = torch.autograd.grad(cost, list(W.values()))
+        return cost, grads
+    return step
+
+
+def main():
+    dev = torch.device("cuda")
+    K, N = 64, 4096
+    rng = np.random.Generator(np.random.PCG64(4))
+    x = torch.tensor(rng.random((N, 784)) < 0.13, dtype=torch.int32, device=dev)
+    out = {}
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        W = build(dev)
+        step = step_fn(W, x, K, dev)
+        for _ in range(3):
+            cost, g = step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        steps = 10
+        e0.record()
+        for _ in range(steps):
+            cost, g = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out["tf32_matmul" if tf32 else "fp32_matmul"] = {
+            "ms_per_step": ms, "particle_elbos_per_s": K * N / (ms * 1e-3),
+            "tflops_dense_layers": 3.97e6 * K * N / (ms * 1e-3) / 1e12,
+            "bound_value": float(-cost)}
+    # CPU baseline: the same graph in torch-CPU (restatement of the TF graph), small batch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Nc = 128
+    Wc = {k: v.detach().cpu().requires_grad_(True) for k, v in build(dev).items()}
+    xc = x[:Nc].cpu().float()
+    eps = torch.randn(K, Nc, 40)
+
+    def cpu_step():
+        h = F.relu(F.linear(xc, Wc["e1"], Wc["e1_b"])); h = F.relu(F.linear(h, Wc["e2"], Wc["e2_b"]))
+        zm, zl = F.linear(h, Wc["em"], Wc["em_b"]), F.linear(h, Wc["es"], Wc["es_b"])
+        z = zm + torch.exp(zl) * eps
+        c = -0.5 * np.log(2 * np.pi)
+        log_q = (c - zl - 0.5 * torch.exp(-2 * zl) * (z - zm) ** 2).sum(-1)
+        log_pz = (c - 0.5 * z ** 2).sum(-1)
+        hh = F.relu(F.linear(z, Wc["d1"], Wc["d1_b"])); hh = F.relu(F.linear(hh, Wc["d2"], Wc["d2_b"]))
+        logits = F.linear(hh, Wc["d3"], Wc["d3_b"])
+        log_px = -F.binary_cross_entropy_with_logits(logits, xc.expand(K, -1, -1), reduction="none").sum(-1)
+        lw = log_pz + log_px - log_q
+        cost = -(torch.logsumexp(lw, 0) - np.log(K)).mean()
+        return torch.autograd.grad(cost, list(Wc.values()))
+    cpu_step()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        cpu_step()
+    dt = (time.perf_counter() - t0) / 3
+    out["cpu_port"] = {"particle_elbos_per_s": K * Nc / dt, "cores": torch.get_num_threads(),
+                       "sample": "batch %d of 4096, K=64, torch-CPU restatement of iwae.py" % Nc}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
