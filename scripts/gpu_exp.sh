@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "== iwae bench"
-timeout 600 python scripts/bench_iwae.py 2>&1 | tail -3 | tee gpurun_out/bench_iwae.json | cut -c1-900
+echo "== model tests"
+timeout 600 python -m pytest tests/test_gpu_models.py -q --no-header -p no:cacheprovider 2>&1 | tail -25
