@@ -1,4 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo "== model tests"
-timeout 600 python -m pytest tests/test_gpu_models.py -q --no-header -p no:cacheprovider 2>&1 | tail -25
+timeout 600 python scripts/bench_kernels.py 2>&1 | tail -30 | tee gpurun_out/bench_kernels.jsonl
