@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
+#include <initializer_list>
 
 #define ZSB_OK 0
 #define ZSB_ERR_INVALID (-1)
@@ -152,6 +153,44 @@ __device__ __forceinline__ float philox_uniform_row(uint64_t seed, uint32_t stre
                                                     uint32_t row) {
   const Philox4 r = philox4x32_10(0u, row, iter, stream, (uint32_t)seed, (uint32_t)(seed >> 32));
   return u32_to_uniform(r.x);
+}
+
+// Vectorised elementwise launcher over a [rows, row_len] matrix with row_len % 4 == 0: one thread
+// handles one float4 = one Philox block; f(i4, row, c4) with i4 the float4 index, c4 the float4
+// column inside the row.  32-bit index math (n4 < 2^31).
+template <class F>
+__global__ void __launch_bounds__(256) ew4_kernel(uint32_t n4, uint32_t q4, F f) {
+  for (uint32_t i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x) {
+    const uint32_t row = i4 / q4;
+    f(i4, row, i4 - row * q4);
+  }
+}
+// same, additionally block-summing the returned value into part[blockIdx.x]
+template <class F>
+__global__ void __launch_bounds__(256) ew4_sum_kernel(uint32_t n4, uint32_t q4,
+                                                      float* __restrict__ part, F f) {
+  __shared__ float red4[32];
+  float s = 0.f;
+  for (uint32_t i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x) {
+    const uint32_t row = i4 / q4;
+    s += f(i4, row, i4 - row * q4);
+  }
+  s = block_sum(s, red4);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__device__ __forceinline__ float4 ld4(const float* p, uint32_t i4) {
+  return reinterpret_cast<const float4*>(p)[i4];
+}
+__device__ __forceinline__ void st4(float* p, uint32_t i4, float4 v) {
+  reinterpret_cast<float4*>(p)[i4] = v;
+}
+// vec4 path is legal when the row length is a multiple of 4, all pointers are 16-byte aligned and
+// the element count fits 32-bit float4 indexing.
+static inline bool zsb_vec4_ok(int64_t chains, int64_t row_len, std::initializer_list<const void*> ptrs) {
+  if (row_len % 4 != 0 || chains * row_len / 4 >= (1LL << 31)) return false;
+  for (const void* q : ptrs)
+    if (q && (reinterpret_cast<uintptr_t>(q) & 15)) return false;
+  return true;
 }
 
 // RNG stream ids (word 3 of the Philox counter)

@@ -15,41 +15,77 @@ namespace {
 
 constexpr float kHalfLog2Pi = 0.9189385332046727f;
 
-// rows of `group` consecutive elements; LANES threads cooperate on one row.
-template <int LANES, class F>
+// Broadcast operands of a [n_out, group] problem.  Element (row, j) of operand o lives at
+// (row*group + j) % n[o]; the modulo is taken ONCE per row (64-bit) and the inner loop only adds
+// (suffix-broadcast operands never wrap inside a row unless they are smaller than the row).
+struct Ops3 {
+  const float* p[3];
+  int64_t n[3];
+};
+__device__ __forceinline__ float op_at(const float* __restrict__ p, int64_t n, int64_t base,
+                                       int64_t j) {
+  if (n == 1) return p[0];
+  int64_t idx = base + j;
+  if (idx >= n) idx %= n;
+  return p[idx];
+}
+
+// rows of `group` consecutive elements; LANES threads cooperate on one row, 4 elements in flight
+// per lane.  F: float f(float v0, float v1, float v2, int64_t i, int64_t row) -> contribution of element i.
+template <int LANES, int NOPS, class F>
 __global__ void __launch_bounds__(256) row_reduce_kernel(float* __restrict__ out, int64_t n_out,
-                                                         int64_t group, F f) {
+                                                         int64_t group, Ops3 ops, F f) {
   const int rows_per_block = 256 / LANES;
   const int lane = threadIdx.x % LANES;
   const int rib = threadIdx.x / LANES;
   for (int64_t row = (int64_t)blockIdx.x * rows_per_block + rib; row < n_out;
        row += (int64_t)gridDim.x * rows_per_block) {
-    const int64_t base = row * group;
+    const int64_t i0 = row * group;
+    int64_t base[3];
+#pragma unroll
+    for (int o = 0; o < NOPS; ++o) base[o] = (ops.n[o] == 1) ? 0 : (i0 % ops.n[o]);
     float acc = 0.f;
-    for (int64_t j = lane; j < group; j += LANES) acc += f(base + j);
+    int64_t j = lane;
+    for (; j + 3 * LANES < group; j += 4 * LANES) {          // 4 independent loads per operand
+      float v[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int o = 0; o < NOPS; ++o) v[u][o] = op_at(ops.p[o], ops.n[o], base[o], j + u * LANES);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc += f(v[u][0], v[u][1], v[u][2], i0 + j + u * LANES, row);
+    }
+    for (; j < group; j += LANES) {
+      float v[3];
+#pragma unroll
+      for (int o = 0; o < NOPS; ++o) v[o] = op_at(ops.p[o], ops.n[o], base[o], j);
+      acc += f(v[0], v[1], v[2], i0 + j, row);
+    }
     acc = sub_warp_sum<LANES>(acc);
-    if (lane == 0) out[row] = acc;
+    if (lane == 0 && out) out[row] = acc;
   }
 }
 
-template <class F>
-int launch_row_reduce(float* out, int64_t n_out, int64_t group, F f, cudaStream_t st,
+template <int NOPS, class F>
+int launch_row_reduce(float* out, int64_t n_out, int64_t group, Ops3 ops, F f, cudaStream_t st,
                       const char* what) {
   if (n_out == 0) return ZSB_OK;
   int lanes = 1;
-  while (lanes < 32 && lanes < group) lanes <<= 1;
+  while (lanes < 32 && lanes * 4 <= group) lanes <<= 1;      // >= 4 elements per lane when possible
   const int rows_per_block = 256 / lanes;
   int64_t blocks = zsb_ceil_div(n_out, rows_per_block);
   const int64_t cap = (int64_t)ZSB_NUM_SMS * 16;
   if (blocks > cap) blocks = cap;
+#define ZSB_RR(LN) row_reduce_kernel<LN, NOPS><<<(unsigned)blocks, 256, 0, st>>>(out, n_out, group, ops, f)
   switch (lanes) {
-    case 1: row_reduce_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(out, n_out, group, f); break;
-    case 2: row_reduce_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(out, n_out, group, f); break;
-    case 4: row_reduce_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(out, n_out, group, f); break;
-    case 8: row_reduce_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(out, n_out, group, f); break;
-    case 16: row_reduce_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(out, n_out, group, f); break;
-    default: row_reduce_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(out, n_out, group, f); break;
+    case 1: ZSB_RR(1); break;
+    case 2: ZSB_RR(2); break;
+    case 4: ZSB_RR(4); break;
+    case 8: ZSB_RR(8); break;
+    case 16: ZSB_RR(16); break;
+    default: ZSB_RR(32); break;
   }
+#undef ZSB_RR
   return zsb_check_launch(what);
 }
 
@@ -271,12 +307,12 @@ int zsb_logprob_normal_f32(const float* given, int64_t given_n, const float* mea
                            int64_t group, void* stream) {
   ZSB_REQUIRE(given_n > 0 && mean_n > 0 && logstd_n > 0 && group > 0 && n_out >= 0,
               "zsb_logprob_normal_f32: bad sizes");
-  auto f = [=] __device__(int64_t i) -> float {
-    const float x = given[i % given_n], mu = mean[i % mean_n], ls = logstd[i % logstd_n];
+  Ops3 ops{{given, mean, logstd}, {given_n, mean_n, logstd_n}};
+  auto f = [=] __device__(float x, float mu, float ls, int64_t, int64_t) -> float {
     const float d = x - mu;
     return -kHalfLog2Pi - ls - 0.5f * expf(-2.f * ls) * d * d;
   };
-  return launch_row_reduce(out, n_out, group, f, (cudaStream_t)stream, "logprob_normal");
+  return launch_row_reduce<3>(out, n_out, group, ops, f, (cudaStream_t)stream, "logprob_normal");
 }
 
 // Elementwise analytic backward; each output (nullable) has n_out*group elements.
@@ -286,15 +322,17 @@ int zsb_logprob_normal_bwd_f32(const float* given, int64_t given_n, const float*
                                float* dmean, float* dlogstd, void* stream) {
   ZSB_REQUIRE(given_n > 0 && mean_n > 0 && logstd_n > 0 && group > 0 && n_out >= 0,
               "zsb_logprob_normal_bwd_f32: bad sizes");
-  auto f = [=] __device__(int64_t i) {
-    const float x = given[i % given_n], mu = mean[i % mean_n], ls = logstd[i % logstd_n];
-    const float g = gout[i / group];
+  Ops3 ops{{given, mean, logstd}, {given_n, mean_n, logstd_n}};
+  auto f = [=] __device__(float x, float mu, float ls, int64_t i, int64_t row) -> float {
+    const float g = gout[row];
     const float prec = expf(-2.f * ls), d = x - mu;
     if (dgiven) dgiven[i] = -g * prec * d;
     if (dmean) dmean[i] = g * prec * d;
     if (dlogstd) dlogstd[i] = g * (prec * d * d - 1.f);
+    return 0.f;
   };
-  return launch_elementwise(n_out * group, f, (cudaStream_t)stream, "logprob_normal_bwd");
+  return launch_row_reduce<3>(nullptr, n_out, group, ops, f, (cudaStream_t)stream,
+                              "logprob_normal_bwd");
 }
 
 // Bernoulli._log_prob, univariate.py:398-403 (given already cast to float by the host, :399).
@@ -303,20 +341,25 @@ int zsb_logprob_bernoulli_f32(const float* given, int64_t given_n, const float* 
                               void* stream) {
   ZSB_REQUIRE(given_n > 0 && logits_n > 0 && group > 0 && n_out >= 0,
               "zsb_logprob_bernoulli_f32: bad sizes");
-  auto f = [=] __device__(int64_t i) -> float {
-    return bernoulli_lp(given[i % given_n], logits[i % logits_n]);
+  Ops3 ops{{given, logits, nullptr}, {given_n, logits_n, 1}};
+  auto f = [=] __device__(float x, float l, float, int64_t, int64_t) -> float {
+    return bernoulli_lp(x, l);
   };
-  return launch_row_reduce(out, n_out, group, f, (cudaStream_t)stream, "logprob_bernoulli");
+  return launch_row_reduce<2>(out, n_out, group, ops, f, (cudaStream_t)stream,
+                              "logprob_bernoulli");
 }
 int zsb_logprob_bernoulli_bwd_f32(const float* given, int64_t given_n, const float* logits,
                                   int64_t logits_n, const float* gout, int64_t n_out,
                                   int64_t group, float* dlogits, void* stream) {
   ZSB_REQUIRE(given_n > 0 && logits_n > 0 && group > 0 && n_out >= 0 && dlogits,
               "zsb_logprob_bernoulli_bwd_f32: bad sizes");
-  auto f = [=] __device__(int64_t i) {
-    dlogits[i] = gout[i / group] * (given[i % given_n] - sigmoidf_(logits[i % logits_n]));
+  Ops3 ops{{given, logits, gout}, {given_n, logits_n, 1}};
+  auto f = [=] __device__(float x, float l, float, int64_t i, int64_t row) -> float {
+    dlogits[i] = gout[row] * (x - sigmoidf_(l));
+    return 0.f;
   };
-  return launch_elementwise(n_out * group, f, (cudaStream_t)stream, "logprob_bernoulli_bwd");
+  return launch_row_reduce<2>(nullptr, n_out, group, ops, f, (cudaStream_t)stream,
+                              "logprob_bernoulli_bwd");
 }
 
 int zsb_logprob_categorical_f32(const int32_t* given, int64_t given_n, const float* logits,
@@ -429,8 +472,9 @@ int zsb_logprob_mvn_chol_bwd_given_f32(const float* x_in, const float* cov_tril,
 // out[r] = sum_{j<group} in[r*group + j]   (Distribution.log_prob's reduce_sum, base.py:303-304)
 int zsb_group_sum_f32(const float* in, float* out, int64_t n_out, int64_t group, void* stream) {
   ZSB_REQUIRE(group > 0 && n_out >= 0, "zsb_group_sum_f32: bad sizes");
-  auto f = [=] __device__(int64_t i) -> float { return in[i]; };
-  return launch_row_reduce(out, n_out, group, f, (cudaStream_t)stream, "group_sum");
+  Ops3 ops{{in, nullptr, nullptr}, {n_out * group > 0 ? n_out * group : 1, 1, 1}};
+  auto f = [=] __device__(float v, float, float, int64_t, int64_t) -> float { return v; };
+  return launch_row_reduce<1>(out, n_out, group, ops, f, (cudaStream_t)stream, "group_sum");
 }
 
 // K7: Normal._sample (univariate.py:161-172) fused with log q(z) of the drawn sample
@@ -445,7 +489,8 @@ int zsb_reparam_normal_f32(const float* mean, int64_t mean_n, const float* logst
                            int64_t group, void* stream) {
   ZSB_REQUIRE(mean_n > 0 && logstd_n > 0 && group > 0 && n_out >= 0 && z_out,
               "zsb_reparam_normal_f32: bad sizes");
-  auto f = [=] __device__(int64_t i) -> float {
+  Ops3 ops{{mean, logstd, nullptr}, {mean_n, logstd_n, 1}};
+  auto f = [=] __device__(float mu, float ls, float, int64_t i, int64_t) -> float {
     float e;
     if (eps) {
       e = eps[i];
@@ -455,17 +500,14 @@ int zsb_reparam_normal_f32(const float* mean, int64_t mean_n, const float* logst
                      (uint32_t)(i >> 2), z4);
       e = z4[i & 3];
     }
-    const float mu = mean[i % mean_n], ls = logstd[i % logstd_n];
     const float z = e * expf(ls) + mu;
     z_out[i] = z;
     if (eps_out) eps_out[i] = e;
     const float d = z - mu;
     return -kHalfLog2Pi - ls - 0.5f * expf(-2.f * ls) * d * d;
   };
-  if (logq_out)
-    return launch_row_reduce(logq_out, n_out, group, f, (cudaStream_t)stream, "reparam_normal");
-  auto g = [=] __device__(int64_t i) { (void)f(i); };
-  return launch_elementwise(n_out * group, g, (cudaStream_t)stream, "reparam_normal");
+  return launch_row_reduce<2>(logq_out, n_out, group, ops, f, (cudaStream_t)stream,
+                              "reparam_normal");
 }
 
 // Bernoulli._sample, univariate.py:386-396: (u < sigmoid(logits)) as int32; u injected or Philox.

@@ -61,15 +61,27 @@ __global__ void __launch_bounds__(256) kinetic_kernel(const float* __restrict__ 
                                                       const float* __restrict__ mass,
                                                       int64_t mass_n, int64_t chains,
                                                       int64_t row_len, float* __restrict__ k_out,
-                                                      int accumulate) {
+                                                      int accumulate, int vec4) {
   const int rows_per_block = 256 / LANES;
   const int lane = threadIdx.x % LANES;
   for (int64_t row = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / LANES; row < chains;
        row += (int64_t)gridDim.x * rows_per_block) {
     float kin = 0.f;
-    for (int64_t c = lane; c < row_len; c += LANES) {
-      const float pv = p[row * row_len + c];
-      kin += fdiv(mul(pv, pv), mass[c % mass_n]);
+    if (vec4) {            // row_len % 4 == 0, mass_n == row_len, 16-byte aligned
+      const float4* pr = reinterpret_cast<const float4*>(p + row * row_len);
+      const float4* mr = reinterpret_cast<const float4*>(mass);
+      for (int64_t c4 = lane; c4 < row_len / 4; c4 += LANES) {
+        const float4 pv = pr[c4], mv = mr[c4];
+        kin += fdiv(mul(pv.x, pv.x), mv.x);
+        kin += fdiv(mul(pv.y, pv.y), mv.y);
+        kin += fdiv(mul(pv.z, pv.z), mv.z);
+        kin += fdiv(mul(pv.w, pv.w), mv.w);
+      }
+    } else {
+      for (int64_t c = lane; c < row_len; c += LANES) {
+        const float pv = p[row * row_len + c];
+        kin += fdiv(mul(pv, pv), mass[c % mass_n]);
+      }
     }
     kin = sub_warp_sum<LANES>(kin);
     if (lane == 0) {
@@ -91,6 +103,42 @@ __global__ void __launch_bounds__(256) leapfrog_q_kernel(float* __restrict__ q,
        i += (int64_t)gridDim.x * blockDim.x)
     q[i] = add(q[i], mul(s1, fdiv(p[i], mass[(i % row_len) % mass_n])));
 }
+// float4 variants (row_len % 4 == 0, mass_n in {1, row_len})
+__global__ void __launch_bounds__(256) leapfrog_q4_kernel(float* __restrict__ q,
+                                                          const float* __restrict__ p,
+                                                          const float* __restrict__ mass,
+                                                          int mass_scalar, uint32_t q4,
+                                                          const float* __restrict__ eps_dev,
+                                                          float scale, uint32_t n4) {
+  const float s1 = mul(*eps_dev, scale);
+  for (uint32_t i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x) {
+    const float4 qv = ld4(q, i4), pv = ld4(p, i4);
+    float4 mv;
+    if (mass_scalar) { const float m = mass[0]; mv = make_float4(m, m, m, m); }
+    else mv = ld4(mass, i4 % q4);
+    st4(q, i4, make_float4(add(qv.x, mul(s1, fdiv(pv.x, mv.x))), add(qv.y, mul(s1, fdiv(pv.y, mv.y))),
+                           add(qv.z, mul(s1, fdiv(pv.z, mv.z))), add(qv.w, mul(s1, fdiv(pv.w, mv.w)))));
+  }
+}
+__global__ void __launch_bounds__(256) leapfrog_p4_kernel(float* __restrict__ p,
+                                                          const float* __restrict__ g,
+                                                          const float* __restrict__ eps_dev,
+                                                          float scale, uint32_t n4) {
+  const float s2 = mul(*eps_dev, scale);
+  for (uint32_t i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x) {
+    const float4 pv = ld4(p, i4), gv = ld4(g, i4);
+    st4(p, i4, make_float4(add(pv.x, mul(s2, gv.x)), add(pv.y, mul(s2, gv.y)),
+                           add(pv.z, mul(s2, gv.z)), add(pv.w, mul(s2, gv.w))));
+  }
+}
+__global__ void __launch_bounds__(256) select4_kernel(float* __restrict__ q,
+                                                      const float* __restrict__ qn,
+                                                      const int32_t* __restrict__ accept,
+                                                      uint32_t q4, uint32_t n4) {
+  for (uint32_t i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x)
+    if (accept[i4 / q4]) st4(q, i4, ld4(qn, i4));
+}
+
 // momentum half (hmc.py:42): p += s2 * grad
 __global__ void __launch_bounds__(256) leapfrog_p_kernel(float* __restrict__ p,
                                                          const float* __restrict__ g,
@@ -228,7 +276,17 @@ __global__ void __launch_bounds__(256) mass_stats_kernel(const float* __restrict
   if (d >= D) return;
   const float m = mean[d];
   float s1 = 0.f, s2 = 0.f;
-  for (int64_t c = blockIdx.x; c < chains; c += gridDim.x) {
+  int64_t c = blockIdx.x;
+  const int64_t st = gridDim.x;
+  for (; c + 3 * st < chains; c += 4 * st) {            // 4 independent loads in flight
+    const float x0 = q[c * D + d] - m, x1 = q[(c + st) * D + d] - m;
+    const float x2 = q[(c + 2 * st) * D + d] - m, x3 = q[(c + 3 * st) * D + d] - m;
+    s1 += x0; s2 += x0 * x0;
+    s1 += x1; s2 += x1 * x1;
+    s1 += x2; s2 += x2 * x2;
+    s1 += x3; s2 += x3 * x3;
+  }
+  for (; c < chains; c += st) {
     const float x = q[c * D + d] - m;
     s1 += x;
     s2 += x * x;
@@ -326,6 +384,11 @@ __global__ void __launch_bounds__(256) diag_normal_traj_kernel(
     }
     // trajectory (hmc.py:347-372): i = 0..L ; search_mode: the 1-step probe of hmc.py:316-321
     const int L = search_mode ? 1 : n_leapfrogs;
+    bool unit = true;                      // p / 1.0f == p exactly: skip the IEEE divide
+#pragma unroll
+    for (int j = 0; j < E; ++j)
+      if ((int64_t)j * 32 + lane < D) unit = unit && (ms[j] == 1.0f);
+    unit = __all_sync(0xffffffffu, unit);
     for (int i = 0; i <= L; ++i) {
       const float s1 = (i > 0) ? eps : 0.f;
       const float s2 = (i > 0 && i < L) ? eps : fdiv(eps, 2.f);
@@ -333,7 +396,7 @@ __global__ void __launch_bounds__(256) diag_normal_traj_kernel(
       for (int j = 0; j < E; ++j) {
         const int64_t c = (int64_t)j * 32 + lane;
         if (c < D) {
-          qc[j] = add(qc[j], mul(s1, fdiv(pc[j], ms[j])));
+          qc[j] = add(qc[j], mul(s1, unit ? pc[j] : fdiv(pc[j], ms[j])));
           const float g = -mul(prec[j], sub(qc[j], mu[j]));     // d/dx Normal log_prob
           pc[j] = add(pc[j], mul(s2, g));
         }
@@ -434,8 +497,9 @@ int zsb_hmc_kinetic_f32(const float* p, const float* mass, int64_t mass_n, int64
   cudaStream_t st = (cudaStream_t)stream;
   const int lanes = pick_lanes(row_len);
   const unsigned g = rows_grid(chains, lanes);
+  const int vec4 = (mass_n == row_len && zsb_vec4_ok(chains, row_len, {p, mass})) ? 1 : 0;
 #define ZSB_L(LN) kinetic_kernel<LN><<<g, 256, 0, st>>>(p, mass, mass_n, chains, row_len, k_out, \
-                                                       accumulate)
+                                                       accumulate, vec4)
   switch (lanes) {
     case 1: ZSB_L(1); break; case 2: ZSB_L(2); break; case 4: ZSB_L(4); break;
     case 8: ZSB_L(8); break; case 16: ZSB_L(16); break; default: ZSB_L(32); break;
@@ -449,6 +513,12 @@ int zsb_hmc_leapfrog_q_f32(float* q, const float* p, const float* mass, int64_t 
                            void* stream) {
   ZSB_REQUIRE(n >= 0 && row_len > 0 && mass_n > 0 && eps_dev, "zsb_hmc_leapfrog_q_f32: bad args");
   if (n == 0) return ZSB_OK;
+  if ((mass_n == 1 || mass_n == row_len) && n % row_len == 0 &&
+      zsb_vec4_ok(n / row_len, row_len, {q, p, mass_n == 1 ? nullptr : mass})) {
+    leapfrog_q4_kernel<<<flat_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(
+        q, p, mass, mass_n == 1, (uint32_t)(row_len / 4), eps_dev, scale, (uint32_t)(n / 4));
+    return zsb_check_launch("hmc_leapfrog_q4");
+  }
   leapfrog_q_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(q, p, mass, mass_n, row_len,
                                                                     eps_dev, scale, n);
   return zsb_check_launch("hmc_leapfrog_q");
@@ -457,6 +527,11 @@ int zsb_hmc_leapfrog_p_f32(float* p, const float* g, const float* eps_dev, float
                            void* stream) {
   ZSB_REQUIRE(n >= 0 && eps_dev, "zsb_hmc_leapfrog_p_f32: bad args");
   if (n == 0) return ZSB_OK;
+  if (zsb_vec4_ok(1, n, {p, g})) {
+    leapfrog_p4_kernel<<<flat_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(p, g, eps_dev, scale,
+                                                                            (uint32_t)(n / 4));
+    return zsb_check_launch("hmc_leapfrog_p4");
+  }
   leapfrog_p_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, eps_dev, scale, n);
   return zsb_check_launch("hmc_leapfrog_p");
 }
@@ -478,6 +553,11 @@ int zsb_hmc_select_f32(float* q, const float* q_new, const int32_t* accept, int6
   ZSB_REQUIRE(chains >= 0 && row_len > 0, "zsb_hmc_select_f32: bad sizes");
   const int64_t n = chains * row_len;
   if (n == 0) return ZSB_OK;
+  if (zsb_vec4_ok(chains, row_len, {q, q_new})) {
+    select4_kernel<<<flat_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(
+        q, q_new, accept, (uint32_t)(row_len / 4), (uint32_t)(n / 4));
+    return zsb_check_launch("hmc_select4");
+  }
   select_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(q, q_new, accept, row_len, n);
   return zsb_check_launch("hmc_select");
 }
@@ -505,12 +585,12 @@ int zsb_hmc_tune_f32(float* state, const float* stats, int has_tuner, int adapt,
 }
 
 // part: scratch of zsb_hmc_mass_parts()*2*D floats; stats: [2*D] local sums out.
-int zsb_hmc_mass_parts(void) { return 64; }
+int zsb_hmc_mass_parts(void) { return ZSB_NUM_SMS * 4; }
 int zsb_hmc_mass_stats_f32(const float* q, const float* ewmv_mean, int64_t chains, int64_t D,
                            float* part, float* stats, void* stream) {
   ZSB_REQUIRE(chains > 0 && D > 0 && part && stats, "zsb_hmc_mass_stats_f32: bad args");
   cudaStream_t st = (cudaStream_t)stream;
-  int nb = (int)(chains < 64 ? chains : 64);
+  int nb = (int)(chains < ZSB_NUM_SMS * 4 ? chains : ZSB_NUM_SMS * 4);
   dim3 grid(nb, (unsigned)zsb_ceil_div(D, 256));
   mass_stats_kernel<<<grid, 256, 0, st>>>(q, ewmv_mean, chains, D, part);
   int rc = zsb_check_launch("hmc_mass_stats");

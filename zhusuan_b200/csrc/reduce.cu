@@ -11,8 +11,7 @@
 //   inner >= 2: one thread per (outer, inner) column, loads coalesced across inner (the IWAE
 //               case: log_w [K, N], outer = 1, inner = N);
 //   inner == 1: one warp per row, warp-shuffle reduction across K.
-// Both are single-pass-over-HBM per stage (max, then sum of exp): 2 reads of x, L2-resident for the
-// sizes involved (log_w is K*N*4 B = 1 MB at config 3).
+// The column kernel makes ONE pass over x (online max with rescaled running sum).
 #include "common.cuh"
 
 namespace {
@@ -30,10 +29,29 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const float* __restric
     const float* p = x + o * K * inner + i;
     float r;
     if (OP == OP_LME || OP == OP_LSE) {
-      float m = -INFINITY;
-      for (int64_t k = 0; k < K; ++k) m = fmaxf(m, p[k * inner]);
-      float s = 0.f;
-      for (int64_t k = 0; k < K; ++k) s += expf(p[k * inner] - m);
+      // single pass over HBM: online max / rescaled sum (one read of x instead of two)
+      float m = -INFINITY, s = 0.f;
+      int64_t k = 0;
+      for (; k + 3 < K; k += 4) {                       // 4 independent loads in flight
+        const float x0 = p[k * inner], x1 = p[(k + 1) * inner];
+        const float x2 = p[(k + 2) * inner], x3 = p[(k + 3) * inner];
+        const float mm = fmaxf(fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)), m);
+        if (mm == -INFINITY || mm == INFINITY) {
+          // all -inf so far (sum stays 0), or a +inf: (inf - inf) = nan as in the reference
+          s = (mm == INFINITY) ? NAN : 0.f;
+        } else {
+          s = s * expf(m - mm) + expf(x0 - mm) + expf(x1 - mm) + expf(x2 - mm) + expf(x3 - mm);
+        }
+        m = mm;
+      }
+      for (; k < K; ++k) {
+        const float x = p[k * inner];
+        const float mm = fmaxf(x, m);
+        if (mm == -INFINITY || mm == INFINITY) s = (mm == INFINITY) ? NAN : 0.f;
+        else s = s * expf(m - mm) + expf(x - mm);
+        m = mm;
+      }
+      if (m == -INFINITY) s = NAN;                      // exp(x - max) = exp(nan), as the reference
       if (OP == OP_LME) s = s / (float)K;
       r = logf(s) + m;
     } else {

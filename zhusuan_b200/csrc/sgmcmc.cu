@@ -25,6 +25,18 @@ struct Noise {
   }
 };
 
+// float4 flavour: one Philox block per thread-iteration (same numbers as Noise::at)
+struct Noise4 {
+  const float* injected; uint64_t seed; uint32_t iter, stream_id; int64_t row0;
+  __device__ __forceinline__ float4 at(uint32_t i4, uint32_t row, uint32_t c4) const {
+    if (injected) return ld4(injected, i4);
+    float z[4];
+    philox_normal4(seed, stream_id, iter, (uint32_t)(row0 + row), c4, z);
+    return make_float4(z[0], z[1], z[2], z[3]);
+  }
+};
+#define ZSB_V4(expr_x, expr_y, expr_z, expr_w) make_float4(expr_x, expr_y, expr_z, expr_w)
+
 template <class F>
 __global__ void __launch_bounds__(256) ew_kernel(int64_t n, F f) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -74,6 +86,19 @@ int zsb_sgmcmc_sgld_f32(float* q, const float* g, const float* noise, float lr, 
   if (n == 0) return ZSB_OK;
   Noise nz{noise, seed, iter, ZSB_STREAM_SGMCMC_NOISE, row0, row_len};
   const float sd = sqrtf(lr), hl = mul(0.5f, lr);
+  if (zsb_vec4_ok(chains, row_len, {q, g, noise})) {
+    Noise4 n4{noise, seed, iter, ZSB_STREAM_SGMCMC_NOISE, row0};
+    auto f4 = [=] __device__(uint32_t i4, uint32_t row, uint32_t c4) {
+      const float4 qv = ld4(q, i4), gv = ld4(g, i4), z = n4.at(i4, row, c4);
+      st4(q, i4, ZSB_V4(add(add(qv.x, mul(hl, gv.x)), mul(z.x, sd)),
+                        add(add(qv.y, mul(hl, gv.y)), mul(z.y, sd)),
+                        add(add(qv.z, mul(hl, gv.z)), mul(z.z, sd)),
+                        add(add(qv.w, mul(hl, gv.w)), mul(z.w, sd))));
+    };
+    ew4_kernel<<<flat_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((uint32_t)(n / 4),
+                                                                  (uint32_t)(row_len / 4), f4);
+    return zsb_check_launch("sgmcmc_sgld4");
+  }
   auto f = [=] __device__(int64_t i) {
     q[i] = add(add(q[i], mul(hl, g[i])), mul(nz.at(i), sd));
   };
@@ -111,6 +136,16 @@ int zsb_sgmcmc_resample_v_f32(float* v, const float* noise, float lr, int64_t ch
   if (n == 0) return ZSB_OK;
   Noise nz{noise, seed, iter, ZSB_STREAM_SGMCMC_RESAMPLE, row0, row_len};
   const float sd = sqrtf(lr);
+  if (zsb_vec4_ok(chains, row_len, {v, noise})) {
+    Noise4 n4{noise, seed, iter, ZSB_STREAM_SGMCMC_RESAMPLE, row0};
+    auto f4 = [=] __device__(uint32_t i4, uint32_t row, uint32_t c4) {
+      const float4 z = n4.at(i4, row, c4);
+      st4(v, i4, ZSB_V4(mul(z.x, sd), mul(z.y, sd), mul(z.z, sd), mul(z.w, sd)));
+    };
+    ew4_kernel<<<flat_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((uint32_t)(n / 4),
+                                                                  (uint32_t)(row_len / 4), f4);
+    return zsb_check_launch("sgmcmc_resample_v4");
+  }
   auto f = [=] __device__(int64_t i) { v[i] = mul(nz.at(i), sd); };
   ew_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(n, f);
   return zsb_check_launch("sgmcmc_resample_v");
@@ -120,6 +155,16 @@ int zsb_sgmcmc_resample_v_f32(float* v, const float* noise, float lr, int64_t ch
 int zsb_sgmcmc_half_q_f32(float* q, const float* v, int64_t n, void* stream) {
   ZSB_REQUIRE(n >= 0, "zsb_sgmcmc_half_q_f32: bad size");
   if (n == 0) return ZSB_OK;
+  if (zsb_vec4_ok(1, n, {q, v})) {
+    auto f4 = [=] __device__(uint32_t i4, uint32_t, uint32_t) {
+      const float4 qv = ld4(q, i4), vv = ld4(v, i4);
+      st4(q, i4, ZSB_V4(add(qv.x, mul(0.5f, vv.x)), add(qv.y, mul(0.5f, vv.y)),
+                        add(qv.z, mul(0.5f, vv.z)), add(qv.w, mul(0.5f, vv.w))));
+    };
+    ew4_kernel<<<flat_grid(n / 4), 256, 0, (cudaStream_t)stream>>>((uint32_t)(n / 4),
+                                                                  (uint32_t)(n / 4), f4);
+    return zsb_check_launch("sgmcmc_half_q4");
+  }
   auto f = [=] __device__(int64_t i) { q[i] = add(q[i], mul(0.5f, v[i])); };
   ew_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(n, f);
   return zsb_check_launch("sgmcmc_half_q");
@@ -139,6 +184,39 @@ int zsb_sgmcmc_sghmc_f32(float* q, float* v, const float* g, const float* noise,
   Noise nz{noise, seed, iter, ZSB_STREAM_SGMCMC_NOISE, row0, row_len};
   const float sd = sqrtf(mul(mul(2.f, sub(alpha, beta)), lr));
   const float dh = expf(mul(-0.5f, alpha)), oma = sub(1.f, alpha);
+  if (zsb_vec4_ok(chains, row_len, {q, v, g, noise})) {
+    Noise4 n4{noise, seed, iter, ZSB_STREAM_SGMCMC_NOISE, row0};
+    auto upd = [=] __device__(float qe, float ve, float ge, float ze, float& nq) -> float {
+      const float xi = mul(ze, sd);
+      float nv;
+      if (second_order) {
+        nv = mul(dh, add(add(mul(dh, ve), mul(lr, ge)), xi));
+        nq = add(qe, mul(0.5f, nv));
+      } else {
+        nv = add(add(mul(oma, ve), mul(lr, ge)), xi);
+        nq = add(qe, nv);
+      }
+      return nv;
+    };
+    auto f4 = [=] __device__(uint32_t i4, uint32_t row, uint32_t c4) -> float {
+      const float4 qv = ld4(q, i4), vv = ld4(v, i4), gv = ld4(g, i4), z = n4.at(i4, row, c4);
+      float4 nq, nv;
+      nv.x = upd(qv.x, vv.x, gv.x, z.x, nq.x);
+      nv.y = upd(qv.y, vv.y, gv.y, z.y, nq.y);
+      nv.z = upd(qv.z, vv.z, gv.z, z.z, nq.z);
+      nv.w = upd(qv.w, vv.w, gv.w, z.w, nq.w);
+      st4(q, i4, nq);
+      st4(v, i4, nv);
+      return nv.x * nv.x + nv.y * nv.y + nv.z * nv.z + nv.w * nv.w;
+    };
+    const unsigned grid4 = flat_grid(n / 4);
+    ew4_sum_kernel<<<grid4, 256, 0, (cudaStream_t)stream>>>((uint32_t)(n / 4),
+                                                           (uint32_t)(row_len / 4), part, f4);
+    int rc4 = zsb_check_launch("sgmcmc_sghmc4");
+    if (rc4) return rc4;
+    final_mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(part, (int)grid4, (float)n, mean_k);
+    return zsb_check_launch("sgmcmc_sghmc_mean_k");
+  }
   auto f = [=] __device__(int64_t i) -> float {
     const float xi = mul(nz.at(i), sd);
     float nv;
