@@ -63,7 +63,7 @@ def main():
     acc = torch.ones(C, dtype=torch.int32, device=dev)
     ms = timeit(lambda: lib.call("zsb_hmc_select_f32", ptr(q), ptr(p_), ptr(acc), C, D, s))
     report("hmc_select", 8 * n, ms, "all accepted: read q_new write q")
-    part = torch.empty(64 * 2 * D, device=dev); st2 = torch.empty(2 * D, device=dev); mean = torch.zeros(D, device=dev)
+    part = torch.empty(lib.load().zsb_hmc_mass_parts() * 2 * D, device=dev); st2 = torch.empty(2 * D, device=dev); mean = torch.zeros(D, device=dev)
     ms = timeit(lambda: lib.call("zsb_hmc_mass_stats_f32", ptr(q), ptr(mean), C, D, ptr(part), ptr(st2), s))
     report("hmc_mass_stats", 4 * n, ms)
     lo = torch.empty(2, C, D, dtype=torch.float16, device=dev); sc = torch.zeros(4, device=dev); sc[3] = 1.0
