@@ -138,7 +138,7 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
   const float u1 = u32_to_uniform_open(a), u2 = u32_to_uniform(b);
   const float r = sqrtf(-2.0f * logf(u1));
   float s, c;
-  sincosf(6.283185307179586f * u2, &s, &c);
+  sincospif(2.0f * u2, &s, &c);          // exact period reduction: cos(2 pi u2), sin(2 pi u2)
   z0 = r * c; z1 = r * s;
 }
 // Four standard normals for (row, 4-element block `blk`) of stream/iteration; counter layout
