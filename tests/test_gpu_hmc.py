@@ -370,3 +370,74 @@ def test_dense_tc_vs_simt_full_size(zs):
         moved0 = np.abs(res[0][3]).sum(1); moved1 = np.abs(res[k][3]).sum(1)
         frac_diff = np.mean(np.abs(moved0 - moved1) > 1e-2 * np.abs(moved0))
         assert frac_diff < 1e-3
+
+
+@pytest.mark.parametrize("L", [0, 1, 2])
+def test_leapfrog_count_edges_all_paths(zs, L):
+    """n_leapfrogs = 0 / 1 / 2 (hmc.py:352-364: L+1 passes, half kicks first and
+    last; L = 0 is a single half-kick pass) on the fused-diag, generic, SIMT-dense
+    and tensor-core dense paths vs the oracle."""
+    rng = np.random.RandomState(10 + L)
+    # diagonal
+    D, C = 12, 20
+    std = (0.5 + rng.random_sample(D)).astype(np.float32)
+    q0 = rng.standard_normal((C, D)).astype(np.float32)
+    npz = rng.standard_normal((C, D)).astype(np.float32)
+    u = rng.random_sample(C).astype(np.float32)
+    om = OM.DiagGaussian(np.zeros(D, np.float32), std)
+    oq, oi = OH.HMC(step_size=0.1, n_leapfrogs=L).step([q0], om.logp, om.grad, [npz], u)
+
+    @zs.meta_bayesian_net()
+    def gaussian():
+        bn = zs.BayesianNet()
+        bn.normal('x', torch.zeros(D, device="cuda"), std=T(std), group_ndims=1)
+        return bn
+
+    def lj(obs):
+        return zs.distributions.Normal(torch.zeros(D, device="cuda"), std=T(std),
+                                       group_ndims=1).log_prob(obs['x'])
+    for model, kind in ((gaussian(), "diag_normal"), (lj, "generic")):
+        x = T(q0)
+        h = zs.HMC(step_size=0.1, n_leapfrogs=L)
+        op, info = h.sample(model, {}, {"x": x})
+        assert (h._fused["kind"] if h._fused else "generic") == kind
+        op(noise={"p": {"x": T(npz)}, "u": T(u)})
+        np.testing.assert_allclose(N(info.acceptance_rate), oi.acceptance_rate, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(N(x), oq[0], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(N(info.log_prob), oi.log_prob, rtol=1e-5, atol=1e-4)
+    # dense: D = 64 so that all three kernels are legal
+    D, C = 64, 40
+    P, const = OM.make_dense_gaussian_problem(D, seed=6)
+    q0 = rng.standard_normal((C, D)).astype(np.float32)
+    npz = rng.standard_normal((C, D)).astype(np.float32)
+    u = rng.random_sample(C).astype(np.float32)
+    om = OM.DenseGaussian(P.astype(np.float32), None, const)
+    oq, oi = OH.HMC(step_size=0.15, n_leapfrogs=L).step([q0], om.logp, om.grad, [npz], u)
+    for impl in (0, 1, 2):
+        x = T(q0)
+        h = zs.HMC(step_size=0.15, n_leapfrogs=L, dense_impl=impl)
+        op, info = h.sample(zs.fused.GaussianLogJoint(P), {}, {"x": x})
+        op(noise={"p": {"x": T(npz)}, "u": T(u)})
+        np.testing.assert_allclose(N(info.acceptance_rate), oi.acceptance_rate, rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(N(x), oq[0], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(N(info.hamiltonian), oi.hamiltonian, rtol=1e-5, atol=1e-4)
+
+
+def test_single_chain_and_tiny_shapes(zs):
+    """1 chain x 1 dim (generic) and 1 chain x 16 dims (SIMT dense): nothing
+    assumes a multiple of the tile size."""
+    x = torch.zeros(1, 1, device="cuda")
+    h = zs.HMC(step_size=0.3, n_leapfrogs=3, seed=1)
+    op, info = h.sample(lambda o: -0.5 * (o['x'] ** 2).sum(-1), {}, {"x": x})
+    for _ in range(5):
+        op()
+    op.synchronize()
+    assert tuple(info.acceptance_rate.shape) == (1,) and torch.isfinite(x).all()
+    P, _ = OM.make_dense_gaussian_problem(16, seed=1)
+    y = torch.randn(1, 16, device="cuda")
+    h = zs.HMC(step_size=0.1, n_leapfrogs=2, seed=2)
+    op, info = h.sample(zs.fused.GaussianLogJoint(P), {}, {"x": y})
+    assert h._impl == 0
+    op(); op.synchronize()
+    ref = -0.5 * N(y).astype(np.float64) @ P @ N(y).astype(np.float64).T
+    assert torch.isfinite(info.log_prob).all()
