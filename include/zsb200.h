@@ -126,7 +126,7 @@ int zsb_hmc_mass_parts(void);  /* mass_stats scratch = zsb_hmc_mass_parts()*2*D 
 int zsb_hmc_momentum_f32(float* p, const float* noise, const float* mass, int64_t mass_n,
                          int64_t chains, int64_t row_len, uint64_t seed, uint32_t iter,
                          uint32_t stream_id, int64_t row0, float* k_out, int accumulate,
-                         void* stream);
+                         const float* iter_state, void* stream);
 int zsb_hmc_kinetic_f32(const float* p, const float* mass, int64_t mass_n, int64_t chains,
                         int64_t row_len, float* k_out, int accumulate, void* stream);
 /* leapfrog_integrator hmc.py:38-43: q += (eps*scale) * (p/mass);  p += (eps*scale) * grad.
@@ -147,7 +147,13 @@ int zsb_hmc_select_f32(float* q, const float* q_new, const int32_t* accept, int6
 /* stats[0] = sum(acc), stats[1] = local chain count; all-reduce(sum) stats across ranks, then tune */
 int zsb_hmc_acc_sum_f32(const float* acc_part, int n_part, int64_t chains, float* stats,
                         void* stream);
+/* Device-driven iterations (CUDA-graph replay): pass start_search = -1 to zsb_hmc_begin_f32 (the
+ * kernel then advances state[T] itself), iter = 0xFFFFFFFF to the kernels that draw Philox numbers
+ * (they read the iteration from the state block; zsb_hmc_momentum_f32 takes it via iter_state),
+ * t_now = -1 to zsb_hmc_tune_f32, use_ones = -(mass_collect_iters + 1) to
+ * zsb_hmc_mass_update_f32, and zsb_hmc_ewmv_bump_f32 after an adaptive mass update. */
 int zsb_hmc_begin_f32(float* state, int start_search, void* stream);
+int zsb_hmc_ewmv_bump_f32(float* state, void* stream);
 /* one pass of _init_step_size's loop bookkeeping hmc.py:326-338 */
 int zsb_hmc_search_update_f32(float* state, const float* stats, float target, void* stream);
 /* StepsizeTuner.tune hmc.py:89-112 + step_size assign hmc.py:379 */

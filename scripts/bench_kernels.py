@@ -56,7 +56,7 @@ def main():
     report("hmc_leapfrog_q", 12 * n, ms, "read q,p write q")
     ms = timeit(lambda: lib.call("zsb_hmc_leapfrog_p_f32", ptr(p_), ptr(g), eps_ptr, 1.0, n, s))
     report("hmc_leapfrog_p", 12 * n, ms)
-    ms = timeit(lambda: lib.call("zsb_hmc_momentum_f32", ptr(p_), None, ptr(mass), D, C, D, 1, 1, 1, 0, ptr(out), 0, s))
+    ms = timeit(lambda: lib.call("zsb_hmc_momentum_f32", ptr(p_), None, ptr(mass), D, C, D, 1, 1, 1, 0, ptr(out), 0, None, s))
     report("hmc_momentum (Philox)", 4 * n, ms, "write p only")
     ms = timeit(lambda: lib.call("zsb_hmc_kinetic_f32", ptr(p_), ptr(mass), D, C, D, ptr(out), 0, s))
     report("hmc_kinetic", 4 * n, ms)
@@ -124,6 +124,29 @@ def main():
     ms = timeit(lambda: op2(adapt_step_size=True, adapt_mass=True), n=100)
     report("config 1 (64 x 100, L=10, adaptation on)", 12 * 64 * D1, ms,
            "launch bound: %.3e chain-steps/s, %.1f us per iteration" % (64 * 10 / (ms * 1e-3), ms * 1e3))
+    # the same, replayed from a CUDA graph (device-driven iteration scalars)
+    xq3 = torch.zeros(64, D1, device=dev)
+    h3 = zs.HMC(step_size=1e-3, n_leapfrogs=10, adapt_step_size=True, adapt_mass=True,
+                target_acceptance_rate=0.9, seed=3, use_cuda_graph=True)
+    op3, info3 = h3.sample(gaussian(), {}, {"x": xq3})
+    for i in range(12):
+        op3(adapt_step_size=True, adapt_mass=True)
+    ms = timeit(lambda: op3(adapt_step_size=True, adapt_mass=True), n=100)
+    report("config 1 via CUDA graph", 12 * 64 * D1, ms,
+           "%.3e chain-steps/s, %.1f us per iteration" % (64 * 10 / (ms * 1e-3), ms * 1e3))
+    # dense D=64, 4096 chains, L=10: small-problem regime for the dense path
+    import oracle.models as OM
+    P, _ = OM.make_dense_gaussian_problem(64, seed=2)
+    for graph in (False, True):
+        xd = torch.randn(4096, 64, device=dev)
+        hd = zs.HMC(step_size=0.05, n_leapfrogs=10, adapt_step_size=True, seed=3,
+                    use_cuda_graph=graph)
+        opd, _i = hd.sample(zs.fused.GaussianLogJoint(P), {}, {"x": xd})
+        for i in range(5):
+            opd()
+        ms = timeit(lambda: opd(), n=100)
+        report("dense 4096 x 64, L=10, graph=%s" % graph, 0, ms,
+               "%.3e chain-steps/s, %.1f us per iteration" % (4096 * 10 / (ms * 1e-3), ms * 1e3))
 
 
 if __name__ == "__main__":

@@ -230,7 +230,7 @@ def test_kernel_philox_matches_oracle():
     mass = torch.ones(D, device="cuda")
     seed, it, row0 = 0x1234567887654321, 9, 1000
     lib.call("zsb_hmc_momentum_f32", ptr(p), None, ptr(mass), D, C, D, seed,
-             it, 1, row0, None, 0, stream())
+             it, 1, row0, None, 0, None, stream())
     ref = philox.normal_matrix(seed, 1, it, row0, C, D)
     np.testing.assert_allclose(N(p), ref, rtol=1e-5, atol=2e-6)
     # uniforms: lp1 - lp0 = log(t) -> acc = t; accept <=> u < t

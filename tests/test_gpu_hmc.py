@@ -441,3 +441,56 @@ def test_single_chain_and_tiny_shapes(zs):
     op(); op.synchronize()
     ref = -0.5 * N(y).astype(np.float64) @ P @ N(y).astype(np.float64).T
     assert torch.isfinite(info.log_prob).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["diag", "dense0", "dense1", "dense2"])
+def test_cuda_graph_replay_is_bitwise_eager(zs, path):
+    """Device-driven iterations replayed from a CUDA graph (use_cuda_graph=True)
+    give bit-identical chains, step sizes and mass estimates to the eager
+    launches, across the step-size search iterations (t == 1 and
+    t == mass_collect_iters, which always run eagerly), adaptation on -> off,
+    and a mid-run switch of the adaptation flags (second captured graph)."""
+    rng = np.random.RandomState(3)
+    if path == "diag":
+        D, C = 100, 64
+        std = (0.5 + rng.random_sample(D)).astype(np.float32)
+        q0 = rng.standard_normal((C, D)).astype(np.float32)
+
+        def model():
+            @zs.meta_bayesian_net()
+            def gaussian():
+                bn = zs.BayesianNet()
+                bn.normal('x', torch.zeros(D, device="cuda"), std=T(std), group_ndims=1)
+                return bn
+            return gaussian()
+        kw = {}
+    else:
+        D, C = 64, 48
+        P, _ = OM.make_dense_gaussian_problem(D, seed=2)
+        q0 = rng.standard_normal((C, D)).astype(np.float32)
+        model = lambda: zs.fused.GaussianLogJoint(P)
+        kw = {"dense_impl": int(path[-1])}
+    runs = []
+    for graph in (False, True):
+        x = T(q0)
+        h = zs.HMC(step_size=0.05, n_leapfrogs=5, adapt_step_size=True, adapt_mass=True,
+                   mass_collect_iters=4, seed=11, use_cuda_graph=graph, **kw)
+        op, info = h.sample(model(), {}, {"x": x})
+        trace = []
+        for i in range(14):
+            adapt = i < 9
+            op(adapt_step_size=adapt, adapt_mass=adapt)
+            trace.append((N(x).copy(), float(h._state[1].item()), N(h._mass[0]).copy(),
+                          N(info.acceptance_rate).copy()))
+        op.synchronize()
+        assert len(h._graphs) == (2 if graph else 0)
+        runs.append((trace, h._t, h._ewmv_t, N(h._state).copy()))
+    (ta, t_a, e_a, st_a), (tb, t_b, e_b, st_b) = runs
+    assert (t_a, e_a) == (t_b, e_b)
+    for i, (a, b) in enumerate(zip(ta, tb)):
+        assert a[1] == b[1], "step size differs at iteration %d" % i
+        np.testing.assert_array_equal(a[0], b[0], err_msg="q, iteration %d" % i)
+        np.testing.assert_array_equal(a[2], b[2], err_msg="mass, iteration %d" % i)
+        np.testing.assert_array_equal(a[3], b[3])
+    np.testing.assert_array_equal(st_a, st_b)

@@ -13,6 +13,14 @@
 
 namespace {
 
+// Device-driven iterations (CUDA-graph replay): when the host passes iter == ZSB_ITER_FROM_STATE the
+// Philox iteration counter is read from the sampler state block, which zsb_hmc_begin_f32 advances
+// on the device, so a captured graph draws fresh numbers on every replay.
+#define ZSB_ITER_FROM_STATE 0xFFFFFFFFu
+__device__ __forceinline__ uint32_t resolve_iter(uint32_t iter, const float* state) {
+  return (iter == ZSB_ITER_FROM_STATE && state) ? (uint32_t)state[ZSB_ST_T] : iter;
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // a1  random_momentum (hmc.py:21-23): p = N(0,1) * sqrt(mass);   optional kinetic 0.5*sum p^2/m.
@@ -23,9 +31,11 @@ __global__ void __launch_bounds__(256) momentum_kernel(float* __restrict__ p,
                                                        const float* __restrict__ mass,
                                                        int64_t mass_n, int64_t chains,
                                                        int64_t row_len, uint64_t seed,
-                                                       uint32_t iter, uint32_t stream_id,
+                                                       uint32_t iter_in, uint32_t stream_id,
                                                        int64_t row0, float* __restrict__ k_out,
-                                                       int accumulate) {
+                                                       int accumulate,
+                                                       const float* __restrict__ state) {
+  const uint32_t iter = resolve_iter(iter_in, state);
   const int rows_per_block = 256 / LANES;
   const int lane = threadIdx.x % LANES;
   const int64_t nblk = (row_len + 3) / 4;
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(256) mh_kernel(const float* __restrict__ lp0,
                                                  const float* __restrict__ k0,
                                                  const float* __restrict__ k1,
                                                  const float* __restrict__ u, uint64_t seed,
-                                                 uint32_t iter, int64_t row0, int64_t chains,
+                                                 uint32_t iter_in, int64_t row0, int64_t chains,
                                                  float* __restrict__ h0o, float* __restrict__ h1o,
                                                  float* __restrict__ acco,
                                                  int32_t* __restrict__ accepto,
@@ -177,6 +187,7 @@ __global__ void __launch_bounds__(256) mh_kernel(const float* __restrict__ lp0,
                                                  float* __restrict__ acc_part,
                                                  float* __restrict__ state) {
   __shared__ float red[32];
+  const uint32_t iter = resolve_iter(iter_in, state);
   float local = 0.f;
   bool any_bad = false;
   for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < chains;
@@ -225,7 +236,7 @@ __global__ void tune_kernel(float* __restrict__ st, const float* __restrict__ st
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float abar = fdiv(stats[0], stats[1]);              // hmc.py:377 reduce_mean (global)
   st[ZSB_ST_ACC_MEAN] = abar;
-  st[ZSB_ST_T] = t_now;
+  if (t_now >= 0.f) st[ZSB_ST_T] = t_now;                   // < 0: the device already advanced t
   if (!has_tuner) return;                                   // hmc.py:504-505
   if (adapt) {
     const float step = add(mul(sub(1.f, fresh), st[ZSB_ST_TUNER_STEP]), 1.f);      // :92
@@ -249,6 +260,10 @@ __global__ void tune_kernel(float* __restrict__ st, const float* __restrict__ st
 // eps_used <- step_size (no search this iteration, hmc.py:472 else-branch / 464)
 __global__ void begin_kernel(float* __restrict__ st, int start_search) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (start_search < 0) {                  // device-driven iteration: t += 1 here (hmc.py:418)
+    st[ZSB_ST_T] = st[ZSB_ST_T] + 1.0f;
+    start_search = 0;
+  }
   st[ZSB_ST_EPS_USED] = st[ZSB_ST_STEP_SIZE];
   if (start_search) { st[ZSB_ST_SEARCH_LAST] = 1.0f; st[ZSB_ST_SEARCH_COND] = 1.0f; }  // :343
 }
@@ -315,7 +330,15 @@ __global__ void __launch_bounds__(256) mass_update_kernel(float* __restrict__ me
                                                           float decay, float tt, int adapt,
                                                           int use_ones, float* __restrict__ st) {
   const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (d == 0 && adapt && st) st[ZSB_ST_EWMV_T] = tt;
+  if (use_ones < 0) {
+    // device-driven iteration: use_ones = -(mass_collect_iters + 1); the EWMV count was advanced
+    // by zsb_hmc_begin/tune on the device (nobody writes the state block in this kernel)
+    const int mci = -use_ones - 1;
+    use_ones = ((int)st[ZSB_ST_T] < mci) ? 1 : 0;
+    tt = st[ZSB_ST_EWMV_T] + 1.0f;
+  } else if (d == 0 && adapt && st) {
+    st[ZSB_ST_EWMV_T] = tt;
+  }
   if (d >= D) return;
   float v = var[d];
   if (adapt) {
@@ -341,12 +364,13 @@ __global__ void __launch_bounds__(256) diag_normal_traj_kernel(
     const float* __restrict__ mean, int64_t mean_n, const float* __restrict__ logstd,
     int64_t logstd_n, const float* __restrict__ mass, int64_t mass_n,
     const float* __restrict__ state, int n_leapfrogs, int64_t chains, int64_t D, uint64_t seed,
-    uint32_t iter, int64_t row0, int search_mode, float* __restrict__ p0_out,
+    uint32_t iter_in, int64_t row0, int search_mode, float* __restrict__ p0_out,
     float* __restrict__ h0o, float* __restrict__ h1o, float* __restrict__ lp0o,
     float* __restrict__ lpselo, float* __restrict__ acco, int32_t* __restrict__ accepto,
     float* __restrict__ acc_part, float* __restrict__ state_flags) {
   __shared__ float red[32];
   const int lane = threadIdx.x & 31;
+  const uint32_t iter = resolve_iter(iter_in, state);
   const float eps = state[ZSB_ST_EPS_USED];
   float local_acc = 0.f;
   bool any_bad = false;
@@ -473,7 +497,7 @@ int zsb_hmc_acc_parts(void) { return ZSB_NUM_SMS * 16; }  // capacity the caller
 int zsb_hmc_momentum_f32(float* p, const float* noise, const float* mass, int64_t mass_n,
                          int64_t chains, int64_t row_len, uint64_t seed, uint32_t iter,
                          uint32_t stream_id, int64_t row0, float* k_out, int accumulate,
-                         void* stream) {
+                         const float* iter_state, void* stream) {
   ZSB_REQUIRE(chains >= 0 && row_len > 0 && mass_n > 0, "zsb_hmc_momentum_f32: bad sizes");
   if (chains == 0) return ZSB_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -481,7 +505,7 @@ int zsb_hmc_momentum_f32(float* p, const float* noise, const float* mass, int64_
   const unsigned g = rows_grid(chains, lanes);
 #define ZSB_L(LN) momentum_kernel<LN><<<g, 256, 0, st>>>(p, noise, mass, mass_n, chains, row_len, \
                                                         seed, iter, stream_id, row0, k_out,      \
-                                                        accumulate)
+                                                        accumulate, iter_state)
   switch (lanes) {
     case 1: ZSB_L(1); break; case 2: ZSB_L(2); break; case 4: ZSB_L(4); break;
     case 8: ZSB_L(8); break; case 16: ZSB_L(16); break; default: ZSB_L(32); break;
@@ -582,6 +606,17 @@ int zsb_hmc_tune_f32(float* state, const float* stats, int has_tuner, int adapt,
   tune_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, stats, has_tuner, adapt, fresh_start,
                                                   gamma, t0, kappa, delta, t_now);
   return zsb_check_launch("hmc_tune");
+}
+
+namespace {
+__global__ void ewmv_bump_kernel(float* __restrict__ st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) st[ZSB_ST_EWMV_T] = st[ZSB_ST_EWMV_T] + 1.0f;
+}
+}  // namespace
+// device-driven iterations: advance the EWMV update count after an adaptive mass update
+int zsb_hmc_ewmv_bump_f32(float* state, void* stream) {
+  ewmv_bump_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state);
+  return zsb_check_launch("hmc_ewmv_bump");
 }
 
 // part: scratch of zsb_hmc_mass_parts()*2*D floats; stats: [2*D] local sums out.

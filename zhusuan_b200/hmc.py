@@ -77,8 +77,13 @@ class _SampleOp(object):
     def __init__(self, hmc):
         self._hmc = hmc
 
-    def __call__(self, adapt_step_size=None, adapt_mass=None, noise=None):
-        return self._hmc._iterate(adapt_step_size, adapt_mass, noise)
+    def __call__(self, adapt_step_size=None, adapt_mass=None, noise=None,
+                 use_graph=None):
+        """One HMC iteration.  ``use_graph`` (default: the sampler's
+        ``use_cuda_graph``) replays the iteration from a captured CUDA graph
+        on the fused paths -- worthwhile when the iteration is launch-bound."""
+        return self._hmc._iterate(adapt_step_size, adapt_mass, noise,
+                                  use_graph)
 
     run = __call__
 
@@ -94,7 +99,7 @@ class HMC(object):
                  target_acceptance_rate=0.8, gamma=0.05, t0=100, kappa=0.75,
                  adapt_mass=None, mass_collect_iters=10, mass_decay=0.99,
                  seed=None, process_group=None, chain_offset=None,
-                 dense_impl=None):
+                 dense_impl=None, use_cuda_graph=False):
         self._init_step_size_value = float(step_size)
         self.n_leapfrogs = int(n_leapfrogs)
         self.target_acceptance_rate = float(target_acceptance_rate)
@@ -116,6 +121,9 @@ class HMC(object):
         self._group = process_group
         self._chain_offset = chain_offset
         self._dense_impl = dense_impl
+        self._use_graph = bool(use_cuda_graph)
+        self._graphs = {}
+        self._dev_mode = False   # True while capturing / replaying a graph
         self._t = 0              # host mirror of hmc.py:264 (deterministic)
         self._ewmv_t = 0         # host mirror of hmc.py:118
         self._built = False
@@ -277,22 +285,65 @@ class HMC(object):
         return self._seed if self._seed is not None else zrandom.get_seed()
 
     # -------------------------------------------------------------- iteration
-    def _iterate(self, adapt_step_size, adapt_mass, noise):
+    def _iterate(self, adapt_step_size, adapt_mass, noise, use_graph=None):
         if not self._built:
             raise RuntimeError("call HMC.sample() first")
         self._check_flags()
-        s = stream()
         adapt_step = _flag(self.adapt_step_size if adapt_step_size is None
                            else adapt_step_size)
         adapt_m = _flag(self.adapt_mass if adapt_mass is None else adapt_mass)
         self._t += 1                                          # hmc.py:418
         t = self._t
-        it = t & 0xFFFFFFFF
+        init = self._has_step and (t == 1 or t == self.mass_collect_iters)
+        want_graph = self._use_graph if use_graph is None else bool(use_graph)
+        if (want_graph and noise is None and not init and self._fused
+                and self._world == 1 and self._state.is_cuda):
+            return self._iterate_graph(adapt_step, adapt_m)
+        return self._iterate_eager(adapt_step, adapt_m, noise, t, init)
+
+    def _iterate_graph(self, adapt_step, adapt_m):
+        """Replay (or first capture) the iteration as a CUDA graph.  All
+        per-iteration scalars (t / Philox iteration, EWMV count, ones-vs-
+        precision mass gating) are read from the device state block, so one
+        graph per (adapt_step, adapt_mass) pair serves every non-search
+        iteration.  Numerically identical to the eager path."""
+        key = (adapt_step, adapt_m, self._seed_now())
+        g = self._graphs.get(key)
+        if g is None:
+            # keep the device copy of t in step with the host mirror, then
+            # capture one iteration without executing it
+            self._state[ST_T] = float(self._t - 1)
+            self._state[ST_EWT] = float(self._ewmv_t)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            self._dev_mode = True
+            try:
+                with torch.cuda.graph(g):
+                    self._iterate_eager(adapt_step, adapt_m, None, self._t,
+                                        False)
+            finally:
+                self._dev_mode = False
+            self._graphs[key] = g
+        if adapt_m and self._has_mass:
+            self._ewmv_t += 1
+        g.replay()
+        self._queue_flag_check()
+        return None
+
+    def _iterate_eager(self, adapt_step, adapt_m, noise, t, init):
+        s = stream()
+        dev = self._dev_mode
+        it = 0xFFFFFFFF if dev else (t & 0xFFFFFFFF)
         seed = self._seed_now()
         noise_p = noise_u = None
         if noise is not None:
             noise_p = [noise["p"][k].contiguous() for k in self._latent_k]
             noise_u = noise["u"].contiguous().view(-1)
+
+        # ---- begin: step size for this iteration (hmc.py:463-472); in device
+        # mode the kernel also advances t (hmc.py:418)
+        lib.call("zsb_hmc_begin_f32", ptr(self._state),
+                 -1 if dev else int(init), s)
 
         # ---- mass (hmc.py:452-456, 283-305)
         if self._has_mass:
@@ -306,8 +357,11 @@ class HMC(object):
                              self._mass_stats.data_ptr() + 4 * off, s)
                     off += 2 * r
                 self._allreduce(self._mass_stats)
-                self._ewmv_t += 1
+                if not dev:
+                    self._ewmv_t += 1
             use_ones = 1 if t < self.mass_collect_iters else 0  # hmc.py:299-302
+            if dev:
+                use_ones = -(self.mass_collect_iters + 1)
             off = 0
             for k in range(len(self._q)):
                 r = self._row_len[k]
@@ -318,10 +372,8 @@ class HMC(object):
                          float(self._ewmv_t), int(adapt_m), use_ones,
                          ptr(self._state), s)
                 off += 2 * r
-
-        # ---- step size for this iteration (hmc.py:463-472)
-        init = self._has_step and (t == 1 or t == self.mass_collect_iters)
-        lib.call("zsb_hmc_begin_f32", ptr(self._state), int(init), s)
+            if dev and adapt_m:
+                lib.call("zsb_hmc_ewmv_bump_f32", ptr(self._state), s)
 
         kind = self._fused["kind"] if self._fused else "generic"
         if kind == "diag_normal":
@@ -338,8 +390,9 @@ class HMC(object):
         lib.call("zsb_hmc_tune_f32", ptr(self._state), ptr(self._stats),
                  int(self._has_step), int(adapt_step), 1.0 if init else 0.0,
                  self.gamma, self.t0, self.kappa, self.target_acceptance_rate,
-                 float(t), s)
-        self._queue_flag_check()
+                 -1.0 if dev else float(t), s)
+        if not dev:
+            self._queue_flag_check()
         return None
 
     def _search(self, probe, s):
@@ -363,7 +416,7 @@ class HMC(object):
                      ptr(noise_p[k]) if noise_p else None, ptr(self._mass[k]),
                      self._row_len[k], self._chains, self._row_len[k], seed,
                      it, STREAM_MOMENTUM + 16 * k, self._row0, ptr(self._k0),
-                     int(k > 0), s)
+                     int(k > 0), ptr(self._state), s)
 
     def _lf_q(self, q, p, scale, s):
         for k in range(len(q)):
@@ -542,6 +595,8 @@ class HMC(object):
         cur, nxt = q0, self._qa
         p_in = self._p0[0]
         prof = getattr(self, "_profile_events", None)
+        if self._dev_mode:
+            prof = None
         if prof is not None:           # bench.py: device time of the L+1 passes
             e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
             e0.record()
@@ -579,6 +634,8 @@ class HMC(object):
     def load_state_dict(self, d):
         self._t, self._ewmv_t = int(d["t"]), int(d["ewmv_t"])
         self._state.copy_(d["state"])
+        self._state[ST_T] = float(self._t)
+        self._state[ST_EWT] = float(self._ewmv_t)
         if self._has_mass:
             for m, s in zip(self._ew_mean, d["ewmv_mean"]):
                 m.copy_(s)
