@@ -17,6 +17,7 @@ per-GPU chain count is fixed); the only exchange is the per-iteration
 all-reduce of the acceptance / mass statistics (8 B + 8*D B).
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -70,54 +71,93 @@ def load_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clock / throttle-reason sampling DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,"
+    """nvidia-smi clock / throttle-reason sampling DURING the timed region.
+
+    nvidia-smi takes a few hundred ms to produce its first row, so the sampler
+    is started ahead of the warm-up and the rows are filtered afterwards by
+    their own timestamps against the [mark_begin, mark_end] host-clock window
+    of the timed region."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,"
          "clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+             "sw_power_cap"]
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_ms=50):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.idx = gpu_index
+        self.period = period_ms
         self.p = None
+        self.windows = {}
 
     def start(self):
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", str(self.period)],
                 stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def wait_first(self, timeout=2.0):
+        """Block until nvidia-smi has written its first row (call BEFORE the
+        warm-up so the GPU does not idle right ahead of the timed region)."""
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                return True
+            time.sleep(0.02)
+        return False
+
+    def mark_begin(self, name):
+        self.windows[name] = [time.time(), None]
+
+    def mark_end(self, name):
+        self.windows[name][1] = time.time()
+
     def stop(self):
+        """-> {window name: clocks dict}"""
         if self.p is not None:
+            time.sleep(2.5 * self.period * 1e-3)
             self.p.terminate()          # exact PID we started
             try:
                 self.p.wait(timeout=5)
             except subprocess.TimeoutExpired:
                 self.p.kill()
         self.f.flush()
-        rows = [r.strip().split(",") for r in open(self.f.name)
-                if r.strip()]
-        os.unlink(self.f.name)
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                 "sw_power_cap"]
-        for r in rows:
+        rows = []
+        for line in open(self.f.name):
+            r = [x.strip() for x in line.strip().split(",")]
             try:
-                sm.append(float(r[1])); smax.append(float(r[2]))
+                ts = datetime.datetime.strptime(
+                    r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(r[1]), float(r[2]), float(r[3]),
+                             [v.lower() == "active" for v in r[4:8]]))
             except (ValueError, IndexError):
                 continue
-            for n, v in zip(names, r[4:8]):
-                if v.strip().lower() == "active":
-                    reasons.add(n)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [],
-                    "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+        os.unlink(self.f.name)
+        out = {}
+        for name, (t0, t1) in self.windows.items():
+            sel = [r for r in rows if t0 <= r[0] <= (t1 or t0)]
+            how = "in-window"
+            if not sel and rows:       # window shorter than the sampling period
+                mid = 0.5 * (t0 + (t1 or t0))
+                sel = sorted(rows, key=lambda r: abs(r[0] - mid))[:2]
+                how = "nearest"
+            if not sel:
+                out[name] = {"sm_mhz": None, "sm_max_mhz": None,
+                             "reasons": [], "samples": 0}
+                continue
+            reasons = sorted({n for r in sel
+                              for n, v in zip(self.NAMES, r[4]) if v})
+            out[name] = {"sm_mhz": float(np.median([r[1] for r in sel])),
+                         "sm_max_mhz": float(max(r[2] for r in sel)),
+                         "power_w": float(np.median([r[3] for r in sel])),
+                         "reasons": reasons, "samples": len(sel),
+                         "sampling": how}
+        return out
 
 
 def run_reference(args):
@@ -200,6 +240,10 @@ def main():
 
     for _ in range(args.burnin):        # setup: adaptive burn-in (untimed)
         step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        sampler.wait_first()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -207,9 +251,8 @@ def main():
         td.barrier()
 
     # ---------------- timed region: device-resident inputs -------------------
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.mark_begin("timed")
     hmc._profile_events = []
     launches0 = lib.launches
     torch.cuda.synchronize()
@@ -225,7 +268,8 @@ def main():
     launches = lib.launches - launches0
     kern_ms = [a.elapsed_time(b) for a, b in hmc._profile_events]
     hmc._profile_events = None
-    clocks = sampler.stop() if sampler else None
+    if sampler:
+        sampler.mark_end("timed")
     if world > 1:
         td.all_reduce(ms, op=td.ReduceOp.MAX)
     total_ms = float(ms.item())
@@ -288,15 +332,15 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             td.barrier()
-        sampler2 = ClockSampler(local_rank) if rank == 0 else None
-        if sampler2:
-            sampler2.start()
+        if sampler:
+            sampler.mark_begin("e2e")
         a, b = torch.cuda.Event(True), torch.cuda.Event(True)
         a.record()
         e2e_loop(n_e2e)
         b.record()
         torch.cuda.synchronize()
-        clocks2 = sampler2.stop() if sampler2 else None
+        if sampler:
+            sampler.mark_end("e2e")
         if world > 1:
             td.barrier()
         t = torch.tensor([a.elapsed_time(b)], device=dev)
@@ -309,12 +353,16 @@ def main():
                # the board is power-capped: the SM clock of THIS region (vs
                # clocks.sm_mhz of the device-resident region) explains e2e
                # landing a few % above or below `value`
-               "sm_mhz": clocks2["sm_mhz"] if clocks2 else None}
+               "sm_mhz": None}
 
     if rank != 0:
         if world > 1:
             td.destroy_process_group()
         return
+    win = sampler.stop() if sampler else {}
+    clocks = win.get("timed")
+    if e2e is not None and "e2e" in win:
+        e2e["sm_mhz"] = win["e2e"]["sm_mhz"]
 
     # ---------------- roofline of the dominant kernel ------------------------
     peaks = load_peaks()

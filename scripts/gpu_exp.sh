@@ -1,11 +1,9 @@
 #!/bin/bash
+# experiment: where does the dense kernel's time go under the power cap? (dbg: 1 = no epilogue,
+# 2 = one MMA product instead of three, 3 = both)
 mkdir -p gpurun_out
-echo "== full gpu suite"
-timeout 1500 python -m pytest tests -m gpu -q -rf --no-header -p no:cacheprovider 2>&1 | tail -25
-timeout 600 python scripts/bench_kernels.py 2>&1 | tail -30 | tee gpurun_out/bench_kernels.jsonl | python -c "
-import sys, json
-for l in sys.stdin:
-    try: d = json.loads(l); print('%-52s %8.4f ms %8.1f GB/s  frac %.3f  %s' % (d['kernel'], d['ms'], d['GBps'], d['frac_of_hbm_peak'], d['note'][:70]))
-    except Exception: print(l.strip()[:200])
-"
-timeout 300 python scripts/bench_iwae.py 2>&1 | tail -1 | tee gpurun_out/bench_iwae.json | cut -c1-700
+for dbg in 0 1 2 3; do
+echo "== dbg $dbg"
+ZSB_TC_DBG=$dbg timeout 200 python bench.py --steps 10 --warmup 3 --no-adapt --burnin 2 --no-e2e --no-cpu-baseline 2>/dev/null > gpurun_out/b_dbg$dbg.json; python scripts/show_bench.py gpurun_out/b_dbg$dbg.json | head -3
+done
+timeout 600 python bench.py --steps 10 --warmup 3 2>gpurun_out/bench.err > gpurun_out/bench.json; python scripts/show_bench.py gpurun_out/bench.json; tail -2 gpurun_out/bench.err

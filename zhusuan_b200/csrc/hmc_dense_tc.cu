@@ -185,81 +185,104 @@ struct EpiArgs {
   int h16; float q_scale; float acc_scale;
 };
 // residual operand(s) of q_next for the next pass's MMA
-__device__ __forceinline__ void store_split(const EpiArgs& a, int64_t idx, float qn) {
-  if (a.h16) {
-    __half* planes = reinterpret_cast<__half*>(a.q_next_lo);
+template <int H16>
+__device__ __forceinline__ void store_split(const EpiArgs& a, float* __restrict__ lo_f32,
+                                            __half* __restrict__ hi_pl, __half* __restrict__ lo_pl,
+                                            uint32_t off, float qn) {
+  if (H16) {
     const float x = qn * a.q_scale;
     const __half h = __float2half_rn(x);
-    planes[idx] = h;
-    planes[(int64_t)a.chains * a.D + idx] = __float2half_rn(x - __half2float(h));
+    hi_pl[off] = h;
+    lo_pl[off] = __float2half_rn(x - __half2float(h));
   } else {
-    a.q_next_lo[idx] = qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
+    lo_f32[off] = qn - __uint_as_float(__float_as_uint(qn) & 0xFFFFE000u);
   }
 }
-template <int MODE>
+// MODE: see above.  NEXT: 1 / 0 = q_next is / is not written (compile time), -1 = decided at run
+// time from a.q_next.  DC: the dimension count when known at compile time (all per-column offsets
+// j*D then fold into the load/store immediates: ~15 instead of ~40 instructions per element), 0 =
+// run-time a.D.  H16: fp16-split planes (impl 2) vs TF32 residual (impl 1).
+template <int MODE, int NEXT, int DC, int H16>
 __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t trow, int n,
                                                    bool n_ok, bool parts_ok, int64_t c0,
                                                    int64_t part_row, int lane, float s2,
                                                    float eps_over_m, float inv_m, float b_n,
                                                    float mu_n, bool skip) {
-  const int D = a.D;
+  const uint32_t D = DC ? (uint32_t)DC : (uint32_t)a.D;
   const int64_t chains = a.chains;
+  const bool has_next = NEXT < 0 ? (a.q_next != nullptr) : (NEXT != 0);
   const bool warp_n_ok = __all_sync(0xffffffffu, n_ok);
   const bool fast_tile = warp_n_ok && (c0 + BN / 2 <= chains) && !skip;
 
-  auto compute = [&](const uint32_t* v, const float* pe, const float* qe, int64_t cbase) {
-    const int64_t off0 = cbase * D + n;
-    float* __restrict__ po = a.p_out + off0;
+  // this thread's element of chain c0 in every array (the same element offset everywhere)
+  const int64_t off_t = c0 * (int64_t)D + n;
+  const float* __restrict__ pin0 = a.p_in + off_t;
+  const float* __restrict__ qc0 = a.q_cur + off_t;
+  float* __restrict__ po0 = a.p_out + off_t;
+  float* __restrict__ qn0 = has_next ? a.q_next + off_t : nullptr;
+  float* __restrict__ lo0 = (has_next && !H16) ? a.q_next_lo + off_t : nullptr;
+  __half* __restrict__ hi_pl0 =
+      (has_next && H16) ? reinterpret_cast<__half*>(a.q_next_lo) + off_t : nullptr;
+  __half* __restrict__ lo_pl0 = (has_next && H16) ? hi_pl0 + chains * (int64_t)D : nullptr;
+
+  // `c`: first column of the 16-column block, relative to c0
+  auto compute = [&](const uint32_t* v, const float* pe, const float* qe, int c) {
+    const size_t cb = (size_t)c * D;
+    float* __restrict__ po = po0 + cb;
+    float* __restrict__ qn_p = has_next ? qn0 + cb : nullptr;
+    float* __restrict__ lo_p = (has_next && !H16) ? lo0 + cb : nullptr;
+    __half* __restrict__ hp = (has_next && H16) ? hi_pl0 + cb : nullptr;
+    __half* __restrict__ lp = (has_next && H16) ? lo_pl0 + cb : nullptr;
     float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float g = b_n - a.acc_scale * __uint_as_float(v[j]);
       const float pn = fmaf(s2, g, pe[j]);
-      po[(uint32_t)(j * D)] = pn;
+      po[(uint32_t)j * D] = pn;
       if (MODE >= 1) lpv[j] = (qe[j] - mu_n) * g;
       if (MODE >= 2) kv[j] = pn * pn * inv_m;
-      if (a.q_next) {
+      if (has_next) {
         const float qn = fmaf(eps_over_m, pn, qe[j]);
-        a.q_next[off0 + (uint32_t)(j * D)] = qn;
-        store_split(a, off0 + (uint32_t)(j * D), qn);
+        qn_p[(uint32_t)j * D] = qn;
+        store_split<H16>(a, lo_p, hp, lp, (uint32_t)j * D, qn);
       }
     }
     if (MODE >= 1) {
       const float sum = warp_transpose_sum16(lpv, lane);
-      if (lane < 16) a.lp_part[part_row + cbase + lane] = sum;
+      if (lane < 16) a.lp_part[part_row + c0 + c + lane] = sum;
     }
     if (MODE >= 2) {
       const float sum = warp_transpose_sum16(kv, lane);
-      if (lane < 16) a.k_part[part_row + cbase + lane] = sum;
+      if (lane < 16) a.k_part[part_row + c0 + c + lane] = sum;
     }
   };
-  auto load = [&](float* pe, float* qe, int64_t cbase) {
-    const int64_t off0 = cbase * D + n;
-    const float* __restrict__ pin = a.p_in + off0;
-    const float* __restrict__ qc = a.q_cur + off0;
+  auto load = [&](float* pe, float* qe, int c) {
+    const float* __restrict__ pin = pin0 + (size_t)c * D;
+    const float* __restrict__ qc = qc0 + (size_t)c * D;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      pe[j] = __ldcs(pin + (uint32_t)(j * D));     // p is streamed: evict-first
-      qe[j] = __ldg(qc + (uint32_t)(j * D));
+      pe[j] = __ldcs(pin + (uint32_t)j * D);       // p is streamed: evict-first
+      qe[j] = __ldg(qc + (uint32_t)j * D);
     }
   };
 
   if (fast_tile) {
-    // software-pipelined: the global loads of block i+1 are in flight while block i is computed
-    // and stored (two register sets A/B, loop unrolled by two blocks)
+    // software-pipelined: the global loads AND the TMEM load of block i+1 are in flight while
+    // block i is computed and stored (two register sets A/B, loop unrolled by two blocks)
     float pa[16], qa[16], pb[16], qb[16];
-    uint32_t v[16];
-    load(pa, qa, c0);
+    uint32_t va[16], vb[16];
+    load(pa, qa, 0);
+    tmem_ld16(trow, va);
 #pragma unroll 1
     for (int c = 0; c < BN / 2; c += 32) {
-      load(pb, qb, c0 + c + 16);
-      tmem_ld16(trow + (uint32_t)c, v);
-      tmem_ld_wait();
-      compute(v, pa, qa, c0 + c);
-      if (c + 32 < BN / 2) load(pa, qa, c0 + c + 32);
-      tmem_ld16(trow + (uint32_t)(c + 16), v);
-      tmem_ld_wait();
-      compute(v, pb, qb, c0 + c + 16);
+      load(pb, qb, c + 16);
+      tmem_ld_wait();                                   // va has landed
+      tmem_ld16(trow + (uint32_t)(c + 16), vb);
+      compute(va, pa, qa, c);
+      if (c + 32 < BN / 2) load(pa, qa, c + 32);
+      tmem_ld_wait();                                   // vb has landed
+      if (c + 32 < BN / 2) tmem_ld16(trow + (uint32_t)(c + 32), va);
+      compute(vb, pb, qb, c + 16);
     }
   } else {
 #pragma unroll 1
@@ -269,17 +292,14 @@ __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t tr
       tmem_ld_wait();
       const int64_t cbase = c0 + c;
       if (cbase < chains && !skip) {
-        const int64_t off0 = cbase * D + n;
-        const float* __restrict__ pin = a.p_in + off0;
-        const float* __restrict__ qc = a.q_cur + off0;
-        float* __restrict__ po = a.p_out + off0;
+        const size_t cb = (size_t)c * D;
         float pe[16], qe[16];
         float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const bool ok = n_ok && cbase + j < chains;
-          pe[j] = ok ? pin[(uint32_t)(j * D)] : 0.f;
-          qe[j] = ok ? qc[(uint32_t)(j * D)] : 0.f;
+          pe[j] = ok ? pin0[cb + (uint32_t)j * D] : 0.f;
+          qe[j] = ok ? qc0[cb + (uint32_t)j * D] : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -289,11 +309,11 @@ __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t tr
           if (MODE >= 1) lpv[j] = ok ? (qe[j] - mu_n) * g : 0.f;
           if (MODE >= 2) kv[j] = ok ? pn * pn * inv_m : 0.f;
           if (ok) {
-            po[(uint32_t)(j * D)] = pn;
-            if (a.q_next) {
+            po0[cb + (uint32_t)j * D] = pn;
+            if (has_next) {
               const float qn = fmaf(eps_over_m, pn, qe[j]);
-              a.q_next[off0 + (uint32_t)(j * D)] = qn;
-              store_split(a, off0 + (uint32_t)(j * D), qn);
+              qn0[cb + (uint32_t)j * D] = qn;
+              store_split<H16>(a, lo0 + cb, hi_pl0 + cb, lo_pl0 + cb, (uint32_t)j * D, qn);
             }
           }
         }
@@ -340,7 +360,9 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(
       smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // broadcast so the compiler knows the role branches are warp-uniform (uniform datapath usable)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const int n_blk = (D + BM - 1) / BM;                     // dimension blocks
   const int64_t c_blk = (chains + BN - 1) / BN;            // chain blocks
   const int64_t n_tiles = c_blk * n_blk;
@@ -468,7 +490,7 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
       const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
       const EpiArgs ea{q_cur, q_next, q_next_lo, p_in, p_out, lp_part, k_part, chains, D,
                        0, 1.f, 1.f};
-      epilogue_half_tile<MODE>(ea, trow, n, n_ok, true, c0, part_row, lane, s2, eps_over_m, inv_m,
+      epilogue_half_tile<MODE, -1, 0, 0>(ea, trow, n, n_ok, true, c0, part_row, lane, s2, eps_over_m, inv_m,
                                b_n, mu_n, (dbg & 1) != 0);
       tc_fence_before();
       mbar_arrive(tempty_bar + 8 * acc);               // all epilogue threads free the accumulator
@@ -568,7 +590,7 @@ __device__ __forceinline__ uint32_t make_idesc_2sm_f16() {   // F16 x F16 -> F32
 // OP 0: TF32 operands (fp32 words, 3xTF32 split).  OP 1: fp16 operands (impl 2): the operand
 // tiles hold (P*sP) and (q*sq) split as hi + lo halves, 2*BK elements per 128/64-byte row, three
 // kind::f16 MMAs per 16-element k-step; `scales` = {sq, 1/(sP*sq)} in device memory.
-template <int BK, int MODE, int OP>
+template <int BK, int MODE, int OP, int NEXT, int DC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
                           const __grid_constant__ CUtensorMap map_plo,
@@ -580,8 +602,9 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
                           const float* __restrict__ mu, const float* __restrict__ mass,
                           const float* __restrict__ state, float p_scale,
                           float* __restrict__ lp_part, float* __restrict__ k_part, int64_t chains,
-                          int D, int dbg, const float* __restrict__ scales) {
+                          int D_rt, int dbg, const float* __restrict__ scales) {
   using C = Cfg2<BK>;
+  const int D = DC ? DC : D_rt;
   constexpr int KELEMS = OP ? 2 * BK : BK;                 // operand elements per smem row
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -594,7 +617,9 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(
       smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // broadcast so the compiler knows the role branches are warp-uniform (uniform datapath usable)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();                 // 0 = leader
   const bool leader = rank == 0;
   const int n_blk = (D + BM - 1) / BM;
@@ -674,7 +699,9 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);
             const uint32_t first = (kb | k) != 0 ? 1u : 0u;
-            if (OP) {               // 32 B per k-step either way: 16 halves or 8 TF32 words
+            if (OP && (dbg & 2)) {  // timing experiment: one product instead of three
+              umma_f16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, first);
+            } else if (OP) {        // 32 B per k-step either way: 16 halves or 8 TF32 words
               umma_f16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
               umma_f16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
               umma_f16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
@@ -720,7 +747,7 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
       const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
       const EpiArgs ea{q_cur, q_next, q_next_lo, p_in, p_out, lp_part, k_part, chains, D,
                        OP, q_scale, acc_scale};
-      epilogue_half_tile<MODE>(ea, trow, n, n_ok, nb < n_blk, c0, part_row, lane, s2, eps_over_m,
+      epilogue_half_tile<MODE, NEXT, DC, OP>(ea, trow, n, n_ok, nb < n_blk, c0, part_row, lane, s2, eps_over_m,
                                inv_m, b_n, mu_n, (dbg & 1) != 0);
       tc_fence_before();
       if (leader) mbar_arrive(tempty_bar + 8 * acc);
@@ -886,29 +913,23 @@ int launch_tc(const float* q_cur, const float* q_cur_lo, float* q_next, float* q
   return zsb_check_launch("hmc_dense_leapfrog_tc");
 }
 
+// one instantiation of the pair kernel: opt in to the dynamic shared memory once, then launch
+template <int BK, int MODE, int OP, int NEXT, int DC>
+struct Tc2Inst {
+  static cudaError_t prepare() {
+    static const cudaError_t e = cudaFuncSetAttribute(
+        dense_leapfrog_tc2_kernel<BK, MODE, OP, NEXT, DC>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BK>::SMEM);
+    return e;
+  }
+};
+
 template <int BK, int OP>
 int launch_tc2(const float* q_cur, const float* q_cur_lo, float* q_next, float* q_next_lo,
                const float* p_in, float* p_out, const float* P_hi, const float* P_lo,
                const float* bvec, const float* mu, const float* mass, const float* state,
                float p_scale, float* lp_part, float* k_part, int64_t chains, int D,
                const float* scales, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dense_leapfrog_tc2_kernel<BK, 0, OP>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg2<BK>::SMEM);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(dense_leapfrog_tc2_kernel<BK, 1, OP>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BK>::SMEM);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(dense_leapfrog_tc2_kernel<BK, 2, OP>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BK>::SMEM);
-    if (e != cudaSuccess) {
-      zsb_set_error("dense_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return ZSB_ERR_CUDA;
-    }
-    attr_set = true;
-  }
   if (k_part && !lp_part) {
     zsb_set_error("dense_tc2: k_part requires lp_part");
     return ZSB_ERR_INVALID;
@@ -938,13 +959,42 @@ int launch_tc2(const float* q_cur, const float* q_cur_lo, float* q_next, float* 
   int64_t pairs = sms / 2;
   if (n_units < pairs) pairs = n_units;
   const unsigned grid = (unsigned)(2 * pairs);
-#define ZSB_TC2_LAUNCH(MODE)                                                                  \
-  dense_leapfrog_tc2_kernel<BK, MODE, OP><<<grid, NUM_THREADS, Cfg2<BK>::SMEM, st>>>(          \
-      m_phi, m_plo, m_qhi, m_qlo, q_cur, q_next, q_next_lo, p_in, p_out, bvec, mu, mass, state, \
-      p_scale, lp_part, k_part, chains, D, g_tc_dbg, scales)
-  if (k_part) ZSB_TC2_LAUNCH(2);
-  else if (lp_part) ZSB_TC2_LAUNCH(1);
-  else ZSB_TC2_LAUNCH(0);
+  cudaError_t prep = cudaSuccess;
+#define ZSB_TC2_LAUNCH(MODE, NEXT, DC)                                                         \
+  do {                                                                                         \
+    prep = Tc2Inst<BK, MODE, OP, NEXT, DC>::prepare();                                         \
+    if (prep == cudaSuccess)                                                                   \
+      dense_leapfrog_tc2_kernel<BK, MODE, OP, NEXT, DC>                                        \
+          <<<grid, NUM_THREADS, Cfg2<BK>::SMEM, st>>>(                                         \
+              m_phi, m_plo, m_qhi, m_qlo, q_cur, q_next, q_next_lo, p_in, p_out, bvec, mu,     \
+              mass, state, p_scale, lp_part, k_part, chains, D, g_tc_dbg, scales);             \
+  } while (0)
+#define ZSB_TC2_MODE(NEXT, DC)                                                                 \
+  do {                                                                                         \
+    if (k_part) ZSB_TC2_LAUNCH(2, NEXT, DC);                                                   \
+    else if (lp_part) ZSB_TC2_LAUNCH(1, NEXT, DC);                                             \
+    else ZSB_TC2_LAUNCH(0, NEXT, DC);                                                          \
+  } while (0)
+#define ZSB_TC2_NEXT(DC)                                                                       \
+  do {                                                                                         \
+    if (q_next) ZSB_TC2_MODE(1, DC);                                                           \
+    else ZSB_TC2_MODE(0, DC);                                                                  \
+  } while (0)
+  // the default configuration (fp16 split, BK = 32) is also compiled with the dimension count as
+  // a constant for the common sizes: the epilogue's per-column offsets become immediates
+  bool done = false;
+  if constexpr (OP == 1 && BK == 32) {
+    if (D == 1024) { ZSB_TC2_NEXT(1024); done = true; }
+    else if (D == 512) { ZSB_TC2_NEXT(512); done = true; }
+    else if (D == 2048) { ZSB_TC2_NEXT(2048); done = true; }
+  }
+  if (!done) ZSB_TC2_NEXT(0);
+  if (prep != cudaSuccess) {
+    zsb_set_error("dense_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(prep));
+    return ZSB_ERR_CUDA;
+  }
+#undef ZSB_TC2_NEXT
+#undef ZSB_TC2_MODE
 #undef ZSB_TC2_LAUNCH
   return zsb_check_launch("hmc_dense_leapfrog_tc2");
 }

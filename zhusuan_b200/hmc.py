@@ -505,7 +505,7 @@ class HMC(object):
         if int(impl) == 2 and D % 64 != 0:
             raise ValueError("dense_impl=2 (fp16 split) needs D % 64 == 0")
         self._impl = int(impl)
-        if self._impl == 1:            # pipeline-shape tuning knob (same results)
+        if self._impl >= 1:            # pipeline-shape tuning knob (same results)
             lib.call("zsb_hmc_dense_tc_config",
                      int(os.environ.get("ZSB_TC_BK", "32"))
                      | (int(os.environ.get("ZSB_TC_DBG", "0")) << 8)
