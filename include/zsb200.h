@@ -119,6 +119,17 @@ int zsb_reduce_fwd_f32(int op, const float* x, float* out, int64_t outer, int64_
 int zsb_reduce_bwd_f32(int op, const float* x, const float* y, const float* gout, float* dx,
                        int64_t outer, int64_t K, int64_t inner, void* stream);
 
+/* ---- K6b: score-function / self-normalised estimators on the same tile (no backward: the
+ * reference wraps them in tf.stop_gradient) ------------------------------------------------------
+ * VIMCO learning signal, monte_carlo.py:194-223: signal[k] = LME_j(x_j) - LME_j(x_j with entry k
+ * replaced by the mean of the others); O(K) per column instead of the reference's [.., K, K] tile.
+ * `lme` (optional, [outer, inner]) receives log_mean_exp(x).  K >= 2 (ValueError in the reference). */
+int zsb_vimco_signal_f32(const float* x, float* signal, float* lme, int64_t outer, int64_t K,
+                         int64_t inner, void* stream);
+/* self-normalised importance weights, inclusive_kl.py:139-143: exp(x - max) / sum exp(x - max) */
+int zsb_normalized_weights_f32(const float* x, float* w, int64_t outer, int64_t K, int64_t inner,
+                               void* stream);
+
 /* ---- K2/K3/K4: HMC building blocks (zhusuan/hmc.py) ----------------------------------------- */
 int zsb_hmc_acc_parts(void);   /* capacity (floats) callers must give every acc_part scratch */
 int zsb_hmc_mass_parts(void);  /* mass_stats scratch = zsb_hmc_mass_parts()*2*D floats */

@@ -70,3 +70,66 @@ def iw_grad_logw(log_w, axis, dtype=np.float32):
     m = log_w.max(axis=axis, keepdims=True)
     e = np.exp(log_w - m)
     return (e / e.sum(axis=axis, keepdims=True, dtype=dtype)).astype(dtype)
+
+
+def vimco_signal(log_w, axis, dtype=np.float32):
+    """monte_carlo.py:194-223, restated the reference's way: an explicit
+    [.., K, K] tile whose row k is log_w with entry k replaced by the mean of
+    the others, reduced with log_mean_exp.  Returns LME(log_w, keepdims) - cv."""
+    l = np.asarray(log_w, dtype)
+    K = l.shape[axis]
+    if K < 2:
+        raise ValueError(
+            "VIMCO is a multi-sample gradient estimator, size along "
+            "`axis` in the objective should be larger than 1.")
+    mean_except = (l.sum(axis=axis, keepdims=True, dtype=dtype) - l) / dtype(K - 1)
+    x = np.moveaxis(l, axis, -1)                 # transpose(perm): axis <-> last
+    sub = np.moveaxis(mean_except, axis, -1)
+    x_ex = np.repeat(x[..., None], K, axis=-1)   # tile: x_ex[..., j, k] = x[..., j]
+    idx = np.arange(K)
+    x_ex[..., idx, idx] = sub                    # - diag(x) + diag(sub_x)
+    cv = log_mean_exp(np.swapaxes(x_ex, -1, -2), axis=-1, dtype=dtype)
+    cv = np.moveaxis(cv, -1, axis)
+    return (log_mean_exp(l, axis, keepdims=True, dtype=dtype) - cv).astype(dtype)
+
+
+def vimco_cost(log_joint, log_q, axis, dtype=np.float32):
+    """monte_carlo.py:221-227 (single latent): fake_term = sum(log q * signal)."""
+    log_w = np.asarray(log_joint, dtype) - np.asarray(log_q, dtype)
+    sig = vimco_signal(log_w, axis, dtype)
+    fake = (np.asarray(log_q, dtype) * sig).sum(axis=axis, dtype=dtype)
+    return (-fake - log_mean_exp(log_w, axis, dtype=dtype)).astype(dtype)
+
+
+def vimco_grad_logq(log_w, axis, dtype=np.float32):
+    """d sum(vimco_cost) / d log q (samples held fixed): -signal + softmax."""
+    return (-vimco_signal(log_w, axis, dtype) + iw_grad_logw(log_w, axis, dtype)).astype(dtype)
+
+
+def normalized_weights(log_w, axis, dtype=np.float32):
+    """inclusive_kl.py:139-143."""
+    l = np.asarray(log_w, dtype)
+    w_u = np.exp(l - l.max(axis=axis, keepdims=True))
+    return (w_u / w_u.sum(axis=axis, keepdims=True, dtype=dtype)).astype(dtype)
+
+
+def importance_cost(log_joint, log_q, axis, dtype=np.float32):
+    """inclusive_kl.py:137-151: sum_axis(w~ * (-log q))."""
+    log_q = np.asarray(log_q, dtype)
+    w = normalized_weights(np.asarray(log_joint, dtype) - log_q, axis, dtype)
+    return (w * (-log_q)).sum(axis=axis, dtype=dtype).astype(dtype)
+
+
+def reinforce_cost(log_joint, log_q, axis, dtype=np.float32):
+    """exclusive_kl.py:213-225 with variance_reduction=False (single latent):
+    cost = mean_axis(-log p + stop_gradient(log p - log q) * (-log q))."""
+    lj, lq = np.asarray(log_joint, dtype), np.asarray(log_q, dtype)
+    cost = -lj + (lj - lq) * (-lq)
+    return cost.mean(axis=axis, dtype=dtype) if axis is not None else cost
+
+
+def reinforce_grad_logq(log_joint, log_q, axis, dtype=np.float32):
+    """d sum(reinforce_cost) / d log q with the signal held constant."""
+    lj, lq = np.asarray(log_joint, dtype), np.asarray(log_q, dtype)
+    k = lq.shape[axis] if axis is not None else 1
+    return (-(lj - lq) / dtype(k)).astype(dtype)

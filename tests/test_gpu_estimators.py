@@ -1,0 +1,172 @@
+"""GPU parity: the score-function / self-normalised estimators --
+VIMCO (monte_carlo.py:166-227), importance / RWS (inclusive_kl.py:119-151) and
+REINFORCE (exclusive_kl.py:161-231) -- against the CPU oracle and the reference's
+own seeded gradient tests (tests/variational/test_monte_carlo.py:104-142,
+test_inclusive_kl.py:26-92, test_exclusive_kl.py:80-122)."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import variational as OV
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a, dtype=torch.float32):
+    return torch.tensor(np.asarray(a), dtype=dtype, device="cuda")
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def zs():
+    import zhusuan_b200 as zs
+    return zs
+
+
+@pytest.mark.parametrize("shape,axis", [((64, 300), 0), ((7, 33), 1), ((3, 5, 11), 1),
+                                        ((2, 1), 0), ((1000, 4), 0)])
+def test_vimco_signal_and_weights_vs_oracle(zs, shape, axis):
+    rng = np.random.RandomState(sum(shape) + axis)
+    l = (rng.standard_normal(shape) * 4).astype(np.float32)
+    sig, lme = zs.ops.vimco_signal(T(l), axis)
+    want = OV.vimco_signal(l, axis, np.float64)
+    np.testing.assert_allclose(N(sig), want, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(N(lme), OV.log_mean_exp(l, axis, keepdims=True, dtype=np.float64),
+                               rtol=1e-6, atol=1e-6)
+    w = zs.ops.normalized_weights(T(l), axis)
+    np.testing.assert_allclose(N(w), OV.normalized_weights(l, axis, np.float64), rtol=1e-5,
+                               atol=1e-9)
+    np.testing.assert_allclose(N(w.sum(axis)), 1.0, rtol=1e-5)
+
+
+def test_vimco_signal_extremes(zs):
+    """One dominant weight (the leave-one-out sum for the arg-max must not cancel), exact ties,
+    and very negative entries."""
+    K, n = 16, 8
+    l = np.full((K, n), -3.0, np.float32)
+    l[3, 0] = 60.0                    # dominant
+    l[:, 1] = 1.5                     # all tied
+    l[5, 2] = l[9, 2] = 20.0          # two-way tie for the maximum
+    l[2, 3] = -1e4                    # exp underflows
+    l[:, 4] = np.linspace(-80, 80, K)
+    sig, _ = zs.ops.vimco_signal(T(l), 0)
+    want = OV.vimco_signal(l, 0, np.float64)
+    np.testing.assert_allclose(N(sig), want, rtol=2e-5, atol=2e-5)
+    assert np.isfinite(N(sig)).all()
+    with pytest.raises(ValueError, match="larger than 1"):
+        zs.ops.vimco_signal(T(l[:1]), 0)
+
+
+@pytest.mark.parametrize("x_mean,x_std,thr", [(0., 1., 1e-2), (2., 3., 1e-6)])
+def test_vimco_reference_test(zs, x_mean, x_std, thr):
+    """tests/variational/test_monte_carlo.py:104-142: VIMCO gradient == SGVB gradient."""
+    rng = np.random.RandomState(1)
+    rng.standard_normal(size=(1, 1000))
+    eps = T(rng.standard_normal(1000).astype(np.float32))
+    mu = T(2.).requires_grad_(True)
+    sigma = T(3.).requires_grad_(True)
+    Normal = zs.distributions.Normal
+    qx = eps * sigma + mu
+    log_qx = Normal(mean=mu, std=sigma).log_prob(qx)
+    v_qx = eps * sigma.detach() + mu.detach()
+    v_log_qx = Normal(mean=mu, std=sigma).log_prob(v_qx)
+
+    def log_joint(observed):
+        return Normal(mean=x_mean, std=x_std).log_prob(observed['x'])
+    with pytest.warns(FutureWarning):
+        lb = zs.variational.importance_weighted_objective(
+            log_joint, observed={}, latent={'x': [qx, log_qx]}, axis=0)
+        v_lb = zs.variational.importance_weighted_objective(
+            log_joint, observed={}, latent={'x': [v_qx, v_log_qx]}, axis=0)
+    g1 = torch.autograd.grad(torch.mean(v_lb.vimco()), [mu, sigma])
+    g2 = torch.autograd.grad(torch.mean(lb.sgvb()), [mu, sigma])
+    np.testing.assert_allclose([float(g1[0]), float(g1[1])], [float(g2[0]), float(g2[1])],
+                               rtol=thr, atol=thr)
+    # the cost itself against the oracle
+    c = OV.vimco_cost(N(log_joint({'x': v_qx})), N(v_log_qx), 0, np.float64)
+    np.testing.assert_allclose(float(v_lb.vimco()), c, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("x_mean,x_std,thr", [(0., 1., 0.01), (2., 3., 0.02)])
+def test_importance_reference_test(zs, x_mean, x_std, thr):
+    """tests/variational/test_inclusive_kl.py:44-72."""
+    eps = T(np.random.RandomState(1).standard_normal(100000).astype(np.float32))
+    mu = T(2.).requires_grad_(True)
+    sigma = T(3.).requires_grad_(True)
+    Normal = zs.distributions.Normal
+    qx = (eps * sigma + mu).detach()
+    log_qx = Normal(mean=mu, std=sigma).log_prob(qx)
+
+    def log_joint(observed):
+        return Normal(mean=x_mean, std=x_std).log_prob(observed['x'])
+    with pytest.warns(FutureWarning):
+        obj = zs.variational.klpq(log_joint, observed={}, latent={'x': [qx, log_qx]}, axis=0)
+    cost = obj.importance()
+    g = torch.autograd.grad(cost, [mu, sigma])
+    true = (-(x_mean - 2.) / 9., 1. / 3. - (x_std ** 2 + (x_mean - 2.) ** 2) / 27.)
+    np.testing.assert_allclose([float(g[0]), float(g[1])], true, rtol=thr, atol=thr)
+    want = OV.importance_cost(N(log_joint({'x': qx})), N(log_qx), 0, np.float64)
+    np.testing.assert_allclose(float(cost), want, rtol=1e-4)
+
+
+def test_klpq_contract(zs):
+    """test_inclusive_kl.py:26-42, 74-92: not evaluable; rws() deprecation; single-sample warning."""
+    Normal = zs.distributions.Normal
+    x = T(np.random.RandomState(0).standard_normal(10))
+    log_q = Normal(mean=0., std=1.).log_prob(x)
+
+    def log_joint(observed):
+        return Normal(std=1.).log_prob(observed['x'])
+    with pytest.warns(FutureWarning):
+        obj = zs.variational.klpq(log_joint, observed={}, latent={'x': [x, log_q]}, axis=0)
+    with pytest.raises(NotImplementedError, match="can only be optimized instead of being evaluated"):
+        obj.tensor
+    with pytest.raises(NotImplementedError):
+        obj + 1.
+    with pytest.warns(FutureWarning, match="renamed to `importance\\(\\)`"):
+        obj.rws()
+    with pytest.warns(FutureWarning):
+        single = zs.variational.klpq(log_joint, observed={}, latent={'x': [x[0], log_q[0]]})
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        single.importance()
+        assert issubclass(w[-1].category, UserWarning)
+        assert "biased and inaccurate when you're using only a single sample" in str(w[-1].message)
+
+
+@pytest.mark.parametrize("x_mean,x_std,rtol,atol", [(0., 1., 1e-2, 1e-6), (2., 3., 1e-6, 1e-6)])
+def test_reinforce_reference_test(zs, x_mean, x_std, rtol, atol):
+    """tests/variational/test_exclusive_kl.py:80-112."""
+    rng = np.random.RandomState(1)
+    rng.standard_normal(100000)
+    eps = T(rng.standard_normal(1000000).astype(np.float32))
+    mu = T(2.).requires_grad_(True)
+    sigma = T(3.).requires_grad_(True)
+    Normal = zs.distributions.Normal
+    qx = (eps * sigma + mu).detach()
+    log_qx = Normal(mean=mu, std=sigma).log_prob(qx)
+
+    def log_joint(observed):
+        return Normal(mean=x_mean, std=x_std).log_prob(observed['x'])
+    with pytest.warns(FutureWarning):
+        lb = zs.variational.elbo(log_joint, observed={}, latent={'x': [qx, log_qx]}, axis=0)
+    cost = lb.reinforce(variance_reduction=False)
+    g = torch.autograd.grad(cost, [mu, sigma])
+    true = ((2. - x_mean) / x_std ** 2, -1 / 3. + 3. / x_std ** 2)
+    np.testing.assert_allclose([float(g[0]), float(g[1])], true, rtol=rtol, atol=atol)
+    want = OV.reinforce_cost(N(log_joint({'x': qx})), N(log_qx), 0, np.float64)
+    np.testing.assert_allclose(float(cost), want, rtol=1e-4, atol=1e-5)
+    # variance-reduced variants: moving-mean baseline, and a learned baseline with its own cost
+    with pytest.warns(FutureWarning):
+        lb2 = zs.variational.elbo(log_joint, observed={}, latent={'x': [qx, log_qx]}, axis=0)
+    c2 = lb2.reinforce()
+    assert torch.isfinite(c2)
+    b = T(0.1).requires_grad_(True)
+    c3, bc = lb2.reinforce(baseline=b)
+    assert torch.isfinite(c3) and torch.isfinite(bc)
+    assert torch.autograd.grad(bc, [b])[0] is not None

@@ -188,3 +188,83 @@ def test_philox_normals_are_standard():
     assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
     u = philox.uniform_vector(7, 2, 3, 0, 20000)
     assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01
+
+
+def _dlogq(x, mu, sigma):
+    """d log N(x; mu, sigma) / d(mu, sigma) with the sample x held fixed."""
+    return (x - mu) / sigma ** 2, -1.0 / sigma + (x - mu) ** 2 / sigma ** 3
+
+
+@pytest.mark.parametrize("x_mean,x_std,thr", [(0., 1., 1e-2), (2., 3., 1e-6)])
+def test_vimco_gradient_matches_sgvb(x_mean, x_std, thr):
+    """tests/variational/test_monte_carlo.py:104-142: with q = N(2, 3) and the
+    1000 `_n3_samples`, the VIMCO gradient wrt (mu, sigma) equals the SGVB one
+    to the reference's thresholds."""
+    mu, sigma = 2., 3.
+    rng = np.random.RandomState(1)
+    rng.standard_normal(size=(1, 1000))           # _n1_samples come first
+    eps = rng.standard_normal(1000).astype(np.float32).astype(np.float64)
+    x = eps * sigma + mu
+    log_w = stats.norm.logpdf(x, x_mean, x_std) - stats.norm.logpdf(x, mu, sigma)
+    # SGVB (reparameterised): -d LME / d(mu, sigma)
+    g_sgvb = _sgvb_grads(OV.iw_grad_logw(log_w, 0, np.float64), x, eps,
+                         x_mean, x_std, sigma)
+    # VIMCO (score function): samples fixed, gradient through log q only
+    gq = OV.vimco_grad_logq(log_w, 0, np.float64)
+    dmu, dsig = _dlogq(x, mu, sigma)
+    g_vimco = ((gq * dmu).sum(), (gq * dsig).sum())
+    np.testing.assert_allclose(g_vimco, g_sgvb, rtol=thr, atol=thr)
+    with pytest.raises(ValueError, match="larger than 1"):
+        OV.vimco_signal(log_w[:1], 0)
+
+
+def test_vimco_signal_is_leave_one_out():
+    """Direct definition: signal[k] = LME(l) - LME(l with l_k := mean of others)."""
+    l = np.random.RandomState(3).standard_normal((5, 7)) * 3
+    sig = OV.vimco_signal(l, 0, np.float64)
+    for k in range(5):
+        for i in range(7):
+            col = l[:, i].copy()
+            col[k] = (l[:, i].sum() - l[k, i]) / 4
+            want = OV.log_mean_exp(l[:, i], 0, dtype=np.float64) - \
+                OV.log_mean_exp(col, 0, dtype=np.float64)
+            assert abs(sig[k, i] - want) < 1e-12
+    sig1 = OV.vimco_signal(l.T, 1, np.float64)        # other axis
+    np.testing.assert_allclose(sig1, sig.T, rtol=1e-12)
+
+
+@pytest.mark.parametrize("x_mean,x_std,thr", [(0., 1., 0.01), (2., 3., 0.02)])
+def test_importance_gradient_vs_kl_grads(x_mean, x_std, thr):
+    """tests/variational/test_inclusive_kl.py:44-72: self-normalised importance
+    gradient of KL(p || q) wrt (mu, sigma), q = N(2, 3), 1e5 samples."""
+    mu, sigma = 2., 3.
+    eps = _n01(100000).astype(np.float64)
+    x = eps * sigma + mu
+    log_q = stats.norm.logpdf(x, mu, sigma)
+    w = OV.normalized_weights(stats.norm.logpdf(x, x_mean, x_std) - log_q, 0,
+                              np.float64)
+    dmu, dsig = _dlogq(x, mu, sigma)
+    g = (-(w * dmu).sum(), -(w * dsig).sum())       # cost = sum w~ * (-log q)
+    # d KL(p || q) / d(mu, sigma), p = N(x_mean, x_std)
+    true = (-(x_mean - mu) / sigma ** 2,
+            1.0 / sigma - (x_std ** 2 + (x_mean - mu) ** 2) / sigma ** 3)
+    np.testing.assert_allclose(g, true, rtol=thr, atol=thr)
+    c = OV.importance_cost(stats.norm.logpdf(x, x_mean, x_std), log_q, 0, np.float64)
+    assert np.isfinite(c)
+
+
+@pytest.mark.parametrize("x_mean,x_std,rtol,atol", [(0., 1., 1e-2, 1e-6), (2., 3., 1e-6, 1e-6)])
+def test_reinforce_gradient_vs_kl_grads(x_mean, x_std, rtol, atol):
+    """tests/variational/test_exclusive_kl.py:80-112 (variance_reduction=False,
+    q = N(2, 3), the 1e6-sample stream that follows the 1e5 one)."""
+    mu, sigma = 2., 3.
+    rng = np.random.RandomState(1)
+    rng.standard_normal(100000)
+    eps = rng.standard_normal(1000000).astype(np.float32).astype(np.float64)
+    x = eps * sigma + mu
+    lj, lq = stats.norm.logpdf(x, x_mean, x_std), stats.norm.logpdf(x, mu, sigma)
+    gq = OV.reinforce_grad_logq(lj, lq, 0, np.float64)
+    dmu, dsig = _dlogq(x, mu, sigma)
+    g = ((gq * dmu).sum(), (gq * dsig).sum())
+    true = ((mu - x_mean) / x_std ** 2, -1.0 / sigma + sigma / x_std ** 2)
+    np.testing.assert_allclose(g, true, rtol=rtol, atol=atol)

@@ -374,6 +374,49 @@ def reduce_axes(x, op, axis=None, keepdims=False):
     return out
 
 
+def _single_axis_view(x, axis):
+    """[outer, K, inner] view of ``x`` for one axis (int)."""
+    nd = x.dim()
+    ax = int(axis) % nd
+    outer = 1
+    for a in range(ax):
+        outer *= int(x.shape[a])
+    inner = 1
+    for a in range(ax + 1, nd):
+        inner *= int(x.shape[a])
+    return ax, outer, int(x.shape[ax]), inner
+
+
+def vimco_signal(log_w, axis):
+    """VIMCO learning signal and log_mean_exp(log_w, axis, keepdims=True)
+    (monte_carlo.py:194-223) in one kernel; both are constants for autograd
+    (the reference stops the gradient of the signal)."""
+    x = _f32c(log_w.detach())
+    ax, outer, K, inner = _single_axis_view(x, axis)
+    if K < 2:
+        raise ValueError(
+            "VIMCO is a multi-sample gradient estimator, size along "
+            "`axis` in the objective should be larger than 1.")
+    sig = torch.empty_like(x)
+    shape = list(x.shape)
+    shape[ax] = 1
+    lme = torch.empty(shape, dtype=torch.float32, device=x.device)
+    lib.call("zsb_vimco_signal_f32", ptr(x), ptr(sig), ptr(lme), outer, K,
+             inner, stream())
+    return sig, lme
+
+
+def normalized_weights(log_w, axis):
+    """Self-normalised importance weights softmax_axis(log_w), detached
+    (inclusive_kl.py:139-143)."""
+    x = _f32c(log_w.detach())
+    ax, outer, K, inner = _single_axis_view(x, axis)
+    w = torch.empty_like(x)
+    lib.call("zsb_normalized_weights_f32", ptr(x), ptr(w), outer, K, inner,
+             stream())
+    return w
+
+
 def group_sum(x, group_ndims):
     """reduce_sum over the last ``group_ndims`` axes (base.py:303-304)."""
     if group_ndims == 0:

@@ -1,8 +1,6 @@
 """Importance-weighted objective (zhusuan/variational/monte_carlo.py:21-268):
 ``.tensor`` / ``.sgvb()`` on the K6 log_mean_exp kernel (forward + softmax
 backward)."""
-import torch
-
 from .. import ops
 from .base import VariationalObjective
 
@@ -31,27 +29,17 @@ class ImportanceWeightedObjective(VariationalObjective):
         return -self.tensor
 
     def vimco(self):
-        """monte_carlo.py:166-227 (host-composed; a "next" row).
-        O(K) per datum instead of the reference's [.., K, K] tile."""
+        """monte_carlo.py:166-227.  The learning signal
+        LME(log_w) - LME(log_w with entry k replaced by the mean of the
+        others) comes from one O(K)-per-datum kernel (zsb_vimco_signal_f32)
+        instead of the reference's [.., K, K] tile; gradients flow through
+        log q (the fake term) and through log_mean_exp(log_w) as in the
+        reference."""
         log_w = self._log_joint_term() + self._entropy_term()
-        ax = self._axis
-        K = log_w.shape[ax]
-        if K < 2:
-            raise ValueError(
-                "VIMCO is a multi-sample gradient estimator, size along "
-                "`axis` in the objective should be larger than 1.")
-        l = log_w.detach()
-        mean_except = (l.sum(ax, keepdim=True) - l) / (K - 1)
-        # log_mean_exp with entry k replaced by mean_except[k]
-        m = torch.maximum(l.max(ax, keepdim=True).values,
-                          mean_except.max(ax, keepdim=True).values)
-        s = torch.exp(l - m).sum(ax, keepdim=True)
-        cv = torch.log((s - torch.exp(l - m) + torch.exp(mean_except - m))
-                       / K) + m
-        lme = ops.reduce_axes(log_w, ops.OP_LME, ax, keepdims=True)
-        l_signal = (lme - cv).detach()
-        fake_term = (-self._entropy_term() * l_signal).sum(ax)
-        return -fake_term - lme.squeeze(ax)
+        l_signal, _ = ops.vimco_signal(log_w, self._axis)   # ValueError if K < 2
+        fake_term = ops.reduce_axes(-self._entropy_term() * l_signal,
+                                    ops.OP_SUM, self._axis)
+        return -fake_term - ops.reduce_axes(log_w, ops.OP_LME, self._axis)
 
 
 def importance_weighted_objective(meta_bn, observed, latent=None, axis=None,
