@@ -110,6 +110,21 @@ int zsb_reparam_normal_f32(const float* mean, int64_t mean_n, const float* logst
 int zsb_sample_bernoulli_i32(const float* logits, int64_t logits_n, const float* u, uint64_t seed,
                              uint32_t iter, int32_t* out, int64_t n, void* stream);
 
+/* ---- K1 (widened): the other elementwise univariate densities behind one entry point.
+ * dist: 0 FoldNormal(mean, logstd) univariate.py:319-329 | 1 Uniform(minval, maxval) :646-660
+ *       2 Gamma(alpha, beta) :737-747 | 3 Beta(alpha, beta) :833-851 | 4 Poisson(rate, NULL) :922-933
+ *       5 Binomial(logits, n) :1047-1064 | 6 InverseGamma(alpha, beta) :1146-1158
+ *       7 Laplace(loc, scale) :1267-1273 | 8 BinConcrete(temperature, logits) :1381-1400
+ * Operands broadcast modularly like zsb_logprob_normal_f32; out [n_out] = sum over `group`.
+ * The backward writes full-size elementwise gradients (each output nullable). */
+int zsb_logprob_univariate_f32(int dist, const float* given, int64_t given_n, const float* a,
+                               int64_t a_n, const float* b, int64_t b_n, float* out,
+                               int64_t n_out, int64_t group, void* stream);
+int zsb_logprob_univariate_bwd_f32(int dist, const float* given, int64_t given_n, const float* a,
+                                   int64_t a_n, const float* b, int64_t b_n, const float* gout,
+                                   int64_t n_out, int64_t group, float* dgiven, float* da,
+                                   float* db, void* stream);
+
 /* ---- K6: sample-axis reductions; x viewed as [outer, K, inner], reduced over K --------------
  * op 0 log_mean_exp (zhusuan/utils.py:177-196; monte_carlo.py:137-141)
  *    1 mean         (exclusive_kl.py:131-137)   2 log_sum_exp (utils.py:153-174)   3 sum       */
@@ -129,6 +144,11 @@ int zsb_vimco_signal_f32(const float* x, float* signal, float* lme, int64_t oute
 /* self-normalised importance weights, inclusive_kl.py:139-143: exp(x - max) / sum exp(x - max) */
 int zsb_normalized_weights_f32(const float* x, float* w, int64_t outer, int64_t K, int64_t inner,
                                void* stream);
+
+/* ---- diagnostics: effective sample size (zhusuan/diagnostics.py:17-64, the Stan estimator) on the
+ * device; samples [M, D] row-major with burn-in already dropped -> ess [D].  M >= 2. */
+int zsb_effective_sample_size_f32(const float* samples, int64_t M, int64_t D, float* ess,
+                                  void* stream);
 
 /* ---- K2/K3/K4: HMC building blocks (zhusuan/hmc.py) ----------------------------------------- */
 int zsb_hmc_acc_parts(void);   /* capacity (floats) callers must give every acc_part scratch */

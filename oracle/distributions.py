@@ -138,3 +138,82 @@ def bernoulli_sample(u, logits, dtype=np.int32):
     (univariate.py:386-392)."""
     p = 1.0 / (1.0 + np.exp(-np.asarray(logits, np.float32)))
     return (np.asarray(u, np.float32) < p.astype(np.float32)).astype(dtype)
+
+
+# ---- the other elementwise univariate families (zhusuan/distributions/univariate.py) ---------
+def _softplus(t):
+    return np.maximum(t, 0) + np.log1p(np.exp(-np.abs(t)))
+
+
+def fold_normal_log_prob(given, mean, logstd, group_ndims=0, dtype=np.float32):
+    """univariate.py:319-329."""
+    x, m, ls = (np.asarray(v, dtype) for v in (given, mean, logstd))
+    c = dtype(-0.5 * (np.log(2.0) + np.log(np.pi)))
+    prec = np.exp(-2 * ls)
+    with np.errstate(divide="ignore"):
+        mask = np.log((x >= 0).astype(dtype))
+    lp = (c - (ls + 0.5 * prec * np.square(x - m)) + _softplus(-2 * m * x * prec)) + mask
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def uniform_log_prob(given, minval, maxval, group_ndims=0, dtype=np.float32):
+    """univariate.py:646-660: log(1/(max-min) * [min <= x < max])."""
+    x, lo, hi = (np.asarray(v, dtype) for v in (given, minval, maxval))
+    mask = np.logical_and(lo <= x, x < hi).astype(dtype)
+    with np.errstate(divide="ignore"):
+        lp = np.log(1 / (hi - lo) * mask)
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def gamma_log_prob(given, alpha, beta, group_ndims=0, dtype=np.float32):
+    """univariate.py:737-747."""
+    x, a, b = (np.asarray(v, dtype) for v in (given, alpha, beta))
+    lp = a * np.log(b) - _sp.gammaln(a) + (a - 1) * np.log(x) - b * x
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def beta_log_prob(given, alpha, beta, group_ndims=0, dtype=np.float32):
+    """univariate.py:833-851."""
+    x, a, b = (np.asarray(v, dtype) for v in (given, alpha, beta))
+    lp = (a - 1) * np.log(x) + (b - 1) * np.log(1 - x) - (
+        _sp.gammaln(a) + _sp.gammaln(b) - _sp.gammaln(a + b))
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def poisson_log_prob(given, rate, group_ndims=0, dtype=np.float32):
+    """univariate.py:922-933."""
+    x, r = np.asarray(given, dtype), np.asarray(rate, dtype)
+    lp = x * np.log(r) - r - _sp.gammaln(x + 1)
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def binomial_log_prob(given, logits, n_experiments, group_ndims=0, dtype=np.float32):
+    """univariate.py:1047-1064."""
+    x, l = np.asarray(given, dtype), np.asarray(logits, dtype)
+    n = dtype(n_experiments)
+    lp = _sp.gammaln(n + 1) - _sp.gammaln(n - x + 1) - _sp.gammaln(x + 1) + x * l + \
+        n * (-_softplus(l))
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def inverse_gamma_log_prob(given, alpha, beta, group_ndims=0, dtype=np.float32):
+    """univariate.py:1146-1158."""
+    x, a, b = (np.asarray(v, dtype) for v in (given, alpha, beta))
+    lp = a * np.log(b) - _sp.gammaln(a) - (a + 1) * np.log(x) - b / x
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def laplace_log_prob(given, loc, scale, group_ndims=0, dtype=np.float32):
+    """univariate.py:1267-1273."""
+    x, m, s = (np.asarray(v, dtype) for v in (given, loc, scale))
+    lp = -np.log(dtype(2.)) - np.log(s) - np.abs(x - m) / s
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def bin_concrete_log_prob(given, temperature, logits, group_ndims=0, dtype=np.float32):
+    """univariate.py:1381-1400."""
+    x, t, l = (np.asarray(v, dtype) for v in (given, temperature, logits))
+    lx, l1x = np.log(x), np.log(1 - x)
+    temp = t * (lx - l1x) - l
+    lp = np.log(t) - lx - l1x + temp - 2 * _softplus(temp)
+    return _group_sum(lp.astype(dtype), group_ndims)

@@ -246,3 +246,165 @@ def test_kernel_philox_matches_oracle():
              it, row0, C, None, None, ptr(acc), ptr(accept), None, ptr(part),
              ctypes.byref(npart), None, stream())
     np.testing.assert_array_equal(N(accept), (u_ref < N(acc)).astype(np.int32))
+
+
+# ---- the nine other elementwise univariate families (univariate_ext.cu) ---------------------
+def _uni_dist(zs, fam, a, b):
+    D = zs.distributions
+    t = lambda v: torch.tensor(np.asarray(v), dtype=torch.float32, device="cuda")
+    if fam == "fold_normal":
+        return D.FoldNormal(t(a), logstd=t(b))
+    if fam == "uniform":
+        return D.Uniform(t(a), t(b))
+    if fam == "gamma":
+        return D.Gamma(t(a), t(b))
+    if fam == "inverse_gamma":
+        return D.InverseGamma(t(a), t(b))
+    if fam == "beta":
+        return D.Beta(t(a), t(b))
+    if fam == "poisson":
+        return D.Poisson(t(a))
+    if fam == "binomial":
+        return D.Binomial(t(a), int(b))
+    if fam == "laplace":
+        return D.Laplace(t(a), t(b))
+    return D.BinConcrete(t(a), t(b))
+
+
+def test_univariate_more_reference_values():
+    """tests/distributions/test_univariate.py `_test_value` literals (cases.py) through the
+    Distribution classes: log_prob and prob against the scipy.stats targets."""
+    import zhusuan_b200 as zs
+    for fam, given, a, b, target, atol in cases.univariate_more_cases():
+        d = _uni_dist(zs, fam, a, b)
+        g = torch.tensor(given, device="cuda")
+        with np.errstate(all="ignore"):
+            lp = d.log_prob(g).cpu().numpy()
+            p = d.prob(g).cpu().numpy()
+            np.testing.assert_allclose(lp, target, rtol=2e-5, atol=max(atol, 1e-4), err_msg=fam)
+            np.testing.assert_allclose(p, np.exp(target), rtol=1e-3, atol=1e-6, err_msg=fam)
+
+
+@pytest.mark.parametrize("fam", ["fold_normal", "gamma", "inverse_gamma", "beta", "poisson",
+                                 "binomial", "laplace", "bin_concrete", "uniform"])
+def test_univariate_more_vs_oracle_with_gradients(fam):
+    """Random broadcast shapes + group_ndims: forward vs the NumPy oracle, backward vs a
+    float64 torch-autograd restatement of the same formula."""
+    import zhusuan_b200 as zs
+    from oracle import distributions as OD
+    rng = np.random.RandomState(sum(map(ord, fam)))
+    shape, pshape = (5, 7, 6), (7, 6)
+    pos = lambda s: (0.3 + 3 * rng.random_sample(s)).astype(np.float32)
+    unit = lambda s: (0.02 + 0.96 * rng.random_sample(s)).astype(np.float32)
+    lgam = torch.lgamma
+    sp = torch.nn.functional.softplus
+    if fam == "fold_normal":
+        x, a, b = pos(shape), rng.standard_normal(pshape).astype(np.float32), \
+            (0.3 * rng.standard_normal((6,))).astype(np.float32)
+        ref = lambda x, a, b: (-0.5 * np.log(2 * np.pi) - (b + 0.5 * torch.exp(-2 * b) * (x - a) ** 2)
+                               + sp(-2 * a * x * torch.exp(-2 * b)))
+    elif fam == "gamma":
+        x, a, b = pos(shape), pos(pshape), pos((6,))
+        ref = lambda x, a, b: a * torch.log(b) - lgam(a) + (a - 1) * torch.log(x) - b * x
+    elif fam == "inverse_gamma":
+        x, a, b = pos(shape), pos(pshape), pos((6,))
+        ref = lambda x, a, b: a * torch.log(b) - lgam(a) - (a + 1) * torch.log(x) - b / x
+    elif fam == "beta":
+        x, a, b = unit(shape), pos(pshape), pos((6,))
+        ref = lambda x, a, b: (a - 1) * torch.log(x) + (b - 1) * torch.log(1 - x) - (
+            lgam(a) + lgam(b) - lgam(a + b))
+    elif fam == "poisson":
+        x, a, b = rng.poisson(3., shape).astype(np.float32), pos(pshape), None
+        ref = lambda x, a, b: x * torch.log(a) - a - lgam(x + 1)
+    elif fam == "binomial":
+        x, a, b = rng.binomial(12, 0.4, shape).astype(np.float32), \
+            rng.standard_normal(pshape).astype(np.float32), 12
+        ref = lambda x, a, b: (lgam(b + 1) - lgam(b - x + 1) - lgam(x + 1) + x * a - b * sp(a))
+    elif fam == "laplace":
+        x, a, b = rng.standard_normal(shape).astype(np.float32), \
+            rng.standard_normal(pshape).astype(np.float32), pos((6,))
+        ref = lambda x, a, b: -np.log(2.) - torch.log(b) - torch.abs(x - a) / b
+    elif fam == "bin_concrete":
+        x, a, b = unit(shape), np.float32(0.7), rng.standard_normal(pshape).astype(np.float32)
+
+        def ref(x, a, b):
+            t = a * (torch.log(x) - torch.log(1 - x)) - b
+            return torch.log(a) - torch.log(x) - torch.log(1 - x) + t - 2 * sp(t)
+    else:  # uniform
+        a, b = (-1 - rng.random_sample(pshape)).astype(np.float32), pos((6,))
+        x = (rng.random_sample(shape) * 0.9 - 0.5).astype(np.float32)
+        ref = lambda x, a, b: -torch.log(b - a) + 0 * x
+    for gnd in (0, 2):
+        tx = torch.tensor(x, device="cuda", requires_grad=(fam not in ("poisson", "binomial")))
+        ta = torch.tensor(a, device="cuda", requires_grad=True)
+        tb = torch.tensor(b, device="cuda", requires_grad=True) \
+            if (b is not None and fam != "binomial") else None
+        if fam == "fold_normal":
+            d = zs.distributions.FoldNormal(ta, logstd=tb, group_ndims=gnd)
+        elif fam == "poisson":
+            d = zs.distributions.Poisson(ta, group_ndims=gnd)
+        elif fam == "binomial":
+            d = zs.distributions.Binomial(ta, 12, group_ndims=gnd)
+        else:
+            cls = dict(gamma="Gamma", inverse_gamma="InverseGamma", beta="Beta", laplace="Laplace",
+                       bin_concrete="BinConcrete", uniform="Uniform")[fam]
+            d = getattr(zs.distributions, cls)(ta, tb, group_ndims=gnd)
+        lp = d.log_prob(tx)
+        ofn = getattr(OD, fam + "_log_prob")
+        want = ofn(x, a, b, group_ndims=gnd, dtype=np.float64) if b is not None else \
+            ofn(x, a, group_ndims=gnd, dtype=np.float64)
+        np.testing.assert_allclose(lp.detach().cpu().numpy(), want, rtol=2e-5, atol=2e-5)
+        w = torch.tensor(rng.standard_normal(tuple(lp.shape)), dtype=torch.float32, device="cuda")
+        ins = [t for t in (tx, ta, tb) if t is not None and t.requires_grad]
+        got = torch.autograd.grad((lp * w).sum(), ins)
+        # float64 reference on the host
+        rx = torch.tensor(x, dtype=torch.float64, requires_grad=tx.requires_grad)
+        ra = torch.tensor(a, dtype=torch.float64, requires_grad=True)
+        rb = torch.tensor(b, dtype=torch.float64, requires_grad=tb is not None) \
+            if b is not None else None
+        rl = ref(rx, ra, rb)
+        if gnd:
+            rl = rl.sum(dim=tuple(range(-gnd, 0)))
+        rins = [t for t in (rx, ra, rb) if t is not None and t.requires_grad]
+        exp = torch.autograd.grad((rl * w.double().cpu()).sum(), rins)
+        for gg, ee in zip(got, exp):
+            np.testing.assert_allclose(gg.cpu().numpy(), ee.numpy(), rtol=3e-4, atol=3e-4)
+
+
+def test_univariate_more_contract_and_sampling():
+    """Constructor checks (messages of the reference) and sample shapes / supports / moments."""
+    import zhusuan_b200 as zs
+    D = zs.distributions
+    dev = "cuda"
+    one = torch.ones(3, device=dev)
+    with pytest.raises(ValueError, match="should be broadcastable to match"):
+        D.Gamma(torch.ones(2, device=dev), one)
+    with pytest.raises(ValueError, match="Either std or logstd"):
+        D.FoldNormal(one)
+    with pytest.raises(ValueError, match="n_experiments must be positive"):
+        D.Binomial(one, 0)
+    with pytest.raises(TypeError, match="n_experiments must be int32"):
+        D.Binomial(one, 2.5)
+    with pytest.raises(TypeError, match="must have the same dtype as"):
+        D.Laplace(one, one.double())
+    with pytest.raises(ValueError, match="should be a scalar"):
+        D.BinConcrete(one, one)
+    n = 20000
+    a, b = torch.tensor([2.0, 5.0], device=dev), torch.tensor([1.5, 0.5], device=dev)
+    for d, mean in [(D.Gamma(a, b), a / b), (D.Beta(a, b), a / (a + b)),
+                    (D.InverseGamma(a + 2, b), b / (a + 1)), (D.Poisson(a), a),
+                    (D.Binomial(torch.zeros(2, device=dev), 10), torch.full((2,), 5.0)),
+                    (D.Laplace(a, b), a), (D.Uniform(a, a + b), a + b / 2)]:
+        s = d.sample(n)
+        assert tuple(s.shape) == (n, 2) and s.dtype == d.dtype
+        np.testing.assert_allclose(s.float().mean(0).cpu().numpy(), mean.cpu().numpy(), rtol=0.08)
+        assert torch.isfinite(d.log_prob(s)).all()
+    s = D.BinConcrete(torch.tensor(0.5, device=dev), torch.zeros(4, device=dev)).sample(100)
+    assert tuple(s.shape) == (100, 4) and bool(((s > 0) & (s < 1)).all())
+    # BayesianNet factories
+    bn = zs.BayesianNet(observed={"g": torch.tensor([1.0, 2.0], device=dev)})
+    g = bn.gamma("g", a, b, group_ndims=1)
+    bn.laplace("l", a, b, n_samples=5)
+    bn.poisson("k", a)
+    assert tuple(g.cond_log_p.shape) == () and tuple(bn["l"].tensor.shape) == (5, 2)
+    assert tuple(bn.log_joint().shape) == (5, 2)

@@ -170,3 +170,26 @@ def test_reinforce_reference_test(zs, x_mean, x_std, rtol, atol):
     c3, bc = lb2.reinforce(baseline=b)
     assert torch.isfinite(c3) and torch.isfinite(bc)
     assert torch.autograd.grad(bc, [b])[0] is not None
+
+
+def test_effective_sample_size_vs_oracle(zs):
+    """zhusuan/diagnostics.py:17-64 on the device vs the NumPy oracle, on the reference test's
+    two chains (tests/test_diagnostics.py:14-42) and a many-dimension AR(1) family."""
+    from oracle import diagnostics as OG
+    from test_oracle_diagnostics import make_chains
+    iid, mcmc = make_chains()
+    for chain in (iid, mcmc):
+        got = N(zs.diagnostics.effective_sample_size_per_dim(T(chain), burn_in=100))
+        np.testing.assert_allclose(got, OG.ess_per_dim(chain.astype(np.float32), 100), rtol=2e-3)
+    assert zs.diagnostics.effective_sample_size(iid, burn_in=100) >= 2000
+    assert zs.diagnostics.effective_sample_size(T(mcmc), burn_in=100) <= 1000
+    rng = np.random.RandomState(5)
+    M, D = 3000, 70                       # 3 blocks of 32 dimensions, last one ragged
+    phi = np.linspace(0.0, 0.95, D)
+    x = np.zeros((M, D), np.float32)
+    e = rng.standard_normal((M, D)).astype(np.float32)
+    for i in range(1, M):
+        x[i] = phi * x[i - 1] + e[i]
+    got = N(zs.diagnostics.effective_sample_size_per_dim(T(x), burn_in=0))
+    np.testing.assert_allclose(got, OG.ess_per_dim(x, 0), rtol=2e-3)
+    assert abs(zs.diagnostics.effective_sample_size_1d(T(x[:, 3])) - OG.ess_1d(x[:, 3])) < 1.0

@@ -268,3 +268,17 @@ def test_reinforce_gradient_vs_kl_grads(x_mean, x_std, rtol, atol):
     g = ((gq * dmu).sum(), (gq * dsig).sum())
     true = ((mu - x_mean) / x_std ** 2, -1.0 / sigma + sigma / x_std ** 2)
     np.testing.assert_allclose(g, true, rtol=rtol, atol=atol)
+
+
+def test_univariate_more_log_prob_vs_reference_targets():
+    """Oracle restatements of the nine other univariate densities against the scipy.stats
+    targets of the reference's own `_test_value` cases (tests/distributions/test_univariate.py)."""
+    n = 0
+    for fam, given, a, b, target, atol in cases.univariate_more_cases():
+        fn = getattr(OD, fam + "_log_prob")
+        with np.errstate(all="ignore"):
+            got = fn(given, a, b, dtype=np.float64) if b is not None else \
+                fn(given, a, dtype=np.float64)
+        np.testing.assert_allclose(got, target, rtol=1e-6, atol=atol, err_msg=fam)
+        n += 1
+    assert n == 29

@@ -11,6 +11,8 @@ from . import distributions
 from . import variational
 from . import fused
 from . import dist
+from . import diagnostics
+from . import ops
 from .framework import *
 from .framework import utils as _fw_utils
 from .hmc import *

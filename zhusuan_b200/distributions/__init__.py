@@ -1,3 +1,4 @@
 from .base import *
 from .univariate import *
 from .multivariate import *
+from .univariate_more import *

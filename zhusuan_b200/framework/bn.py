@@ -291,6 +291,80 @@ class BayesianNet(_BayesianNet, Context):
                                        **kwargs)
         return self.stochastic(name, dist, n_samples=n_samples, **kwargs)
 
+    # ---- the other elementwise univariate families (bn.py:592-626, 686-838,
+    # 1027-1121); one generic factory body, the reference's signatures
+    def _univariate(self, cls, name, args, n_samples, kwargs, **dist_kw):
+        dist = cls(*args, **dict(dist_kw, **kwargs))
+        return self.stochastic(name, dist, n_samples=n_samples, **kwargs)
+
+    def fold_normal(self, name, mean=0., _sentinel=None, std=None, logstd=None,
+                    n_samples=None, group_ndims=0, is_reparameterized=True,
+                    check_numerics=False, **kwargs):
+        return self._univariate(
+            distributions.FoldNormal, name, (mean,), n_samples, kwargs,
+            _sentinel=_sentinel, std=std, logstd=logstd,
+            group_ndims=group_ndims, is_reparameterized=is_reparameterized,
+            check_numerics=check_numerics)
+
+    def uniform(self, name, minval=0., maxval=1., n_samples=None,
+                group_ndims=0, is_reparameterized=True, check_numerics=False,
+                **kwargs):
+        return self._univariate(
+            distributions.Uniform, name, (minval, maxval), n_samples, kwargs,
+            group_ndims=group_ndims, is_reparameterized=is_reparameterized,
+            check_numerics=check_numerics)
+
+    def gamma(self, name, alpha, beta, n_samples=None, group_ndims=0,
+              check_numerics=False, **kwargs):
+        return self._univariate(
+            distributions.Gamma, name, (alpha, beta), n_samples, kwargs,
+            group_ndims=group_ndims, check_numerics=check_numerics)
+
+    def beta(self, name, alpha, beta, n_samples=None, group_ndims=0,
+             check_numerics=False, **kwargs):
+        return self._univariate(
+            distributions.Beta, name, (alpha, beta), n_samples, kwargs,
+            group_ndims=group_ndims, check_numerics=check_numerics)
+
+    def inverse_gamma(self, name, alpha, beta, n_samples=None, group_ndims=0,
+                      check_numerics=False, **kwargs):
+        return self._univariate(
+            distributions.InverseGamma, name, (alpha, beta), n_samples, kwargs,
+            group_ndims=group_ndims, check_numerics=check_numerics)
+
+    def poisson(self, name, rate, n_samples=None, group_ndims=0,
+                dtype=torch.int32, check_numerics=False, **kwargs):
+        return self._univariate(
+            distributions.Poisson, name, (rate,), n_samples, kwargs,
+            group_ndims=group_ndims, dtype=dtype,
+            check_numerics=check_numerics)
+
+    def binomial(self, name, logits, n_experiments, n_samples=None,
+                 group_ndims=0, dtype=torch.int32, check_numerics=False,
+                 **kwargs):
+        return self._univariate(
+            distributions.Binomial, name, (logits, n_experiments), n_samples,
+            kwargs, group_ndims=group_ndims, dtype=dtype,
+            check_numerics=check_numerics)
+
+    def laplace(self, name, loc, scale, n_samples=None, group_ndims=0,
+                is_reparameterized=True, check_numerics=False, **kwargs):
+        return self._univariate(
+            distributions.Laplace, name, (loc, scale), n_samples, kwargs,
+            group_ndims=group_ndims, is_reparameterized=is_reparameterized,
+            check_numerics=check_numerics)
+
+    def bin_concrete(self, name, temperature, logits, n_samples=None,
+                     group_ndims=0, is_reparameterized=True,
+                     check_numerics=False, **kwargs):
+        return self._univariate(
+            distributions.BinConcrete, name, (temperature, logits), n_samples,
+            kwargs, group_ndims=group_ndims,
+            is_reparameterized=is_reparameterized,
+            check_numerics=check_numerics)
+
+    bin_gumbel_softmax = bin_concrete
+
     def unnormalized_multinomial(self, name, logits, normalize_logits=True,
                                  n_samples=None, group_ndims=0,
                                  dtype=torch.int32, **kwargs):

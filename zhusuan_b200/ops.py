@@ -130,6 +130,59 @@ def bernoulli_log_prob(given, logits, group_ndims=0):
     return _BernoulliLogProb.apply(given.to(_F32), logits, int(group_ndims))
 
 
+# ids of zsb_logprob_univariate_f32 (include/zsb200.h)
+UNI_FOLDNORMAL, UNI_UNIFORM, UNI_GAMMA, UNI_BETA, UNI_POISSON, UNI_BINOMIAL, \
+    UNI_INVGAMMA, UNI_LAPLACE, UNI_BINCONCRETE = range(9)
+
+
+class _UnivariateLogProb(torch.autograd.Function):
+    """Elementwise density ``dist`` of ``given`` under parameters (a, b) with
+    the group sum; analytic gradients wrt all three (univariate_ext.cu)."""
+
+    @staticmethod
+    def forward(ctx, dist, given, a, b, group_ndims):
+        shapes = [given.shape, a.shape] + ([b.shape] if b is not None else [])
+        full = torch.broadcast_shapes(*shapes)
+        group, out_shape = _group_of(full, group_ndims)
+        g, gn = _prep(given, full)
+        pa, an = _prep(a, full)
+        pb, bn = _prep(b, full) if b is not None else (None, 0)
+        n_out = 1
+        for d in out_shape:
+            n_out *= int(d)
+        out = torch.empty(out_shape, dtype=_F32, device=a.device)
+        lib.call("zsb_logprob_univariate_f32", dist, ptr(g), gn, ptr(pa), an,
+                 ptr(pb), bn, ptr(out), n_out, group, stream())
+        ctx.save_for_backward(g, pa, pb)
+        ctx.meta = (dist, gn, an, bn, n_out, group, full, given.shape, a.shape,
+                    b.shape if b is not None else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        g, pa, pb = ctx.saved_tensors
+        dist, gn, an, bn, n_out, group, full, gs, as_, bs = ctx.meta
+        need = ctx.needs_input_grad
+        gout = _f32c(gout)
+        dev = gout.device
+        dg = torch.empty(full, dtype=_F32, device=dev) if need[1] else None
+        da = torch.empty(full, dtype=_F32, device=dev) if need[2] else None
+        db = torch.empty(full, dtype=_F32, device=dev) \
+            if (need[3] and pb is not None) else None
+        lib.call("zsb_logprob_univariate_bwd_f32", dist, ptr(g), gn, ptr(pa),
+                 an, ptr(pb), bn, ptr(gout), n_out, group, ptr(dg), ptr(da),
+                 ptr(db), stream())
+        return (None, _sum_to(dg, gs) if dg is not None else None,
+                _sum_to(da, as_) if da is not None else None,
+                _sum_to(db, bs) if db is not None else None, None)
+
+
+def univariate_log_prob(dist, given, a, b=None, group_ndims=0):
+    """log-density of one of the UNI_* families + group sum."""
+    return _UnivariateLogProb.apply(int(dist), given.to(_F32), a, b,
+                                    int(group_ndims))
+
+
 def _rows_prep(t, batch_shape, C):
     """[..., C] operand against a broadcast batch shape -> (flat, rows)."""
     full = tuple(batch_shape) + (C,)
