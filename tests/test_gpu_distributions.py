@@ -390,7 +390,7 @@ def test_univariate_more_contract_and_sampling():
     with pytest.raises(ValueError, match="should be a scalar"):
         D.BinConcrete(one, one)
     n = 20000
-    a, b = torch.tensor([2.0, 5.0], device=dev), torch.tensor([1.5, 0.5], device=dev)
+    a, b = torch.tensor([2.0, 5.0], device=dev), torch.tensor([1.5, 2.5], device=dev)
     for d, mean in [(D.Gamma(a, b), a / b), (D.Beta(a, b), a / (a + b)),
                     (D.InverseGamma(a + 2, b), b / (a + 1)), (D.Poisson(a), a),
                     (D.Binomial(torch.zeros(2, device=dev), 10), torch.full((2,), 5.0)),
