@@ -145,6 +145,24 @@ int zsb_vimco_signal_f32(const float* x, float* signal, float* lme, int64_t oute
 int zsb_normalized_weights_f32(const float* x, float* w, int64_t outer, int64_t K, int64_t inner,
                                void* stream);
 
+/* ---- K8: dense layer of a VAE/BNN log-joint on tcgen05 with the likelihood fused into the GEMM
+ * epilogue (the model code of examples/variational_autoencoders/iwae.py:23-32: tf.layers.dense +
+ * bn.bernoulli('x', logits, group_ndims=1)); fp32 accuracy from a 3-product fp16 hi/lo split.
+ * Operands are fp16 plane pairs [2][rows][Kp], Kp = zsb_linear_tc_kpad(K), produced by
+ * zsb_split16_pad_f32 together with their power-of-two scale (device float[4], zeroed once).
+ *   epi 0: out [R, J] = h W^T + bias (ReLU if relu)
+ *   epi 1: out [R]    = sum_j Bernoulli(logits).log_prob(x[r % n_x, j])   (univariate.py:398-403,
+ *          base.py:303-304); part = scratch of zsb_linear_tc_nparts(J) * R floats
+ *   epi 2: out [R, J] = gout[r] * (x - sigmoid(logits))   (gradient of epi 1 wrt the logits)   */
+int zsb_linear_tc_kpad(int K);
+int zsb_linear_tc_nparts(int J);
+int zsb_split16_pad_f32(const float* src, int64_t rows, int K, void* planes, float* scale,
+                        void* stream);
+int zsb_linear_tc_f32(int epi, const void* w_planes, const float* scale_w, const void* h_planes,
+                      const float* scale_h, const float* bias, const float* x_obs, int64_t n_x,
+                      const float* gout, float* out, float* part, int64_t R, int J, int K,
+                      int relu, void* stream);
+
 /* ---- diagnostics: effective sample size (zhusuan/diagnostics.py:17-64, the Stan estimator) on the
  * device; samples [M, D] row-major with burn-in already dropped -> ess [D].  M >= 2. */
 int zsb_effective_sample_size_f32(const float* samples, int64_t M, int64_t D, float* ess,

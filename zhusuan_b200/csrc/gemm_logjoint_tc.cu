@@ -1,0 +1,352 @@
+// K8: dense layer of a VAE / BNN log-joint on the tensor cores, with the likelihood fused into the
+// GEMM epilogue so the [rows, features] logit matrix never reaches HBM (at
+// config 3 the decoder output is 262 144 x 784 logits = 822 MB in fp32).
+//
+//   acc[j, r] = sum_k W[j, k] * h[r, k]          (A = weight rows j, B = activation rows r)
+//   l[r, j]   = acc + bias[j]
+//   EPI 0  out[r, j] = l  (optionally ReLU)                      plain dense layer
+//   EPI 1  part[(j / 32), r] = sum_{j in 32-lane group} x[r % n_x, j] * l - softplus(l)
+//          = Bernoulli(logits = l).log_prob(x) summed over the feature axis (univariate.py:398-403
+//            + group_ndims = 1, base.py:303-304) once the partial rows are added up
+//   EPI 2  out[r, j] = g[r] * (x - sigmoid(l))                   d(sum_r g[r] * log_prob[r]) / dl
+//
+// fp32 accuracy on fp16 tensor cores: both operands are pre-split into scaled fp16 hi + lo planes
+// (zsb_split16_pad_f32), three kind::f16 tcgen05.mma per k-step accumulate hi*hi + hi*lo + lo*hi
+// in fp32 in TMEM (dropped term ~2^-22 relative) -- the scheme of the dense-Gaussian HMC kernel
+// (hmc_dense_tc.cu), whose pipeline this kernel shares: CTA pairs (cta_group::2, M = 256
+// features x N = 256 rows per unit), TMA producer warp, single-thread MMA issuer, 8 epilogue
+// warps, double-buffered TMEM accumulators.  As there, the product is computed transposed
+// (TMEM lane = feature j, column = row r) so an epilogue warp touches 32 consecutive features of
+// one row per instruction: coalesced x loads and out stores.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int GBK = 32;                       // 64 halves = 128 B per smem row (SWIZZLE_128B)
+using GC = Cfg2<GBK>;
+
+__device__ __forceinline__ float bern_lp(float x, float l) {   // -sigmoid_cross_entropy(x, l)
+  return -(fmaxf(l, 0.f) - l * x + __logf(1.f + __expf(-fabsf(l))));
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
+                  const __grid_constant__ CUtensorMap map_wlo,
+                  const __grid_constant__ CUtensorMap map_hhi,
+                  const __grid_constant__ CUtensorMap map_hlo, const float* __restrict__ bias,
+                  const float* __restrict__ x_obs, int64_t n_x, const float* __restrict__ gout,
+                  float* __restrict__ out, float* __restrict__ part, int64_t R, int J, int Kp,
+                  int relu, const float* __restrict__ scale_w, const float* __restrict__ scale_h) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + GC::STAGES * GC::STAGE;
+  const uint32_t full_bar = bars;
+  const uint32_t empty_bar = bars + 8 * GC::STAGES;
+  const uint32_t tfull_bar = bars + 16 * GC::STAGES;
+  const uint32_t tempty_bar = bars + 16 * GC::STAGES + 16;
+  const uint32_t tmem_slot = bars + 16 * GC::STAGES + 32;
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_blk = (J + BM - 1) / BM;                     // 128-feature blocks
+  const int n_pair = (n_blk + 1) / 2;
+  const int64_t c_blk = (R + BN - 1) / BN;                 // 256-row blocks
+  const int64_t n_units = c_blk * n_pair;
+  const int64_t unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
+  const int n_kb = Kp / (2 * GBK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GC::STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, 2 * 32 * NUM_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_whi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wlo) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hhi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hlo) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t u = unit0; u < n_units; u += unit_step) {
+        const int j0 = ((int)(u % n_pair) * 2 + (int)rank) * BM;         // own feature block
+        const int r0 = (int)((u / n_pair) * BN) + (int)rank * (BN / 2);  // own half of the rows
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t fb = full_bar + 8 * stage;
+          const uint32_t sa = smem_base + stage * GC::STAGE;
+          if (leader) mbar_expect_tx(fb, 2 * GC::STAGE);
+          tma_load_2d_2sm(sa, &map_whi, fb, kb * 2 * GBK, j0);
+          tma_load_2d_2sm(sa + GC::A_TILE, &map_wlo, fb, kb * 2 * GBK, j0);
+          tma_load_2d_2sm(sa + 2 * GC::A_TILE, &map_hhi, fb, kb * 2 * GBK, r0);
+          tma_load_2d_2sm(sa + 2 * GC::A_TILE + GC::B_TILE, &map_hlo, fb, kb * 2 * GBK, r0);
+          if (++stage == GC::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_2sm_f16();
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t u = unit0; u < n_units; u += unit_step) {
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * GC::STAGE;
+          const uint64_t a_hi = make_smem_desc<GBK>(sa);
+          const uint64_t a_lo = make_smem_desc<GBK>(sa + GC::A_TILE);
+          const uint64_t b_hi = make_smem_desc<GBK>(sa + 2 * GC::A_TILE);
+          const uint64_t b_lo = make_smem_desc<GBK>(sa + 2 * GC::A_TILE + GC::B_TILE);
+#pragma unroll
+          for (int k = 0; k < GBK / 8; ++k) {              // 16 halves = 32 B per k-step
+            const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);
+            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+            umma_f16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+            umma_f16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+            umma_f16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+          }
+          umma_commit_2sm(empty_bar + 8 * stage);
+          if (++stage == GC::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(tfull_bar + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9, both CTAs) =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const float acc_scale = 1.f / (scale_w[0] * scale_h[0]);   // powers of two: exact
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t u = unit0; u < n_units; u += unit_step) {
+      const int nb = (int)(u % n_pair) * 2 + (int)rank;
+      const int j = nb * BM + quarter * 32 + lane;
+      const bool j_ok = j < J;
+      const float b_j = (j_ok && bias) ? bias[j] : 0.f;
+      const int64_t r0 = (u / n_pair) * BN + half * (BN / 2);
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                            (uint32_t)(acc * BN + half * (BN / 2));
+      const int64_t part_row = (int64_t)(nb * 4 + quarter) * R;
+#pragma unroll 1
+      for (int c = 0; c < BN / 2; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + (uint32_t)c, v);           // all 32 lanes participate (sync.aligned)
+        tmem_ld_wait();
+        const int64_t rbase = r0 + c;
+        if (rbase >= R) continue;                   // warp-uniform
+        float lpv[16];
+        int64_t xr = (EPI != 0) ? rbase % n_x : 0;  // row of x for column 0 of the block
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int64_t r = rbase + jj;
+          const bool ok = j_ok && r < R;
+          const float l = fmaf(__uint_as_float(v[jj]), acc_scale, b_j);
+          if (EPI == 0) {
+            if (ok) out[r * J + j] = relu ? fmaxf(l, 0.f) : l;
+          } else {
+            const float xv = ok ? x_obs[xr * J + j] : 0.f;
+            if (EPI == 1) lpv[jj] = ok ? bern_lp(xv, l) : 0.f;
+            else if (ok) out[r * J + j] = gout[r] * (xv - 1.f / (1.f + __expf(-l)));
+            if (++xr == n_x) xr = 0;
+          }
+        }
+        if (EPI == 1) {
+          const float sum = warp_transpose_sum16(lpv, lane);
+          if (nb < n_blk && lane < 16 && rbase + lane < R) part[part_row + rbase + lane] = sum;
+        }
+      }
+      tc_fence_before();
+      if (leader) mbar_arrive(tempty_bar + 8 * acc);
+      else mbar_arrive_remote(tempty_bar + 8 * acc, 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
+                 ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// scale[0] = power of two s with max|src| * s in [2^11, 2^12); scale[2] = running max bits
+__global__ void __launch_bounds__(256) absmax2_kernel(const float* __restrict__ src, int64_t n,
+                                                      float* __restrict__ scale) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = fabsf(src[i]);
+    m = (a == a && a <= 3.0e38f) ? fmaxf(m, a) : m;
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0)
+    atomicMax(reinterpret_cast<unsigned int*>(scale) + 2, __float_as_uint(m));
+}
+__global__ void pow2_scale_kernel(float* __restrict__ scale) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float m = __uint_as_float(reinterpret_cast<unsigned int*>(scale)[2]);
+  int e = 0;
+  if (m > 0.f) frexpf(m, &e);
+  scale[0] = ldexpf(1.f, 12 - e);
+  reinterpret_cast<unsigned int*>(scale)[2] = 0u;
+}
+// src [rows, K] fp32 -> planes [2][rows][Kp] fp16 (hi, lo) of src * scale, zero padded to Kp
+__global__ void __launch_bounds__(256) split16_pad_kernel(const float* __restrict__ src,
+                                                          int64_t rows, int K, int Kp,
+                                                          __half* __restrict__ planes,
+                                                          const float* __restrict__ scale) {
+  const float s = scale[0];
+  const int64_t n = rows * Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Kp;
+    const int k = (int)(i - r * Kp);
+    const float x = (k < K) ? src[r * K + k] * s : 0.f;
+    const __half h = __float2half_rn(x);
+    planes[i] = h;
+    planes[n + i] = __float2half_rn(x - __half2float(h));
+  }
+}
+__global__ void __launch_bounds__(256) part_sum_kernel(const float* __restrict__ part,
+                                                       int n_parts, int64_t R,
+                                                       float* __restrict__ out) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < n_parts; ++p) s += part[(int64_t)p * R + r];
+    out[r] = s;
+  }
+}
+
+template <int EPI>
+cudaError_t linear_prepare() {
+  static const cudaError_t e =
+      cudaFuncSetAttribute(linear_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           GC::SMEM);
+  return e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zsb_linear_tc_kpad(int K) { return ((K + 63) / 64) * 64; }
+// rows of the partial-sum scratch of epi 1 (each [R] floats)
+int zsb_linear_tc_nparts(int J) { return 4 * 2 * ((((J + BM - 1) / BM) + 1) / 2); }
+
+// Operand preparation: src [rows, K] fp32 -> planes [2][rows][Kp] fp16 (Kp = zsb_linear_tc_kpad(K))
+// and scale[0] (device float[4] scratch, zero-initialised once by the caller).
+int zsb_split16_pad_f32(const float* src, int64_t rows, int K, void* planes, float* scale,
+                        void* stream) {
+  ZSB_REQUIRE(src && planes && scale && rows > 0 && K > 0, "zsb_split16_pad_f32: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kp = zsb_linear_tc_kpad(K);
+  const int64_t n = rows * (int64_t)K;
+  int64_t blocks = zsb_ceil_div(n, 256 * 8);
+  if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
+  if (blocks < 1) blocks = 1;
+  absmax2_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n, scale);
+  pow2_scale_kernel<<<1, 32, 0, st>>>(scale);
+  int64_t blocks2 = zsb_ceil_div(rows * (int64_t)Kp, 256 * 4);
+  if (blocks2 > ZSB_NUM_SMS * 32) blocks2 = ZSB_NUM_SMS * 32;
+  split16_pad_kernel<<<(unsigned)blocks2, 256, 0, st>>>(src, rows, K, Kp,
+                                                        reinterpret_cast<__half*>(planes), scale);
+  return zsb_check_launch("split16_pad");
+}
+
+// Fused dense layer on the tensor cores.  w_planes [2][J][Kp], h_planes [2][R][Kp] (fp16 planes
+// from zsb_split16_pad_f32 with their scales); bias [J] or NULL.
+//   epi 0: out [R, J] = h W^T + bias (ReLU if relu != 0)
+//   epi 1: out [R] = sum_j Bernoulli(logits = h W^T + bias).log_prob(x[r % n_x, j]);
+//          part = scratch of zsb_linear_tc_nparts(J) * R floats
+//   epi 2: out [R, J] = gout[r] * (x - sigmoid(logits))
+int zsb_linear_tc_f32(int epi, const void* w_planes, const float* scale_w, const void* h_planes,
+                      const float* scale_h, const float* bias, const float* x_obs, int64_t n_x,
+                      const float* gout, float* out, float* part, int64_t R, int J, int K,
+                      int relu, void* stream) {
+  ZSB_REQUIRE(epi >= 0 && epi <= 2, "zsb_linear_tc_f32: unknown epilogue");
+  ZSB_REQUIRE(w_planes && h_planes && scale_w && scale_h && out && R > 0 && J > 0 && K > 0,
+              "zsb_linear_tc_f32: bad args");
+  ZSB_REQUIRE(R < (1LL << 31), "zsb_linear_tc_f32: too many rows");
+  ZSB_REQUIRE(epi == 0 || (x_obs && n_x > 0), "zsb_linear_tc_f32: observations missing");
+  ZSB_REQUIRE(epi != 1 || part, "zsb_linear_tc_f32: partial-sum scratch missing");
+  ZSB_REQUIRE(epi != 2 || gout, "zsb_linear_tc_f32: upstream gradient missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kp = zsb_linear_tc_kpad(K);
+  const __half* wp = reinterpret_cast<const __half*>(w_planes);
+  const __half* hp = reinterpret_cast<const __half*>(h_planes);
+  CUtensorMap m_whi, m_wlo, m_hhi, m_hlo;
+  int rc;
+  if ((rc = make_map(&m_whi, wp, (uint64_t)J, (uint64_t)Kp, BM, GBK, 1))) return rc;
+  if ((rc = make_map(&m_wlo, wp + (int64_t)J * Kp, (uint64_t)J, (uint64_t)Kp, BM, GBK, 1)))
+    return rc;
+  if ((rc = make_map(&m_hhi, hp, (uint64_t)R, (uint64_t)Kp, BN / 2, GBK, 1))) return rc;
+  if ((rc = make_map(&m_hlo, hp + R * Kp, (uint64_t)R, (uint64_t)Kp, BN / 2, GBK, 1))) return rc;
+  const int n_blk = (J + BM - 1) / BM;
+  const int64_t n_units = ((R + BN - 1) / BN) * ((n_blk + 1) / 2);
+  int dev = 0, sms = ZSB_NUM_SMS;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t pairs = sms / 2;
+  if (n_units < pairs) pairs = n_units;
+  const unsigned grid = (unsigned)(2 * pairs);
+  cudaError_t prep;
+#define ZSB_LIN(EPI)                                                                           \
+  do {                                                                                         \
+    prep = linear_prepare<EPI>();                                                              \
+    if (prep == cudaSuccess)                                                                   \
+      linear_tc2_kernel<EPI><<<grid, NUM_THREADS, GC::SMEM, st>>>(                             \
+          m_whi, m_wlo, m_hhi, m_hlo, bias, x_obs, n_x, gout, epi == 1 ? nullptr : out, part,  \
+          R, J, Kp, relu, scale_w, scale_h);                                                   \
+  } while (0)
+  if (epi == 0) ZSB_LIN(0);
+  else if (epi == 1) ZSB_LIN(1);
+  else ZSB_LIN(2);
+#undef ZSB_LIN
+  if (prep != cudaSuccess) {
+    zsb_set_error("linear_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(prep));
+    return ZSB_ERR_CUDA;
+  }
+  rc = zsb_check_launch("linear_tc");
+  if (rc != ZSB_OK || epi != 1) return rc;
+  int64_t blocks = zsb_ceil_div(R, 256);
+  if (blocks > ZSB_NUM_SMS * 8) blocks = ZSB_NUM_SMS * 8;
+  part_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(part, 4 * n_blk, R, out);
+  return zsb_check_launch("linear_tc_part_sum");
+}
+
+}  // extern "C"

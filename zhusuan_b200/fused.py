@@ -7,7 +7,8 @@ import math
 import numpy as np
 import torch
 
-__all__ = ["GaussianLogJoint", "BNNRegressionLogJoint"]
+__all__ = ["GaussianLogJoint", "BNNRegressionLogJoint", "linear",
+           "linear_bernoulli_log_prob", "LinearBernoulli"]
 
 
 class GaussianLogJoint(object):
@@ -126,3 +127,171 @@ class BNNRegressionLogJoint(object):
                                                          self.y_logstd)
                            ).log_prob(y.unsqueeze(0))
         return lp + lpy.mean(1) * self.n_train
+
+
+
+# ---------------------------------------------------------------------------
+# K8: dense layers of a VAE / BNN log-joint on tcgen05 (gemm_logjoint_tc.cu)
+# ---------------------------------------------------------------------------
+def _tc_split(t2d):
+    """fp32 [rows, K] -> (fp16 planes [2, rows, Kp], scale float[4]) for the
+    tensor-core dense kernels (zsb_split16_pad_f32)."""
+    from ._lib import lib, ptr, stream
+    t2d = t2d.detach().to(torch.float32).contiguous()
+    rows, K = int(t2d.shape[0]), int(t2d.shape[1])
+    Kp = lib.load().zsb_linear_tc_kpad(K)
+    planes = torch.empty((2, rows, Kp), dtype=torch.float16, device=t2d.device)
+    scale = torch.zeros(4, dtype=torch.float32, device=t2d.device)
+    lib.call("zsb_split16_pad_f32", ptr(t2d), rows, K, ptr(planes), ptr(scale),
+             stream())
+    return planes, scale
+
+
+def _tc_linear(epi, wp, ws, hp, hs, bias, x, gout, R, J, K, relu=False):
+    from ._lib import lib, ptr, stream
+    dev = hp.device
+    part = None
+    if epi == 1:
+        out = torch.empty(R, dtype=torch.float32, device=dev)
+        part = torch.empty(lib.load().zsb_linear_tc_nparts(J) * R,
+                           dtype=torch.float32, device=dev)
+    else:
+        out = torch.empty((R, J), dtype=torch.float32, device=dev)
+    lib.call("zsb_linear_tc_f32", epi, ptr(wp), ptr(ws), ptr(hp), ptr(hs),
+             ptr(bias), ptr(x), int(x.shape[0]) if x is not None else 0,
+             ptr(gout), ptr(out), ptr(part), R, J, K, int(bool(relu)), stream())
+    return out
+
+
+class _Linear(torch.autograd.Function):
+    """y = relu?(h W^T + b) with the forward GEMM on the tensor cores at fp32
+    accuracy (epi 0).  The backward products are plain GEMMs (cuBLAS through
+    torch.matmul: library code, as the task allows for un-fused GEMMs)."""
+
+    @staticmethod
+    def forward(ctx, h, W, b, relu):
+        lead = h.shape[:-1]
+        h2 = h.reshape(-1, h.shape[-1])
+        R, K, J = int(h2.shape[0]), int(h2.shape[1]), int(W.shape[0])
+        wp, ws = _tc_split(W)
+        hp, hs = _tc_split(h2)
+        bias = b.detach().to(torch.float32).contiguous() if b is not None else None
+        y = _tc_linear(0, wp, ws, hp, hs, bias, None, None, R, J, K, relu)
+        ctx.save_for_backward(h2, W, y if relu else None)
+        ctx.meta = (lead, relu, b is not None)
+        return y.reshape(tuple(lead) + (J,))
+
+    @staticmethod
+    def backward(ctx, gy):
+        h2, W, y = ctx.saved_tensors
+        lead, relu, has_b = ctx.meta
+        g = gy.reshape(-1, gy.shape[-1])
+        if relu:
+            g = g * (y > 0)
+        need = ctx.needs_input_grad
+        dh = (g @ W).reshape(tuple(lead) + (W.shape[1],)) if need[0] else None
+        dW = g.t() @ h2 if need[1] else None
+        db = g.sum(0) if (has_b and need[2]) else None
+        return dh, dW, db, None
+
+
+def linear(h, W, b=None, relu=False):
+    """``relu?(h @ W.T + b)`` (``tf.layers.dense``) on the tcgen05 kernel."""
+    return _Linear.apply(h, W, b, bool(relu))
+
+
+class _LinearBernoulliLogProb(torch.autograd.Function):
+    """sum_j Bernoulli(logits = h W^T + b).log_prob(x)[..., j] without ever
+    writing the logits: forward = GEMM with the Bernoulli row-sum epilogue
+    (epi 1); backward = the same GEMM with the d/dlogits epilogue (epi 2),
+    then two plain GEMMs for dh and dW."""
+
+    @staticmethod
+    def forward(ctx, h, W, b, x):
+        lead = h.shape[:-1]
+        h2 = h.reshape(-1, h.shape[-1])
+        R, K, J = int(h2.shape[0]), int(h2.shape[1]), int(W.shape[0])
+        x2 = x.reshape(-1, J).to(torch.float32).contiguous()
+        if R % int(x2.shape[0]) != 0:
+            raise ValueError("rows of the observation (%d) must divide the rows "
+                             "of the activations (%d)" % (x2.shape[0], R))
+        wp, ws = _tc_split(W)
+        hp, hs = _tc_split(h2)
+        bias = b.detach().to(torch.float32).contiguous() if b is not None else None
+        lp = _tc_linear(1, wp, ws, hp, hs, bias, x2, None, R, J, K)
+        ctx.save_for_backward(h2, W, bias, x2, wp, ws, hp, hs)
+        ctx.meta = (lead, R, J, K, b is not None)
+        return lp.reshape(tuple(lead))
+
+    @staticmethod
+    def backward(ctx, glp):
+        h2, W, bias, x2, wp, ws, hp, hs = ctx.saved_tensors
+        lead, R, J, K, has_b = ctx.meta
+        g = glp.reshape(-1).to(torch.float32).contiguous()
+        dl = _tc_linear(2, wp, ws, hp, hs, bias, x2, g, R, J, K)
+        need = ctx.needs_input_grad
+        dh = (dl @ W).reshape(tuple(lead) + (K,)) if need[0] else None
+        dW = dl.t() @ h2 if need[1] else None
+        db = dl.sum(0) if (has_b and need[2]) else None
+        return dh, dW, db, None
+
+
+def linear_bernoulli_log_prob(h, W, b, x):
+    """log p(x | logits = h @ W.T + b) summed over the last axis, fused.
+    ``x`` ([n_x, J], 0/1) is broadcast over the leading rows of ``h``
+    (row r of h uses x[r % n_x]: the [particles, batch] layout of
+    iwae.py:23-32 flattened)."""
+    return _LinearBernoulliLogProb.apply(h, W, b, x)
+
+
+class LinearBernoulli(object):
+    """Drop-in for ``Bernoulli(logits=dense(h), group_ndims=1)`` as a
+    distribution plugin (duck-typed contract of bn.py:96-115): ``log_prob`` runs
+    the fused GEMM + Bernoulli epilogue; the logits are only materialised when
+    the node is *sampled* rather than observed."""
+
+    def __init__(self, h, W, b=None, dtype=torch.int32, group_ndims=1):
+        if group_ndims != 1:
+            raise ValueError("LinearBernoulli sums over the feature axis: "
+                             "group_ndims must be 1")
+        self._h, self._W, self._b = h, W, b
+        self.dtype = dtype
+        self.param_dtype = torch.float32
+        self.is_continuous = False
+        self.is_reparameterized = False
+        self.group_ndims = 1
+
+    @property
+    def logits(self):
+        return linear(self._h, self._W, self._b)
+
+    def get_batch_shape(self):
+        return torch.Size(tuple(self._h.shape[:-1]) + (int(self._W.shape[0]),))
+
+    def get_value_shape(self):
+        return torch.Size([])
+
+    batch_shape = property(lambda self: self.get_batch_shape())
+    value_shape = property(lambda self: self.get_value_shape())
+
+    def sample(self, n_samples=None):
+        from .distributions import Bernoulli
+        return Bernoulli(self.logits, dtype=self.dtype).sample(n_samples)
+
+    def log_prob(self, given):
+        J = int(self._W.shape[0])
+        lead = tuple(self._h.shape[:-1])
+        g = given.reshape(-1, J)
+        n_x = int(g.shape[0])
+        rows = 1
+        for d in lead:
+            rows *= int(d)
+        if tuple(given.shape) != lead + (J,):
+            # suffix-broadcast observation (e.g. x [N, J] against h [K, N, H])
+            if rows % n_x != 0 or tuple(given.shape[:-1]) != lead[len(lead) - (given.dim() - 1):]:
+                raise ValueError("given %s is not a suffix-broadcast of the "
+                                 "batch shape %s" % (tuple(given.shape), lead + (J,)))
+        return linear_bernoulli_log_prob(self._h, self._W, self._b, g)
+
+    def prob(self, given):
+        return torch.exp(self.log_prob(given))
