@@ -158,6 +158,11 @@ int zsb_linear_tc_kpad(int K);
 int zsb_linear_tc_nparts(int J);
 int zsb_split16_pad_f32(const float* src, int64_t rows, int K, void* planes, float* scale,
                         void* stream);
+/* src [R, C] -> planes [2][C][kpad(R)] of src^T (operands of the weight-gradient product) */
+int zsb_split16_pad_t_f32(const float* src, int64_t R, int C, void* planes, float* scale,
+                          void* stream);
+/* split-K slices an epi-0 launch uses when `part` (slices * R * J floats) is supplied */
+int zsb_linear_tc_slices(int64_t R, int J, int K);
 int zsb_linear_tc_f32(int epi, const void* w_planes, const float* scale_w, const void* h_planes,
                       const float* scale_h, const float* bias, const float* x_obs, int64_t n_x,
                       const float* gout, float* out, float* part, int64_t R, int J, int K,

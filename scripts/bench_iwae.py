@@ -38,25 +38,33 @@ def build(dev, seed=5, x_dim=784, z_dim=40, h=500):
     return W
 
 
-def step_fn(W, x, K, dev):
+def step_fn(W, x, K, dev, fused=False):
     n, x_dim = x.shape
     z_dim = W["em"].shape[0]
+    if fused:      # every dense layer on the tcgen05 kernel; Bernoulli fused into the last GEMM
+        lin = lambda h, w, b, relu=False: zs.fused.linear(h, w, b, relu=relu)
+    else:
+        lin = lambda h, w, b, relu=False: (F.relu(F.linear(h, w, b)) if relu
+                                           else F.linear(h, w, b))
 
     @zs.meta_bayesian_net(scope="gen", reuse_variables=True)
     def build_gen(n, n_particles):                                   # iwae.py:23-32
         bn = zs.BayesianNet()
         z = bn.normal("z", torch.zeros(n, z_dim, device=dev), std=1., group_ndims=1,
                       n_samples=n_particles)
-        hh = F.relu(F.linear(z.tensor, W["d1"], W["d1_b"]))
-        hh = F.relu(F.linear(hh, W["d2"], W["d2_b"]))
-        bn.bernoulli("x", F.linear(hh, W["d3"], W["d3_b"]), group_ndims=1)
+        hh = lin(z.tensor, W["d1"], W["d1_b"], True)
+        hh = lin(hh, W["d2"], W["d2_b"], True)
+        if fused:
+            bn.stochastic("x", zs.fused.LinearBernoulli(hh, W["d3"], W["d3_b"]))
+        else:
+            bn.bernoulli("x", F.linear(hh, W["d3"], W["d3_b"]), group_ndims=1)
         return bn
 
     def build_q_net(x, n_particles):                                 # iwae.py:35-44
         bn = zs.BayesianNet()
-        hh = F.relu(F.linear(x.float(), W["e1"], W["e1_b"]))
-        hh = F.relu(F.linear(hh, W["e2"], W["e2_b"]))
-        bn.normal("z", F.linear(hh, W["em"], W["em_b"]), logstd=F.linear(hh, W["es"], W["es_b"]),
+        hh = lin(x.float(), W["e1"], W["e1_b"], True)
+        hh = lin(hh, W["e2"], W["e2_b"], True)
+        bn.normal("z", lin(hh, W["em"], W["em_b"]), logstd=lin(hh, W["es"], W["es_b"]),
                   group_ndims=1, n_samples=n_particles)
         return bn
 
@@ -76,10 +84,13 @@ def main():
     rng = np.random.Generator(np.random.PCG64(4))
     x = torch.tensor(rng.random((N, 784)) < 0.13, dtype=torch.int32, device=dev)
     out = {}
-    for tf32 in (False, True):
+    grads = {}
+    for mode in ("fp32_matmul", "tf32_matmul", "tcgen05_split_fused"):
+        tf32 = mode == "tf32_matmul"
         torch.backends.cuda.matmul.allow_tf32 = tf32
         W = build(dev)
-        step = step_fn(W, x, K, dev)
+        zs.set_random_seed(1234)           # same eps in every mode
+        step = step_fn(W, x, K, dev, fused=(mode == "tcgen05_split_fused"))
         for _ in range(3):
             cost, g = step()
         torch.cuda.synchronize()
@@ -91,10 +102,14 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        out["tf32_matmul" if tf32 else "fp32_matmul"] = {
+        grads[mode] = torch.cat([t.reshape(-1) for t in g]).double()
+        out[mode] = {
             "ms_per_step": ms, "particle_elbos_per_s": K * N / (ms * 1e-3),
             "tflops_dense_layers": 3.97e6 * K * N / (ms * 1e-3) / 1e12,
             "bound_value": float(-cost)}
+    ref = grads["fp32_matmul"]
+    for mode in ("tf32_matmul", "tcgen05_split_fused"):
+        out[mode]["grad_rel_err_vs_fp32"] = float((grads[mode] - ref).norm() / ref.norm())
     # CPU baseline: the same graph in torch-CPU (restatement of the TF graph), small batch
     torch.backends.cuda.matmul.allow_tf32 = False
     Nc = 128

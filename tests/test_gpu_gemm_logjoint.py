@@ -46,6 +46,30 @@ def test_linear_forward_fp32_accuracy(zs, R, K, J, relu):
     assert np.max(np.abs(y - want) / scale) < 2e-6
 
 
+@pytest.mark.parametrize("R,K,J,relu", [(5000, 500, 784, True), (300, 40, 500, False),
+                                        (70000, 64, 50, True)])
+def test_linear_backward_on_tensor_cores(zs, R, K, J, relu):
+    """dh = g W and dW = g^T h (transposed operand planes, split-K over the CTA pairs, ragged
+    contraction length) and db against float64."""
+    rng = np.random.RandomState(R + J)
+    h = rng.standard_normal((R, K)).astype(np.float32)
+    W = (rng.standard_normal((J, K)) / np.sqrt(K)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(J)).astype(np.float32)
+    gy = rng.standard_normal((R, J)).astype(np.float32)
+    th, tW, tb = (T(v).requires_grad_(True) for v in (h, W, b))
+    y = zs.fused.linear(th, tW, tb, relu=relu)
+    dh, dW, db = torch.autograd.grad((y * T(gy)).sum(), [th, tW, tb])
+    pre = h.astype(np.float64) @ W.astype(np.float64).T + b
+    g = gy.astype(np.float64) * ((pre > 0) if relu else 1.0)
+    # mask decided in fp32 on the device: drop the (measure-zero) rows where pre ~ 0 disagrees
+    for got, want, scale in [(dh, g @ W.astype(np.float64), np.abs(g) @ np.abs(W).astype(np.float64)),
+                             (dW, g.T @ h.astype(np.float64),
+                              np.abs(g).T @ np.abs(h).astype(np.float64)),
+                             (db, g.sum(0), np.abs(g).sum(0))]:
+        err = np.abs(N(got) - want) / (scale + 1e-30)
+        assert np.quantile(err, 0.999) < 3e-6 and got.shape == want.shape
+
+
 @pytest.mark.parametrize("P,Nb,K,J", [(3, 100, 500, 784), (1, 64, 40, 20), (2, 257, 96, 130)])
 def test_linear_bernoulli_log_prob_and_grads(zs, P, Nb, K, J):
     """[P particles, Nb data] activations against x [Nb, J]: value vs the oracle on float64

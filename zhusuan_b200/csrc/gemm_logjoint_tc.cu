@@ -37,7 +37,8 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
                   const __grid_constant__ CUtensorMap map_hlo, const float* __restrict__ bias,
                   const float* __restrict__ x_obs, int64_t n_x, const float* __restrict__ gout,
                   float* __restrict__ out, float* __restrict__ part, int64_t R, int J, int Kp,
-                  int relu, const float* __restrict__ scale_w, const float* __restrict__ scale_h) {
+                  int relu, const float* __restrict__ scale_w, const float* __restrict__ scale_h,
+                  int k_slices) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + GC::STAGES * GC::STAGE;
@@ -56,9 +57,13 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
   const int n_blk = (J + BM - 1) / BM;                     // 128-feature blocks
   const int n_pair = (n_blk + 1) / 2;
   const int64_t c_blk = (R + BN - 1) / BN;                 // 256-row blocks
-  const int64_t n_units = c_blk * n_pair;
+  // work unit = (tile, k-slice): split-K (EPI 0 only) keeps all CTA pairs busy when the output
+  // is small and the contraction is long (dW = dl^T h: 784 x 500 outputs, K = 262 144 rows)
+  const int64_t n_tiles = c_blk * n_pair;
+  const int64_t n_units = n_tiles * k_slices;
   const int64_t unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
-  const int n_kb = Kp / (2 * GBK);
+  const int n_kb_all = Kp / (2 * GBK);
+  const int kb_per = (n_kb_all + k_slices - 1) / k_slices;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < GC::STAGES; ++s) {
@@ -90,10 +95,13 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hlo) : "memory");
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t u = unit0; u < n_units; u += unit_step) {
+      for (int64_t uu = unit0; uu < n_units; uu += unit_step) {
+        const int64_t u = uu % n_tiles;
+        const int kb0 = (int)(uu / n_tiles) * kb_per;
+        const int kb1 = min(kb0 + kb_per, n_kb_all);
         const int j0 = ((int)(u % n_pair) * 2 + (int)rank) * BM;         // own feature block
         const int r0 = (int)((u / n_pair) * BN) + (int)rank * (BN / 2);  // own half of the rows
-        for (int kb = 0; kb < n_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb = full_bar + 8 * stage;
           const uint32_t sa = smem_base + stage * GC::STAGE;
@@ -114,11 +122,13 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t u = unit0; u < n_units; u += unit_step) {
+      for (int64_t uu = unit0; uu < n_units; uu += unit_step) {
+        const int kb0 = (int)(uu / n_tiles) * kb_per;
+        const int kb1 = min(kb0 + kb_per, n_kb_all);
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < n_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * GC::STAGE;
@@ -129,7 +139,7 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
 #pragma unroll
           for (int k = 0; k < GBK / 8; ++k) {              // 16 halves = 32 B per k-step
             const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);
-            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+            const uint32_t first = ((kb - kb0) | k) != 0 ? 1u : 0u;
             umma_f16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
             umma_f16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
             umma_f16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
@@ -148,7 +158,11 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
     const float acc_scale = 1.f / (scale_w[0] * scale_h[0]);   // powers of two: exact
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t u = unit0; u < n_units; u += unit_step) {
+    for (int64_t uu = unit0; uu < n_units; uu += unit_step) {
+      const int64_t u = uu % n_tiles;
+      const int slice = (int)(uu / n_tiles);
+      const bool empty_slice = slice * kb_per >= n_kb_all;   // accumulator never written
+      float* __restrict__ out_s = (EPI == 0 && out) ? out + (int64_t)slice * R * J : out;
       const int nb = (int)(u % n_pair) * 2 + (int)rank;
       const int j = nb * BM + quarter * 32 + lane;
       const bool j_ok = j < J;
@@ -159,33 +173,71 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                             (uint32_t)(acc * BN + half * (BN / 2));
       const int64_t part_row = (int64_t)(nb * 4 + quarter) * R;
-#pragma unroll 1
-      for (int c = 0; c < BN / 2; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(trow + (uint32_t)c, v);           // all 32 lanes participate (sync.aligned)
-        tmem_ld_wait();
+      const float b_use = (slice == 0) ? b_j : 0.f;           // bias once across the slices
+      const bool warp_j_ok = __all_sync(0xffffffffu, j_ok);
+      // observations of one 16-column block (rows rbase .. rbase+15, this lane's feature j); all
+      // 16 loads are issued back to back, one block AHEAD of their use (L2 latency ~1 us)
+      auto load_x = [&](float* xe, float& ge, int c) {
+        if (EPI == 0) return;
         const int64_t rbase = r0 + c;
-        if (rbase >= R) continue;                   // warp-uniform
+        if (rbase >= R) return;                     // warp-uniform
+        int64_t xr = rbase % n_x;
+        const float* __restrict__ xp = x_obs + xr * J + j;
+        const bool full = warp_j_ok && rbase + 16 <= R;
+        if (full && xr + 16 <= n_x) {               // common case: no wrap, no predicates
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) xe[jj] = __ldg(xp + (uint32_t)jj * (uint32_t)J);
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            xe[jj] = (j_ok && rbase + jj < R) ? __ldg(xp) : 0.f;
+            if (++xr == n_x) { xr = 0; xp = x_obs + j; } else xp += J;
+          }
+        }
+        // upstream gradient of the 16 rows: lane jj holds gout[rbase + jj]
+        if (EPI == 2) ge = (lane < 16 && rbase + lane < R) ? __ldg(gout + rbase + lane) : 0.f;
+      };
+      auto process = [&](const uint32_t* v, const float* xe, float ge, int c) {
+        const int64_t rbase = r0 + c;
+        if (rbase >= R) return;                     // warp-uniform
         float lpv[16];
-        int64_t xr = (EPI != 0) ? rbase % n_x : 0;  // row of x for column 0 of the block
+        float* __restrict__ po = (EPI != 1) ? out_s + rbase * J + j : nullptr;
+        const bool full = warp_j_ok && rbase + 16 <= R;   // no per-element predicates
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
-          const int64_t r = rbase + jj;
-          const bool ok = j_ok && r < R;
-          const float l = fmaf(__uint_as_float(v[jj]), acc_scale, b_j);
+          const bool ok = full || (j_ok && rbase + jj < R);
+          const float l = empty_slice ? b_use : fmaf(__uint_as_float(v[jj]), acc_scale, b_use);
           if (EPI == 0) {
-            if (ok) out[r * J + j] = relu ? fmaxf(l, 0.f) : l;
+            if (ok) *po = relu ? fmaxf(l, 0.f) : l;
+          } else if (EPI == 1) {
+            lpv[jj] = ok ? bern_lp(xe[jj], l) : 0.f;
           } else {
-            const float xv = ok ? x_obs[xr * J + j] : 0.f;
-            if (EPI == 1) lpv[jj] = ok ? bern_lp(xv, l) : 0.f;
-            else if (ok) out[r * J + j] = gout[r] * (xv - 1.f / (1.f + __expf(-l)));
-            if (++xr == n_x) xr = 0;
+            const float g = __shfl_sync(0xffffffffu, ge, jj);
+            if (ok) *po = g * (xe[jj] - __fdividef(1.f, 1.f + __expf(-l)));
           }
+          if (EPI != 1) po += J;
         }
         if (EPI == 1) {
           const float sum = warp_transpose_sum16(lpv, lane);
           if (nb < n_blk && lane < 16 && rbase + lane < R) part[part_row + rbase + lane] = sum;
         }
+      };
+      // the TMEM load and the observation loads of block i+1 are in flight while block i is
+      // processed
+      uint32_t va[16], vb[16];
+      float xa[EPI ? 16 : 1], xb[EPI ? 16 : 1], ga = 0.f, gb = 0.f;
+      load_x(xa, ga, 0);
+      tmem_ld16(trow, va);
+#pragma unroll 1
+      for (int c = 0; c < BN / 2; c += 32) {
+        load_x(xb, gb, c + 16);
+        tmem_ld_wait();
+        tmem_ld16(trow + (uint32_t)(c + 16), vb);
+        process(va, xa, ga, c);
+        if (c + 32 < BN / 2) load_x(xa, ga, c + 32);
+        tmem_ld_wait();
+        if (c + 32 < BN / 2) tmem_ld16(trow + (uint32_t)(c + 32), va);
+        process(vb, xb, gb, c + 16);
       }
       tc_fence_before();
       if (leader) mbar_arrive(tempty_bar + 8 * acc);
@@ -241,6 +293,53 @@ __global__ void __launch_bounds__(256) split16_pad_kernel(const float* __restric
     planes[n + i] = __float2half_rn(x - __half2float(h));
   }
 }
+// src [R, C] fp32 -> planes [2][C][Rp] fp16 of (src * scale)^T, zero padded along R: the operand
+// layout of the weight-gradient product dW = dl^T h, whose contraction runs over the rows.
+__global__ void __launch_bounds__(256) split16_pad_t_kernel(const float* __restrict__ src,
+                                                            int64_t R, int C, int64_t Rp,
+                                                            __half* __restrict__ planes,
+                                                            const float* __restrict__ scale) {
+  __shared__ float tile[32][33];
+  const float s = scale[0];
+  const int64_t n = (int64_t)C * Rp;
+  const int64_t r_tiles = (Rp + 31) / 32;
+  const int c_tiles = (C + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  for (int64_t t = blockIdx.x; t < r_tiles * c_tiles; t += gridDim.x) {
+    const int64_t r0 = (t / c_tiles) * 32;
+    const int c0 = (int)(t % c_tiles) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = r0 + ty + 8 * i;
+      const int c = c0 + tx;
+      tile[ty + 8 * i][tx] = (r < R && c < C) ? src[r * C + c] * s : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + ty + 8 * i;
+      const int64_t r = r0 + tx;
+      if (c < C && r < Rp) {
+        const float x = tile[tx][ty + 8 * i];
+        const __half h = __float2half_rn(x);
+        planes[(int64_t)c * Rp + r] = h;
+        planes[n + (int64_t)c * Rp + r] = __float2half_rn(x - __half2float(h));
+      }
+    }
+    __syncthreads();
+  }
+}
+// out[i] = sum_s scratch[s][i]
+__global__ void __launch_bounds__(256) slice_sum_kernel(const float* __restrict__ scratch,
+                                                        int slices, int64_t n,
+                                                        float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < slices; ++k) s += scratch[(int64_t)k * n + i];
+    out[i] = s;
+  }
+}
 __global__ void __launch_bounds__(256) part_sum_kernel(const float* __restrict__ part,
                                                        int n_parts, int64_t R,
                                                        float* __restrict__ out) {
@@ -288,12 +387,44 @@ int zsb_split16_pad_f32(const float* src, int64_t rows, int K, void* planes, flo
   return zsb_check_launch("split16_pad");
 }
 
+// Transposed variant: src [R, C] -> planes [2][C][Rp] (Rp = zsb_linear_tc_kpad(R)) of src^T.
+int zsb_split16_pad_t_f32(const float* src, int64_t R, int C, void* planes, float* scale,
+                          void* stream) {
+  ZSB_REQUIRE(src && planes && scale && R > 0 && C > 0, "zsb_split16_pad_t_f32: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t Rp = ((R + 63) / 64) * 64;
+  const int64_t n = R * (int64_t)C;
+  int64_t blocks = zsb_ceil_div(n, 256 * 8);
+  if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
+  absmax2_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n, scale);
+  pow2_scale_kernel<<<1, 32, 0, st>>>(scale);
+  int64_t tiles = ((Rp + 31) / 32) * ((C + 31) / 32);
+  if (tiles > ZSB_NUM_SMS * 32) tiles = ZSB_NUM_SMS * 32;
+  split16_pad_t_kernel<<<(unsigned)tiles, 256, 0, st>>>(src, R, C, Rp,
+                                                        reinterpret_cast<__half*>(planes), scale);
+  return zsb_check_launch("split16_pad_t");
+}
+
 // Fused dense layer on the tensor cores.  w_planes [2][J][Kp], h_planes [2][R][Kp] (fp16 planes
 // from zsb_split16_pad_f32 with their scales); bias [J] or NULL.
 //   epi 0: out [R, J] = h W^T + bias (ReLU if relu != 0)
 //   epi 1: out [R] = sum_j Bernoulli(logits = h W^T + bias).log_prob(x[r % n_x, j]);
 //          part = scratch of zsb_linear_tc_nparts(J) * R floats
 //   epi 2: out [R, J] = gout[r] * (x - sigmoid(logits))
+// Split-K (epi 0 only): when the output has fewer than one 256 x 256 tile per CTA pair and `part`
+// is given (zsb_linear_tc_slices(R, J, K) * R * J floats), the contraction is cut into slices that
+// run on different CTA pairs and are summed afterwards (the weight-gradient shape dW = dl^T h).
+int zsb_linear_tc_slices(int64_t R, int J, int K) {
+  const int n_blk = (J + BM - 1) / BM;
+  const int64_t tiles = ((R + BN - 1) / BN) * ((n_blk + 1) / 2);
+  const int n_kb = zsb_linear_tc_kpad(K) / 64;
+  int64_t want = (ZSB_NUM_SMS / 2) / tiles;                 // CTA pairs per tile
+  if (want < 1) want = 1;
+  if (want > n_kb / 8) want = n_kb / 8;                      // >= 8 k-blocks per slice
+  if (want < 1) want = 1;
+  const int kb_per = (int)((n_kb + want - 1) / want);
+  return (n_kb + kb_per - 1) / kb_per;                       // no empty slice
+}
 int zsb_linear_tc_f32(int epi, const void* w_planes, const float* scale_w, const void* h_planes,
                       const float* scale_h, const float* bias, const float* x_obs, int64_t n_x,
                       const float* gout, float* out, float* part, int64_t R, int J, int K,
@@ -323,15 +454,26 @@ int zsb_linear_tc_f32(int epi, const void* w_planes, const float* scale_w, const
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int64_t pairs = sms / 2;
   if (n_units < pairs) pairs = n_units;
+  int k_slices = 1;
+  if (epi == 0 && part) {
+    k_slices = zsb_linear_tc_slices(R, J, K);
+    if (k_slices > 1 && relu) {
+      zsb_set_error("zsb_linear_tc_f32: ReLU cannot be fused into a split-K launch");
+      return ZSB_ERR_INVALID;
+    }
+  }
+  pairs = sms / 2;
+  if (n_units * k_slices < pairs) pairs = n_units * k_slices;
   const unsigned grid = (unsigned)(2 * pairs);
+  float* out_k = (k_slices > 1) ? part : out;
   cudaError_t prep;
 #define ZSB_LIN(EPI)                                                                           \
   do {                                                                                         \
     prep = linear_prepare<EPI>();                                                              \
     if (prep == cudaSuccess)                                                                   \
       linear_tc2_kernel<EPI><<<grid, NUM_THREADS, GC::SMEM, st>>>(                             \
-          m_whi, m_wlo, m_hhi, m_hlo, bias, x_obs, n_x, gout, epi == 1 ? nullptr : out, part,  \
-          R, J, Kp, relu, scale_w, scale_h);                                                   \
+          m_whi, m_wlo, m_hhi, m_hlo, bias, x_obs, n_x, gout, epi == 1 ? nullptr : out_k,      \
+          part, R, J, Kp, relu, scale_w, scale_h, k_slices);                                   \
   } while (0)
   if (epi == 0) ZSB_LIN(0);
   else if (epi == 1) ZSB_LIN(1);
@@ -342,6 +484,13 @@ int zsb_linear_tc_f32(int epi, const void* w_planes, const float* scale_w, const
     return ZSB_ERR_CUDA;
   }
   rc = zsb_check_launch("linear_tc");
+  if (rc == ZSB_OK && k_slices > 1) {
+    const int64_t n = R * (int64_t)J;
+    int64_t blocks = zsb_ceil_div(n, 256);
+    if (blocks > ZSB_NUM_SMS * 8) blocks = ZSB_NUM_SMS * 8;
+    slice_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(part, k_slices, n, out);
+    return zsb_check_launch("linear_tc_slice_sum");
+  }
   if (rc != ZSB_OK || epi != 1) return rc;
   int64_t blocks = zsb_ceil_div(R, 256);
   if (blocks > ZSB_NUM_SMS * 8) blocks = ZSB_NUM_SMS * 8;

@@ -147,10 +147,45 @@ def _tc_split(t2d):
     return planes, scale
 
 
-def _tc_linear(epi, wp, ws, hp, hs, bias, x, gout, R, J, K, relu=False):
+def _tc_split_t(t2d):
+    """fp32 [R, C] -> (fp16 planes [2, C, Rp] of the transpose, scale)."""
+    from ._lib import lib, ptr, stream
+    t2d = t2d.detach().to(torch.float32).contiguous()
+    R, C = int(t2d.shape[0]), int(t2d.shape[1])
+    Rp = lib.load().zsb_linear_tc_kpad(R)
+    planes = torch.empty((2, C, Rp), dtype=torch.float16, device=t2d.device)
+    scale = torch.zeros(4, dtype=torch.float32, device=t2d.device)
+    lib.call("zsb_split16_pad_t_f32", ptr(t2d), R, C, ptr(planes), ptr(scale),
+             stream())
+    return planes, scale
+
+
+def _tc_grad_input(g, W):
+    """dh [R, K] = g [R, J] @ W [J, K] on the tensor cores."""
+    wtp, wts = _tc_split(W.detach().t())
+    gp, gs = _tc_split(g)
+    return _tc_linear(0, wtp, wts, gp, gs, None, None, None, int(g.shape[0]),
+                      int(W.shape[1]), int(W.shape[0]))
+
+
+def _tc_grad_weight(g, h2):
+    """dW [J, K] = g^T [J, R] @ h [R, K]: contraction over the rows, split-K
+    over the CTA pairs."""
+    htp, hts = _tc_split_t(h2)
+    gtp, gts = _tc_split_t(g)
+    return _tc_linear(0, htp, hts, gtp, gts, None, None, None, int(g.shape[1]),
+                      int(h2.shape[1]), int(h2.shape[0]), split_k=True)
+
+
+def _tc_linear(epi, wp, ws, hp, hs, bias, x, gout, R, J, K, relu=False,
+               split_k=False):
     from ._lib import lib, ptr, stream
     dev = hp.device
     part = None
+    if epi == 0 and split_k:
+        slices = lib.load().zsb_linear_tc_slices(R, J, K)
+        if slices > 1:
+            part = torch.empty(slices * R * J, dtype=torch.float32, device=dev)
     if epi == 1:
         out = torch.empty(R, dtype=torch.float32, device=dev)
         part = torch.empty(lib.load().zsb_linear_tc_nparts(J) * R,
@@ -164,9 +199,9 @@ def _tc_linear(epi, wp, ws, hp, hs, bias, x, gout, R, J, K, relu=False):
 
 
 class _Linear(torch.autograd.Function):
-    """y = relu?(h W^T + b) with the forward GEMM on the tensor cores at fp32
-    accuracy (epi 0).  The backward products are plain GEMMs (cuBLAS through
-    torch.matmul: library code, as the task allows for un-fused GEMMs)."""
+    """y = relu?(h W^T + b): forward and both backward products on the
+    tcgen05 kernel at fp32 accuracy (epi 0; the weight gradient uses the
+    transposed operand planes and split-K)."""
 
     @staticmethod
     def forward(ctx, h, W, b, relu):
@@ -188,9 +223,11 @@ class _Linear(torch.autograd.Function):
         g = gy.reshape(-1, gy.shape[-1])
         if relu:
             g = g * (y > 0)
+        g = g.to(torch.float32).contiguous()
         need = ctx.needs_input_grad
-        dh = (g @ W).reshape(tuple(lead) + (W.shape[1],)) if need[0] else None
-        dW = g.t() @ h2 if need[1] else None
+        dh = _tc_grad_input(g, W).reshape(tuple(lead) + (W.shape[1],)) \
+            if need[0] else None
+        dW = _tc_grad_weight(g, h2) if need[1] else None
         db = g.sum(0) if (has_b and need[2]) else None
         return dh, dW, db, None
 
@@ -204,7 +241,7 @@ class _LinearBernoulliLogProb(torch.autograd.Function):
     """sum_j Bernoulli(logits = h W^T + b).log_prob(x)[..., j] without ever
     writing the logits: forward = GEMM with the Bernoulli row-sum epilogue
     (epi 1); backward = the same GEMM with the d/dlogits epilogue (epi 2),
-    then two plain GEMMs for dh and dW."""
+    then the input / weight gradient products on the same kernel."""
 
     @staticmethod
     def forward(ctx, h, W, b, x):
@@ -230,8 +267,9 @@ class _LinearBernoulliLogProb(torch.autograd.Function):
         g = glp.reshape(-1).to(torch.float32).contiguous()
         dl = _tc_linear(2, wp, ws, hp, hs, bias, x2, g, R, J, K)
         need = ctx.needs_input_grad
-        dh = (dl @ W).reshape(tuple(lead) + (K,)) if need[0] else None
-        dW = dl.t() @ h2 if need[1] else None
+        dh = _tc_grad_input(dl, W).reshape(tuple(lead) + (K,)) \
+            if need[0] else None
+        dW = _tc_grad_weight(dl, h2) if need[1] else None
         db = dl.sum(0) if (has_b and need[2]) else None
         return dh, dW, db, None
 
