@@ -259,6 +259,16 @@ int zsb_hmc_dense_leapfrog_h16_f32(const float* q_cur, const void* q_cur_planes,
                                    const float* bvec, const float* mu, const float* mass,
                                    const float* state, float p_scale, float* lp_part,
                                    float* k_part, int64_t chains, int64_t D, void* stream);
+/* impl 3: impl 2 with the fp16 planes of q produced inside the kernel (converter warps between
+ * TMA and MMA): HBM traffic per pass = the algorithmic 16*D bytes per chain.  scales: device
+ * float[8], [3] = sP, [4..6] rotating max|q| slots; prepare before pass 0 of each trajectory. */
+int zsb_hmc_dense_h16i_prepare_f32(const float* q, float* scales, int64_t n, void* stream);
+int zsb_hmc_dense_leapfrog_h16i_f32(const float* q_cur, float* q_next, const float* p_in,
+                                    float* p_out, const void* P_h16, const void* P_l16,
+                                    float* scales, int pass_index, const float* bvec,
+                                    const float* mu, const float* mass, const float* state,
+                                    float p_scale, float* lp_part, float* k_part, int64_t chains,
+                                    int64_t D, void* stream);
 int zsb_hmc_dense_finish_f32(const float* lp_part, const float* k_part, int ntiles, int64_t chains,
                              float const_term, float* lp_out, float* k_out, void* stream);
 

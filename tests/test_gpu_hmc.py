@@ -264,7 +264,7 @@ def _dense_pass_reference(q, p, P, b, mu, mass, eps, scale):
     return pn, qn, lp, k
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 @pytest.mark.parametrize("C,D", [(300, 512), (24, 32), (129, 288), (1000, 1024),
                                  (130, 64), (515, 192)])
 def test_dense_single_pass_vs_float64(zs, impl, C, D):
@@ -272,7 +272,7 @@ def test_dense_single_pass_vs_float64(zs, impl, C, D):
     (impl 0) and tcgen05 3xTF32 (impl 1) kernels, including ragged M / N tiles.
     Bar: per-evaluation log-prob and gradient-derived p within 1e-5 relative."""
     from zhusuan_b200._lib import lib, ptr, stream
-    if impl == 2 and D % 64:
+    if impl >= 2 and D % 64:
         pytest.skip("fp16-split path needs D % 64 == 0")
     rng = np.random.RandomState(C + D)
     P64, _ = OM.make_dense_gaussian_problem(D, seed=4)
@@ -293,7 +293,14 @@ def test_dense_single_pass_vs_float64(zs, impl, C, D):
     lpp = torch.zeros(nt * C, device="cuda"); kp = torch.zeros(nt * C, device="cuda")
     lp = torch.empty(C, device="cuda"); k = torch.empty(C, device="cuda")
     s = stream()
-    if impl == 2:
+    if impl == 3:   # planes built inside the kernel; scale from the max|q| slot
+        lj = zs.fused.GaussianLogJoint(P64, device="cuda")._zsb_fused
+        scales = torch.zeros(8, device="cuda"); scales[3] = lj["sP"]
+        lib.call("zsb_hmc_dense_h16i_prepare_f32", ptr(qt), ptr(scales), qt.numel(), s)
+        lib.call("zsb_hmc_dense_leapfrog_h16i_f32", ptr(qt), ptr(qn), ptr(pt), ptr(pn),
+                 ptr(lj["P_h16"]), ptr(lj["P_l16"]), ptr(scales), 0, ptr(bt), ptr(mut),
+                 ptr(mt), ptr(state), scale, ptr(lpp), ptr(kp), C, D, s)
+    elif impl == 2:
         lj = zs.fused.GaussianLogJoint(P64, device="cuda")._zsb_fused
         planes = torch.empty(2, C, D, dtype=torch.float16, device="cuda")
         nplanes = torch.empty_like(planes)
@@ -330,6 +337,9 @@ def test_dense_single_pass_vs_float64(zs, impl, C, D):
         qn32 = N(qn)
         res = qn32 - (qn32.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
         np.testing.assert_array_equal(N(qnlo), res)
+    if impl == 3:   # slot 1 now holds max|q_next| for the next pass, slot 2 is clear
+        slots = scales.view(torch.int32)[4:7].cpu().numpy().view(np.float32)
+        assert slots[1] == np.abs(N(qn)).max() and slots[2] == 0
     if impl == 2:   # the planes reconstruct q_next * sq to ~2^-22 relative
         sq = float(scales[0])
         rec = (N(nplanes[0]).astype(np.float64) + N(nplanes[1]).astype(np.float64)) / sq
@@ -353,7 +363,7 @@ def test_dense_tc_vs_simt_full_size(zs):
     D, C = 1024, 65536
     P, const = OM.make_dense_gaussian_problem(D, seed=2)
     res = []
-    for impl in (0, 1, 2):
+    for impl in (0, 1, 2, 3):
         lj = zs.fused.GaussianLogJoint(P)
         torch.manual_seed(3)
         x = torch.randn(C, D, device="cuda")
@@ -363,7 +373,7 @@ def test_dense_tc_vs_simt_full_size(zs):
         op.synchronize()
         res.append((N(info.hamiltonian), N(info.orig_hamiltonian),
                     N(info.acceptance_rate), N(x)))
-    for k in (1, 2):
+    for k in (1, 2, 3):
         np.testing.assert_allclose(res[k][1], res[0][1], rtol=1e-5)
         np.testing.assert_allclose(res[k][0], res[0][0], rtol=1e-5)
         np.testing.assert_allclose(res[k][2], res[0][2], rtol=0, atol=2e-3)
@@ -413,7 +423,7 @@ def test_leapfrog_count_edges_all_paths(zs, L):
     u = rng.random_sample(C).astype(np.float32)
     om = OM.DenseGaussian(P.astype(np.float32), None, const)
     oq, oi = OH.HMC(step_size=0.15, n_leapfrogs=L).step([q0], om.logp, om.grad, [npz], u)
-    for impl in (0, 1, 2):
+    for impl in (0, 1, 2, 3):
         x = T(q0)
         h = zs.HMC(step_size=0.15, n_leapfrogs=L, dense_impl=impl)
         op, info = h.sample(zs.fused.GaussianLogJoint(P), {}, {"x": x})
@@ -444,7 +454,7 @@ def test_single_chain_and_tiny_shapes(zs):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("path", ["diag", "dense0", "dense1", "dense2"])
+@pytest.mark.parametrize("path", ["diag", "dense0", "dense1", "dense2", "dense3"])
 def test_cuda_graph_replay_is_bitwise_eager(zs, path):
     """Device-driven iterations replayed from a CUDA graph (use_cuda_graph=True)
     give bit-identical chains, step sizes and mass estimates to the eager

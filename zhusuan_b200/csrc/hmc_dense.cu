@@ -191,6 +191,13 @@ int zsb_dense_leapfrog_h16_launch(const float* q_cur, const void* q_cur_planes, 
                                   int64_t chains, int D, cudaStream_t st);
 int zsb_dense_h16_prepare_launch(const float* q, void* planes, float* scales, int64_t n,
                                  cudaStream_t st);
+int zsb_dense_leapfrog_h16i_launch(const float* q_cur, float* q_next, const float* p_in,
+                                   float* p_out, const void* P_h16, const void* P_l16,
+                                   float* scales, int pass_index, const float* bvec,
+                                   const float* mu, const float* mass, const float* state,
+                                   float p_scale, float* lp_part, float* k_part, int64_t chains,
+                                   int D, cudaStream_t st);
+int zsb_dense_h16i_prepare_launch(const float* q, float* scales, int64_t n, cudaStream_t st);
 
 extern "C" {
 
@@ -263,6 +270,28 @@ int zsb_hmc_dense_leapfrog_h16_f32(const float* q_cur, const void* q_cur_planes,
   return zsb_dense_leapfrog_h16_launch(q_cur, q_cur_planes, q_next, q_next_planes, p_in, p_out,
                                        P_h16, P_l16, scales, bvec, mu, mass, state, p_scale,
                                        lp_part, k_part, chains, (int)D, (cudaStream_t)stream);
+}
+
+// impl 3: as impl 2, but the fp16 planes of q are built inside the kernel from the fp32 tile, so
+// a pass moves only the algorithmic 16*D bytes per chain through HBM.  scales: device float[8],
+// [3] = sP (caller), [4..6] = rotating max|q| slots.  Call the prepare entry point before pass 0
+// of every trajectory; pass_index counts the passes of that trajectory from 0.
+int zsb_hmc_dense_h16i_prepare_f32(const float* q, float* scales, int64_t n, void* stream) {
+  ZSB_REQUIRE(q && scales && n > 0, "zsb_hmc_dense_h16i_prepare_f32: bad args");
+  return zsb_dense_h16i_prepare_launch(q, scales, n, (cudaStream_t)stream);
+}
+int zsb_hmc_dense_leapfrog_h16i_f32(const float* q_cur, float* q_next, const float* p_in,
+                                    float* p_out, const void* P_h16, const void* P_l16,
+                                    float* scales, int pass_index, const float* bvec,
+                                    const float* mu, const float* mass, const float* state,
+                                    float p_scale, float* lp_part, float* k_part, int64_t chains,
+                                    int64_t D, void* stream) {
+  ZSB_REQUIRE(q_cur && p_in && p_out && P_h16 && P_l16 && mass && state && scales,
+              "zsb_hmc_dense_leapfrog_h16i_f32: null arg");
+  ZSB_REQUIRE(q_next != q_cur, "zsb_hmc_dense_leapfrog_h16i_f32: q_next must not alias q_cur");
+  return zsb_dense_leapfrog_h16i_launch(q_cur, q_next, p_in, p_out, P_h16, P_l16, scales,
+                                        pass_index, bvec, mu, mass, state, p_scale, lp_part,
+                                        k_part, chains, (int)D, (cudaStream_t)stream);
 }
 
 int zsb_hmc_dense_finish_f32(const float* lp_part, const float* k_part, int ntiles, int64_t chains,

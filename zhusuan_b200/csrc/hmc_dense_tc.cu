@@ -38,7 +38,7 @@ struct EpiArgs {
   int h16; float q_scale; float acc_scale;
 };
 // residual operand(s) of q_next for the next pass's MMA
-template <int H16>
+template <int H16>   // 0: TF32 residual, 1: fp16 hi/lo planes
 __device__ __forceinline__ void store_split(const EpiArgs& a, float* __restrict__ lo_f32,
                                             __half* __restrict__ hi_pl, __half* __restrict__ lo_pl,
                                             uint32_t off, float qn) {
@@ -60,7 +60,7 @@ __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t tr
                                                    bool n_ok, bool parts_ok, int64_t c0,
                                                    int64_t part_row, int lane, float s2,
                                                    float eps_over_m, float inv_m, float b_n,
-                                                   float mu_n, bool skip) {
+                                                   float mu_n, bool skip, float& amax) {
   const uint32_t D = DC ? (uint32_t)DC : (uint32_t)a.D;
   const int64_t chains = a.chains;
   const bool has_next = NEXT < 0 ? (a.q_next != nullptr) : (NEXT != 0);
@@ -73,19 +73,21 @@ __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t tr
   const float* __restrict__ qc0 = a.q_cur + off_t;
   float* __restrict__ po0 = a.p_out + off_t;
   float* __restrict__ qn0 = has_next ? a.q_next + off_t : nullptr;
-  float* __restrict__ lo0 = (has_next && !H16) ? a.q_next_lo + off_t : nullptr;
+  // H16 == 2: the next pass splits q_next itself (in-kernel conversion); only max|q_next| is
+  // tracked here for its scale
+  float* __restrict__ lo0 = (has_next && H16 == 0) ? a.q_next_lo + off_t : nullptr;
   __half* __restrict__ hi_pl0 =
-      (has_next && H16) ? reinterpret_cast<__half*>(a.q_next_lo) + off_t : nullptr;
-  __half* __restrict__ lo_pl0 = (has_next && H16) ? hi_pl0 + chains * (int64_t)D : nullptr;
+      (has_next && H16 == 1) ? reinterpret_cast<__half*>(a.q_next_lo) + off_t : nullptr;
+  __half* __restrict__ lo_pl0 = (has_next && H16 == 1) ? hi_pl0 + chains * (int64_t)D : nullptr;
 
   // `c`: first column of the 16-column block, relative to c0
   auto compute = [&](const uint32_t* v, const float* pe, const float* qe, int c) {
     const size_t cb = (size_t)c * D;
     float* __restrict__ po = po0 + cb;
     float* __restrict__ qn_p = has_next ? qn0 + cb : nullptr;
-    float* __restrict__ lo_p = (has_next && !H16) ? lo0 + cb : nullptr;
-    __half* __restrict__ hp = (has_next && H16) ? hi_pl0 + cb : nullptr;
-    __half* __restrict__ lp = (has_next && H16) ? lo_pl0 + cb : nullptr;
+    float* __restrict__ lo_p = (has_next && H16 == 0) ? lo0 + cb : nullptr;
+    __half* __restrict__ hp = (has_next && H16 == 1) ? hi_pl0 + cb : nullptr;
+    __half* __restrict__ lp = (has_next && H16 == 1) ? lo_pl0 + cb : nullptr;
     float lpv[MODE >= 1 ? 16 : 1], kv[MODE >= 2 ? 16 : 1];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -97,7 +99,12 @@ __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t tr
       if (has_next) {
         const float qn = fmaf(eps_over_m, pn, qe[j]);
         qn_p[(uint32_t)j * D] = qn;
-        store_split<H16>(a, lo_p, hp, lp, (uint32_t)j * D, qn);
+        if (H16 == 2) {
+          const float aq = fabsf(qn);
+          amax = (aq <= 3.0e38f) ? fmaxf(amax, aq) : amax;      // ignores NaN / inf
+        } else {
+          store_split<H16>(a, lo_p, hp, lp, (uint32_t)j * D, qn);
+        }
       }
     }
     if (MODE >= 1) {
@@ -166,7 +173,12 @@ __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t tr
             if (has_next) {
               const float qn = fmaf(eps_over_m, pn, qe[j]);
               qn0[cb + (uint32_t)j * D] = qn;
-              store_split<H16>(a, lo0 + cb, hi_pl0 + cb, lo_pl0 + cb, (uint32_t)j * D, qn);
+              if (H16 == 2) {
+                const float aq = fabsf(qn);
+                amax = (aq <= 3.0e38f) ? fmaxf(amax, aq) : amax;
+              } else {
+                store_split<H16>(a, lo0 + cb, hi_pl0 + cb, lo_pl0 + cb, (uint32_t)j * D, qn);
+              }
             }
           }
         }
@@ -343,8 +355,10 @@ dense_leapfrog_tc_kernel(const __grid_constant__ CUtensorMap map_phi,
       const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
       const EpiArgs ea{q_cur, q_next, q_next_lo, p_in, p_out, lp_part, k_part, chains, D,
                        0, 1.f, 1.f};
-      epilogue_half_tile<MODE, -1, 0, 0>(ea, trow, n, n_ok, true, c0, part_row, lane, s2, eps_over_m, inv_m,
-                               b_n, mu_n, (dbg & 1) != 0);
+      float unused_amax = 0.f;
+      epilogue_half_tile<MODE, -1, 0, 0>(ea, trow, n, n_ok, true, c0, part_row, lane, s2,
+                                         eps_over_m, inv_m, b_n, mu_n, (dbg & 1) != 0,
+                                         unused_amax);
       tc_fence_before();
       mbar_arrive(tempty_bar + 8 * acc);               // all epilogue threads free the accumulator
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -533,8 +547,10 @@ dense_leapfrog_tc2_kernel(const __grid_constant__ CUtensorMap map_phi,
       const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
       const EpiArgs ea{q_cur, q_next, q_next_lo, p_in, p_out, lp_part, k_part, chains, D,
                        OP, q_scale, acc_scale};
-      epilogue_half_tile<MODE, NEXT, DC, OP>(ea, trow, n, n_ok, nb < n_blk, c0, part_row, lane, s2, eps_over_m,
-                               inv_m, b_n, mu_n, (dbg & 1) != 0);
+      float unused_amax = 0.f;
+      epilogue_half_tile<MODE, NEXT, DC, OP>(ea, trow, n, n_ok, nb < n_blk, c0, part_row, lane,
+                                             s2, eps_over_m, inv_m, b_n, mu_n, (dbg & 1) != 0,
+                                             unused_amax);
       tc_fence_before();
       if (leader) mbar_arrive(tempty_bar + 8 * acc);
       else mbar_arrive_remote(tempty_bar + 8 * acc, 0);   // leader's barrier counts both CTAs
@@ -655,6 +671,358 @@ int launch_tc(const float* q_cur, const float* q_cur_lo, float* q_next, float* q
   else ZSB_TC_LAUNCH(0);
 #undef ZSB_TC_LAUNCH
   return zsb_check_launch("hmc_dense_leapfrog_tc");
+}
+
+// ------------------------------------------------------------------------------------------------
+// impl 3: the fp16 hi/lo planes of q are produced INSIDE the kernel.  HBM traffic per launch drops
+// from 24*D to the algorithmic 16*D bytes per chain (read q, p; write q_next, p_out): the planes of
+// q_next are no longer written by one pass and read back by the next.
+//
+//   warp 0        TMA producer of the P planes (as the pair kernel)          -> a_full  (leader)
+//   warp 1        MMA issuer (leader): waits a_full + cvt_full               -> op_empty (both CTAs)
+//   warp 2        TMA producer of the fp32 q tile [128 chains x 64] (unswizzled staging ring,
+//                 3 deep: this is the HBM stream)                            -> raw_full (local)
+//   warps 3-6     converters: q * sq -> fp16 hi + lo, written in the SWIZZLE_128B K-major operand
+//                 layout (16-byte chunk index XOR row % 8); fence.proxy.async -> cvt_full (leader,
+//                 remote arrive from the peer), raw_empty (local)
+//   warps 7-14    epilogue (as the pair kernel, without the plane stores); tracks max|q_next|
+// The scale sq of a pass is derived from max|q_cur|, which the PREVIOUS pass's epilogue left in
+// one of three rotating device slots (pass k reads slot k%3, accumulates max|q_next| into slot
+// (k+1)%3 and clears slot (k+2)%3); zsb_hmc_dense_h16i_prepare_f32 seeds slot 0 from q itself.
+struct Cfg3 {
+  static constexpr int A_TILE = BM * 128;                    // 128 rows x 64 halves
+  static constexpr int B_TILE = (BN / 2) * 128;
+  static constexpr int OP_STAGE = 2 * A_TILE + 2 * B_TILE;   // 64 KB
+  static constexpr int OP_STAGES = 2;
+  static constexpr int RAW_STAGE = (BN / 2) * 64 * 4;        // 32 KB: 128 chains x 64 fp32
+  static constexpr int RAW_STAGES = 3;
+  static constexpr int BARS = OP_STAGES * OP_STAGE + RAW_STAGES * RAW_STAGE;   // 224 KB
+  static constexpr int SMEM = BARS + 256 + 1024;
+  static constexpr int CVT_WARPS = 4;
+  static constexpr int EPI_WARP0 = 3 + CVT_WARPS;            // first epilogue warp
+  static constexpr int THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);   // 480
+};
+
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
+
+template <int MODE, int NEXT, int DC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg3::THREADS, 1)
+dense_leapfrog_tc3_kernel(const __grid_constant__ CUtensorMap map_phi,
+                          const __grid_constant__ CUtensorMap map_plo,
+                          const __grid_constant__ CUtensorMap map_q32,
+                          const float* __restrict__ q_cur, float* __restrict__ q_next,
+                          const float* __restrict__ p_in, float* __restrict__ p_out,
+                          const float* __restrict__ bvec, const float* __restrict__ mu,
+                          const float* __restrict__ mass, const float* __restrict__ state,
+                          float p_scale, float* __restrict__ lp_part, float* __restrict__ k_part,
+                          int64_t chains, int D_rt, float* __restrict__ scales, int pass_index) {
+  using C = Cfg3;
+  const int D = DC ? DC : D_rt;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t raw_base = smem_base + C::OP_STAGES * C::OP_STAGE;
+  const uint32_t bars = smem_base + C::BARS;
+  const uint32_t a_full = bars;               // [2]  leader: bytes of both CTAs' P tiles
+  const uint32_t op_empty = bars + 16;        // [2]  each CTA: MMA commit (multicast)
+  const uint32_t raw_full = bars + 32;        // [3]  local: fp32 q tile landed
+  const uint32_t raw_empty = bars + 56;       // [3]  local: converters done with the tile
+  const uint32_t cvt_full = bars + 80;        // [2]  leader: both CTAs' planes written
+  const uint32_t tfull_bar = bars + 96;       // [2]
+  const uint32_t tempty_bar = bars + 112;     // [2]
+  const uint32_t tmem_slot = bars + 128;
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_blk = (D + BM - 1) / BM;
+  const int n_pair = (n_blk + 1) / 2;
+  const int64_t c_blk = (chains + BN - 1) / BN;
+  const int64_t n_units = c_blk * n_pair;
+  const int64_t unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
+  const int n_kb = D / 64;
+
+  // scale of this pass's q_cur from the running-max slot the previous pass (or prepare) filled
+  unsigned int* slots = reinterpret_cast<unsigned int*>(scales) + 4;      // scales[4..6]
+  const float qmax = __uint_as_float(slots[pass_index % 3]);
+  int qe = 0;
+  if (qmax > 0.f) frexpf(qmax, &qe);
+  const float sq = ldexpf(1.f, 12 - qe);                                 // max|q| * sq in [2^11, 2^12)
+  if (blockIdx.x == 0 && threadIdx.x == 0) slots[(pass_index + 2) % 3] = 0u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::OP_STAGES; ++s) {
+      mbar_init(a_full + 8 * s, 1);
+      mbar_init(op_empty + 8 * s, 1);
+      mbar_init(cvt_full + 8 * s, 2 * C::CVT_WARPS);
+    }
+    for (int s = 0; s < C::RAW_STAGES; ++s) {
+      mbar_init(raw_full + 8 * s, 1);
+      mbar_init(raw_empty + 8 * s, C::CVT_WARPS);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, 2 * 32 * NUM_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer: P planes (both CTAs) =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_phi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_plo) : "memory");
+      int os = 0;
+      uint32_t oph = 0;
+      for (int64_t u = unit0; u < n_units; u += unit_step) {
+        const int n0 = ((int)(u % n_pair) * 2 + (int)rank) * BM;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(op_empty + 8 * os, oph ^ 1);
+          const uint32_t fb = a_full + 8 * os;
+          const uint32_t sa = smem_base + os * C::OP_STAGE;
+          if (leader) mbar_expect_tx(fb, 2 * 2 * C::A_TILE);
+          tma_load_2d_2sm(sa, &map_phi, fb, kb * 64, n0);
+          tma_load_2d_2sm(sa + C::A_TILE, &map_plo, fb, kb * 64, n0);
+          if (++os == C::OP_STAGES) { os = 0; oph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_2sm_f16();
+      int os = 0;
+      uint32_t oph = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t u = unit0; u < n_units; u += unit_step) {
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(a_full + 8 * os, oph);            // both CTAs' P tiles have landed
+          mbar_wait(cvt_full + 8 * os, oph);          // both CTAs' q planes are written
+          tc_fence_after();
+          const uint32_t sa = smem_base + os * C::OP_STAGE;
+          const uint64_t a_hi = make_smem_desc<32>(sa);
+          const uint64_t a_lo = make_smem_desc<32>(sa + C::A_TILE);
+          const uint64_t b_hi = make_smem_desc<32>(sa + 2 * C::A_TILE);
+          const uint64_t b_lo = make_smem_desc<32>(sa + 2 * C::A_TILE + C::B_TILE);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                 // 16 halves = 32 B per k-step
+            const uint64_t ko = (uint64_t)((k * 32) >> 4);
+            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+            umma_f16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+            umma_f16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+            umma_f16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+          }
+          umma_commit_2sm(op_empty + 8 * os);
+          if (++os == C::OP_STAGES) { os = 0; oph ^= 1; }
+        }
+        umma_commit_2sm(tfull_bar + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== TMA producer: fp32 q tiles (both CTAs, local barriers) ==============
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q32) : "memory");
+      int rs = 0;
+      uint32_t rph = 0;
+      for (int64_t u = unit0; u < n_units; u += unit_step) {
+        const int c0 = (int)((u / n_pair) * BN) + (int)rank * (BN / 2);   // own chain half
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(raw_empty + 8 * rs, rph ^ 1);
+          const uint32_t fb = raw_full + 8 * rs;
+          mbar_expect_tx(fb, C::RAW_STAGE);
+          tma_load_2d(raw_base + rs * C::RAW_STAGE, &map_q32, fb, kb * 64, c0);
+          if (++rs == C::RAW_STAGES) { rs = 0; rph ^= 1; }
+        }
+      }
+    }
+  } else if (warp < C::EPI_WARP0) {
+    // ===================== converters (warps 3..6, both CTAs) =====================
+    const int cw = warp - 3;                              // rows cw*32 .. cw*32+31 of the tile
+    int os = 0, rs = 0;
+    uint32_t oph = 0, rph = 0;
+    const uint32_t chunk = (uint32_t)lane >> 2, sub = ((uint32_t)lane & 3u) << 2;
+    for (int64_t u = unit0; u < n_units; u += unit_step) {
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(raw_full + 8 * rs, rph);                // fp32 tile landed (async proxy write)
+        mbar_wait(op_empty + 8 * os, oph ^ 1);            // plane slot drained by the MMAs
+        const uint8_t* src = smem_raw + (raw_base - smem_u32(smem_raw)) + rs * C::RAW_STAGE;
+        uint8_t* dst_hi = smem_raw + (smem_base - smem_u32(smem_raw)) + os * C::OP_STAGE +
+                          2 * C::A_TILE;
+        uint8_t* dst_lo = dst_hi + C::B_TILE;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          const int r = cw * 32 + i;
+          const float2 v = *reinterpret_cast<const float2*>(src + r * 256 + lane * 8);
+          const float x0 = v.x * sq, x1 = v.y * sq;
+          const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+          const __half l0 = __float2half_rn(x0 - __half2float(h0));
+          const __half l1 = __float2half_rn(x1 - __half2float(h1));
+          const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+                               ((chunk ^ (uint32_t)(r & 7)) << 4) + sub;
+          *reinterpret_cast<__half2*>(dst_hi + off) = __halves2half2(h0, h1);
+          *reinterpret_cast<__half2*>(dst_lo + off) = __halves2half2(l0, l1);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the MMA proxy
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(raw_empty + 8 * rs);
+          if (leader) mbar_arrive(cvt_full + 8 * os);
+          else mbar_arrive_cluster(cvt_full + 8 * os, 0);
+        }
+        if (++os == C::OP_STAGES) { os = 0; oph ^= 1; }
+        if (++rs == C::RAW_STAGES) { rs = 0; rph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 7..14, both CTAs) =====================
+    const int quarter = warp & 3;
+    const int half = (warp - C::EPI_WARP0) >> 2;
+    const float eps = state[ZSB_ST_EPS_USED];
+    const float s2 = mul(eps, p_scale);
+    const float acc_scale = 1.f / (scales[3] * sq);      // powers of two: exact
+    float amax = 0.f;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t u = unit0; u < n_units; u += unit_step) {
+      const int nb = (int)(u % n_pair) * 2 + (int)rank;
+      const int n = nb * BM + quarter * 32 + lane;
+      const int64_t c0 = (u / n_pair) * BN + half * (BN / 2);
+      const bool n_ok = n < D;
+      const float m_n = n_ok ? mass[n] : 1.f;
+      const float eps_over_m = fdiv(eps, m_n);
+      const float inv_m = fdiv(1.f, m_n);
+      const float b_n = (n_ok && bvec) ? bvec[n] : 0.f;
+      const float mu_n = (n_ok && mu) ? mu[n] : 0.f;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                            (uint32_t)(acc * BN + half * (BN / 2));
+      const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
+      const EpiArgs ea{q_cur, q_next, nullptr, p_in, p_out, lp_part, k_part, chains, D,
+                       2, 1.f, acc_scale};
+      epilogue_half_tile<MODE, NEXT, DC, 2>(ea, trow, n, n_ok, nb < n_blk, c0, part_row, lane,
+                                            s2, eps_over_m, inv_m, b_n, mu_n, false, amax);
+      tc_fence_before();
+      if (leader) mbar_arrive(tempty_bar + 8 * acc);
+      else mbar_arrive_remote(tempty_bar + 8 * acc, 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (NEXT) {
+      amax = warp_max(amax);
+      if (lane == 0) atomicMax(slots + (pass_index + 1) % 3, __float_as_uint(amax));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
+                 ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int MODE, int NEXT, int DC>
+struct Tc3Inst {
+  static cudaError_t prepare() {
+    static const cudaError_t e = cudaFuncSetAttribute(
+        dense_leapfrog_tc3_kernel<MODE, NEXT, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        Cfg3::SMEM);
+    return e;
+  }
+};
+
+int launch_tc3(const float* q_cur, float* q_next, const float* p_in, float* p_out,
+               const void* P_h16, const void* P_l16, const float* bvec, const float* mu,
+               const float* mass, const float* state, float p_scale, float* lp_part,
+               float* k_part, int64_t chains, int D, float* scales, int pass_index,
+               cudaStream_t st) {
+  if (k_part && !lp_part) {
+    zsb_set_error("dense_tc3: k_part requires lp_part");
+    return ZSB_ERR_INVALID;
+  }
+  CUtensorMap m_phi, m_plo, m_q32;
+  int rc;
+  if ((rc = make_map(&m_phi, P_h16, (uint64_t)D, (uint64_t)D, BM, 32, 1))) return rc;
+  if ((rc = make_map(&m_plo, P_l16, (uint64_t)D, (uint64_t)D, BM, 32, 1))) return rc;
+  if ((rc = make_map_plain(&m_q32, q_cur, (uint64_t)chains, (uint64_t)D, BN / 2, 64))) return rc;
+  const int n_blk = (D + BM - 1) / BM;
+  const int64_t n_units = ((chains + BN - 1) / BN) * ((n_blk + 1) / 2);
+  int dev = 0, sms = ZSB_NUM_SMS;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t pairs = sms / 2;
+  if (n_units < pairs) pairs = n_units;
+  const unsigned grid = (unsigned)(2 * pairs);
+  cudaError_t prep = cudaSuccess;
+#define ZSB_TC3_LAUNCH(MODE, NEXT, DC)                                                         \
+  do {                                                                                         \
+    prep = Tc3Inst<MODE, NEXT, DC>::prepare();                                                 \
+    if (prep == cudaSuccess)                                                                   \
+      dense_leapfrog_tc3_kernel<MODE, NEXT, DC><<<grid, Cfg3::THREADS, Cfg3::SMEM, st>>>(      \
+          m_phi, m_plo, m_q32, q_cur, q_next, p_in, p_out, bvec, mu, mass, state, p_scale,     \
+          lp_part, k_part, chains, D, scales, pass_index);                                     \
+  } while (0)
+#define ZSB_TC3_MODE(NEXT, DC)                                                                 \
+  do {                                                                                         \
+    if (k_part) ZSB_TC3_LAUNCH(2, NEXT, DC);                                                   \
+    else if (lp_part) ZSB_TC3_LAUNCH(1, NEXT, DC);                                             \
+    else ZSB_TC3_LAUNCH(0, NEXT, DC);                                                          \
+  } while (0)
+#define ZSB_TC3_NEXT(DC)                                                                       \
+  do {                                                                                         \
+    if (q_next) ZSB_TC3_MODE(1, DC);                                                           \
+    else ZSB_TC3_MODE(0, DC);                                                                  \
+  } while (0)
+  if (D == 1024) ZSB_TC3_NEXT(1024);
+  else ZSB_TC3_NEXT(0);
+#undef ZSB_TC3_NEXT
+#undef ZSB_TC3_MODE
+#undef ZSB_TC3_LAUNCH
+  if (prep != cudaSuccess) {
+    zsb_set_error("dense_tc3: cudaFuncSetAttribute: %s", cudaGetErrorString(prep));
+    return ZSB_ERR_CUDA;
+  }
+  return zsb_check_launch("hmc_dense_leapfrog_tc3");
+}
+
+// seeds running-max slot 0 with max|q| and clears slots 1, 2 (scales[4..6])
+__global__ void __launch_bounds__(256) absmax_slot_kernel(const float* __restrict__ q, int64_t n,
+                                                          float* __restrict__ scales) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = fabsf(q[i]);
+    m = (a <= 3.0e38f) ? fmaxf(m, a) : m;
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0)
+    atomicMax(reinterpret_cast<unsigned int*>(scales) + 4, __float_as_uint(m));
+}
+__global__ void clear_slots_kernel(float* __restrict__ scales) {
+  if (threadIdx.x < 3 && blockIdx.x == 0) reinterpret_cast<unsigned int*>(scales)[4 + threadIdx.x] = 0u;
 }
 
 // one instantiation of the pair kernel: opt in to the dynamic shared memory once, then launch
@@ -820,6 +1188,33 @@ int zsb_dense_leapfrog_h16_launch(const float* q_cur, const void* q_cur_planes, 
                            reinterpret_cast<const float*>(P_h16),
                            reinterpret_cast<const float*>(P_l16), bvec, mu, mass, state, p_scale,
                            lp_part, k_part, chains, D, scales, st);
+}
+
+// impl 3 (in-kernel split).  scales: float[8] device scratch with scales[3] = sP.
+int zsb_dense_leapfrog_h16i_launch(const float* q_cur, float* q_next, const float* p_in,
+                                   float* p_out, const void* P_h16, const void* P_l16,
+                                   float* scales, int pass_index, const float* bvec,
+                                   const float* mu, const float* mass, const float* state,
+                                   float p_scale, float* lp_part, float* k_part, int64_t chains,
+                                   int D, cudaStream_t st) {
+  if (D % 64 != 0 || D < 64) {
+    zsb_set_error("dense_h16i: D must be a multiple of 64");
+    return ZSB_ERR_INVALID;
+  }
+  if (chains >= (1LL << 31) || !scales || pass_index < 0) {
+    zsb_set_error("dense_h16i: bad arguments");
+    return ZSB_ERR_INVALID;
+  }
+  return launch_tc3(q_cur, q_next, p_in, p_out, P_h16, P_l16, bvec, mu, mass, state, p_scale,
+                    lp_part, k_part, chains, D, scales, pass_index, st);
+}
+int zsb_dense_h16i_prepare_launch(const float* q, float* scales, int64_t n, cudaStream_t st) {
+  int64_t blocks = zsb_ceil_div(n, 256 * 8);
+  if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
+  if (blocks < 1) blocks = 1;
+  clear_slots_kernel<<<1, 32, 0, st>>>(scales);
+  absmax_slot_kernel<<<(unsigned)blocks, 256, 0, st>>>(q, n, scales);
+  return zsb_check_launch("hmc_dense_h16i_prepare");
 }
 
 // scales[3] must hold sP on entry; computes sq from max|q| and writes the fp16 hi/lo planes.

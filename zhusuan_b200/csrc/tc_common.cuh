@@ -265,4 +265,27 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
   return ZSB_OK;
 }
 
+// 2-D row-major [rows, cols] fp32 tensor, box = [box_rows, box_cols], NO swizzle: a staging tile
+// that ordinary threads read back (the in-kernel fp16 split of hmc_dense_tc.cu).
+int make_map_plain(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                   uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    zsb_set_error("dense_tc: cuTensorMapEncodeTiled unavailable");
+    return ZSB_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    zsb_set_error("dense_tc: cuTensorMapEncodeTiled (plain) failed (%d)", (int)r);
+    return ZSB_ERR_CUDA;
+  }
+  return ZSB_OK;
+}
+
 }  // namespace

@@ -502,8 +502,8 @@ class HMC(object):
             impl = f.get("impl")
         if impl is None:               # default: fastest legal tensor-core path
             impl = 2 if D % 64 == 0 else (1 if D % 32 == 0 else 0)
-        if int(impl) == 2 and D % 64 != 0:
-            raise ValueError("dense_impl=2 (fp16 split) needs D % 64 == 0")
+        if int(impl) in (2, 3) and D % 64 != 0:
+            raise ValueError("dense_impl=2/3 (fp16 split) needs D % 64 == 0")
         self._impl = int(impl)
         if self._impl >= 1:            # pipeline-shape tuning knob (same results)
             lib.call("zsb_hmc_dense_tc_config",
@@ -525,6 +525,10 @@ class HMC(object):
                     (2,) + tuple(t.shape), dtype=torch.float16, device=dev)
             self._scales = z(4)
             self._scales[3] = f["sP"]
+        if self._impl == 3:            # planes are built inside the kernel
+            self._scales = z(8)
+            self._scales[3] = f["sP"]
+        self._pass_k = 0
         self._lp0_part, self._lp1_part = z(nt * self._chains), \
             z(nt * self._chains)
         self._k_part = z(nt * self._chains)
@@ -533,6 +537,14 @@ class HMC(object):
     def _dense_pass(self, q_cur, q_next, p_in, p_out, scale, lp_part, k_part,
                     s):
         f = self._fused
+        if self._impl == 3:
+            lib.call("zsb_hmc_dense_leapfrog_h16i_f32", ptr(q_cur), ptr(q_next),
+                     ptr(p_in), ptr(p_out), ptr(f["P_h16"]), ptr(f["P_l16"]),
+                     ptr(self._scales), self._pass_k, ptr(f.get("b")),
+                     ptr(f.get("mu")), ptr(self._mass[0]), ptr(self._state),
+                     scale, ptr(lp_part), ptr(k_part), self._chains, f["D"], s)
+            self._pass_k += 1
+            return
         if self._impl == 2:
             lib.call("zsb_hmc_dense_leapfrog_h16_f32", ptr(q_cur),
                      ptr(self._lo[q_cur.data_ptr()]), ptr(q_next),
@@ -583,8 +595,14 @@ class HMC(object):
             lib.call("zsb_hmc_dense_h16_prepare_f32", ptr(q0),
                      ptr(self._lo[q0.data_ptr()]), ptr(self._scales),
                      q0.numel(), s)
+        def prepare3():                # impl 3: seed the max|q| slot, restart the pass count
+            if self._impl == 3:
+                lib.call("zsb_hmc_dense_h16i_prepare_f32", ptr(q0),
+                         ptr(self._scales), q0.numel(), s)
+                self._pass_k = 0
         if init:
             def probe():
+                prepare3()
                 self._dense_pass(q0, self._qa, self._p0[0], self._pw, 0.5,
                                  self._lp0_part, None, s)
                 self._dense_pass(self._qa, None, self._pw, self._pw, 0.5,
@@ -594,6 +612,7 @@ class HMC(object):
         L = self.n_leapfrogs
         cur, nxt = q0, self._qa
         p_in = self._p0[0]
+        prepare3()
         prof = getattr(self, "_profile_events", None)
         if self._dev_mode:
             prof = None
