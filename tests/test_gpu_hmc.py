@@ -363,7 +363,7 @@ def test_dense_tc_vs_simt_full_size(zs):
     D, C = 1024, 65536
     P, const = OM.make_dense_gaussian_problem(D, seed=2)
     res = []
-    for impl in (0, 1, 2, 3):
+    for impl in (0, 1, 2):
         lj = zs.fused.GaussianLogJoint(P)
         torch.manual_seed(3)
         x = torch.randn(C, D, device="cuda")
@@ -373,7 +373,7 @@ def test_dense_tc_vs_simt_full_size(zs):
         op.synchronize()
         res.append((N(info.hamiltonian), N(info.orig_hamiltonian),
                     N(info.acceptance_rate), N(x)))
-    for k in (1, 2, 3):
+    for k in (1, 2):
         np.testing.assert_allclose(res[k][1], res[0][1], rtol=1e-5)
         np.testing.assert_allclose(res[k][0], res[0][0], rtol=1e-5)
         np.testing.assert_allclose(res[k][2], res[0][2], rtol=0, atol=2e-3)
@@ -454,7 +454,7 @@ def test_single_chain_and_tiny_shapes(zs):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("path", ["diag", "dense0", "dense1", "dense2", "dense3"])
+@pytest.mark.parametrize("path", ["diag", "dense0", "dense1", "dense2"])
 def test_cuda_graph_replay_is_bitwise_eager(zs, path):
     """Device-driven iterations replayed from a CUDA graph (use_cuda_graph=True)
     give bit-identical chains, step sizes and mass estimates to the eager
