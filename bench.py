@@ -390,6 +390,13 @@ def main():
                            "unit": "TFLOP/s (fp32-equivalent 2*D^2 per "
                                    "chain-step vs measured bf16 dense peak)",
                            "frac": f_t}}
+        if impl >= 1:
+            # what the tensor pipe actually executes: 3 split products per algorithmic
+            # product (fp16 for impl 2/3; TF32, half the bf16 rate, for impl 1)
+            issued = 3.0 * tfl
+            pk = peaks["tf"] if impl >= 2 else peaks["tf"] / 2.0
+            roof["tensor"]["mma_issued_tflops"] = issued
+            roof["tensor"]["mma_issued_frac_of_peak"] = issued / pk
 
     # ---------------- CPU baseline on this box's host cores ------------------
     cpu = None

@@ -308,3 +308,41 @@ def test_shard_chains_partition():
     from zhusuan_b200 import dist
     assert dist.world() == (1, 0)
     assert dist.shard_chains(65536) == (0, 65536)
+
+
+def test_added_distribution_and_estimator_contracts_need_no_gpu():
+    """Argument checks of the added distributions / objectives fire before any kernel call
+    (messages of zhusuan/distributions/univariate.py and variational/*.py)."""
+    import warnings
+    import torch
+    import zhusuan_b200 as zs
+    D = zs.distributions
+    one = torch.ones(3)
+    with pytest.raises(ValueError, match="should be broadcastable to match"):
+        D.Beta(torch.ones(2), one)
+    with pytest.raises(ValueError, match="Either std or logstd"):
+        D.FoldNormal(one, std=one, logstd=one)
+    with pytest.raises(ValueError, match="n_experiments must be positive"):
+        D.Binomial(one, -1)
+    with pytest.raises(TypeError, match="must have the same dtype as"):
+        D.Uniform(one, one.double())
+    with pytest.raises(TypeError):
+        D.Poisson(torch.ones(3, dtype=torch.int32))
+    assert tuple(D.Laplace(torch.zeros(4, 1), one).get_batch_shape()) == (4, 3)
+    assert D.Gamma(one, one).is_reparameterized is False and D.Poisson(one).dtype == torch.int32
+    with pytest.raises(ValueError, match="group_ndims must be 1"):
+        zs.fused.LinearBernoulli(torch.ones(2, 4), torch.ones(5, 4), group_ndims=0)
+    x = torch.zeros(6)
+    lj = lambda obs: -obs["x"] ** 2
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        obj = zs.variational.klpq(lj, observed={}, latent={"x": [x, -x]}, axis=0)
+        iw = zs.variational.iw_objective(lj, observed={}, latent={"x": [x[:1], -x[:1]]}, axis=0)
+    with pytest.raises(NotImplementedError, match="can only be optimized"):
+        obj.tensor
+    with pytest.raises(ValueError, match="larger than 1"):
+        iw.vimco()
+    bn = zs.BayesianNet()
+    for name in ("gamma", "beta", "inverse_gamma", "poisson", "binomial", "laplace", "uniform",
+                 "fold_normal", "bin_concrete", "bin_gumbel_softmax"):
+        assert callable(getattr(bn, name))
