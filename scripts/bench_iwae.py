@@ -79,18 +79,33 @@ def step_fn(W, x, K, dev, fused=False):
 
 
 def main():
+    # one process per GPU under torchrun: the batch axis is sharded (weak scaling: 4096 data per
+    # GPU), particles stay local, ONE all-reduce of the packed gradient + bound per step
+    # (zhusuan_b200/dist.py)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        import torch.distributed as td
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        td.init_process_group("nccl")
     dev = torch.device("cuda")
     K, N = 64, 4096
-    rng = np.random.Generator(np.random.PCG64(4))
+    rng = np.random.Generator(np.random.PCG64(4 + rank))
     x = torch.tensor(rng.random((N, 784)) < 0.13, dtype=torch.int32, device=dev)
-    out = {}
+    out = {"n_gpus": world, "batch_per_gpu": N}
     grads = {}
     for mode in ("fp32_matmul", "tf32_matmul", "tcgen05_split_fused"):
         tf32 = mode == "tf32_matmul"
         torch.backends.cuda.matmul.allow_tf32 = tf32
         W = build(dev)
         zs.set_random_seed(1234)           # same eps in every mode
-        step = step_fn(W, x, K, dev, fused=(mode == "tcgen05_split_fused"))
+        local_step = step_fn(W, x, K, dev, fused=(mode == "tcgen05_split_fused"))
+
+        def step():
+            cost, g = local_step()
+            if world > 1:
+                g, (cost,) = zs.dist.all_reduce_mean_gradients(g, [cost.detach()], n_local=N)
+            return cost, g
         for _ in range(3):
             cost, g = step()
         torch.cuda.synchronize()
@@ -102,14 +117,21 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
+        if world > 1:                      # max over ranks, whole-job throughput
+            t = torch.tensor([ms], device=dev)
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            ms = float(t.item())
         grads[mode] = torch.cat([t.reshape(-1) for t in g]).double()
         out[mode] = {
-            "ms_per_step": ms, "particle_elbos_per_s": K * N / (ms * 1e-3),
-            "tflops_dense_layers": 3.97e6 * K * N / (ms * 1e-3) / 1e12,
+            "ms_per_step": ms, "particle_elbos_per_s": world * K * N / (ms * 1e-3),
+            "tflops_dense_layers": world * 3.97e6 * K * N / (ms * 1e-3) / 1e12,
             "bound_value": float(-cost)}
     ref = grads["fp32_matmul"]
     for mode in ("tf32_matmul", "tcgen05_split_fused"):
         out[mode]["grad_rel_err_vs_fp32"] = float((grads[mode] - ref).norm() / ref.norm())
+    if rank != 0:
+        td.destroy_process_group()
+        return
     # CPU baseline: the same graph in torch-CPU (restatement of the TF graph), small batch
     torch.backends.cuda.matmul.allow_tf32 = False
     Nc = 128
@@ -138,6 +160,8 @@ def main():
     out["cpu_port"] = {"particle_elbos_per_s": K * Nc / dt, "cores": torch.get_num_threads(),
                        "sample": "batch %d of 4096, K=64, torch-CPU restatement of iwae.py" % Nc}
     print(json.dumps(out))
+    if world > 1:
+        td.destroy_process_group()
 
 
 if __name__ == "__main__":
