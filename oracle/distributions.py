@@ -217,3 +217,23 @@ def bin_concrete_log_prob(given, temperature, logits, group_ndims=0, dtype=np.fl
     temp = t * (lx - l1x) - l
     lp = np.log(t) - lx - l1x + temp - 2 * _softplus(temp)
     return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def multinomial_log_prob(given, logits, n_experiments=None, normalize_logits=True,
+                         group_ndims=0, dtype=np.float32):
+    """multivariate.py:313-331: log n! - sum log k_i! + sum k_i * logits_i (normalised)."""
+    g, l = np.broadcast_arrays(np.asarray(given, dtype), np.asarray(logits, dtype))
+    if normalize_logits:
+        m = l.max(-1, keepdims=True)
+        l = l - (np.log(np.exp(l - m).sum(-1, keepdims=True)) + m)
+    n = g.sum(-1) if n_experiments is None else dtype(n_experiments)
+    lp = _sp.gammaln(n + 1) - _sp.gammaln(g + 1).sum(-1) + (g * l).sum(-1)
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def onehot_categorical_log_prob(given, logits, group_ndims=0, dtype=np.float32):
+    """multivariate.py:517-536: -softmax_cross_entropy(labels=given, logits)."""
+    g, l = np.broadcast_arrays(np.asarray(given, dtype), np.asarray(logits, dtype))
+    m = l.max(-1, keepdims=True)
+    l = l - (np.log(np.exp(l - m).sum(-1, keepdims=True)) + m)
+    return _group_sum((g * l).sum(-1).astype(dtype), group_ndims)

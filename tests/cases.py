@@ -177,3 +177,23 @@ def univariate_more_cases():
             2 * np.log(np.exp(logits) * (g ** -t) + (1 - g) ** -t)
         out.append(("bin_concrete", f32(given), f32(t), f32(logits), tgt, 1e-4))
     return out
+
+
+def multinomial_cases():
+    """tests/distributions/test_multivariate.py:218-253 `_test_value` literals with the target the
+    reference test computes (factorials + normalised logits).
+    -> list of (logits, n_experiments, given, normalize_logits, target)."""
+    from scipy.special import factorial, logsumexp
+    out = []
+    for normalize in (True, False):
+        for logits, n, given in [([-50., -20., 0.], 4, [1, 0, 3]),
+                                 ([1., 10., 1000.], 1, [1, 0, 0]),
+                                 ([[2., 3., 1.], [5., 7., 4.]], 7, np.array([3, 1, 3], np.int32)),
+                                 ([-10., 10., 20., 50.], 100, [[0, 1, 49, 50], [50, 49, 1, 0]])]:
+            l = np.array(logits, np.float32)
+            g = np.array(given)
+            ml = l - logsumexp(l, axis=-1, keepdims=True) if normalize else l
+            ne = np.sum(g, axis=-1)
+            tgt = np.log(factorial(ne)) - np.sum(np.log(factorial(g)), -1) + np.sum(g * ml, -1)
+            out.append((l, n, g, normalize, tgt))
+    return out

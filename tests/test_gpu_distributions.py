@@ -408,3 +408,43 @@ def test_univariate_more_contract_and_sampling():
     bn.poisson("k", a)
     assert tuple(g.cond_log_p.shape) == () and tuple(bn["l"].tensor.shape) == (5, 2)
     assert tuple(bn.log_joint().shape) == (5, 2)
+
+
+def test_multinomial_and_onehot_categorical():
+    """tests/distributions/test_multivariate.py:218-253, 505-533 through the classes (log_prob on
+    the unnormalised-multinomial kernel), gradients wrt logits, sampling, factories."""
+    import zhusuan_b200 as zs
+    D = zs.distributions
+    for l, n, g, normalize, tgt in cases.multinomial_cases():
+        for ne in (None, n):
+            d = D.Multinomial(torch.tensor(l, device="cuda"), ne, normalize_logits=normalize)
+            lp = d.log_prob(torch.tensor(g, device="cuda"))
+            np.testing.assert_allclose(lp.cpu().numpy(), tgt, rtol=1e-5, atol=1e-4)
+    rng = np.random.RandomState(0)
+    logits = rng.standard_normal((4, 6)).astype(np.float32)
+    tl = torch.tensor(logits, device="cuda", requires_grad=True)
+    counts = rng.multinomial(9, np.ones(6) / 6, size=(3, 4)).astype(np.int32)
+    d = D.Multinomial(tl, 9, group_ndims=1)
+    lp = d.log_prob(torch.tensor(counts, device="cuda"))
+    np.testing.assert_allclose(lp.detach().cpu().numpy(),
+                               OD.multinomial_log_prob(counts, logits, 9, group_ndims=1,
+                                                       dtype=np.float64), rtol=1e-5, atol=1e-4)
+    g, = torch.autograd.grad(lp.sum(), [tl])
+    soft = np.exp(logits - logits.max(-1, keepdims=True)); soft /= soft.sum(-1, keepdims=True)
+    np.testing.assert_allclose(g.cpu().numpy(), (counts - 9 * soft).sum(0), rtol=1e-4, atol=1e-4)
+    s = d.sample(5)
+    assert tuple(s.shape) == (5, 4, 6) and s.dtype == torch.int32
+    assert bool((s.sum(-1) == 9).all())
+    with pytest.raises(ValueError, match="Cannot sample"):
+        D.Multinomial(tl, None).sample(1)
+    oh = D.OnehotCategorical(tl)
+    so = oh.sample(7)
+    assert tuple(so.shape) == (7, 4, 6) and bool((so.sum(-1) == 1).all())
+    idx = so.argmax(-1)
+    np.testing.assert_allclose(oh.log_prob(so).detach().cpu().numpy(),
+                               D.Categorical(tl).log_prob(idx).detach().cpu().numpy(), rtol=1e-5,
+                               atol=1e-6)
+    bn = zs.BayesianNet()
+    bn.multinomial("m", tl, 9, n_samples=2)
+    bn.onehot_categorical("o", tl)
+    assert tuple(bn["m"].tensor.shape) == (2, 4, 6) and tuple(bn["o"].tensor.shape) == (4, 6)

@@ -282,3 +282,20 @@ def test_univariate_more_log_prob_vs_reference_targets():
         np.testing.assert_allclose(got, target, rtol=1e-6, atol=atol, err_msg=fam)
         n += 1
     assert n == 29
+
+
+def test_multinomial_and_onehot_vs_reference_targets():
+    """tests/distributions/test_multivariate.py:218-253 (Multinomial) and 505-533
+    (OnehotCategorical: one-hot of the Categorical cases, target = normalised logit)."""
+    for l, n, g, normalize, tgt in cases.multinomial_cases():
+        for ne in (None, n):
+            got = OD.multinomial_log_prob(g, l, ne, normalize, dtype=np.float64)
+            np.testing.assert_allclose(got, tgt, rtol=1e-6, atol=1e-6)
+    logits = np.array([[2., 3., 1.], [5., 7., 4.]], np.float32)
+    idx = np.array([1, 0])
+    onehot = np.eye(3)[idx]
+    want = (logits - np.log(np.exp(logits).sum(-1, keepdims=True)))[np.arange(2), idx]
+    np.testing.assert_allclose(OD.onehot_categorical_log_prob(onehot, logits, dtype=np.float64),
+                               want, rtol=1e-6)
+    np.testing.assert_allclose(OD.onehot_categorical_log_prob(onehot, logits, dtype=np.float64),
+                               OD.categorical_log_prob(idx, logits, dtype=np.float64), rtol=1e-6)

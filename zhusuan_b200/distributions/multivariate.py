@@ -9,7 +9,8 @@ from .utils import (assert_same_float_dtype, assert_dtype_is_int_or_float,
                     assert_rank_at_least)
 
 __all__ = ["MultivariateNormalCholesky", "UnnormalizedMultinomial",
-           "BagofCategoricals", "Dirichlet"]
+           "BagofCategoricals", "Dirichlet", "Multinomial",
+           "OnehotCategorical", "OnehotDiscrete"]
 
 
 class MultivariateNormalCholesky(Distribution):
@@ -103,6 +104,99 @@ class UnnormalizedMultinomial(Distribution):
 
 
 BagofCategoricals = UnnormalizedMultinomial
+
+
+class Multinomial(UnnormalizedMultinomial):
+    """multivariate.py:195-336: counts over ``n_categories`` from
+    ``n_experiments`` draws (``None``: inferred from ``given``, no sampling).
+    log_prob = log n! - sum log k_i! + sum k_i * log-softmax(logits)_i: the
+    last term is the zsb_logprob_unnorm_multinomial_f32 kernel, the
+    combinatorial term has no gradient."""
+
+    def __init__(self, logits, n_experiments, normalize_logits=True,
+                 dtype=torch.int32, group_ndims=0, **kwargs):
+        super(Multinomial, self).__init__(
+            logits, normalize_logits=normalize_logits, dtype=dtype,
+            group_ndims=group_ndims, **kwargs)
+        if n_experiments is not None:
+            if isinstance(n_experiments, torch.Tensor):
+                if n_experiments.dtype not in (torch.int32, torch.int64) or \
+                        n_experiments.dim() != 0:
+                    raise TypeError("Multinomial.n_experiments must be a 0-D "
+                                    "int32 Tensor")
+                n_experiments = int(n_experiments)
+            elif not isinstance(n_experiments, int):
+                raise TypeError("Multinomial.n_experiments must be int32")
+            if n_experiments <= 0:
+                raise ValueError("Multinomial.n_experiments must be positive")
+        self._n_experiments = n_experiments
+
+    n_experiments = property(lambda self: self._n_experiments)
+
+    def _sample(self, n_samples):
+        if self._n_experiments is None:
+            raise ValueError('Cannot sample when `n_experiments` is None')
+        probs = torch.softmax(self._logits.detach(), -1)
+        flat = probs.reshape(-1, self._n_categories)
+        draws = torch.multinomial(flat, int(n_samples) * self._n_experiments,
+                                  replacement=True)           # [B, S * n]
+        onehot = torch.nn.functional.one_hot(draws, self._n_categories)
+        counts = onehot.reshape(flat.shape[0], int(n_samples),
+                                self._n_experiments,
+                                self._n_categories).sum(2)    # [B, S, C]
+        counts = counts.permute(1, 0, 2).reshape(
+            (int(n_samples),) + tuple(self._logits.shape))
+        return counts.to(self.dtype)
+
+    def _log_prob(self, given):
+        g = given.to(torch.float32)
+        n = g.sum(-1) if self._n_experiments is None else \
+            torch.full((), float(self._n_experiments), device=g.device)
+        log_comb = torch.lgamma(n + 1) - torch.lgamma(g + 1).sum(-1)
+        lp = ops.unnormalized_multinomial_log_prob(
+            given, self._logits, self.normalize_logits, 0)
+        return ops.group_sum(log_comb.detach() + lp, self._group_ndims)
+
+
+class OnehotCategorical(Distribution):
+    """multivariate.py:452-567: one-hot valued categorical;
+    log_prob = -softmax_cross_entropy(labels=given, logits) = sum_i given_i *
+    log-softmax(logits)_i, i.e. the same kernel with normalised logits."""
+
+    def __init__(self, logits, dtype=torch.int32, group_ndims=0, **kwargs):
+        self._logits = convert_to_tensor(logits)
+        param_dtype = assert_same_float_dtype(
+            [(self._logits, 'OnehotCategorical.logits')])
+        assert_dtype_is_int_or_float(dtype)
+        assert_rank_at_least(self._logits, 1, 'OnehotCategorical.logits')
+        self._n_categories = int(self._logits.shape[-1])
+        super(OnehotCategorical, self).__init__(
+            dtype=dtype, param_dtype=param_dtype, is_continuous=False,
+            is_reparameterized=False, group_ndims=group_ndims, **kwargs)
+
+    logits = property(lambda self: self._logits)
+    n_categories = property(lambda self: self._n_categories)
+
+    def _get_value_shape(self):
+        return torch.Size([self._n_categories])
+
+    def _get_batch_shape(self):
+        return self._logits.shape[:-1]
+
+    def _sample(self, n_samples):
+        flat = torch.softmax(self._logits.detach(), -1).reshape(
+            -1, self._n_categories)
+        draws = torch.multinomial(flat, int(n_samples), replacement=True)
+        onehot = torch.nn.functional.one_hot(draws.t(), self._n_categories)
+        return onehot.reshape((int(n_samples),) + tuple(self._logits.shape)) \
+            .to(self.dtype)
+
+    def _log_prob(self, given):
+        return ops.unnormalized_multinomial_log_prob(
+            given, self._logits, True, self._group_ndims)
+
+
+OnehotDiscrete = OnehotCategorical
 
 
 class Dirichlet(Distribution):

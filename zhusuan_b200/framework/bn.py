@@ -376,6 +376,24 @@ class BayesianNet(_BayesianNet, Context):
 
     bag_of_categoricals = unnormalized_multinomial
 
+    def multinomial(self, name, logits, n_experiments, normalize_logits=True,
+                    n_samples=None, group_ndims=0, dtype=torch.int32,
+                    **kwargs):
+        """bn.py:872-904."""
+        dist = distributions.Multinomial(
+            logits, n_experiments, normalize_logits=normalize_logits,
+            group_ndims=group_ndims, dtype=dtype, **kwargs)
+        return self.stochastic(name, dist, n_samples=n_samples, **kwargs)
+
+    def onehot_categorical(self, name, logits, n_samples=None, group_ndims=0,
+                           dtype=torch.int32, **kwargs):
+        """bn.py:906-934."""
+        dist = distributions.OnehotCategorical(
+            logits, group_ndims=group_ndims, dtype=dtype, **kwargs)
+        return self.stochastic(name, dist, n_samples=n_samples, **kwargs)
+
+    onehot_discrete = onehot_categorical
+
     def multivariate_normal_cholesky(self, name, mean, cov_tril,
                                      n_samples=None, group_ndims=0,
                                      is_reparameterized=True,
