@@ -237,3 +237,44 @@ def onehot_categorical_log_prob(given, logits, group_ndims=0, dtype=np.float32):
     m = l.max(-1, keepdims=True)
     l = l - (np.log(np.exp(l - m).sum(-1, keepdims=True)) + m)
     return _group_sum((g * l).sum(-1).astype(dtype), group_ndims)
+
+
+def exp_concrete_log_prob(given, temperature, logits, group_ndims=0, dtype=np.float32):
+    """multivariate.py:800-812."""
+    x, l = np.asarray(given, dtype), np.asarray(logits, dtype)
+    t = dtype(temperature)
+    n = l.shape[-1]
+    temp = l - t * x
+    m = temp.max(-1, keepdims=True)
+    lse = (np.log(np.exp(temp - m).sum(-1, keepdims=True)) + m)[..., 0]
+    lp = _sp.gammaln(n) + (n - 1) * np.log(t) + temp.sum(-1) - n * lse
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def concrete_log_prob(given, temperature, logits, group_ndims=0, dtype=np.float32):
+    """multivariate.py:938-955."""
+    x, l = np.asarray(given, dtype), np.asarray(logits, dtype)
+    t = dtype(temperature)
+    n = l.shape[-1]
+    lx = np.log(x)
+    temp = l - t * lx
+    m = temp.max(-1, keepdims=True)
+    lse = (np.log(np.exp(temp - m).sum(-1, keepdims=True)) + m)[..., 0]
+    lp = _sp.gammaln(n) + (n - 1) * np.log(t) + (temp - lx).sum(-1) - n * lse
+    return _group_sum(lp.astype(dtype), group_ndims)
+
+
+def matrix_normal_cholesky_log_prob(given, mean, u_tril, v_tril, dtype=np.float64):
+    """multivariate.py:1123-1157 for a single (unbatched) distribution; given [..., r, c]."""
+    from scipy.linalg import solve_triangular
+    y = np.asarray(given, dtype) - np.asarray(mean, dtype)
+    lu, lv = np.asarray(u_tril, dtype), np.asarray(v_tril, dtype)
+    r, c = y.shape[-2:]
+    log_z = -(r * c) / 2. * np.log(2 * np.pi) - r / 2. * 2 * np.log(np.diag(lv)).sum() \
+        - c / 2. * 2 * np.log(np.diag(lu)).sum()
+    out = np.empty(y.shape[:-2], dtype)
+    for idx in np.ndindex(*y.shape[:-2]):
+        a = solve_triangular(lu, y[idx], lower=True)
+        x = solve_triangular(lv, a.T, lower=True)
+        out[idx] = log_z - 0.5 * np.square(x).sum()
+    return out

@@ -448,3 +448,53 @@ def test_multinomial_and_onehot_categorical():
     bn.multinomial("m", tl, 9, n_samples=2)
     bn.onehot_categorical("o", tl)
     assert tuple(bn["m"].tensor.shape) == (2, 4, 6) and tuple(bn["o"].tensor.shape) == (4, 6)
+
+
+def test_concrete_family_and_matrix_variate_normal():
+    """ExpConcrete / Concrete (multivariate.py:683-958) and MatrixVariateNormalCholesky
+    (:961-1160) through the classes: values vs the oracle / scipy, reparameterised sampling."""
+    import zhusuan_b200 as zs
+    from scipy import stats
+    D = zs.distributions
+    rng = np.random.RandomState(4)
+    logits = rng.standard_normal((5, 7)).astype(np.float32)
+    tl = torch.tensor(logits, device="cuda", requires_grad=True)
+    tt = torch.tensor(0.7, device="cuda", requires_grad=True)
+    for cls, ofn in ((D.Concrete, OD.concrete_log_prob), (D.ExpConcrete, OD.exp_concrete_log_prob)):
+        d = cls(tt, tl, group_ndims=0)
+        s = d.sample(6)
+        assert tuple(s.shape) == (6, 5, 7)
+        tot = s.sum(-1) if cls is D.Concrete else torch.exp(s).sum(-1)
+        np.testing.assert_allclose(tot.detach().cpu().numpy(), 1.0, rtol=1e-4)
+        lp = d.log_prob(s.detach())
+        want = ofn(s.detach().cpu().numpy(), 0.7, logits, dtype=np.float64)
+        np.testing.assert_allclose(lp.detach().cpu().numpy(), want, rtol=1e-4, atol=1e-3)
+        g = torch.autograd.grad(lp.sum() + s.sum() * 0, [tl, tt], allow_unused=True)
+        assert g[0] is not None and torch.isfinite(g[0]).all()
+        assert tuple(cls(tt, tl, group_ndims=1).log_prob(s.detach()).shape) == (6,)
+    with pytest.raises(ValueError, match="should be a scalar"):
+        D.Concrete(torch.ones(2, device="cuda"), tl)
+    # matrix-variate normal, batch [2]
+    r, c = 3, 4
+    us, vs, lus, lvs = [], [], [], []
+    for _ in range(2):
+        a = rng.standard_normal((r, r)); u = a @ a.T + r * np.eye(r)
+        b = rng.standard_normal((c, c)); v = b @ b.T + c * np.eye(c)
+        us.append(u); vs.append(v)
+        lus.append(np.linalg.cholesky(u)); lvs.append(np.linalg.cholesky(v))
+    mean = rng.standard_normal((2, r, c)).astype(np.float32)
+    f = lambda a: torch.tensor(np.asarray(a), dtype=torch.float32, device="cuda")
+    tm = f(mean).requires_grad_(True)
+    dst = D.MatrixVariateNormalCholesky(tm, f(lus), f(lvs))
+    x = dst.sample(50)
+    assert tuple(x.shape) == (50, 2, r, c) and x.requires_grad
+    lp = dst.log_prob(x.detach())
+    assert tuple(lp.shape) == (50, 2)
+    for b in range(2):
+        want = stats.matrix_normal.logpdf(x[:, b].detach().cpu().numpy().astype(np.float64),
+                                          mean[b], us[b], vs[b])
+        np.testing.assert_allclose(lp[:, b].detach().cpu().numpy(), want, rtol=1e-4, atol=1e-3)
+    bn = zs.BayesianNet()
+    bn.concrete("c", tt, tl, n_samples=2)
+    bn.matrix_variate_normal_cholesky("m", tm, f(lus), f(lvs))
+    assert tuple(bn["c"].tensor.shape) == (2, 5, 7) and tuple(bn["m"].tensor.shape) == (2, r, c)

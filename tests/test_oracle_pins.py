@@ -299,3 +299,32 @@ def test_multinomial_and_onehot_vs_reference_targets():
                                want, rtol=1e-6)
     np.testing.assert_allclose(OD.onehot_categorical_log_prob(onehot, logits, dtype=np.float64),
                                OD.categorical_log_prob(idx, logits, dtype=np.float64), rtol=1e-6)
+
+
+def test_concrete_family_and_matrix_normal_vs_reference_targets():
+    """tests/distributions/test_multivariate.py: ExpConcrete :735-759 and Concrete :870-894
+    `_test_value` literals (targets restated as the tests compute them); the matrix-variate
+    normal against scipy.stats.matrix_normal as in :1030-1046."""
+    from scipy.special import gammaln
+    for given, t, logits in [([0.25, 0.25, 0.5], 0.1, [1., 1., 1.2]),
+                             ([[0.25, 0.25, 0.5], [0.1, 0.5, 0.4]], 0.5,
+                              [[1., 1., 1.], [.5, .5, .4]])]:
+        g = np.array(given, np.float32).astype(np.float64)
+        l = np.array(logits, np.float32).astype(np.float64)
+        n = l.shape[-1]
+        tgt = gammaln(n) + (n - 1) * np.log(t) + (l - t * np.log(g) - np.log(g)).sum(-1) - \
+            n * np.log(np.exp(l - t * np.log(g)).sum(-1))
+        np.testing.assert_allclose(OD.concrete_log_prob(g, t, l, dtype=np.float64), tgt, rtol=1e-6)
+        lg = np.log(g)
+        tgt_e = gammaln(n) + (n - 1) * np.log(t) + (l - t * lg).sum(-1) - \
+            n * np.log(np.exp(l - t * lg).sum(-1))
+        np.testing.assert_allclose(OD.exp_concrete_log_prob(lg, t, l, dtype=np.float64), tgt_e,
+                                   rtol=1e-6)
+    rng = np.random.RandomState(23)
+    r, c = 3, 4
+    a = rng.standard_normal((r, r)); u = a @ a.T + r * np.eye(r)
+    b = rng.standard_normal((c, c)); v = b @ b.T + c * np.eye(c)
+    mean = rng.standard_normal((r, c))
+    x = rng.standard_normal((5, r, c))
+    got = OD.matrix_normal_cholesky_log_prob(x, mean, np.linalg.cholesky(u), np.linalg.cholesky(v))
+    np.testing.assert_allclose(got, stats.matrix_normal.logpdf(x, mean, u, v), rtol=1e-9)

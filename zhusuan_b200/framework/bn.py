@@ -394,6 +394,41 @@ class BayesianNet(_BayesianNet, Context):
 
     onehot_discrete = onehot_categorical
 
+    def exp_concrete(self, name, temperature, logits, n_samples=None,
+                     group_ndims=0, is_reparameterized=True,
+                     check_numerics=False, **kwargs):
+        """bn.py:1123-1155."""
+        dist = distributions.ExpConcrete(
+            temperature, logits, group_ndims=group_ndims,
+            is_reparameterized=is_reparameterized,
+            check_numerics=check_numerics, **kwargs)
+        return self.stochastic(name, dist, n_samples=n_samples, **kwargs)
+
+    exp_gumbel_softmax = exp_concrete
+
+    def concrete(self, name, temperature, logits, n_samples=None,
+                 group_ndims=0, is_reparameterized=True, check_numerics=False,
+                 **kwargs):
+        """bn.py:1157-1189."""
+        dist = distributions.Concrete(
+            temperature, logits, group_ndims=group_ndims,
+            is_reparameterized=is_reparameterized,
+            check_numerics=check_numerics, **kwargs)
+        return self.stochastic(name, dist, n_samples=n_samples, **kwargs)
+
+    gumbel_softmax = concrete
+
+    def matrix_variate_normal_cholesky(self, name, mean, u_tril, v_tril,
+                                       n_samples=None, group_ndims=0,
+                                       is_reparameterized=True,
+                                       check_numerics=False, **kwargs):
+        """bn.py:967-997."""
+        dist = distributions.MatrixVariateNormalCholesky(
+            mean, u_tril, v_tril, group_ndims=group_ndims,
+            is_reparameterized=is_reparameterized,
+            check_numerics=check_numerics, **kwargs)
+        return self.stochastic(name, dist, n_samples=n_samples, **kwargs)
+
     def multivariate_normal_cholesky(self, name, mean, cov_tril,
                                      n_samples=None, group_ndims=0,
                                      is_reparameterized=True,
