@@ -70,6 +70,14 @@ class TensorArithmeticMixin(object):
     def __rpow__(self, o): return _u(o) ** self._t()
     def __matmul__(self, o): return self._t() @ _u(o)
     def __rmatmul__(self, o): return _u(o) @ self._t()
+    # logical operators (zhusuan/utils.py:95-117)
+    def __invert__(self): return ~self._t()
+    def __and__(self, o): return self._t() & _u(o)
+    def __rand__(self, o): return _u(o) & self._t()
+    def __or__(self, o): return self._t() | _u(o)
+    def __ror__(self, o): return _u(o) | self._t()
+    def __xor__(self, o): return self._t() ^ _u(o)
+    def __rxor__(self, o): return _u(o) ^ self._t()
     def __lt__(self, o): return self._t() < _u(o)
     def __le__(self, o): return self._t() <= _u(o)
     def __gt__(self, o): return self._t() > _u(o)
