@@ -498,3 +498,43 @@ def test_concrete_family_and_matrix_variate_normal():
     bn.concrete("c", tt, tl, n_samples=2)
     bn.matrix_variate_normal_cholesky("m", tm, f(lus), f(lvs))
     assert tuple(bn["c"].tensor.shape) == (2, 5, 7) and tuple(bn["m"].tensor.shape) == (2, r, c)
+
+
+def test_plugin_distribution_subclass_group_sum_on_device():
+    """A user-defined Distribution (the plugin contract, tests/distributions/test_base.py:15-140)
+    returning the un-grouped log density gets the `group_ndims` sum from the base class, through
+    the group-sum kernel, and works as a BayesianNet node."""
+    import zhusuan_b200 as zs
+
+    class Scaled(zs.distributions.Distribution):
+        def __init__(self, scale, group_ndims=0):
+            self.scale = scale
+            super(Scaled, self).__init__(torch.float32, torch.float32, is_continuous=True,
+                                         is_reparameterized=True, group_ndims=group_ndims)
+
+        def _get_value_shape(self):
+            return torch.Size([])
+
+        def _get_batch_shape(self):
+            return self.scale.shape
+
+        def _sample(self, n_samples):
+            return torch.ones((n_samples,) + tuple(self.scale.shape), device=self.scale.device)
+
+        def _log_prob(self, given):
+            return -given * self.scale
+
+    scale = torch.arange(1., 25., device="cuda").reshape(2, 3, 4).requires_grad_(True)
+    x = torch.ones(5, 2, 3, 4, device="cuda")
+    for g, shape in ((0, (5, 2, 3, 4)), (1, (5, 2, 3)), (3, (5,))):
+        lp = Scaled(scale, group_ndims=g).log_prob(x)
+        assert tuple(lp.shape) == shape
+        want = -(x * scale).detach()
+        if g:
+            want = want.sum(dim=tuple(range(-g, 0)))
+        np.testing.assert_allclose(lp.detach().cpu().numpy(), want.cpu().numpy(), rtol=1e-6)
+    gr, = torch.autograd.grad(Scaled(scale, group_ndims=2).log_prob(x).sum(), [scale])
+    np.testing.assert_allclose(gr.cpu().numpy(), -5.0)
+    bn = zs.BayesianNet(observed={"y": x})
+    node = bn.stochastic("y", Scaled(scale, group_ndims=3))
+    assert tuple(node.cond_log_p.shape) == (5,) and tuple(bn.log_joint().shape) == (5,)

@@ -346,3 +346,62 @@ def test_added_distribution_and_estimator_contracts_need_no_gpu():
     for name in ("gamma", "beta", "inverse_gamma", "poisson", "binomial", "laplace", "uniform",
                  "fold_normal", "bin_concrete", "bin_gumbel_softmax"):
         assert callable(getattr(bn, name))
+
+
+def test_user_defined_distribution_subclass_gets_the_group_sum():
+    """tests/distributions/test_base.py:15-140: a plugin subclass returns the UN-grouped log
+    density from `_log_prob`; the base class checks shapes and sums the last `group_ndims`
+    axes (here with the kernel entry point patched by a torch sum: no GPU in this test)."""
+    from zhusuan_b200.distributions import Distribution
+    from zhusuan_b200 import ops
+
+    class Dist(Distribution):
+        def __init__(self, group_ndims=0):
+            super(Dist, self).__init__(torch.float32, torch.float32, is_continuous=True,
+                                       is_reparameterized=True, group_ndims=group_ndims)
+
+        def _get_value_shape(self):
+            return torch.Size([5])
+
+        def _get_batch_shape(self):
+            return torch.Size([2, 3, 4])
+
+        def _sample(self, n_samples):
+            return torch.ones(n_samples, 2, 3, 4, 5)
+
+        def _log_prob(self, given):
+            return torch.zeros_like(given).sum(-1)
+
+    base = Distribution(torch.float32, torch.float32, True, True, group_ndims=2)
+    assert (base.dtype, base.is_continuous, base.group_ndims) == (torch.float32, True, 2)
+    for call in (base._get_value_shape, base._get_batch_shape) if hasattr(
+            base, "_get_value_shape") else ():
+        with pytest.raises((NotImplementedError, AttributeError)):
+            call()
+    with pytest.raises(NotImplementedError):
+        base._sample(1)
+    with pytest.raises(NotImplementedError):
+        base._log_prob(torch.ones(2, 3, 4, 5))
+    with pytest.raises(ValueError, match="must be non-negative"):
+        Distribution(torch.float32, torch.float32, True, True, False, -1)
+
+    d = Dist(group_ndims=2)
+    assert tuple(d.get_value_shape()) == (5,) and tuple(d.batch_shape) == (2, 3, 4)
+    assert tuple(d.sample().shape) == (2, 3, 4, 5)
+    for n in (1, 2):
+        assert tuple(d.sample(n_samples=n).shape) == (n, 2, 3, 4, 5)
+    assert tuple(d.sample(torch.tensor(3)).shape) == (3, 2, 3, 4, 5)
+    with pytest.raises(ValueError, match="should be a scalar"):
+        d.sample(torch.tensor([1, 2]))
+    fake = lambda x, g: x.sum(dim=tuple(range(-g, 0))) if g else x
+    with mock.patch.object(ops, "group_sum", side_effect=fake) as gs:
+        lp = d.log_prob(torch.ones(2, 3, 4, 5))
+        assert tuple(lp.shape) == (2,) and float(lp.abs().sum()) == 0.0
+        assert tuple(d.log_prob(torch.ones(1, 2, 3, 4, 5)).shape) == (1, 2)
+        assert gs.call_count == 2
+        assert tuple(Dist(0).log_prob(torch.ones(2, 3, 4, 5)).shape) == (2, 3, 4)
+        assert gs.call_count == 2                      # group_ndims = 0: no call
+    with pytest.raises(ValueError, match=r"broadcast to match batch_shape \+ value_shape"):
+        d.log_prob(torch.ones(3, 3, 4, 5))
+    # built-in classes fuse the sum into their kernels
+    assert zs.distributions.Normal(0., std=1.)._group_sum_in_log_prob is True

@@ -8,6 +8,12 @@ __all__ = ["Distribution"]
 
 
 class Distribution(object):
+    # The reference's contract (base.py:290-304): `_log_prob` returns the UN-grouped log density
+    # and `log_prob` sums the last `group_ndims` axes.  The built-in classes fuse that sum into
+    # their kernels and say so here; a user-defined subclass (the plugin case) keeps the
+    # reference behaviour and gets the sum from the base class.
+    _group_sum_in_log_prob = False
+
     def __init__(self, dtype, param_dtype, is_continuous, is_reparameterized,
                  use_path_derivative=False, group_ndims=0, **kwargs):
         if 'group_event_ndims' in kwargs:
@@ -93,13 +99,24 @@ class Distribution(object):
         return given
 
     def log_prob(self, given):
-        """base.py:290-304; the group sum is fused into the kernels."""
+        """base.py:290-304: shape check, `_log_prob`, sum over the last
+        `group_ndims` axes (fused into the kernels of the built-in classes)."""
         given = self._check_input_shape(given)
-        return self._log_prob(given)
+        lp = self._log_prob(given)
+        if not self._group_sum_in_log_prob and self._group_ndims > 0:
+            from .. import ops
+            lp = ops.group_sum(lp, self._group_ndims)
+        return lp
 
     def prob(self, given):
         """base.py:306-320 (exp of the grouped log-prob == prod of probs)."""
         return torch.exp(self.log_prob(given))
+
+    def _get_value_shape(self):
+        raise NotImplementedError()
+
+    def _get_batch_shape(self):
+        raise NotImplementedError()
 
     def _sample(self, n_samples):
         raise NotImplementedError()

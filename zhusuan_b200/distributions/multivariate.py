@@ -15,6 +15,7 @@ __all__ = ["MultivariateNormalCholesky", "UnnormalizedMultinomial",
 
 class MultivariateNormalCholesky(Distribution):
     """multivariate.py:41-192."""
+    _group_sum_in_log_prob = True
 
     def __init__(self, mean, cov_tril, group_ndims=0, is_reparameterized=True,
                  use_path_derivative=False, check_numerics=False, **kwargs):
@@ -68,6 +69,7 @@ class MultivariateNormalCholesky(Distribution):
 
 class UnnormalizedMultinomial(Distribution):
     """multivariate.py:339-446 (a.k.a. BagofCategoricals)."""
+    _group_sum_in_log_prob = True
 
     def __init__(self, logits, normalize_logits=True, dtype=torch.int32,
                  group_ndims=0, **kwargs):
@@ -162,6 +164,7 @@ class OnehotCategorical(Distribution):
     """multivariate.py:452-567: one-hot valued categorical;
     log_prob = -softmax_cross_entropy(labels=given, logits) = sum_i given_i *
     log-softmax(logits)_i, i.e. the same kernel with normalised logits."""
+    _group_sum_in_log_prob = True
 
     def __init__(self, logits, dtype=torch.int32, group_ndims=0, **kwargs):
         self._logits = convert_to_tensor(logits)
@@ -201,6 +204,7 @@ OnehotDiscrete = OnehotCategorical
 
 class Dirichlet(Distribution):
     """multivariate.py:570-680."""
+    _group_sum_in_log_prob = True
 
     def __init__(self, alpha, group_ndims=0, check_numerics=False, **kwargs):
         self._alpha = convert_to_tensor(alpha)

@@ -23,6 +23,7 @@ __all__ = ["ExpConcrete", "ExpGumbelSoftmax", "Concrete", "GumbelSoftmax",
 class ExpConcrete(Distribution):
     """multivariate.py:683-815: log of a Concrete sample (values are
     log-probabilities on the simplex)."""
+    _group_sum_in_log_prob = True
     _name = "ExpConcrete"
 
     def __init__(self, temperature, logits, group_ndims=0,
@@ -112,6 +113,7 @@ GumbelSoftmax = Concrete
 class MatrixVariateNormalCholesky(Distribution):
     """multivariate.py:961-1160: X ~ MN(mean, U = Lu Lu^T, V = Lv Lv^T) with
     the row / column covariances given by their Cholesky factors."""
+    _group_sum_in_log_prob = True
 
     def __init__(self, mean, u_tril, v_tril, group_ndims=0,
                  is_reparameterized=True, use_path_derivative=False,

@@ -14,6 +14,7 @@ __all__ = ["Normal", "Bernoulli", "Categorical", "Discrete"]
 
 class Normal(Distribution):
     """univariate.py:43-184.  ``std`` xor ``logstd`` (ValueError otherwise)."""
+    _group_sum_in_log_prob = True
 
     def __init__(self, mean=0., _sentinel=None, std=None, logstd=None,
                  group_ndims=0, is_reparameterized=True,
@@ -80,6 +81,7 @@ class Normal(Distribution):
 
 class Bernoulli(Distribution):
     """univariate.py:334-406."""
+    _group_sum_in_log_prob = True
 
     def __init__(self, logits, dtype=torch.int32, group_ndims=0, **kwargs):
         self._logits = convert_to_tensor(logits)
@@ -109,6 +111,7 @@ class Bernoulli(Distribution):
 
 class Categorical(Distribution):
     """univariate.py:409-551."""
+    _group_sum_in_log_prob = True
 
     def __init__(self, logits, dtype=torch.int32, group_ndims=0, **kwargs):
         self._logits = convert_to_tensor(logits)

@@ -47,6 +47,7 @@ def _sample_shape(n_samples, batch_shape):
 class _TwoParam(Distribution):
     """Scalar-valued distribution whose batch shape is the broadcast of two
     parameters held in ``self._a`` / ``self._b``."""
+    _group_sum_in_log_prob = True
     _dist_id = None
 
     def _get_value_shape(self):
@@ -260,6 +261,7 @@ BinGumbelSoftmax = BinConcrete
 
 class Poisson(Distribution):
     """univariate.py:857-936."""
+    _group_sum_in_log_prob = True
 
     def __init__(self, rate, dtype=torch.int32, group_ndims=0,
                  check_numerics=False, **kwargs):
@@ -292,6 +294,7 @@ class Poisson(Distribution):
 
 class Binomial(Distribution):
     """univariate.py:939-1067."""
+    _group_sum_in_log_prob = True
 
     def __init__(self, logits, n_experiments, dtype=torch.int32, group_ndims=0,
                  check_numerics=False, **kwargs):
