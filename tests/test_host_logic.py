@@ -405,3 +405,48 @@ def test_user_defined_distribution_subclass_gets_the_group_sum():
         d.log_prob(torch.ones(3, 3, 4, 5))
     # built-in classes fuse the sum into their kernels
     assert zs.distributions.Normal(0., std=1.)._group_sum_in_log_prob is True
+
+
+def test_deprecated_query_api_of_bayesian_net():
+    """bn.py:1200-1249: outputs / local_log_prob / query still answer, with FutureWarnings."""
+    def dist(v):
+        d = mock.Mock(dtype=torch.float32, sample=mock.Mock(return_value=torch.full((2,), v)),
+                      log_prob=mock.Mock(side_effect=lambda g: g * 3))
+        del d.get_batch_shape
+        return d
+    bn = zs.BayesianNet()
+    bn.stochastic('a', dist(1.)); bn.stochastic('b', dist(2.))
+    with pytest.warns(FutureWarning, match="outputs"):
+        assert torch.equal(bn.outputs('a'), torch.full((2,), 1.))
+    with pytest.warns(FutureWarning):
+        outs = bn.outputs(['a', 'b'])
+    assert torch.equal(outs[1], torch.full((2,), 2.))
+    with pytest.warns(FutureWarning, match="local_log_prob"):
+        assert torch.equal(bn.local_log_prob('b'), torch.full((2,), 6.))
+    with pytest.warns(FutureWarning, match="query"):
+        o, lp = bn.query('a', outputs=True, local_log_prob=True)
+    assert torch.equal(o, torch.full((2,), 1.)) and torch.equal(lp, torch.full((2,), 3.))
+    with pytest.warns(FutureWarning):
+        pairs = bn.query(['a', 'b'], outputs=True, local_log_prob=True)
+    assert torch.equal(pairs[1][0], torch.full((2,), 2.)) and torch.equal(pairs[1][1],
+                                                                          torch.full((2,), 6.))
+    with pytest.warns(FutureWarning), pytest.raises(ValueError, match="No query options"):
+        bn.query('a')
+
+
+def test_top_level_names_of_the_reference_package():
+    """zhusuan/__init__.py and the `__all__` lists it pulls in (hmc.py:15-18, sgmcmc.py:15-21,
+    evaluation.py:17-19, utils.py:11-15, framework/{bn,meta_bn,utils}.py)."""
+    for name in ["distributions", "variational", "StochasticTensor", "BayesianNet",
+                 "MetaBayesianNet", "meta_bayesian_net", "reuse_variables", "reuse", "HMCInfo",
+                 "HMC", "SGMCMC", "SGLD", "PSGLD", "SGHMC", "SGNHT", "is_loglikelihood", "AIS",
+                 "TensorArithmeticMixin", "log_mean_exp", "merge_dicts"]:
+        assert hasattr(zs, name), name
+    for name in ["elbo", "klpq", "iw_objective", "importance_weighted_objective",
+                 "EvidenceLowerBoundObjective", "InclusiveKLObjective",
+                 "ImportanceWeightedObjective", "VariationalObjective"]:
+        assert hasattr(zs.variational, name), name
+    with pytest.warns(FutureWarning, match="renamed to `reuse_variables\\(\\)`"):
+        deco = zs.reuse("scope")
+    assert deco(lambda: 3)() == 3
+    assert zs.merge_dicts({"a": 1}, {"b": 2}, {"a": 3}) == {"a": 3, "b": 2}

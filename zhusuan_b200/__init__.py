@@ -18,7 +18,8 @@ from .framework import utils as _fw_utils
 from .hmc import *
 from .sgmcmc import *
 from .evaluation import *
-from .utils import log_mean_exp, log_sum_exp, merge_dicts
+from .utils import (TensorArithmeticMixin, log_mean_exp, log_sum_exp,
+                    merge_dicts)
 from .random import set_random_seed
 
 __version__ = "0.1.0"

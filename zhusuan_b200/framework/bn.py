@@ -257,6 +257,39 @@ class BayesianNet(_BayesianNet, Context):
         self._observed = observed if observed else {}
         super(BayesianNet, self).__init__()
 
+    # ---- the 0.3-era query API, kept (deprecated) by the reference: bn.py:1200-1249
+    def outputs(self, name_or_names):
+        warnings.warn(
+            "BayesianNet: `outputs()` has been deprecated in 0.4 and will "
+            "be removed in 0.4.1, use `get()` instead.", FutureWarning)
+        nodes = self.get(name_or_names)
+        if isinstance(nodes, list):
+            return [getattr(n, "tensor", n) for n in nodes]
+        return getattr(nodes, "tensor", nodes)
+
+    def local_log_prob(self, name_or_names):
+        warnings.warn(
+            "BayesianNet: `local_log_prob()` has been deprecated in 0.4 "
+            "and will be removed in 0.4.1, use `cond_log_prob()` instead.",
+            FutureWarning)
+        return self.cond_log_prob(name_or_names)
+
+    def query(self, name_or_names, outputs=False, local_log_prob=False):
+        warnings.warn(
+            "BayesianNet: `query()` has been deprecated in 0.4 "
+            "and will be removed in 0.4.1, use `get()` and "
+            "`cond_log_prob()` instead.", FutureWarning)
+        ret = []
+        if outputs:
+            ret.append(self.outputs(name_or_names))
+        if local_log_prob:
+            ret.append(self.local_log_prob(name_or_names))
+        if not ret:
+            raise ValueError("No query options are selected.")
+        if not isinstance(name_or_names, str):
+            return list(zip(*ret))
+        return tuple(ret)
+
     def normal(self, name, mean=0., _sentinel=None, std=None, logstd=None,
                group_ndims=0, n_samples=None, is_reparameterized=True,
                check_numerics=False, **kwargs):

@@ -1,7 +1,7 @@
 """Context stack (zhusuan/framework/utils.py:20-46) and ``reuse_variables``."""
 from functools import wraps
 
-__all__ = ["Context", "reuse_variables"]
+__all__ = ["Context", "reuse_variables", "reuse"]
 
 
 class Context(object):
@@ -41,3 +41,13 @@ def reuse_variables(scope):
         _wrapped.scope = scope
         return _wrapped
     return wrapper
+
+
+def reuse(scope):
+    """(Deprecated) alias of :func:`reuse_variables` (framework/utils.py:109-117)."""
+    import warnings
+    warnings.warn(
+        "The `reuse()` function has been renamed to `reuse_variables()`, "
+        "`reuse()` will be removed in the coming version (0.4.1)",
+        FutureWarning)
+    return reuse_variables(scope)
