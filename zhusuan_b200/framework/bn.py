@@ -399,13 +399,12 @@ class BayesianNet(_BayesianNet, Context):
     bin_gumbel_softmax = bin_concrete
 
     def unnormalized_multinomial(self, name, logits, normalize_logits=True,
-                                 n_samples=None, group_ndims=0,
-                                 dtype=torch.int32, **kwargs):
-        """bn.py:840-870."""
+                                 group_ndims=0, dtype=torch.int32, **kwargs):
+        """bn.py:938-965 (no ``n_samples``: the distribution cannot sample)."""
         dist = distributions.UnnormalizedMultinomial(
             logits, normalize_logits=normalize_logits,
             group_ndims=group_ndims, dtype=dtype, **kwargs)
-        return self.stochastic(name, dist, n_samples=n_samples, **kwargs)
+        return self.stochastic(name, dist, **kwargs)
 
     bag_of_categoricals = unnormalized_multinomial
 
