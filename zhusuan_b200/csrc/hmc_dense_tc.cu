@@ -1,3 +1,9 @@
+// Replaces, for a dense-Gaussian log-joint, one iteration of the leapfrog `tf.while_loop` of
+// zhusuan/hmc.py:347-372 (body = leapfrog_integrator, hmc.py:38-43: q += eps1 * p / mass;
+// g = tf.gradients(log_posterior, q); p += eps2 * g) plus the log p / kinetic terms of
+// hamiltonian(), hmc.py:30-35, which get_acceptance_rate (hmc.py:46-61) would otherwise
+// recompute with two extra forward evaluations.
+//
 // Dense-Gaussian leapfrog pass on 5th-gen tensor cores (impl 1): tcgen05.mma kind::tf32 with a
 // 3xTF32 split so the fp32 gradient  g = b - P q  keeps ~fp32 accuracy:
 //     q = q_hi + q_lo,  P = P_hi + P_lo   (hi = top 19 bits, exactly what the TF32 datapath reads)

@@ -2,6 +2,8 @@
 // gemm_logjoint_tc.cu): tile constants, pipeline barriers, TMA loads, UMMA issue / commit,
 // TMEM loads, shared-memory and instruction descriptors, the CTA-pair (cta_group::2) variants,
 // the warp-transpose reduction of the epilogues and the host-side tensor-map encoder.
+// (No reference counterpart: ZhuSuan has no kernels; these serve the GEMMs inside the log-joints of
+// zhusuan/hmc.py:347-372 and examples/variational_autoencoders/iwae.py:23-32.)
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
