@@ -269,6 +269,18 @@ int zsb_hmc_dense_leapfrog_h16i_f32(const float* q_cur, float* q_next, const flo
                                     const float* mu, const float* mass, const float* state,
                                     float p_scale, float* lp_part, float* k_part, int64_t chains,
                                     int64_t D, void* stream);
+/* impl 4 -- EXPERIMENTAL, written at the end of round 1 and NOT yet validated on hardware: the
+ * whole leapfrog `while_loop` of hmc.py:347-372 (L+1 passes) in one persistent launch; a cluster of
+ * 8 CTAs keeps a 256-chain block's q / p / planes in L2 across the passes.  D == 1024, L >= 1.
+ * Buffers as impl 2 (planes0 from zsb_hmc_dense_h16_prepare_f32); the proposal ends in qa when
+ * L - 1 is even, else in qb; pw holds the final momentum. */
+int zsb_hmc_dense_trajectory_h16_f32(const float* q0, const void* planes0, float* qa,
+                                     void* planes_a, float* qb, void* planes_b, const float* p0,
+                                     float* pw, const void* P_h16, const void* P_l16,
+                                     const float* scales, const float* bvec, const float* mu,
+                                     const float* mass, const float* state, float* lp0_part,
+                                     float* lp1_part, float* k_part, int64_t chains, int64_t D,
+                                     int n_leapfrogs, void* stream);
 int zsb_hmc_dense_finish_f32(const float* lp_part, const float* k_part, int ntiles, int64_t chains,
                              float const_term, float* lp_out, float* k_out, void* stream);
 

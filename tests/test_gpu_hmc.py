@@ -504,3 +504,29 @@ def test_cuda_graph_replay_is_bitwise_eager(zs, path):
         np.testing.assert_array_equal(a[2], b[2], err_msg="mass, iteration %d" % i)
         np.testing.assert_array_equal(a[3], b[3])
     np.testing.assert_array_equal(st_a, st_b)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("ZSB_EXPERIMENTAL") != "1",
+                    reason="impl 4 (trajectory-fused kernel) was written at the end of round 1 and "
+                           "has not been run on hardware yet; set ZSB_EXPERIMENTAL=1 to try it")
+@pytest.mark.parametrize("C,L", [(300, 3), (2048, 5), (8192, 2)])
+def test_experimental_trajectory_kernel_matches_per_pass_kernel(zs, C, L):
+    """dense_impl=4 (one persistent launch per trajectory, L2-resident chain blocks) against
+    dense_impl=2 (one launch per pass): same operands, same epilogue arithmetic, so the chains
+    must agree to fp32 rounding."""
+    D = 1024
+    P, _ = OM.make_dense_gaussian_problem(D, seed=2)
+    res = []
+    for impl in (2, 4):
+        torch.manual_seed(5)
+        x = torch.randn(C, D, device="cuda")
+        h = zs.HMC(step_size=0.1, n_leapfrogs=L, seed=7, dense_impl=impl)
+        op, info = h.sample(zs.fused.GaussianLogJoint(P), {}, {"x": x})
+        for _ in range(2):
+            op()
+        op.synchronize()
+        res.append((N(x), N(info.hamiltonian), N(info.acceptance_rate)))
+    np.testing.assert_allclose(res[1][1], res[0][1], rtol=1e-5)
+    np.testing.assert_allclose(res[1][2], res[0][2], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(res[1][0], res[0][0], rtol=1e-4, atol=1e-4)

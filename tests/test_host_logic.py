@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
                 "zsb_dense_tc_ntiles", "zsb_dense_split_lo_launch",
                 "zsb_dense_tc_set_bk", "zsb_dense_leapfrog_h16_launch",
                 "zsb_dense_h16_prepare_launch", "zsb_dense_leapfrog_h16i_launch",
-                "zsb_dense_h16i_prepare_launch"}
+                "zsb_dense_h16i_prepare_launch", "zsb_dense_traj_h16_launch"}
     assert defined - internal <= set(protos), defined - internal - set(protos)
 
 

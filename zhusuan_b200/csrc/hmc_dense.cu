@@ -198,6 +198,12 @@ int zsb_dense_leapfrog_h16i_launch(const float* q_cur, float* q_next, const floa
                                    float p_scale, float* lp_part, float* k_part, int64_t chains,
                                    int D, cudaStream_t st);
 int zsb_dense_h16i_prepare_launch(const float* q, float* scales, int64_t n, cudaStream_t st);
+int zsb_dense_traj_h16_launch(const float* q0, const void* planes0, float* qa, void* planes_a,
+                              float* qb, void* planes_b, const float* p0, float* pw,
+                              const void* P_h16, const void* P_l16, const float* scales,
+                              const float* bvec, const float* mu, const float* mass,
+                              const float* state, float* lp0_part, float* lp1_part,
+                              float* k_part, int64_t chains, int D, int L, cudaStream_t st);
 
 extern "C" {
 
@@ -292,6 +298,23 @@ int zsb_hmc_dense_leapfrog_h16i_f32(const float* q_cur, float* q_next, const flo
   return zsb_dense_leapfrog_h16i_launch(q_cur, q_next, p_in, p_out, P_h16, P_l16, scales,
                                         pass_index, bvec, mu, mass, state, p_scale, lp_part,
                                         k_part, chains, (int)D, (cudaStream_t)stream);
+}
+
+// EXPERIMENTAL (impl 4, not yet validated on hardware): the L+1 passes of a trajectory in one
+// persistent launch with L2-resident chain blocks (hmc_dense_traj.cu).  D == 1024, n_leapfrogs >= 1.
+int zsb_hmc_dense_trajectory_h16_f32(const float* q0, const void* planes0, float* qa,
+                                     void* planes_a, float* qb, void* planes_b, const float* p0,
+                                     float* pw, const void* P_h16, const void* P_l16,
+                                     const float* scales, const float* bvec, const float* mu,
+                                     const float* mass, const float* state, float* lp0_part,
+                                     float* lp1_part, float* k_part, int64_t chains, int64_t D,
+                                     int n_leapfrogs, void* stream) {
+  ZSB_REQUIRE(q0 && planes0 && qa && planes_a && qb && planes_b && p0 && pw && P_h16 && P_l16 &&
+                  scales && mass && state && lp0_part && lp1_part && k_part,
+              "zsb_hmc_dense_trajectory_h16_f32: null arg");
+  return zsb_dense_traj_h16_launch(q0, planes0, qa, planes_a, qb, planes_b, p0, pw, P_h16, P_l16,
+                                   scales, bvec, mu, mass, state, lp0_part, lp1_part, k_part,
+                                   chains, (int)D, n_leapfrogs, (cudaStream_t)stream);
 }
 
 int zsb_hmc_dense_finish_f32(const float* lp_part, const float* k_part, int ntiles, int64_t chains,

@@ -504,6 +504,13 @@ class HMC(object):
             impl = 2 if D % 64 == 0 else (1 if D % 32 == 0 else 0)
         if int(impl) in (2, 3) and D % 64 != 0:
             raise ValueError("dense_impl=2/3 (fp16 split) needs D % 64 == 0")
+        # impl 4 (EXPERIMENTAL, not validated on hardware): impl 2's buffers and probe passes,
+        # but the L+1 passes of the main trajectory in ONE persistent launch (hmc_dense_traj.cu)
+        self._traj = int(impl) == 4
+        if self._traj:
+            if D != 1024 or self.n_leapfrogs < 1:
+                raise ValueError("dense_impl=4 needs D == 1024 and n_leapfrogs >= 1")
+            impl = 2
         self._impl = int(impl)
         if self._impl >= 1:            # pipeline-shape tuning knob (same results)
             lib.call("zsb_hmc_dense_tc_config",
@@ -613,6 +620,29 @@ class HMC(object):
         cur, nxt = q0, self._qa
         p_in = self._p0[0]
         prepare3()
+        if self._traj:
+            f = self._fused
+            prof = None if self._dev_mode else getattr(self, "_profile_events", None)
+            if prof is not None:
+                e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+                e0.record()
+            lib.call("zsb_hmc_dense_trajectory_h16_f32", ptr(q0),
+                     ptr(self._lo[q0.data_ptr()]), ptr(self._qa),
+                     ptr(self._lo[self._qa.data_ptr()]), ptr(self._qb),
+                     ptr(self._lo[self._qb.data_ptr()]), ptr(self._p0[0]),
+                     ptr(self._pw), ptr(f["P_h16"]), ptr(f["P_l16"]),
+                     ptr(self._scales), ptr(f.get("b")), ptr(f.get("mu")),
+                     ptr(self._mass[0]), ptr(self._state), ptr(self._lp0_part),
+                     ptr(self._lp1_part), ptr(self._k_part), self._chains, f["D"],
+                     L, s)
+            if prof is not None:
+                e1.record()
+                prof.append((e0, e1))
+            cur = self._qa if (L - 1) % 2 == 0 else self._qb
+            self._dense_finish_mh(noise_u, seed, it, s, full=True)
+            lib.call("zsb_hmc_select_f32", ptr(q0), ptr(cur), ptr(self._accept),
+                     self._chains, self._row_len[0], s)
+            return
         prof = getattr(self, "_profile_events", None)
         if self._dev_mode:
             prof = None
