@@ -39,7 +39,9 @@ __device__ __forceinline__ void store_split(const EpiArgs& a, float* __restrict_
 // time from a.q_next.  DC: the dimension count when known at compile time (all per-column offsets
 // j*D then fold into the load/store immediates: ~15 instead of ~40 instructions per element), 0 =
 // run-time a.D.  H16: fp16-split planes (impl 2) vs TF32 residual (impl 1).
-template <int MODE, int NEXT, int DC, int H16, int NCOL = BN / 2>
+// COHERENT: 1 when q_cur may have been written earlier in the SAME launch (trajectory kernel): the
+// non-coherent ld.global.nc path of __ldg could then return a stale L1 line.
+template <int MODE, int NEXT, int DC, int H16, int NCOL = BN / 2, int COHERENT = 0>
 __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t trow, int n,
                                                    bool n_ok, bool parts_ok, int64_t c0,
                                                    int64_t part_row, int lane, float s2,
@@ -106,7 +108,7 @@ __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t tr
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       pe[j] = __ldcs(pin + (uint32_t)j * D);       // p is streamed: evict-first
-      qe[j] = __ldg(qc + (uint32_t)j * D);
+      qe[j] = COHERENT ? __ldcg(qc + (uint32_t)j * D) : __ldg(qc + (uint32_t)j * D);
     }
   };
 
@@ -142,8 +144,13 @@ __device__ __forceinline__ void epilogue_half_tile(const EpiArgs& a, uint32_t tr
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const bool ok = n_ok && cbase + j < chains;
-          pe[j] = ok ? pin0[cb + (uint32_t)j * D] : 0.f;
-          qe[j] = ok ? qc0[cb + (uint32_t)j * D] : 0.f;
+          if (COHERENT) {     // written earlier in this launch: no ld.global.nc
+            pe[j] = ok ? __ldcg(pin0 + cb + (uint32_t)j * D) : 0.f;
+            qe[j] = ok ? __ldcg(qc0 + cb + (uint32_t)j * D) : 0.f;
+          } else {
+            pe[j] = ok ? pin0[cb + (uint32_t)j * D] : 0.f;
+            qe[j] = ok ? qc0[cb + (uint32_t)j * D] : 0.f;
+          }
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {

@@ -254,15 +254,15 @@ dense_traj_kernel(const __grid_constant__ TrajMaps maps, const float* __restrict
                            i == 0 ? p0 : pw, pw, i == 0 ? lp0_part : lp1_part, k_part,
                            chains, D, 1, q_scale, acc_scale};
           if (last)
-            epilogue_half_tile<2, 0, DC, 1, TN / 2>(ea, trow, n, true, true, c0, part_row, lane,
+            epilogue_half_tile<2, 0, DC, 1, TN / 2, 1>(ea, trow, n, true, true, c0, part_row, lane,
                                                     s2, eps_over_m, inv_m, b_n, mu_n, false,
                                                     unused_amax);
           else if (i == 0)
-            epilogue_half_tile<1, 1, DC, 1, TN / 2>(ea, trow, n, true, true, c0, part_row, lane,
+            epilogue_half_tile<1, 1, DC, 1, TN / 2, 1>(ea, trow, n, true, true, c0, part_row, lane,
                                                     s2, eps_over_m, inv_m, b_n, mu_n, false,
                                                     unused_amax);
           else
-            epilogue_half_tile<0, 1, DC, 1, TN / 2>(ea, trow, n, true, true, c0, part_row, lane,
+            epilogue_half_tile<0, 1, DC, 1, TN / 2, 1>(ea, trow, n, true, true, c0, part_row, lane,
                                                     s2, eps_over_m, inv_m, b_n, mu_n, false,
                                                     unused_amax);
           tc_fence_before();
