@@ -76,3 +76,20 @@ def test_overflow_headroom_of_the_hmc_scale():
         assert np.isfinite((x * growth * s).astype(np.float16)).all()
     with np.errstate(over="ignore"):
         assert not np.isfinite((x * 32 * s).astype(np.float16)).all()
+
+
+def test_trajectory_kernel_buffer_schedule_matches_the_per_pass_host_loop():
+    """hmc_dense_traj.cu (experimental impl 4) hard-codes the ping-pong of the per-pass host loop
+    (zhusuan_b200/hmc.py::_iterate_dense): pass i reads traj_cur(i) and writes traj_nxt(i) with
+    0 = q0, 1 = qa, 2 = qb; the proposal ends in qa when L - 1 is even, else in qb."""
+    traj_cur = lambda i: 0 if i == 0 else (1 if i & 1 else 2)
+    traj_nxt = lambda i: 2 if i & 1 else 1
+    for L in range(1, 12):
+        cur, nxt = 0, 1                               # host loop: cur, nxt = q0, qa
+        for i in range(L + 1):
+            last = i == L
+            assert traj_cur(i) == cur
+            if not last:
+                assert traj_nxt(i) == nxt
+                cur, nxt = nxt, (2 if nxt == 1 else 1)
+        assert cur == (1 if (L - 1) % 2 == 0 else 2)
