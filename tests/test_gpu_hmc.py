@@ -356,6 +356,95 @@ def test_golden_dense_fused_tc(zs):
     _replay(zs, g, lj, "dense_gaussian", q_tol=1e-4, dense_impl=1)
 
 
+def _replay_big(zs, name, impl, use_graph=False):
+    """Replay tests/golden/<name>.npz (L = 50, adaptive, mass != 1, both step-size searches,
+    diverging and healthy iterations; see make_golden.py BIG) on one dense kernel.
+
+    Budget: the fixture carries the float32 oracle's outputs and a float64 re-evaluation of each
+    iteration; `floor` = max |acc32 - acc64| is the rounding noise floor of a float32 HMC at this
+    size (|H| ~ D).  The CUDA path must stay within 4 x floor (+1e-5) of the float64 acceptance,
+    within 1e-5 relative of the Hamiltonians / log-probs, and -- because every uniform was pushed
+    >= 2 x u_guard away from the acceptance when the fixture was made -- reproduce EVERY accept
+    decision."""
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_golden as MG
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    cfg = dict(MG.BIG[name])
+    for k, v in cfg.items():
+        assert float(g["cfg_" + k]) == float(v), "fixture made with another BIG config"
+    D, C, L = cfg["D"], cfg["C"], cfg["L"]
+    P, const, mu, q0 = MG.big_problem(cfg)
+    np.testing.assert_allclose(np.abs(P).sum(), float(g["P_checksum"]), rtol=1e-12)
+    np.testing.assert_allclose(np.abs(q0.astype(np.float64)).sum(), float(g["q0_checksum"]),
+                               rtol=1e-12)
+    lj = zs.fused.GaussianLogJoint(P, mean=mu, log_det_cov=-2 * const - D * np.log(2 * np.pi))
+    x = T(q0)
+    h = zs.HMC(step_size=cfg["eps0"], n_leapfrogs=L, adapt_step_size=True, adapt_mass=True,
+               mass_collect_iters=cfg["mci"], dense_impl=impl)
+    op, info = h.sample(lj, {}, {"x": x})
+    assert h._fused["kind"] == "dense_gaussian"
+    floor = float(np.abs(g["acc"] - g["acc64"]).max())
+    acc_tol = 4 * floor + 1e-5
+    assert acc_tol < cfg["u_guard"]
+    stride = D // 16
+    worst = {"acc": 0.0, "h": 0.0, "q": 0.0}
+    for i in range(cfg["iters"]):
+        adapt = i < cfg["n_adapt"]
+        op(adapt_step_size=adapt, adapt_mass=adapt,
+           noise={"p": {"x": T(MG.big_noise(cfg, i))}, "u": T(g["noise_u"][i])})
+        acc = N(info.acceptance_rate)
+        msg = "%s impl %d iteration %d" % (name, impl, i)
+        np.testing.assert_allclose(float(h._state[7]), g["eps_used"][i], rtol=2e-5, err_msg=msg)
+        np.testing.assert_allclose(acc, g["acc64"][i], rtol=0, atol=acc_tol, err_msg=msg)
+        np.testing.assert_array_equal((g["noise_u"][i] < acc).astype(np.int32), g["accept"][i],
+                                      err_msg=msg)
+        np.testing.assert_allclose(N(info.orig_hamiltonian), g["h0_64"][i], rtol=1e-5,
+                                   err_msg=msg)
+        np.testing.assert_allclose(N(info.orig_log_prob), g["lp0"][i], rtol=1e-5, atol=1e-4,
+                                   err_msg=msg)
+        fin = np.isfinite(g["h1"][i])
+        assert np.all(acc[~fin] == 0), msg          # hmc.py:56-59: non-finite -> rejected
+        np.testing.assert_allclose(N(info.hamiltonian)[fin], g["h1_64"][i][fin], rtol=1e-5,
+                                   err_msg=msg)
+        np.testing.assert_allclose(N(info.log_prob), g["lp"][i], rtol=1e-5, atol=1e-4,
+                                   err_msg=msg)
+        xq = N(x)
+        np.testing.assert_allclose(xq[:, ::stride], g["q_sub"][i], rtol=1e-4, atol=1e-4,
+                                   err_msg=msg)
+        np.testing.assert_allclose(xq.astype(np.float64).sum(1), g["q_rowsum"][i], rtol=0,
+                                   atol=2e-4 * D ** 0.5 * max(1.0, np.abs(xq).max()),
+                                   err_msg=msg)
+        np.testing.assert_allclose(float(info.updated_step_size), g["step_size"][i], rtol=1e-4,
+                                   err_msg=msg)
+        np.testing.assert_allclose(N(h._mass[0]), g["mass"][i], rtol=2e-4, err_msg=msg)
+        worst["acc"] = max(worst["acc"], float(np.abs(acc - g["acc64"][i]).max()))
+        if fin.any():
+            worst["h"] = max(worst["h"], float(np.abs(
+                N(info.hamiltonian)[fin] / g["h1_64"][i][fin] - 1).max()))
+        worst["q"] = max(worst["q"], float(np.abs(xq[:, ::stride] - g["q_sub"][i]).max()))
+    op.synchronize()
+    assert h.n_search_iters == int(g["n_search_iters"])
+    print("replay %s impl %d: max|acc-acc64| %.2e (float32-oracle floor %.2e), max H rel err "
+          "%.2e, max |dq| %.2e" % (name, impl, worst["acc"], floor, worst["h"], worst["q"]))
+    return h
+
+
+@pytest.mark.parametrize("impl", [0, 1, 2])
+def test_golden_dense64_l50_adaptive(zs, impl):
+    """D = 64, 160 chains (ragged tile), L = 50, 24 adaptive iterations on the SIMT, 3xTF32 and
+    fp16-split (the benchmarked) kernels vs the oracle."""
+    _replay_big(zs, "hmc_dense64", impl)
+
+
+@pytest.mark.parametrize("impl", [2, 4])
+def test_golden_dense1024_l50_adaptive(zs, impl):
+    """The benchmark configuration's shape (D = 1024, L = 50, step + mass adaptation) at 320
+    chains on the benchmarked kernels: impl 2 (fp16-split, one launch per pass) and impl 4 (the
+    trajectory-fused launch) vs the oracle -- accept decisions, Hamiltonians, step sizes, mass."""
+    _replay_big(zs, "hmc_dense1024", impl)
+
+
 def test_dense_tc_vs_simt_full_size(zs):
     """65 536 x 1024, L=3: the tensor-core and SIMT paths agree on the
     per-chain Hamiltonians to 1e-5 relative and make identical MH decisions

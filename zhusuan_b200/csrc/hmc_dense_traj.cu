@@ -99,7 +99,7 @@ dense_traj_kernel(const __grid_constant__ TrajMaps maps, const float* __restrict
                   const float* __restrict__ mass, const float* __restrict__ state,
                   float* __restrict__ lp0_part, float* __restrict__ lp1_part,
                   float* __restrict__ k_part, int64_t chains, int L,
-                  const float* __restrict__ scales) {
+                  const float* __restrict__ scales, int dbg) {
   using C = CfgT;
   constexpr int D = DC;
   extern __shared__ uint8_t smem_raw[];
@@ -158,7 +158,7 @@ dense_traj_kernel(const __grid_constant__ TrajMaps maps, const float* __restrict
         for (int i = 0; i <= L; ++i) {
           const int cb = traj_cur(i);
           for (int h = 0; h < 2; ++h) {
-            if (i > 0) {                                  // planes of (h, i) come from pass i-1
+            if (i > 0 && !(dbg & 4)) {                    // planes of (h, i) come from pass i-1
               mbar_wait_cluster(qready_bar + 8 * h, qphase[h]);
               qphase[h] ^= 1;
               asm volatile("fence.proxy.async;" ::: "memory");
@@ -205,9 +205,13 @@ dense_traj_kernel(const __grid_constant__ TrajMaps maps, const float* __restrict
               for (int k = 0; k < 4; ++k) {
                 const uint64_t ko = (uint64_t)((k * 32) >> 4);
                 const uint32_t first = (kb | k) != 0 ? 1u : 0u;
-                umma_f16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
-                umma_f16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-                umma_f16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+                if (dbg & 2) {          // timing experiment: one product instead of three
+                  umma_f16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, first);
+                } else {
+                  umma_f16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
+                  umma_f16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
+                  umma_f16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+                }
               }
               umma_commit_pair(empty_bar + 8 * stage, pair_mask);
               if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -255,20 +259,20 @@ dense_traj_kernel(const __grid_constant__ TrajMaps maps, const float* __restrict
                            chains, D, 1, q_scale, acc_scale};
           if (last)
             epilogue_half_tile<2, 0, DC, 1, TN / 2, 1>(ea, trow, n, true, true, c0, part_row, lane,
-                                                    s2, eps_over_m, inv_m, b_n, mu_n, false,
+                                                    s2, eps_over_m, inv_m, b_n, mu_n, (dbg & 1) != 0,
                                                     unused_amax);
           else if (i == 0)
             epilogue_half_tile<1, 1, DC, 1, TN / 2, 1>(ea, trow, n, true, true, c0, part_row, lane,
-                                                    s2, eps_over_m, inv_m, b_n, mu_n, false,
+                                                    s2, eps_over_m, inv_m, b_n, mu_n, (dbg & 1) != 0,
                                                     unused_amax);
           else
             epilogue_half_tile<0, 1, DC, 1, TN / 2, 1>(ea, trow, n, true, true, c0, part_row, lane,
-                                                    s2, eps_over_m, inv_m, b_n, mu_n, false,
+                                                    s2, eps_over_m, inv_m, b_n, mu_n, (dbg & 1) != 0,
                                                     unused_amax);
           tc_fence_before();
           if (leader) mbar_arrive(tempty_bar + 8 * h);
           else mbar_arrive_remote(tempty_bar + 8 * h, leader_rank);
-          if (!last) {
+          if (!last && !(dbg & 4)) {
             // publish q_next + planes of this warp's share of (h, i) to the whole cluster
             __threadfence();
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -335,10 +339,13 @@ int zsb_dense_traj_h16_launch(const float* q0, const void* planes0, float* qa, v
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t n_blocks = (chains + TBLOCK - 1) / TBLOCK;
   int64_t clusters = 16;                                     // 2 clusters of 8 per GPC
+  static const int env_clusters = getenv("ZSB_TRAJ_CLUSTERS") ? atoi(getenv("ZSB_TRAJ_CLUSTERS")) : 0;
+  static const int env_dbg = getenv("ZSB_TRAJ_DBG") ? atoi(getenv("ZSB_TRAJ_DBG")) : 0;
+  if (env_clusters > 0) clusters = env_clusters;
   if (clusters * CLUSTER > sms) clusters = sms / CLUSTER;
   if (n_blocks < clusters) clusters = n_blocks;
   dense_traj_kernel<1024><<<(unsigned)(clusters * CLUSTER), NUM_THREADS, CfgT::SMEM, st>>>(
       m, q0, qa, qb, planes_a, planes_b, p0, pw, bvec, mu, mass, state, lp0_part, lp1_part,
-      k_part, chains, L, scales);
+      k_part, chains, L, scales, env_dbg);
   return zsb_check_launch("hmc_dense_trajectory");
 }
