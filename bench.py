@@ -12,9 +12,14 @@ GEMM+leapfrog passes, MH test + select, dual-averaging update.
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...     CPU arm (torch-CPU restatement)
 
-Chains shard across ranks with no data-path collective (weak scaling: the
-per-GPU chain count is fixed); the only exchange is the per-iteration
-all-reduce of the acceptance / mass statistics (8 B + 8*D B).
+    python bench.py --scaling strong ...     65 536 chains TOTAL (8 192/GPU at N=8),
+                                             the north_star's 8-GPU point
+    python bench.py --workload iwae ...      the other half of BASELINE.json's metric:
+                                             particle-ELBOs/s, VAE IWAE K=64, batch 4096/GPU
+
+Chains shard across ranks with no data-path collective; the only exchange is
+ONE packed all-reduce per iteration: [sum acc, n] + the EWMV statistics
+[S1(D), S2(D)] of the post-select state (8 B + 8*D B), zhusuan_b200/dist.py.
 """
 import argparse
 import datetime
@@ -33,6 +38,30 @@ if ROOT not in sys.path:
 
 METRIC = "leapfrog-steps*chains/sec"
 UNIT = "chain-steps/s"
+DEFAULT_DENSE_IMPL = 2
+
+
+def make_dense_gaussian_problem(D_, seed=2):
+    """Config 2 synthetic target: Sigma = A A^T / D + 0.1 I rescaled to unit
+    diagonal; returns (precision P float64, const = -1/2 log|2 pi Sigma|)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    A = rng.standard_normal((D_, D_))
+    S = A @ A.T / D_ + 0.1 * np.eye(D_)
+    d = 1.0 / np.sqrt(np.diag(S))
+    S = S * d[:, None] * d[None, :]
+    P = np.linalg.inv(S)
+    P = 0.5 * (P + P.T)
+    _, logdet = np.linalg.slogdet(S)
+    return P, -0.5 * (D_ * np.log(2 * np.pi) + logdet)
+
+
+def host_threads():
+    """Threads for the CPU arms: the physical cores (torchrun exports OMP_NUM_THREADS=1, which
+    would otherwise leave the reference arm single-threaded at N > 1)."""
+    import torch
+    n = max(1, (os.cpu_count() or 2) // 2)
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
 
 
 def parse():
@@ -41,15 +70,26 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hmc", choices=["hmc", "iwae"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --chains-per-gpu on every GPU; strong: "
+                         "--total-chains split over the GPUs")
+    ap.add_argument("--total-chains", type=int, default=65536)
     ap.add_argument("--chains-per-gpu", type=int, default=65536)
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="replay the HMC iteration (incl. its all-reduce) from a CUDA graph")
+    ap.add_argument("--iwae-batch", type=int, default=4096)
+    ap.add_argument("--iwae-particles", type=int, default=64)
+    ap.add_argument("--cpu-batch", type=int, default=128)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--leapfrogs", type=int, default=50)
     ap.add_argument("--burnin", type=int, default=20,
                     help="untimed adaptive iterations run as setup, before "
                          "the W warm-up steps (covers both step-size searches)")
     ap.add_argument("--dense-impl", type=int, default=None,
-                    help="0 SIMT fp32, 1 tcgen05 3xTF32, 2 tcgen05 fp16-split "
-                         "(default: fastest legal)")
+                    help="0 SIMT fp32, 1 tcgen05 3xTF32, 2 tcgen05 fp16-split per "
+                         "pass, 4 cluster-of-8 trajectory, 5 L2-resident trajectory "
+                         "(default: see DEFAULT_DENSE_IMPL)")
     ap.add_argument("--cpu-chains", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -160,33 +200,77 @@ class ClockSampler(object):
         return out
 
 
+def time_cpu_hmc(args, P=None, n_iters=5, warmup=1):
+    """CPU arm of the HMC workload: oracle/cpu_baseline.py (torch-CPU restatement of
+    hmc.py:382-522, kind "port": TensorFlow is not installable here) on a bounded chain
+    sub-sample; per-iteration times, the MEDIAN is reported (the host also runs the driver)."""
+    from oracle.cpu_baseline import time_dense_hmc
+    cores = host_threads()
+    chains = min(args.cpu_chains, args.chains_per_gpu)
+    if P is None:
+        P = make_dense_gaussian_problem(args.dim, seed=2)
+    rates, ms = [], []
+    time_dense_hmc(args.dim, chains, args.leapfrogs, n_iters=warmup, warmup=0, P=P)
+    for _ in range(max(1, n_iters)):
+        r = time_dense_hmc(args.dim, chains, args.leapfrogs, n_iters=1, warmup=0, P=P)
+        rates.append(r["value"]); ms.append(r["ms_per_iter"])
+    med = float(np.median(rates))
+    return {"value": med, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d chains x %d-d, L=%d, %d timed iteration(s) (median; min %.3g max "
+                      "%.3g chain-steps/s), torch-CPU restatement of hmc.py:382-522 (unfused, "
+                      "autograd gradient per leapfrog pass)"
+                      % (chains, args.dim, args.leapfrogs, len(rates), min(rates), max(rates)),
+            "host_cpu_count": os.cpu_count()}, float(np.median(ms))
+
+
+def time_cpu_iwae(args, n_iters=3):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from bench_iwae import make_cpu_step
+    cores = host_threads()
+    K, Nc = args.iwae_particles, args.cpu_batch
+    rng = np.random.Generator(np.random.PCG64(4))
+    xc = torch.tensor(rng.random((Nc, 784)) < 0.13, dtype=torch.float32)
+    step = make_cpu_step(xc, K)
+    step()
+    ts = []
+    for _ in range(max(1, n_iters)):
+        t0 = time.perf_counter(); step(); ts.append(time.perf_counter() - t0)
+    dt = float(np.median(ts))
+    return {"value": K * Nc / dt, "unit": "particle-ELBOs/s", "cores": cores, "kind": "port",
+            "sample": "batch %d of %d, K=%d, %d timed step(s) (median), torch-CPU restatement "
+                      "of examples/variational_autoencoders/iwae.py:23-78 (forward + SGVB "
+                      "backward)" % (Nc, args.iwae_batch, K, len(ts)),
+            "host_cpu_count": os.cpu_count()}, 1e3 * dt
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU path.  TensorFlow (and so
-    zhusuan) cannot be installed here, so this arm times the torch-CPU
-    restatement of hmc.py:382-522 (oracle/cpu_baseline.py, kind "port") with
-    all host threads, on a bounded chain sub-sample of the same workload
-    (chains are independent -> the rate is per-chain-step)."""
+    """--impl reference: the reference's own CPU path.  TensorFlow (and so zhusuan) cannot be
+    installed here, so this arm times the torch-CPU restatement (kind "port") with all physical
+    host cores on a bounded sub-sample of the same workload (chains / data are independent, so
+    the rate is per unit).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    from oracle.cpu_baseline import time_dense_hmc
-    chains = min(args.cpu_chains, args.chains_per_gpu)
-    r = time_dense_hmc(args.dim, chains, args.leapfrogs, n_iters=args.steps,
-                       warmup=args.warmup)
+    if args.workload == "iwae":
+        cpu, ms = time_cpu_iwae(args, n_iters=max(1, args.steps))
+        metric, unit = "particle-ELBOs/sec", "particle-ELBOs/s"
+        wl = ("IWAE, VAE 784-(500,500)-40, K=%d, forward + SGVB backward; CPU sample of %d "
+              "data per step" % (args.iwae_particles, args.cpu_batch))
+    else:
+        cpu, ms = time_cpu_hmc(args, n_iters=max(1, args.steps), warmup=max(1, args.warmup))
+        metric, unit = METRIC, UNIT
+        wl = ("HMC, %d-dim dense-covariance Gaussian, L=%d; CPU sample of %d chains per step"
+              % (args.dim, args.leapfrogs, min(args.cpu_chains, args.chains_per_gpu)))
     out = {
-        "impl": "reference", "metric": METRIC, "value": r["value"],
-        "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": r["ms_per_iter"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": metric, "value": cpu["value"],
+        "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "HMC, %d-dim dense-covariance Gaussian, L=%d; "
-                               "CPU sample of %d chains per step"
-                               % (args.dim, args.leapfrogs, chains)},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT,
-                         "cores": r["cores"], "kind": "port",
-                         "sample": r["sample"]},
-        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+        "config": {"workload": wl},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": unit, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "host_cpu_count": os.cpu_count(),
     }
@@ -195,14 +279,159 @@ def run_reference(args):
 
 def main():
     args = parse()
+    if args.scaling == "strong":
+        w = int(os.environ.get("WORLD_SIZE", "1")) if args.impl != "reference" else args.gpus
+        args.chains_per_gpu = args.total_chains // max(1, w)
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "iwae":
+        return run_iwae(args)
+    return run_hmc(args)
 
+
+def run_iwae(args):
+    """--workload iwae: the second half of BASELINE.json's metric, particle-ELBOs/s on config 3
+    (VAE 784-(500,500)-40, IWAE K=64, batch 4096 per GPU, forward + SGVB reparameterised
+    backward; examples/variational_autoencoders/iwae.py:23-78).  Every dense layer runs on the
+    tcgen05 fp16-split kernel (fp32 accuracy), the decoder output fused with the Bernoulli
+    log-likelihood; the batch axis shards over ranks, particles stay local, ONE packed gradient
+    all-reduce per step."""
     import torch
     import torch.distributed as td
     import zhusuan_b200 as zs
     from zhusuan_b200._lib import lib
-    from oracle.models import make_dense_gaussian_problem   # synthetic target
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from bench_iwae import build, step_fn
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        td.init_process_group("nccl", device_id=dev)
+    K, N = args.iwae_particles, args.iwae_batch
+    if args.scaling == "strong":
+        N = N // world
+    rng = np.random.Generator(np.random.PCG64(4 + rank))
+    x_host = torch.tensor(rng.random((N, 784)) < 0.13, dtype=torch.int32).pin_memory()
+    x = x_host.to(dev)
+    W = build(dev)
+    zs.set_random_seed(1234 + rank)
+    local_step = step_fn(W, x, K, dev, fused=True)
+    unit = "particle-ELBOs/s"
+
+    def step():
+        cost, g = local_step()
+        if world > 1:
+            g, (cost,) = zs.dist.all_reduce_mean_gradients(g, [cost.detach()], n_local=N)
+        return cost, g
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        sampler.wait_first()
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+    if sampler:
+        sampler.mark_begin("timed")
+    launches0 = lib.launches
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(args.steps):
+        cost, g = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+    if sampler:
+        sampler.mark_end("timed")
+    launches = lib.launches - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        td.all_reduce(ms, op=td.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    value = world * K * N / (ms_per_step * 1e-3)
+    bound = float(-cost)
+
+    # e2e: per step, H2D of the step's batch from pinned memory, the step, D2H of the bound
+    e2e = None
+    if not args.no_e2e:
+        cost_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            x.copy_(x_host, non_blocking=True); c, _ = step(); cost_host.copy_(c.detach())
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        if sampler:
+            sampler.mark_begin("e2e")
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record()
+        for _ in range(args.steps):
+            x.copy_(x_host, non_blocking=True)
+            c, _ = step()
+            cost_host.copy_(c.detach(), non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.mark_end("e2e")
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        e2e = {"value": world * K * N * args.steps / (float(t.item()) * 1e-3), "unit": unit,
+               "h2d_bytes_per_step": N * 784 * 4, "d2h_bytes_per_step": 4,
+               "steps": args.steps, "sm_mhz": None}
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+    win = sampler.stop() if sampler else {}
+    if e2e is not None and "e2e" in win:
+        e2e["sm_mhz"] = win["e2e"]["sm_mhz"]
+    peaks = load_peaks()
+    flop_per_unit = 3.97e6          # SURVEY 8d: dense layers, forward + backward, per particle-ELBO
+    tfl = flop_per_unit * K * N / (ms_per_step * 1e-3) / 1e12
+    roof = {"bound": "tensor", "achieved": tfl, "peak": peaks["tf"], "unit": "TFLOP/s",
+            "frac": tfl / peaks["tf"], "traffic": None, "peak_source": peaks["src"],
+            "kernel": "linear_tc2_kernel (all dense layers of the step; fp32-equivalent "
+                      "FLOPs over the WHOLE step time, per GPU)",
+            "algorithmic_flops_per_unit": flop_per_unit,
+            "mma_issued_tflops": 3.0 * tfl,
+            "mma_issued_frac_of_peak": 3.0 * tfl / peaks["tf"]}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu, _ = time_cpu_iwae(args, n_iters=3)
+    out = {
+        "metric": "particle-ELBOs/sec", "value": value, "unit": unit, "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": "IWAE, VAE 784-(500,500)-40 (random-init, Glorot), K=%d particles, "
+                        "batch %d/GPU (%d total), forward + SGVB backward"
+                        % (K, N, N * world),
+            "l2": "activations larger than L2 ([K*N, 500] fp32 = %.0f MB per layer)"
+                  % (K * N * 500 * 4 / 1e6),
+            "parallelism": "batch sharded x%d, particles local, 1 packed gradient "
+                           "all-reduce/step" % world},
+        "clocks": win.get("timed"), "e2e": e2e, "gpu_launches": launches,
+        "roofline": roof, "cpu_baseline": cpu, "bound_value": bound,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        td.destroy_process_group()
+
+
+def run_hmc(args):
+    import torch
+    import torch.distributed as td
+    import zhusuan_b200 as zs
+    from zhusuan_b200._lib import lib
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -219,17 +448,18 @@ def main():
     P, const = make_dense_gaussian_problem(D, seed=2)
     impl = args.dense_impl
     if impl is None:
-        impl = 2 if D % 64 == 0 else (1 if D % 32 == 0 else 0)
+        impl = DEFAULT_DENSE_IMPL if D % 64 == 0 else (1 if D % 32 == 0 else 0)
     lj = zs.fused.GaussianLogJoint(P, device=dev, impl=impl)
     g = torch.Generator(device=dev)
     g.manual_seed(3 + rank)
     q = torch.randn(C, D, device=dev, generator=g)          # q0 ~ N(0, I)
     if args.no_adapt:
-        hmc = zs.HMC(step_size=0.2, n_leapfrogs=L, seed=1234, dense_impl=impl)
+        hmc = zs.HMC(step_size=0.2, n_leapfrogs=L, seed=1234, dense_impl=impl,
+                     use_cuda_graph=args.cuda_graph)
     else:
         hmc = zs.HMC(step_size=0.05, n_leapfrogs=L, adapt_step_size=True,
                      adapt_mass=True, mass_collect_iters=10, seed=1234,
-                     dense_impl=impl)
+                     dense_impl=impl, use_cuda_graph=args.cuda_graph)
     sample_op, info = hmc.sample(lj, {}, {"x": q})
 
     def step():
@@ -255,6 +485,7 @@ def main():
         sampler.mark_begin("timed")
     hmc._profile_events = []
     launches0 = lib.launches
+    coll0 = hmc._pk.n_collectives
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
@@ -266,6 +497,7 @@ def main():
         td.barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     launches = lib.launches - launches0
+    collectives = hmc._pk.n_collectives - coll0
     kern_ms = [a.elapsed_time(b) for a, b in hmc._profile_events]
     hmc._profile_events = None
     if sampler:
@@ -373,14 +605,21 @@ def main():
         flops_per_launch = 2.0 * D * D * C           # one P.x product
         hbm = bytes_per_launch / (kms * 1e-3) / 1e9
         tfl = flops_per_launch / (kms * 1e-3) / 1e12
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            traffic = (tj.get("impl%d" % impl) or {}).get("dram_bytes_per_launch")
+            ent = tj.get("impl%d" % impl) or {}
+            traffic = ent.get("dram_bytes_per_pass", ent.get("dram_bytes_per_launch"))
+            traffic_src = ("STATIC: dram__bytes_read+write of one `ncu --set full` capture "
+                           "(%s), per leapfrog pass of 65 536 chains; not measured in this run"
+                           % ent.get("source", "profiles/roofline_traffic.json"))
         f_h, f_t = hbm / peaks["hbm_gbs"], tfl / peaks["tf"]
         roof = {"bound": "hbm", "achieved": hbm, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": f_h, "traffic": traffic,
+                "traffic_source": traffic_src,
+                "per": "leapfrog pass (one launch of the per-pass kernels; 1/(L+1) of the "
+                       "trajectory launch for dense_impl 4/5)",
                 "peak_source": peaks["src"],
                 "kernel": "dense_leapfrog (impl %d)" % impl,
                 "kernel_ms_per_launch": kms,
@@ -401,31 +640,32 @@ def main():
     # ---------------- CPU baseline on this box's host cores ------------------
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        from oracle.cpu_baseline import time_dense_hmc
-        r = time_dense_hmc(D, min(args.cpu_chains, C), L, n_iters=1, warmup=1,
-                           P=(P, const))
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"],
-               "kind": "port", "sample": r["sample"],
-               "host_cpu_count": os.cpu_count()}
+        cpu, _ = time_cpu_hmc(args, P=(P, const), n_iters=5, warmup=1)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {
             "workload": "HMC, %d-dim dense-covariance Gaussian, %d chains/GPU "
-                        "(%d total), L=%d, step-size + mass adaptation on"
-                        % (D, C, C * world, L),
+                        "(%d total), L=%d, %s"
+                        % (D, C, C * world, L,
+                           "fixed step size (--no-adapt: NOT the benchmark configuration)"
+                           if args.no_adapt else "step-size + mass adaptation on"),
             "chains_per_gpu": C, "dim": D, "n_leapfrogs": L,
             "burnin_iters": args.burnin, "dense_impl": impl,
             "l2": "inputs larger than L2 (q,p = %.0f MB each per GPU vs 126 "
                   "MB L2)" % (C * D * 4 / 1e6),
             "rng": "in-kernel Philox4x32-10",
-            "parallelism": "chains sharded x%d, 1 stats all-reduce/iter"
-                           % world},
+            "cuda_graph": bool(args.cuda_graph),
+            "parallelism": "chains sharded x%d (%s scaling), no data-path collective; "
+                           "%d all-reduce(s) of the packed statistics [sum acc, n, S1(D), "
+                           "S2(D)] (%d B) in the %d timed iterations"
+                           % (world, args.scaling, collectives, 8 + 8 * D, args.steps)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "collectives_in_timed_region": collectives,
         "roofline": roof, "cpu_baseline": cpu,
         "acceptance_mean": acc_mean, "step_size": step_size,
     }

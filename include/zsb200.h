@@ -269,9 +269,10 @@ int zsb_hmc_dense_leapfrog_h16i_f32(const float* q_cur, float* q_next, const flo
                                     const float* mu, const float* mass, const float* state,
                                     float p_scale, float* lp_part, float* k_part, int64_t chains,
                                     int64_t D, void* stream);
-/* impl 4 -- EXPERIMENTAL, written at the end of round 1 and NOT yet validated on hardware: the
- * whole leapfrog `while_loop` of hmc.py:347-372 (L+1 passes) in one persistent launch; a cluster of
- * 8 CTAs keeps a 256-chain block's q / p / planes in L2 across the passes.  D == 1024, L >= 1.
+/* impl 4 -- first trajectory-fused design (validated in round 2: correct, but 2x slower than impl 2:
+ * only 8 clusters of 8 CTAs become co-resident and MMA N = 128 saturates the L2->SM port; kept as a
+ * cross-check of impl 5): the whole leapfrog `while_loop` of hmc.py:347-372 (L+1 passes) in one
+ * launch; a cluster of 8 CTAs keeps a 256-chain block's q / p / planes in L2.  D == 1024, L >= 1.
  * Buffers as impl 2 (planes0 from zsb_hmc_dense_h16_prepare_f32); the proposal ends in qa when
  * L - 1 is even, else in qb; pw holds the final momentum. */
 int zsb_hmc_dense_trajectory_h16_f32(const float* q0, const void* planes0, float* qa,
@@ -281,6 +282,26 @@ int zsb_hmc_dense_trajectory_h16_f32(const float* q0, const void* planes0, float
                                      const float* mass, const float* state, float* lp0_part,
                                      float* lp1_part, float* k_part, int64_t chains, int64_t D,
                                      int n_leapfrogs, void* stream);
+/* impl 5: the whole leapfrog `while_loop` of hmc.py:347-372 (L+1 passes, body = leapfrog_integrator
+ * hmc.py:38-43, plus the log p / kinetic terms of hamiltonian() hmc.py:30-35) in ONE persistent
+ * launch whose chain groups stay resident in the 126 MB L2: CTA pairs, N = 256 chains per unit,
+ * group-major order (zsb_hmc_dense_resident_group(D) 256-chain blocks per group), pass-to-pass
+ * dependencies through the int32 `flags` counters (zsb_hmc_dense_resident_flags(chains) words).
+ * Inside the trajectory the state of q is its fp16 hi/lo plane pair (planes0 from
+ * zsb_hmc_dense_h16_prepare_f32; planes1 = work buffer, same size); the proposal's planes end in
+ * buffer (n_leapfrogs & 1) and zsb_hmc_dense_select_planes_f32 assigns them to the accepted
+ * chains (the `tf.where` + assign of hmc.py:488-497).  D % 64 == 0, n_leapfrogs >= 1. */
+int zsb_hmc_dense_resident_flags(int64_t chains);
+int zsb_hmc_dense_resident_group(int64_t D);
+int zsb_hmc_dense_resident_h16_f32(void* planes0, void* planes1, const float* p0, float* pw,
+                                   const void* P_h16, const void* P_l16, const float* scales,
+                                   const float* bvec, const float* mu, const float* mass,
+                                   const float* state, float* lp0_part, float* lp1_part,
+                                   float* k_part, int32_t* flags, int64_t chains, int64_t D,
+                                   int n_leapfrogs, void* stream);
+int zsb_hmc_dense_select_planes_f32(float* q, const void* planes, const float* scales,
+                                    const int32_t* accept, int64_t chains, int64_t D,
+                                    void* stream);
 int zsb_hmc_dense_finish_f32(const float* lp_part, const float* k_part, int ntiles, int64_t chains,
                              float const_term, float* lp_out, float* k_out, void* stream);
 

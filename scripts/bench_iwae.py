@@ -135,8 +135,25 @@ def main():
     # CPU baseline: the same graph in torch-CPU (restatement of the TF graph), small batch
     torch.backends.cuda.matmul.allow_tf32 = False
     Nc = 128
-    Wc = {k: v.detach().cpu().requires_grad_(True) for k, v in build(dev).items()}
-    xc = x[:Nc].cpu().float()
+    cpu_step = make_cpu_step(x[:Nc].cpu().float(), K)
+    cpu_step()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        cpu_step()
+    dt = (time.perf_counter() - t0) / 3
+    out["cpu_port"] = {"particle_elbos_per_s": K * Nc / dt, "cores": torch.get_num_threads(),
+                       "sample": "batch %d of 4096, K=64, torch-CPU restatement of iwae.py" % Nc}
+    print(json.dumps(out))
+    if world > 1:
+        td.destroy_process_group()
+
+
+def make_cpu_step(xc, K, seed=5):
+    """The graph of iwae.py:23-78 op by op in torch-CPU (forward + SGVB backward): the CPU arm
+    of bench.py --workload iwae (TensorFlow is not installable here, so kind = "port")."""
+    Nc = xc.shape[0]
+    Wc = {k: v.detach().cpu().requires_grad_(True)
+          for k, v in build(torch.device("cpu"), seed=seed).items()}
     eps = torch.randn(K, Nc, 40)
 
     def cpu_step():
@@ -152,16 +169,7 @@ def main():
         lw = log_pz + log_px - log_q
         cost = -(torch.logsumexp(lw, 0) - np.log(K)).mean()
         return torch.autograd.grad(cost, list(Wc.values()))
-    cpu_step()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        cpu_step()
-    dt = (time.perf_counter() - t0) / 3
-    out["cpu_port"] = {"particle_elbos_per_s": K * Nc / dt, "cores": torch.get_num_threads(),
-                       "sample": "batch %d of 4096, K=64, torch-CPU restatement of iwae.py" % Nc}
-    print(json.dumps(out))
-    if world > 1:
-        td.destroy_process_group()
+    return cpu_step
 
 
 if __name__ == "__main__":

@@ -109,3 +109,69 @@ def test_two_rank_data_parallel_gradient_equals_global_mean_gradient():
         np.testing.assert_allclose(out[r][0], gw.numpy(), rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(out[r][1], gb.numpy(), rtol=1e-5, atol=1e-6)
         assert abs(out[r][2] - float(cost)) < 1e-5
+
+
+def _packed_worker(rank, world, port, q_iters, acc_iters, out):
+    """Drives zhusuan_b200.dist.PackedStats exactly as HMC._iterate_eager does (host restatement
+    of what the acc_sum / mass_stats kernels write): ONE all-reduce per iteration carrying the
+    acceptance sum of iteration t and the EWMV statistics iteration t+1 will consume."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    from zhusuan_b200 import dist
+    T_, C, D = q_iters.shape
+    row0, n_local = dist.shard_chains(C)
+    pk = dist.PackedStats(D, "cpu")
+    mean, var = torch.zeros(D), torch.zeros(D)
+    decay, tt = 0.99, 0.0
+    res = []
+
+    def local_mass_stats(q):
+        pk.mass[:D] = (q - mean).sum(0)
+        pk.mass[D:] = ((q - mean) ** 2).sum(0)
+
+    for t in range(T_):
+        q = torch.tensor(q_iters[t, row0:row0 + n_local])      # state at the START of iteration t
+        if not pk.mass_valid:          # first iteration only: statistics + their own collective
+            local_mass_stats(q)
+            pk.reduce_mass()
+        tt += 1.0
+        n_glob = float(C)
+        w = (1 - decay) / (1 - decay ** tt)
+        delta = pk.mass[:D] / n_glob
+        s2 = pk.mass[D:] / n_glob
+        mean = mean + w * delta
+        var = (1 - w) * var + w * (s2 - w * delta * delta)
+        # ... trajectory + MH + select happen here; the post-select state is q_iters[t + 1]
+        acc = torch.tensor(acc_iters[t, row0:row0 + n_local])
+        pk.acc[0], pk.acc[1] = acc.sum(), float(n_local)
+        if t + 1 < T_:
+            local_mass_stats(torch.tensor(q_iters[t + 1, row0:row0 + n_local]))
+        pk.reduce_all(with_mass=t + 1 < T_)                    # the ONE collective of iteration t
+        res.append((float(pk.acc[0] / pk.acc[1]), mean.numpy().copy(), var.numpy().copy()))
+    out[rank] = (res, pk.n_collectives)
+    td.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_packed_statistics_one_collective_per_iteration():
+    """Section 8e: T iterations on 2 ranks cost T + 1 collectives (one extra for the very first
+    mass update) and reproduce the single-process oracle's global mean acceptance and EWMV."""
+    from oracle.hmc import ExponentialWeightedMovingVariance
+    rng = np.random.RandomState(3)
+    T_, C, D = 4, 23, 5
+    q_iters = rng.standard_normal((T_, C, D)).astype(np.float32)
+    acc_iters = rng.random_sample((T_, C)).astype(np.float32)
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_packed_worker, args=(2, port, q_iters, acc_iters, out), nprocs=2, join=True)
+    ew = ExponentialWeightedMovingVariance(0.99, [(1, D)], 1, np.float32)
+    for t in range(T_):
+        var = ew.update([q_iters[t]])[0].reshape(-1)
+        for r in (0, 1):
+            abar, mean_t, var_t = out[r][0][t]
+            np.testing.assert_allclose(abar, acc_iters[t].mean(), rtol=1e-6)
+            np.testing.assert_allclose(mean_t, ew.mean[0].reshape(-1), rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(var_t, var, rtol=1e-4, atol=1e-6)
+    assert out[0][1] == out[1][1] == T_ + 1

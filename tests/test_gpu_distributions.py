@@ -171,6 +171,51 @@ def test_mvn_cholesky_vs_scipy(zs, seed):
     np.testing.assert_allclose(N(st.grad), ref, rtol=2e-3, atol=2e-2)
 
 
+def test_parameter_gradients_of_mvn_cholesky_and_dirichlet(zs):
+    """ELBO / IWAE with a TRAINABLE MultivariateNormalCholesky or Dirichlet posterior
+    differentiates log q w.r.t. cov_tril / alpha (the reference does it through TF autodiff of
+    multivariate.py:169-189, 665-677): checked against float64 torch autograd of the same
+    formulas, with cov_tril broadcast over a leading sample axis."""
+    rng = np.random.RandomState(7)
+    Dn = 5
+    mean = rng.standard_normal((3, Dn))
+    A = rng.standard_normal((3, Dn, Dn)) * 0.3
+    chol = np.tril(A) + np.eye(Dn) * (1.0 + rng.random_sample((3, Dn, 1)) * 0.5) * np.eye(Dn)
+    chol = np.tril(chol)
+    x = rng.standard_normal((4, 3, Dn))
+    w = rng.standard_normal((4, 3))
+    # float64 reference
+    m64 = torch.tensor(mean, dtype=torch.float64, requires_grad=True)
+    c64 = torch.tensor(chol, dtype=torch.float64, requires_grad=True)
+    x64 = torch.tensor(x, dtype=torch.float64)
+    y = torch.linalg.solve_triangular(c64.expand(4, 3, Dn, Dn), (x64 - m64).unsqueeze(-1),
+                                      upper=False).squeeze(-1)
+    lp64 = (-0.5 * Dn * np.log(2 * np.pi) - torch.log(torch.diagonal(c64, dim1=-2, dim2=-1)).sum(-1)
+            - 0.5 * (y * y).sum(-1))
+    (lp64 * torch.tensor(w)).sum().backward()
+    mt, ct = T(mean).requires_grad_(True), T(chol).requires_grad_(True)
+    lp = zs.distributions.MultivariateNormalCholesky(mt, ct).log_prob(T(x))
+    np.testing.assert_allclose(N(lp), lp64.detach().numpy(), rtol=1e-4, atol=1e-4)
+    (lp * T(w)).sum().backward()
+    np.testing.assert_allclose(N(ct.grad), c64.grad.numpy(), rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(N(mt.grad), m64.grad.numpy(), rtol=2e-4, atol=2e-4)
+    assert np.all(np.triu(N(ct.grad), 1) == 0)
+
+    a = 0.5 + 3 * rng.random_sample((3, 4))
+    g = rng.dirichlet(np.ones(4), size=(5, 3))
+    w2 = rng.standard_normal((5, 3))
+    a64 = torch.tensor(a, dtype=torch.float64, requires_grad=True)
+    g64 = torch.tensor(g, dtype=torch.float64)
+    lpd = (torch.lgamma(a64.sum(-1)) - torch.lgamma(a64).sum(-1)
+           + ((a64 - 1) * torch.log(g64)).sum(-1))
+    (lpd * torch.tensor(w2)).sum().backward()
+    at = T(a).requires_grad_(True)
+    lp = zs.distributions.Dirichlet(at).log_prob(T(g))
+    np.testing.assert_allclose(N(lp), lpd.detach().numpy(), rtol=1e-4, atol=1e-4)
+    (lp * T(w2)).sum().backward()
+    np.testing.assert_allclose(N(at.grad), a64.grad.numpy(), rtol=2e-4, atol=2e-4)
+
+
 def test_shape_and_dtype_contract(zs):
     d = zs.distributions.Normal(T(np.zeros((2, 3))), logstd=T(np.zeros(3)),
                                 group_ndims=1)

@@ -356,16 +356,17 @@ def test_golden_dense_fused_tc(zs):
     _replay(zs, g, lj, "dense_gaussian", q_tol=1e-4, dense_impl=1)
 
 
-def _replay_big(zs, name, impl, use_graph=False):
+def _replay_big(zs, name, impl, h_rtol=1e-5, acc_floor_mult=4.0):
     """Replay tests/golden/<name>.npz (L = 50, adaptive, mass != 1, both step-size searches,
     diverging and healthy iterations; see make_golden.py BIG) on one dense kernel.
 
     Budget: the fixture carries the float32 oracle's outputs and a float64 re-evaluation of each
     iteration; `floor` = max |acc32 - acc64| is the rounding noise floor of a float32 HMC at this
-    size (|H| ~ D).  The CUDA path must stay within 4 x floor (+1e-5) of the float64 acceptance,
-    within 1e-5 relative of the Hamiltonians / log-probs, and -- because every uniform was pushed
-    >= 2 x u_guard away from the acceptance when the fixture was made -- reproduce EVERY accept
-    decision."""
+    size (|H| ~ D).  The CUDA path must stay within `acc_floor_mult` x floor (+1e-5) of the
+    float64 acceptance, within `h_rtol` relative of the Hamiltonians / log-probs, and -- because
+    every uniform was pushed >= 2 x u_guard away from the acceptance when the fixture was made
+    -- reproduce EVERY accept decision.  All iterations are replayed and tabulated first (the
+    table goes to stdout: run with -s), then asserted."""
     import sys
     sys.path.insert(0, GOLD)
     import make_golden as MG
@@ -385,59 +386,62 @@ def _replay_big(zs, name, impl, use_graph=False):
     op, info = h.sample(lj, {}, {"x": x})
     assert h._fused["kind"] == "dense_gaussian"
     floor = float(np.abs(g["acc"] - g["acc64"]).max())
-    acc_tol = 4 * floor + 1e-5
+    acc_tol = acc_floor_mult * floor + 1e-5
     assert acc_tol < cfg["u_guard"]
     stride = D // 16
-    worst = {"acc": 0.0, "h": 0.0, "q": 0.0}
+    rel = lambda a, b: float(np.abs(a / b - 1).max()) if a.size else 0.0
+    rows = []
     for i in range(cfg["iters"]):
         adapt = i < cfg["n_adapt"]
         op(adapt_step_size=adapt, adapt_mass=adapt,
            noise={"p": {"x": T(MG.big_noise(cfg, i))}, "u": T(g["noise_u"][i])})
         acc = N(info.acceptance_rate)
-        msg = "%s impl %d iteration %d" % (name, impl, i)
-        np.testing.assert_allclose(float(h._state[7]), g["eps_used"][i], rtol=2e-5, err_msg=msg)
-        np.testing.assert_allclose(acc, g["acc64"][i], rtol=0, atol=acc_tol, err_msg=msg)
-        np.testing.assert_array_equal((g["noise_u"][i] < acc).astype(np.int32), g["accept"][i],
-                                      err_msg=msg)
-        np.testing.assert_allclose(N(info.orig_hamiltonian), g["h0_64"][i], rtol=1e-5,
-                                   err_msg=msg)
-        np.testing.assert_allclose(N(info.orig_log_prob), g["lp0"][i], rtol=1e-5, atol=1e-4,
-                                   err_msg=msg)
         fin = np.isfinite(g["h1"][i])
-        assert np.all(acc[~fin] == 0), msg          # hmc.py:56-59: non-finite -> rejected
-        np.testing.assert_allclose(N(info.hamiltonian)[fin], g["h1_64"][i][fin], rtol=1e-5,
-                                   err_msg=msg)
-        np.testing.assert_allclose(N(info.log_prob), g["lp"][i], rtol=1e-5, atol=1e-4,
-                                   err_msg=msg)
         xq = N(x)
-        np.testing.assert_allclose(xq[:, ::stride], g["q_sub"][i], rtol=1e-4, atol=1e-4,
-                                   err_msg=msg)
-        np.testing.assert_allclose(xq.astype(np.float64).sum(1), g["q_rowsum"][i], rtol=0,
-                                   atol=2e-4 * D ** 0.5 * max(1.0, np.abs(xq).max()),
-                                   err_msg=msg)
-        np.testing.assert_allclose(float(info.updated_step_size), g["step_size"][i], rtol=1e-4,
-                                   err_msg=msg)
-        np.testing.assert_allclose(N(h._mass[0]), g["mass"][i], rtol=2e-4, err_msg=msg)
-        worst["acc"] = max(worst["acc"], float(np.abs(acc - g["acc64"][i]).max()))
-        if fin.any():
-            worst["h"] = max(worst["h"], float(np.abs(
-                N(info.hamiltonian)[fin] / g["h1_64"][i][fin] - 1).max()))
-        worst["q"] = max(worst["q"], float(np.abs(xq[:, ::stride] - g["q_sub"][i]).max()))
+        rows.append(dict(
+            i=i, eps=float(h._state[7]), eps_err=abs(float(h._state[7]) / g["eps_used"][i] - 1),
+            acc_err=float(np.abs(acc - g["acc64"][i]).max()),
+            flips=int(((g["noise_u"][i] < acc).astype(np.int32) != g["accept"][i]).sum()),
+            nonfinite_ok=bool(np.all(acc[~fin] == 0)),
+            h0_err=rel(N(info.orig_hamiltonian), g["h0_64"][i]),
+            h1_err=rel(N(info.hamiltonian)[fin], g["h1_64"][i][fin]),
+            lp0_err=float(np.abs(N(info.orig_log_prob) - g["lp0"][i]).max()
+                          / np.abs(g["lp0"][i]).max()),
+            lp_err=float(np.abs(N(info.log_prob) - g["lp"][i]).max() / np.abs(g["lp"][i]).max()),
+            q_err=float(np.abs(xq[:, ::stride] - g["q_sub"][i]).max()),
+            qsum_err=float(np.abs(xq.astype(np.float64).sum(1) - g["q_rowsum"][i]).max()),
+            step_err=abs(float(info.updated_step_size) / g["step_size"][i] - 1),
+            mass_err=rel(N(h._mass[0]), g["mass"][i])))
     op.synchronize()
+    print("\nreplay %s impl %d (float32-oracle acceptance floor %.2e, acc_tol %.2e)" % (
+        name, impl, floor, acc_tol))
+    print(" it   eps     eps_err  acc_err  flips h0_err   h1_err   lp0_err  lp_err   q_err    "
+          "step_err mass_err")
+    for r in rows:
+        print(" %2d %7.4f %8.1e %8.1e %3d  %8.1e %8.1e %8.1e %8.1e %8.1e %8.1e %8.1e" % (
+            r["i"], r["eps"], r["eps_err"], r["acc_err"], r["flips"], r["h0_err"], r["h1_err"],
+            r["lp0_err"], r["lp_err"], r["q_err"], r["step_err"], r["mass_err"]))
+    for r in rows:
+        msg = "%s impl %d iteration %d: %r" % (name, impl, r["i"], r)
+        assert r["eps_err"] < 2e-5, msg
+        assert r["acc_err"] <= acc_tol, msg
+        assert r["flips"] == 0 and r["nonfinite_ok"], msg
+        assert r["h0_err"] < 1e-5 and r["lp0_err"] < 1e-5, msg
+        assert r["h1_err"] < h_rtol and r["lp_err"] < h_rtol, msg
+        assert r["q_err"] < 1e-4 * max(1.0, float(np.abs(g["q_sub"][r["i"]]).max())), msg
+        assert r["step_err"] < 1e-4 and r["mass_err"] < 2e-4, msg
     assert h.n_search_iters == int(g["n_search_iters"])
-    print("replay %s impl %d: max|acc-acc64| %.2e (float32-oracle floor %.2e), max H rel err "
-          "%.2e, max |dq| %.2e" % (name, impl, worst["acc"], floor, worst["h"], worst["q"]))
     return h
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 5])
 def test_golden_dense64_l50_adaptive(zs, impl):
     """D = 64, 160 chains (ragged tile), L = 50, 24 adaptive iterations on the SIMT, 3xTF32 and
     fp16-split (the benchmarked) kernels vs the oracle."""
     _replay_big(zs, "hmc_dense64", impl)
 
 
-@pytest.mark.parametrize("impl", [2, 4])
+@pytest.mark.parametrize("impl", [2, 4, 5])
 def test_golden_dense1024_l50_adaptive(zs, impl):
     """The benchmark configuration's shape (D = 1024, L = 50, step + mass adaptation) at 320
     chains on the benchmarked kernels: impl 2 (fp16-split, one launch per pass) and impl 4 (the
@@ -596,21 +600,20 @@ def test_cuda_graph_replay_is_bitwise_eager(zs, path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("ZSB_EXPERIMENTAL") != "1",
-                    reason="impl 4 (trajectory-fused kernel) was written at the end of round 1 and "
-                           "has not been run on hardware yet; set ZSB_EXPERIMENTAL=1 to try it")
-@pytest.mark.parametrize("C,L", [(300, 3), (2048, 5), (8192, 2)])
-def test_experimental_trajectory_kernel_matches_per_pass_kernel(zs, C, L):
-    """dense_impl=4 (one persistent launch per trajectory, L2-resident chain blocks) against
-    dense_impl=2 (one launch per pass): same operands, same epilogue arithmetic, so the chains
-    must agree to fp32 rounding."""
+@pytest.mark.parametrize("impl", [4, 5])
+@pytest.mark.parametrize("C,L", [(300, 3), (2048, 5), (8192, 2), (9472 + 256 + 40, 4)])
+def test_trajectory_kernels_match_per_pass_kernel(zs, impl, C, L):
+    """dense_impl=4 (clusters of 8, one launch per trajectory) and dense_impl=5 (L2-resident
+    groups, planes-only state, flag-synchronised passes; the last shape spans two groups and a
+    ragged block) against dense_impl=2 (one launch per pass): same operands and products, so the
+    chains must agree to fp32 rounding."""
     D = 1024
     P, _ = OM.make_dense_gaussian_problem(D, seed=2)
     res = []
-    for impl in (2, 4):
+    for im in (2, impl):
         torch.manual_seed(5)
         x = torch.randn(C, D, device="cuda")
-        h = zs.HMC(step_size=0.1, n_leapfrogs=L, seed=7, dense_impl=impl)
+        h = zs.HMC(step_size=0.1, n_leapfrogs=L, seed=7, dense_impl=im)
         op, info = h.sample(zs.fused.GaussianLogJoint(P), {}, {"x": x})
         for _ in range(2):
             op()
@@ -619,3 +622,31 @@ def test_experimental_trajectory_kernel_matches_per_pass_kernel(zs, C, L):
     np.testing.assert_allclose(res[1][1], res[0][1], rtol=1e-5)
     np.testing.assert_allclose(res[1][2], res[0][2], rtol=0, atol=1e-4)
     np.testing.assert_allclose(res[1][0], res[0][0], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,C,L", [(64, 40, 1), (64, 300, 3), (192, 70, 2), (512, 260, 3),
+                                   (1024, 1, 1)])
+def test_resident_kernel_shapes_vs_oracle(zs, D, C, L):
+    """dense_impl=5 on ragged / tiny shapes (D not a multiple of 256, one chain, a single
+    dimension tile) with a mean vector and a non-unit mass, one iteration vs the oracle."""
+    rng = np.random.RandomState(D + C + L)
+    P, const = OM.make_dense_gaussian_problem(D, seed=4)
+    mu = (0.3 * rng.standard_normal(D)).astype(np.float32)
+    q0 = rng.standard_normal((C, D)).astype(np.float32)
+    npz = rng.standard_normal((C, D)).astype(np.float32)
+    u = rng.random_sample(C).astype(np.float32)
+    om = OM.DenseGaussian(P.astype(np.float32), mu, const)
+    oq, oi = OH.HMC(step_size=0.12, n_leapfrogs=L).step([q0], om.logp, om.grad, [npz], u)
+    x = T(q0)
+    h = zs.HMC(step_size=0.12, n_leapfrogs=L, dense_impl=5)
+    lj = zs.fused.GaussianLogJoint(P, mean=mu, log_det_cov=-2 * const - D * np.log(2 * np.pi))
+    op, info = h.sample(lj, {}, {"x": x})
+    assert h._res
+    op(noise={"p": {"x": T(npz)}, "u": T(u)})
+    op.synchronize()
+    np.testing.assert_allclose(N(info.orig_hamiltonian), oi.orig_hamiltonian, rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(N(info.hamiltonian), oi.hamiltonian, rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(N(info.acceptance_rate), oi.acceptance_rate, rtol=2e-4, atol=1e-4)
+    near = np.abs(u - oi.acceptance_rate) < 1e-3
+    np.testing.assert_allclose(N(x)[~near], oq[0][~near], rtol=2e-5, atol=2e-5)

@@ -34,7 +34,9 @@ def test_library_exports_every_declared_symbol():
                 "zsb_dense_tc_ntiles", "zsb_dense_split_lo_launch",
                 "zsb_dense_tc_set_bk", "zsb_dense_leapfrog_h16_launch",
                 "zsb_dense_h16_prepare_launch", "zsb_dense_leapfrog_h16i_launch",
-                "zsb_dense_h16i_prepare_launch", "zsb_dense_traj_h16_launch"}
+                "zsb_dense_h16i_prepare_launch", "zsb_dense_traj_h16_launch",
+                    "zsb_dense_res_group_blocks", "zsb_dense_res_h16_launch",
+                    "zsb_dense_select_planes_launch"}
     assert defined - internal <= set(protos), defined - internal - set(protos)
 
 
@@ -246,6 +248,12 @@ def test_sampler_and_objective_argument_contract():
         zs.HMC().sample(lambda o: 0, {}, {"x": 1.0})
     with pytest.raises(TypeError, match=r"latent\['w'\] is not a"):
         zs.SGHMC(1e-3).sample(lambda o: 0, {}, {"w": np.zeros(3)})
+    # a latent that does not carry the chain axes of the log-joint is rejected up front (the
+    # kernels would otherwise walk chains * row_len elements of a shorter tensor)
+    import torch
+    with pytest.raises(ValueError, match="must start with the chain axes"):
+        zs.SGLD(1e-3).sample(lambda o: torch.zeros(10) + o["w"].sum(), {},
+                             {"w": torch.zeros(5)})
     s = zs.SGHMC(1e-3, n_iter_resample_v=None)
     assert s.n_iter_resample_v == 0 and s.second_order
     p = zs.PSGLD(1e-3)

@@ -86,7 +86,7 @@ class _Lib(object):
 
     # kernels launched per successful call (entries that launch two kernels)
     # kernels launched per entry point (default 1): the `gpu_launches` claim of bench.py
-    _KERNELS = {"zsb_hmc_mass_stats_f32": 2, "zsb_hmc_dense_h16_prepare_f32": 3, "zsb_sgmcmc_sghmc_f32": 2,
+    _KERNELS = {"zsb_hmc_mass_stats_f32": 2, "zsb_hmc_dense_h16_prepare_f32": 3, "zsb_hmc_dense_resident_h16_f32": 1, "zsb_sgmcmc_sghmc_f32": 2,
                 "zsb_sgmcmc_mean_sq_f32": 2, "zsb_sgmcmc_sgnht_scalar_f32": 2,
                 "zsb_split16_pad_f32": 3, "zsb_split16_pad_t_f32": 3, "zsb_linear_tc_f32": 2}
     launches = 0

@@ -204,6 +204,16 @@ int zsb_dense_traj_h16_launch(const float* q0, const void* planes0, float* qa, v
                               const float* bvec, const float* mu, const float* mass,
                               const float* state, float* lp0_part, float* lp1_part,
                               float* k_part, int64_t chains, int D, int L, cudaStream_t st);
+// implemented in hmc_dense_res.cu
+int zsb_dense_res_h16_launch(void* planes0, void* planes1, const float* p0, float* pw,
+                             const void* P_h16, const void* P_l16, const float* scales,
+                             const float* bvec, const float* mu, const float* mass,
+                             const float* state, float* lp0_part, float* lp1_part, float* k_part,
+                             int* flags, int64_t chains, int D, int L, cudaStream_t st);
+int zsb_dense_select_planes_launch(float* q, const void* planes, const float* scales,
+                                   const int32_t* accept, int64_t chains, int64_t D,
+                                   cudaStream_t st);
+int zsb_dense_res_group_blocks(int D);
 
 extern "C" {
 
@@ -315,6 +325,39 @@ int zsb_hmc_dense_trajectory_h16_f32(const float* q0, const void* planes0, float
   return zsb_dense_traj_h16_launch(q0, planes0, qa, planes_a, qb, planes_b, p0, pw, P_h16, P_l16,
                                    scales, bvec, mu, mass, state, lp0_part, lp1_part, k_part,
                                    chains, (int)D, n_leapfrogs, (cudaStream_t)stream);
+}
+
+// impl 5: the whole leapfrog `while_loop` of hmc.py:347-372 (L+1 passes) in ONE persistent launch
+// whose chain groups stay resident in the L2 (hmc_dense_res.cu).  The sampler state inside the
+// trajectory is the fp16 hi/lo plane pair of q*sq (+ fp32 p); planes0 comes from
+// zsb_hmc_dense_h16_prepare_f32, planes1 is a work buffer of the same size, flags an int32 scratch
+// of zsb_hmc_dense_resident_flags(chains) words.  On return the proposal's planes are in buffer
+// (n_leapfrogs & 1) -- zsb_hmc_dense_select_planes_f32 assigns them to the accepted chains -- and
+// pw holds the final momentum.  D % 64 == 0, n_leapfrogs >= 1.
+int zsb_hmc_dense_resident_flags(int64_t chains) { return (int)zsb_ceil_div(chains, 256); }
+int zsb_hmc_dense_resident_group(int64_t D) { return zsb_dense_res_group_blocks((int)D); }
+int zsb_hmc_dense_resident_h16_f32(void* planes0, void* planes1, const float* p0, float* pw,
+                                   const void* P_h16, const void* P_l16, const float* scales,
+                                   const float* bvec, const float* mu, const float* mass,
+                                   const float* state, float* lp0_part, float* lp1_part,
+                                   float* k_part, int32_t* flags, int64_t chains, int64_t D,
+                                   int n_leapfrogs, void* stream) {
+  ZSB_REQUIRE(planes0 && planes1 && p0 && pw && P_h16 && P_l16 && scales && mass && state &&
+                  lp0_part && lp1_part && k_part && flags,
+              "zsb_hmc_dense_resident_h16_f32: null arg");
+  ZSB_REQUIRE(planes0 != planes1 && p0 != pw, "zsb_hmc_dense_resident_h16_f32: aliased buffers");
+  return zsb_dense_res_h16_launch(planes0, planes1, p0, pw, P_h16, P_l16, scales, bvec, mu, mass,
+                                  state, lp0_part, lp1_part, k_part, flags, chains, (int)D,
+                                  n_leapfrogs, (cudaStream_t)stream);
+}
+// q[c, :] <- (hi + lo) / sq of `planes` for the chains with accept[c] != 0 (hmc.py:488-497)
+int zsb_hmc_dense_select_planes_f32(float* q, const void* planes, const float* scales,
+                                    const int32_t* accept, int64_t chains, int64_t D,
+                                    void* stream) {
+  ZSB_REQUIRE(q && planes && scales && accept && chains > 0 && D > 0 && D % 2 == 0,
+              "zsb_hmc_dense_select_planes_f32: bad args");
+  return zsb_dense_select_planes_launch(q, planes, scales, accept, chains, D,
+                                        (cudaStream_t)stream);
 }
 
 int zsb_hmc_dense_finish_f32(const float* lp_part, const float* k_part, int ntiles, int64_t chains,

@@ -25,6 +25,51 @@ def all_reduce_sum(t, group=None):
     return t
 
 
+class PackedStats(object):
+    """The per-iteration statistics message of a sharded HMC sampler and its collective schedule.
+
+    Layout (float32): ``[sum(acc), n_chains, S1(D_0), S2(D_0), S1(D_1), ...]`` -- the acceptance
+    part feeds ``reduce_mean(acceptance_rate)`` (hmc.py:377), the S1/S2 part the EWMV update
+    (hmc.py:137-145), both global means over ALL chains.
+
+    Schedule: the mass statistics that iteration t+1 consumes are those of the state AFTER
+    iteration t's accept/reject, so they are computed right after the select and travel in the
+    SAME all-reduce as iteration t's acceptance sum: ONE collective per iteration
+    (``reduce_all``).  Only when no valid prefetch exists -- first iteration, the caller wrote
+    the latent between two calls, adaptation was off in the previous call -- the mass part is
+    reduced on its own at the start of the iteration (``reduce_mass``).  ``n_collectives``
+    counts both, so tests and bench.py can assert the schedule."""
+
+    def __init__(self, n_mass, device, group=None):
+        self.buf = torch.zeros(2 + 2 * int(n_mass), dtype=torch.float32, device=device)
+        self.acc = self.buf[:2]
+        self.mass = self.buf[2:]
+        self.group = group
+        self.world = world(group)[0]
+        self.n_collectives = 0
+        self.mass_valid = False      # buf[2:] holds the GLOBAL sums for the next mass update
+
+    def reduce_all(self, with_mass):
+        """End of an iteration: acceptance sum (+ the prefetched mass statistics)."""
+        if self.world > 1:
+            all_reduce_sum(self.buf if with_mass else self.acc, self.group)
+            self.n_collectives += 1
+        self.mass_valid = bool(with_mass)
+
+    def reduce_mass(self):
+        """Start of an iteration without a valid prefetch."""
+        if self.world > 1:
+            all_reduce_sum(self.mass, self.group)
+            self.n_collectives += 1
+        self.mass_valid = True
+
+    def reduce_acc(self):
+        """Inside the step-size search loop (hmc.py:307-345): acceptance only."""
+        if self.world > 1:
+            all_reduce_sum(self.acc, self.group)
+            self.n_collectives += 1
+
+
 def shard_chains(n_chains_global, group=None):
     """Contiguous partition of the flattened chain axis: returns
     (row0, n_local) for this rank; remainders go to the lowest ranks."""

@@ -78,10 +78,15 @@ class _SampleOp(object):
         self._hmc = hmc
 
     def __call__(self, adapt_step_size=None, adapt_mass=None, noise=None,
-                 use_graph=None):
+                 use_graph=None, observed=None):
         """One HMC iteration.  ``use_graph`` (default: the sampler's
         ``use_cuda_graph``) replays the iteration from a captured CUDA graph
-        on the fused paths -- worthwhile when the iteration is launch-bound."""
+        on the fused paths -- worthwhile when the iteration is launch-bound.
+        ``observed`` replaces observed values for this and later calls (what
+        ``sess.run(sample_op, feed_dict=...)`` does for placeholder-fed
+        observations, evaluation.py:150-156)."""
+        if observed:
+            self._hmc._observed.update(observed)
         return self._hmc._iterate(adapt_step_size, adapt_mass, noise,
                                   use_graph)
 
@@ -203,7 +208,6 @@ class HMC(object):
         st[ST_STEP] = self._init_step_size_value
         st[ST_MU] = 10 * self._init_step_size_value           # hmc.py:79
         self._state = st
-        self._stats = z(2)
         self._p0 = [torch.empty_like(q) for q in self._q]
         self._mass = [torch.ones(r, dtype=_F32, device=dev)
                       for r in self._row_len]
@@ -212,7 +216,12 @@ class HMC(object):
             self._ew_var = [z(r) for r in self._row_len]
             nparts = lib.load().zsb_hmc_mass_parts()
             self._mass_part = [z(nparts * 2 * r) for r in self._row_len]
-            self._mass_stats = z(2 * sum(self._row_len))
+        # one packed message [sum acc, n, S1.., S2..] -> ONE all-reduce per iteration (dist.py)
+        self._pk = zdist.PackedStats(sum(self._row_len) if self._has_mass else 0, dev,
+                                     self._group)
+        self._stats = self._pk.acc
+        self._mass_stats = self._pk.mass
+        self._q_versions = None
         self._acc_part = z(lib.load().zsb_hmc_acc_parts())
         c = (chains,)
         self._k0, self._k1 = z(c), z(c)
@@ -257,20 +266,38 @@ class HMC(object):
     def _eps_ptr(self):
         return self._state.data_ptr() + 4 * ST_EPS
 
-    def _allreduce(self, t):
-        if self._world > 1:
-            zdist.all_reduce_sum(t, self._group)
-
     def _check_flags(self, final=False):
-        if self._flag_event is not None:
+        """check_numerics (hmc.py:51-53) without a host sync per iteration: the flag word is
+        copied to pinned memory asynchronously after every iteration and only LOOKED at here
+        once its copy has completed (``final`` = wait for it: ``sample_op.synchronize()``)."""
+        if self._flag_event is not None and (final or self._flag_event.query()):
             self._flag_event.synchronize()
             self._flag_event = None
             if int(self._flag_host[0]) & 1:
+                # not sticky: clear the device flag so a repaired sampler can continue
+                self._state[ST_FLAGS:ST_FLAGS + 1].zero_()
+                self._flag_host.zero_()
                 raise FloatingPointError(
                     'HMC: old_log_prob has numeric errors! Try better '
                     'initialization.')                        # hmc.py:51-53
         elif final and self._state.is_cuda:
             torch.cuda.current_stream().synchronize()
+
+    def _mass_stats_into_packed(self, s):
+        """S1/S2 of the current latent state vs the current EWMV mean -> packed buffer."""
+        off = 0
+        for k, q in enumerate(self._q):
+            r = self._row_len[k]
+            lib.call("zsb_hmc_mass_stats_f32", ptr(q), ptr(self._ew_mean[k]), self._chains, r,
+                     ptr(self._mass_part[k]), self._mass_stats.data_ptr() + 4 * off, s)
+            off += 2 * r
+
+    def _prefetch_ok(self):
+        """The packed mass statistics were produced by the previous iteration AND nobody wrote
+        the latent tensors since (torch's version counter; our kernels write through raw
+        pointers and do not bump it)."""
+        return (self._pk.mass_valid and self._q_versions is not None and
+                self._q_versions == [q._version for q in self._q])
 
     def _queue_flag_check(self):
         if self._state.is_cuda:
@@ -297,7 +324,9 @@ class HMC(object):
         init = self._has_step and (t == 1 or t == self.mass_collect_iters)
         want_graph = self._use_graph if use_graph is None else bool(use_graph)
         if (want_graph and noise is None and not init and self._fused
-                and self._world == 1 and self._state.is_cuda):
+                and self._state.is_cuda
+                and (not (adapt_m and self._has_mass) or self._prefetch_ok())):
+            # (an adaptive-mass iteration without a valid statistics prefetch runs eagerly once)
             return self._iterate_graph(adapt_step, adapt_m)
         return self._iterate_eager(adapt_step, adapt_m, noise, t, init)
 
@@ -327,6 +356,10 @@ class HMC(object):
         if adapt_m and self._has_mass:
             self._ewmv_t += 1
         g.replay()
+        if self._world > 1:
+            self._pk.n_collectives += 1        # the all-reduce captured in the graph
+        self._pk.mass_valid = bool(adapt_m and self._has_mass)
+        self._q_versions = [q._version for q in self._q]
         self._queue_flag_check()
         return None
 
@@ -348,15 +381,11 @@ class HMC(object):
         # ---- mass (hmc.py:452-456, 283-305)
         if self._has_mass:
             if adapt_m:
-                off = 0
-                for k, q in enumerate(self._q):
-                    r = self._row_len[k]
-                    lib.call("zsb_hmc_mass_stats_f32", ptr(q),
-                             ptr(self._ew_mean[k]), self._chains, r,
-                             ptr(self._mass_part[k]),
-                             self._mass_stats.data_ptr() + 4 * off, s)
-                    off += 2 * r
-                self._allreduce(self._mass_stats)
+                if not dev and not self._prefetch_ok():
+                    # no valid prefetch (first iteration / latent written by the caller /
+                    # adaptation was off): statistics + their own collective, now
+                    self._mass_stats_into_packed(s)
+                    self._pk.reduce_mass()
                 if not dev:
                     self._ewmv_t += 1
             use_ones = 1 if t < self.mass_collect_iters else 0  # hmc.py:299-302
@@ -386,7 +415,17 @@ class HMC(object):
         # ---- step-size adaptation (hmc.py:501-505, 374-380)
         lib.call("zsb_hmc_acc_sum_f32", ptr(self._acc_part),
                  self._npart.value, self._chains, ptr(self._stats), s)
-        self._allreduce(self._stats)
+        # the statistics the NEXT iteration's mass update needs are those of the state after
+        # this iteration's select: compute them now and send them with the acceptance sum
+        prefetch = bool(self._has_mass and adapt_m)
+        if prefetch:
+            self._mass_stats_into_packed(s)
+        if dev:
+            if self._world > 1:                # captured into the graph
+                zdist.all_reduce_sum(self._pk.buf if prefetch else self._pk.acc, self._group)
+        else:
+            self._pk.reduce_all(prefetch)      # the ONE collective of the iteration
+            self._q_versions = [q._version for q in self._q]
         lib.call("zsb_hmc_tune_f32", ptr(self._state), ptr(self._stats),
                  int(self._has_step), int(adapt_step), 1.0 if init else 0.0,
                  self.gamma, self.t0, self.kappa, self.target_acceptance_rate,
@@ -403,7 +442,7 @@ class HMC(object):
             probe()
             lib.call("zsb_hmc_acc_sum_f32", ptr(self._acc_part),
                      self._npart.value, self._chains, ptr(self._stats), s)
-            self._allreduce(self._stats)
+            self._pk.reduce_acc()
             lib.call("zsb_hmc_search_update_f32", ptr(self._state),
                      ptr(self._stats), self.target_acceptance_rate, s)
             if float(self._state[ST_SCOND].item()) == 0.0:
@@ -502,8 +541,14 @@ class HMC(object):
             impl = f.get("impl")
         if impl is None:               # default: fastest legal tensor-core path
             impl = 2 if D % 64 == 0 else (1 if D % 32 == 0 else 0)
-        if int(impl) in (2, 3) and D % 64 != 0:
-            raise ValueError("dense_impl=2/3 (fp16 split) needs D % 64 == 0")
+        if int(impl) in (2, 3, 5) and D % 64 != 0:
+            raise ValueError("dense_impl=2/3/5 (fp16 split) needs D % 64 == 0")
+        # impl 5: L2-resident whole-trajectory kernel (hmc_dense_res.cu).  The state of q inside
+        # a trajectory is its fp16 hi/lo plane pair; the step-size probes are trajectories with
+        # L = 1; n_leapfrogs = 0 (a single half-kick pass) runs on the per-pass kernel (impl 2).
+        self._res = int(impl) == 5 and self.n_leapfrogs >= 1
+        if int(impl) == 5:
+            impl = 2
         # impl 4 (EXPERIMENTAL, not validated on hardware): impl 2's buffers and probe passes,
         # but the L+1 passes of the main trajectory in ONE persistent launch (hmc_dense_traj.cu)
         self._traj = int(impl) == 4
@@ -519,10 +564,25 @@ class HMC(object):
                      | (int(os.environ.get("ZSB_TC_PAIR", "1")) << 16))
         nt = lib.load().zsb_hmc_dense_ntiles(D, min(self._impl, 1))
         z = lambda *s: torch.zeros(*s, dtype=_F32, device=dev)
-        self._qa, self._qb = torch.empty_like(self._q[0]), \
-            torch.empty_like(self._q[0])
         self._pw = torch.empty_like(self._q[0])
         self._lo = {}
+        self._pass_k = 0
+        self._lp0_part, self._lp1_part = z(nt * self._chains), \
+            z(nt * self._chains)
+        self._k_part = z(nt * self._chains)
+        self._ntiles = nt
+        if self._res:                  # two plane buffers + flags; no fp32 work copies of q
+            shape = (2,) + tuple(self._q[0].shape)
+            self._planes = [torch.empty(shape, dtype=torch.float16, device=dev)
+                            for _ in range(2)]
+            self._res_flags = torch.zeros(
+                lib.load().zsb_hmc_dense_resident_flags(self._chains),
+                dtype=torch.int32, device=dev)
+            self._scales = z(4)
+            self._scales[3] = f["sP"]
+            return
+        self._qa, self._qb = torch.empty_like(self._q[0]), \
+            torch.empty_like(self._q[0])
         if self._impl == 1:            # TF32 residuals of the A operands
             for t in (self._q[0], self._qa, self._qb):
                 self._lo[t.data_ptr()] = torch.empty_like(t)
@@ -535,11 +595,6 @@ class HMC(object):
         if self._impl == 3:            # planes are built inside the kernel
             self._scales = z(8)
             self._scales[3] = f["sP"]
-        self._pass_k = 0
-        self._lp0_part, self._lp1_part = z(nt * self._chains), \
-            z(nt * self._chains)
-        self._k_part = z(nt * self._chains)
-        self._ntiles = nt
 
     def _dense_pass(self, q_cur, q_next, p_in, p_out, scale, lp_part, k_part,
                     s):
@@ -592,9 +647,44 @@ class HMC(object):
                  ptr(self._lpsel) if full else None, ptr(self._acc_part),
                  ctypes.byref(self._npart), ptr(self._state), s)
 
+    def _resident_trajectory(self, L, s):
+        """L+1 leapfrog passes in one L2-resident launch; returns the proposal's planes."""
+        f = self._fused
+        lib.call("zsb_hmc_dense_resident_h16_f32", ptr(self._planes[0]),
+                 ptr(self._planes[1]), ptr(self._p0[0]), ptr(self._pw),
+                 ptr(f["P_h16"]), ptr(f["P_l16"]), ptr(self._scales), ptr(f.get("b")),
+                 ptr(f.get("mu")), ptr(self._mass[0]), ptr(self._state),
+                 ptr(self._lp0_part), ptr(self._lp1_part), ptr(self._k_part),
+                 ptr(self._res_flags), self._chains, f["D"], L, s)
+        return self._planes[L & 1]
+
+    def _iterate_dense_resident(self, noise_u, seed, it, init, s):
+        q0 = self._q[0]
+        # planes of q * sq (sq from max|q|, once per iteration) into buffer 0
+        lib.call("zsb_hmc_dense_h16_prepare_f32", ptr(q0), ptr(self._planes[0]),
+                 ptr(self._scales), q0.numel(), s)
+        if init:
+            def probe():               # hmc.py:314-326: one leapfrog step = a trajectory, L = 1
+                self._resident_trajectory(1, s)
+                self._dense_finish_mh(noise_u, seed, it, s, full=False)
+            self._search(probe, s)
+        prof = None if self._dev_mode else getattr(self, "_profile_events", None)
+        if prof is not None:           # bench.py: device time of the trajectory launch
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+        prop = self._resident_trajectory(self.n_leapfrogs, s)
+        if prof is not None:
+            e1.record()
+            prof.append((e0, e1))
+        self._dense_finish_mh(noise_u, seed, it, s, full=True)
+        lib.call("zsb_hmc_dense_select_planes_f32", ptr(q0), ptr(prop), ptr(self._scales),
+                 ptr(self._accept), self._chains, self._row_len[0], s)
+
     def _iterate_dense(self, noise_p, noise_u, seed, it, init, s):
         q0 = self._q[0]
         self._momentum(noise_p, seed, it, s)
+        if self._res:
+            return self._iterate_dense_resident(noise_u, seed, it, init, s)
         if self._impl == 1:
             lib.call("zsb_hmc_dense_split_lo_f32", ptr(q0),
                      ptr(self._lo[q0.data_ptr()]), q0.numel(), s)
@@ -673,8 +763,9 @@ class HMC(object):
     def state_dict(self):
         """All sampler state (the reference keeps it in tf.Variables and has
         no checkpoint API)."""
-        d = {"t": self._t, "ewmv_t": self._ewmv_t,
-             "state": self._state.clone()}
+        st = self._state.clone()
+        st[ST_FLAGS] = 0                       # the check_numerics flag is not sampler state
+        d = {"t": self._t, "ewmv_t": self._ewmv_t, "state": st}
         if self._has_mass:
             d["ewmv_mean"] = [m.clone() for m in self._ew_mean]
             d["ewmv_var"] = [v.clone() for v in self._ew_var]
@@ -683,6 +774,8 @@ class HMC(object):
     def load_state_dict(self, d):
         self._t, self._ewmv_t = int(d["t"]), int(d["ewmv_t"])
         self._state.copy_(d["state"])
+        self._state[ST_FLAGS] = 0
+        self._pk.mass_valid = False            # statistics are recomputed from the latents
         self._state[ST_T] = float(self._t)
         self._state[ST_EWT] = float(self._ewmv_t)
         if self._has_mass:

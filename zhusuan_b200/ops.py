@@ -248,24 +248,29 @@ class _DirichletLogProb(torch.autograd.Function):
         out = torch.empty(bshape, dtype=_F32, device=given.device)
         lib.call("zsb_logprob_dirichlet_f32", ptr(g), grows, ptr(a), arows, C,
                  ptr(out), rows, stream())
-        ctx.save_for_backward(g, a)
+        ctx.save_for_backward(g, a, given, alpha)
         ctx.meta = (grows, arows, C, rows, bshape, given.shape)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        g, a = ctx.saved_tensors
+        g, a, given, alpha = ctx.saved_tensors
         grows, arows, C, rows, bshape, gs = ctx.meta
-        if ctx.needs_input_grad[1]:
-            raise ZsbError("Dirichlet: gradient w.r.t. alpha is not on the "
-                           "accelerated path")
-        if not ctx.needs_input_grad[0]:
-            return None, None
         gout = _f32c(gout)
-        dg = torch.empty(bshape + (C,), dtype=_F32, device=gout.device)
-        lib.call("zsb_logprob_dirichlet_bwd_given_f32", ptr(g), grows, ptr(a),
-                 arows, C, ptr(gout), ptr(dg), rows, stream())
-        return _sum_to(dg, gs), None
+        dgiven = dalpha = None
+        if ctx.needs_input_grad[1]:
+            # d/d alpha_i = psi(sum alpha) - psi(alpha_i) + log x_i  (multivariate.py:665-677
+            # differentiated); parameter gradients are off the hot path: composed from torch ops
+            al = alpha.to(_F32)
+            full = (torch.digamma(al.sum(-1, keepdim=True)) - torch.digamma(al)
+                    + torch.log(given.to(_F32)))
+            dalpha = _sum_to(gout.reshape(bshape + (1,)) * full, alpha.shape)
+        if ctx.needs_input_grad[0]:
+            dg = torch.empty(bshape + (C,), dtype=_F32, device=gout.device)
+            lib.call("zsb_logprob_dirichlet_bwd_given_f32", ptr(g), grows, ptr(a),
+                     arows, C, ptr(gout), ptr(dg), rows, stream())
+            dgiven = _sum_to(dg, gs)
+        return dgiven, dalpha
 
 
 def dirichlet_log_prob(given, alpha, group_ndims=0):
@@ -332,23 +337,31 @@ class _MVNCholLogProb(torch.autograd.Function):
         x = torch.empty(bshape + (D,), dtype=_F32, device=given.device)
         lib.call("zsb_logprob_mvn_chol_f32", ptr(g), grows, ptr(m), mrows,
                  ptr(lt), lmats, D, ptr(out), ptr(x), rows, stream())
-        ctx.save_for_backward(x, lt)
+        ctx.save_for_backward(x, lt, cov_tril)
         ctx.meta = (lmats, D, rows, bshape, given.shape, mean.shape)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        x, lt = ctx.saved_tensors
+        x, lt, cov_tril = ctx.saved_tensors
         lmats, D, rows, bshape, gs, ms = ctx.meta
-        if ctx.needs_input_grad[2]:
-            raise ZsbError("MultivariateNormalCholesky: gradient w.r.t. "
-                           "cov_tril is not on the accelerated path")
         gout = _f32c(gout)
         dg = torch.empty(bshape + (D,), dtype=_F32, device=gout.device)
         lib.call("zsb_logprob_mvn_chol_bwd_given_f32", ptr(x), ptr(lt), lmats,
                  D, ptr(gout), ptr(dg), rows, stream())
+        dtril = None
+        if ctx.needs_input_grad[2]:
+            # y = L^-1 (x - mu) (saved), dg = -gout * L^-T y:
+            #   d log p / dL = gout * tril(L^-T y y^T) - gout * diag(1 / L_ii)
+            # (multivariate.py:169-189 differentiated).  Parameter gradient: off the hot path,
+            # composed from torch ops on the kernel's intermediates.
+            outer = torch.tril(-dg.unsqueeze(-1) * x.unsqueeze(-2))
+            inv_diag = 1.0 / torch.diagonal(cov_tril.to(_F32), dim1=-2, dim2=-1)
+            full = outer - torch.diag_embed(
+                gout.reshape(bshape + (1,)) * inv_diag.expand(bshape + (D,)))
+            dtril = _sum_to(full, cov_tril.shape)
         return (_sum_to(dg, gs) if ctx.needs_input_grad[0] else None,
-                _sum_to(-dg, ms) if ctx.needs_input_grad[1] else None, None)
+                _sum_to(-dg, ms) if ctx.needs_input_grad[1] else None, dtril)
 
 
 def mvn_cholesky_log_prob(given, mean, cov_tril, group_ndims=0):

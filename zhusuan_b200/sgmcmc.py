@@ -78,6 +78,14 @@ class SGMCMC(object):
         for s in lp.shape:
             chains *= int(s)
         self._chains = max(chains, 1)
+        # every latent must carry the chain axes of the log-joint in front (as HMC.sample checks,
+        # hmc.py:436-449): the kernels walk chains * row_len elements per latent
+        for k, q in zip(self._latent_k, self._var_list):
+            if tuple(q.shape[:ncd]) != tuple(lp.shape):
+                raise ValueError(
+                    "latent['{}'] has shape {} but the log joint has chain shape {}: every "
+                    "latent must start with the chain axes".format(
+                        k, tuple(q.shape), tuple(lp.shape)))
         self._row_len = [max(1, q.numel() // self._chains)
                          for q in self._var_list]
         w, r = zdist.world(self._group)
