@@ -305,6 +305,21 @@ int zsb_hmc_dense_select_planes_f32(float* q, const void* planes, const float* s
 int zsb_hmc_dense_finish_f32(const float* lp_part, const float* k_part, int ntiles, int64_t chains,
                              float const_term, float* lp_out, float* k_out, void* stream);
 
+/* ---- device samplers of the discrete / gamma-family distributions (csrc/samplers.cu) ----------
+ * Categorical._sample (univariate.py:478-494, tf.random.categorical): inverse CDF of
+ * softmax(logits) with one uniform per draw (u injected [n_samples*rows] or Philox); out[s, r].
+ * Dirichlet._sample (multivariate.py:660-663): Gamma(alpha, 1) by Marsaglia-Tsang on Philox
+ * (or injected gamma variates) normalised by the row sum.  Gamma._sample: Gamma(alpha, 1) / beta. */
+int zsb_sample_categorical_i32(const float* logits, int64_t logit_rows, int64_t rows,
+                               int64_t n_categories, int64_t n_samples, const float* u,
+                               uint64_t seed, uint32_t iter, int32_t* out, void* stream);
+int zsb_sample_dirichlet_f32(const float* alpha, int64_t alpha_rows, int64_t n_rows,
+                             int64_t n_categories, const float* gammas, uint64_t seed,
+                             uint32_t iter, float* out, void* stream);
+int zsb_sample_gamma_f32(const float* alpha, int64_t alpha_rows, const float* beta,
+                         int64_t beta_rows, int64_t n_rows, int64_t row_len, uint64_t seed,
+                         uint32_t iter, float* out, void* stream);
+
 /* ---- K5: SG-MCMC updates (zhusuan/sgmcmc.py) ------------------------------------------------ */
 int zsb_sgmcmc_parts(void);   /* capacity (floats) of every `part` scratch */
 int zsb_sgmcmc_sgld_f32(float* q, const float* g, const float* noise, float lr, int64_t chains,

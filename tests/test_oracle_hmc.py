@@ -155,32 +155,32 @@ def test_hmc_constructor_errors():
 @pytest.mark.parametrize("name", ["hmc_dense64", "hmc_dense1024"])
 def test_oracle_reproduces_big_dense_golden(name):
     """The L = 50 adaptive fixtures of the tensor-core kernels (make_golden.py BIG): the float32
-    oracle, fed the re-generated Philox noise and the stored (guard-pushed) uniforms, reproduces
-    the stored decisions / step sizes, and the stored float64 re-evaluation bounds its error."""
+    oracle, fed the re-generated states / Philox noise and the stored (guard-pushed) uniforms,
+    reproduces the stored decisions / step sizes, and the stored float64 re-evaluation bounds its
+    error."""
     import sys
     sys.path.insert(0, GOLD)
     import make_golden as MG
     g = np.load(os.path.join(GOLD, name + ".npz"))
     cfg = MG.BIG[name]
-    P, const, mu, q0 = MG.big_problem(cfg)
+    P, const, mu, chol = MG.big_problem(cfg)
     np.testing.assert_allclose(np.abs(P).sum(), float(g["P_checksum"]), rtol=1e-12)
     model = OM.DenseGaussian(P.astype(np.float32), mu, const)
     h = OH.HMC(step_size=cfg["eps0"], n_leapfrogs=cfg["L"], adapt_step_size=True,
                adapt_mass=True, mass_collect_iters=cfg["mci"])
-    q = [q0.copy()]
     n_iters = cfg["iters"] if cfg["D"] <= 64 else 9     # keep the CPU suite short
     with np.errstate(all="ignore"):
         for i in range(n_iters):
             adapt = i < cfg["n_adapt"]
-            q, info = h.step(q, model.logp, model.grad, [MG.big_noise(cfg, i)],
-                             g["noise_u"][i], adapt, adapt)
+            q, info = h.step([MG.big_state(cfg, i)], model.logp, model.grad,
+                             [MG.big_noise(cfg, i)], g["noise_u"][i], adapt, adapt)
             np.testing.assert_array_equal(info.if_accept.astype(np.int32), g["accept"][i])
-            np.testing.assert_allclose(info.acceptance_rate, g["acc"][i], rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(info.acceptance_rate, g["acc"][i], rtol=1e-5, atol=1e-6)
             np.testing.assert_allclose(info.updated_step_size, g["step_size"][i], rtol=1e-6)
             # every stored uniform sits >= u_guard / 2 away from the acceptance probability
             assert np.all(np.abs(g["noise_u"][i] - info.acceptance_rate) >= cfg["u_guard"] / 2)
     floor = np.abs(g["acc"] - g["acc64"]).max()
     assert floor < cfg["u_guard"] / 8
-    fin = np.isfinite(g["h1"])
-    assert np.abs(g["h1"][fin] / g["h1_64"][fin] - 1).max() < 2e-6
-    assert (~fin).any() and fin.any()          # covers diverging and healthy trajectories
+    live = g["acc64"] > 1e-6
+    assert np.abs(g["h1"][live] / g["h1_64"][live] - 1).max() < 2e-6
+    assert (~np.isfinite(g["h1"])).any() and live.any()   # diverging and healthy trajectories

@@ -138,16 +138,13 @@ class Multinomial(UnnormalizedMultinomial):
     def _sample(self, n_samples):
         if self._n_experiments is None:
             raise ValueError('Cannot sample when `n_experiments` is None')
-        probs = torch.softmax(self._logits.detach(), -1)
-        flat = probs.reshape(-1, self._n_categories)
-        draws = torch.multinomial(flat, int(n_samples) * self._n_experiments,
-                                  replacement=True)           # [B, S * n]
+        # n_experiments categorical draws per sample on the device sampler, then counted
+        seed, it = self._next_rng()
+        draws = ops.sample_categorical(self._logits, int(n_samples) * self._n_experiments,
+                                       seed=seed, it=it).long()     # [S * n] + batch
         onehot = torch.nn.functional.one_hot(draws, self._n_categories)
-        counts = onehot.reshape(flat.shape[0], int(n_samples),
-                                self._n_experiments,
-                                self._n_categories).sum(2)    # [B, S, C]
-        counts = counts.permute(1, 0, 2).reshape(
-            (int(n_samples),) + tuple(self._logits.shape))
+        counts = onehot.reshape((int(n_samples), self._n_experiments)
+                                + tuple(self._logits.shape)).sum(1)
         return counts.to(self.dtype)
 
     def _log_prob(self, given):
@@ -187,12 +184,10 @@ class OnehotCategorical(Distribution):
         return self._logits.shape[:-1]
 
     def _sample(self, n_samples):
-        flat = torch.softmax(self._logits.detach(), -1).reshape(
-            -1, self._n_categories)
-        draws = torch.multinomial(flat, int(n_samples), replacement=True)
-        onehot = torch.nn.functional.one_hot(draws.t(), self._n_categories)
-        return onehot.reshape((int(n_samples),) + tuple(self._logits.shape)) \
-            .to(self.dtype)
+        seed, it = self._next_rng()
+        draws = ops.sample_categorical(self._logits, int(n_samples), seed=seed, it=it).long()
+        onehot = torch.nn.functional.one_hot(draws, self._n_categories)
+        return onehot.to(self.dtype)
 
     def _log_prob(self, given):
         return ops.unnormalized_multinomial_log_prob(
@@ -229,12 +224,11 @@ class Dirichlet(Distribution):
     def _get_batch_shape(self):
         return self._alpha.shape[:-1]
 
-    def _sample(self, n_samples):
-        # multivariate.py:660-663: Gamma(alpha, 1) normalised (torch's gamma
-        # sampler; Dirichlet sampling is not on the accelerated path).
-        a = self._alpha.detach().expand((n_samples,) + tuple(self._alpha.shape))
-        g = torch._standard_gamma(a.contiguous())
-        return g / g.sum(-1, keepdim=True)
+    def _sample(self, n_samples, gammas=None):
+        # multivariate.py:660-663: Gamma(alpha, 1) normalised -> device sampler
+        # (Marsaglia-Tsang on Philox; ``gammas``: injected variates for parity)
+        seed, it = self._next_rng()
+        return ops.sample_dirichlet(self._alpha, n_samples, gammas=gammas, seed=seed, it=it)
 
     def _log_prob(self, given):
         return ops.dirichlet_log_prob(given, self._alpha, self._group_ndims)

@@ -133,15 +133,12 @@ class Categorical(Distribution):
     def _get_batch_shape(self):
         return self._logits.shape[:-1]
 
-    def _sample(self, n_samples):
-        # tf.random.categorical (univariate.py:478-494) == Gumbel-max; the
-        # uniforms come from torch's generator (sampling a Categorical is not
-        # on the accelerated path; its log_prob is).
-        flat = self._logits.detach().reshape(-1, self._n_categories)
-        idx = torch.multinomial(torch.softmax(flat, -1), n_samples,
-                                replacement=True)            # [B, n]
-        out = idx.t().reshape((n_samples,) + tuple(self.get_batch_shape()))
-        return out.to(self.dtype)
+    def _sample(self, n_samples, u=None):
+        # tf.random.categorical (univariate.py:478-494) -> device sampler: inverse CDF of
+        # softmax(logits), one Philox uniform per draw (``u``: injected uniforms for parity)
+        seed, it = self._next_rng()
+        out = ops.sample_categorical(self._logits, n_samples, u=u, seed=seed, it=it)
+        return out if self.dtype == torch.int32 else out.to(self.dtype)
 
     def _log_prob(self, given):
         return ops.categorical_log_prob(given, self._logits,

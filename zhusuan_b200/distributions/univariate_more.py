@@ -157,8 +157,10 @@ class Gamma(_TwoParam):
     beta = property(lambda self: self._b)
 
     def _gamma_draw(self, n_samples, conc):
+        # Gamma(conc, 1) on the device sampler (Marsaglia-Tsang on Philox, csrc/samplers.cu)
         shape = _sample_shape(n_samples, self._get_batch_shape())
-        return torch._standard_gamma(conc.detach().expand(shape).contiguous())
+        seed, it = self._next_rng()
+        return ops.sample_gamma(conc, None, shape, seed=seed, it=it)
 
     def _sample(self, n_samples):
         return self._gamma_draw(n_samples, self._a) / self._b.detach()

@@ -553,4 +553,48 @@ def sample_bernoulli(logits, n_samples, u=None, seed=0, it=0,
     return out if dtype == torch.int32 else out.to(dtype)
 
 
+def sample_categorical(logits, n_samples, u=None, seed=0, it=0):
+    """Categorical._sample (univariate.py:478-494) on the device sampler: int32
+    [n_samples] + logits.shape[:-1]; ``u`` = injected uniforms of that shape."""
+    lg = _f32c(logits.detach())
+    C = int(lg.shape[-1])
+    bshape = tuple(lg.shape[:-1])
+    rows = 1
+    for d in bshape:
+        rows *= int(d)
+    out = torch.empty((int(n_samples),) + bshape, dtype=torch.int32, device=lg.device)
+    uu = None if u is None else _f32c(u.expand(out.shape)).reshape(-1)
+    lib.call("zsb_sample_categorical_i32", ptr(lg.reshape(-1)), max(rows, 1), max(rows, 1), C,
+             int(n_samples), ptr(uu), int(seed), int(it), ptr(out), stream())
+    return out
+
+
+def sample_dirichlet(alpha, n_samples, gammas=None, seed=0, it=0):
+    """Dirichlet._sample (multivariate.py:660-663): float32 [n_samples] + alpha.shape;
+    ``gammas`` = injected Gamma(alpha, 1) variates of that shape."""
+    a = _f32c(alpha.detach())
+    C = int(a.shape[-1])
+    arows = max(1, a.numel() // C)
+    out = torch.empty((int(n_samples),) + tuple(a.shape), dtype=_F32, device=a.device)
+    g = None if gammas is None else _f32c(gammas.expand(out.shape)).reshape(-1)
+    lib.call("zsb_sample_dirichlet_f32", ptr(a.reshape(-1)), arows, int(n_samples) * arows, C,
+             ptr(g), int(seed), int(it), ptr(out), stream())
+    return out
+
+
+def sample_gamma(alpha, beta, shape, seed=0, it=0):
+    """Gamma(alpha, beta) draws of ``shape`` (alpha / beta broadcast against it)."""
+    a = _f32c(alpha.detach().to(_F32).expand(shape))
+    b = None if beta is None else _f32c(beta.detach().to(_F32).expand(shape))
+    out = torch.empty(tuple(shape), dtype=_F32, device=a.device)
+    n = out.numel()
+    if n == 0:
+        return out
+    row_len = int(shape[-1]) if len(shape) else 1
+    rows = n // row_len
+    lib.call("zsb_sample_gamma_f32", ptr(a.reshape(-1)), rows, ptr(b.reshape(-1)) if b is not None
+             else None, rows, rows, row_len, int(seed), int(it), ptr(out), stream())
+    return out
+
+
 LOG_2PI = math.log(2.0 * math.pi)
