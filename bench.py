@@ -38,7 +38,7 @@ if ROOT not in sys.path:
 
 METRIC = "leapfrog-steps*chains/sec"
 UNIT = "chain-steps/s"
-DEFAULT_DENSE_IMPL = 2
+DEFAULT_DENSE_IMPL = 5
 
 
 def make_dense_gaussian_problem(D_, seed=2):

@@ -356,13 +356,13 @@ def test_golden_dense_fused_tc(zs):
     _replay(zs, g, lj, "dense_gaussian", q_tol=1e-4, dense_impl=1)
 
 
-# Hamiltonian tolerance after a 50-step trajectory, per kernel family.  One evaluation of log p is
-# within 1e-5 of float64 on every path (asserted on H0 / lp0 below and in
-# test_dense_single_pass_vs_float64); fifty chained gradient evaluations at a step size up to
-# 0.75 x the stability limit amplify the per-evaluation error: SIMT fp32 FMA ~1e-6, fp16-split
-# tcgen05 ~1e-5 (fp32 accumulation inside the tensor core truncates, measured in round 2), 3xTF32
-# ~3e-5.
-H1_RTOL = {0: 1e-5, 1: 1e-4, 2: 5e-5, 4: 5e-5, 5: 5e-5}
+# Tolerances after a 50-step trajectory (measured in round 2 on every kernel, restart protocol):
+# the Hamiltonian of the proposal stays within 5e-6 of float64 on all kernels (energy is conserved
+# to first order, so position errors cancel between log p and the kinetic term) -> 1e-5 as for a
+# single evaluation; the log-prob ALONE does not enjoy that cancellation (a position error dq
+# moves it by g.dq): up to 1.5e-5 of max|log p| at D = 64 -> 5e-5.
+H1_RTOL = 1e-5
+LP1_RTOL = 5e-5
 
 
 def _replay_big(zs, name, impl):
@@ -374,7 +374,7 @@ def _replay_big(zs, name, impl):
     iteration.  The CUDA path must keep |acc - acc64| below u_guard -- every stored uniform sits
     >= u_guard (pushed ones 2 x u_guard) away from acc64, so EVERY accept decision must then be
     reproduced -- the Hamiltonians / log-probs of a single evaluation within 1e-5, after the
-    trajectory within H1_RTOL.  All iterations are tabulated first (stdout, run with -s), then
+    trajectory within H1_RTOL (log-prob alone: LP1_RTOL).  All iterations are tabulated first (stdout, run with -s), then
     asserted."""
     import sys
     sys.path.insert(0, GOLD)
@@ -428,15 +428,14 @@ def _replay_big(zs, name, impl):
         print(" %2d %7.4f %8.1e %8.1e %3d  %4d %8.1e %8.1e %8.1e %8.1e %8.1e %8.1e %8.1e" % (
             r["i"], r["eps"], r["eps_err"], r["acc_err"], r["flips"], r["n_live"], r["h0_err"],
             r["h1_err"], r["lp0_err"], r["lp_err"], r["q_err"], r["step_err"], r["mass_err"]))
-    h1_rtol = H1_RTOL[impl]
     for r in rows:
         msg = "%s impl %d iteration %d: %r" % (name, impl, r["i"], r)
         assert r["eps_err"] < 1e-4, msg
         assert r["acc_err"] <= cfg["u_guard"], msg
         assert r["flips"] == 0, msg
         assert r["h0_err"] < 1e-5 and r["lp0_err"] < 1e-5, msg
-        assert r["h1_err"] < h1_rtol and r["lp_err"] < h1_rtol, msg
-        assert r["q_err"] < 40 * h1_rtol * max(1.0, float(np.abs(g["q_sub"][r["i"]]).max())), msg
+        assert r["h1_err"] < H1_RTOL and r["lp_err"] < LP1_RTOL, msg
+        assert r["q_err"] < 2e-4 * max(1.0, float(np.abs(g["q_sub"][r["i"]]).max())), msg
         assert r["step_err"] < 1e-3 and r["mass_err"] < 2e-4, msg
     assert h.n_search_iters == int(g["n_search_iters"])
     return h
@@ -524,7 +523,7 @@ def test_leapfrog_count_edges_all_paths(zs, L):
     u = rng.random_sample(C).astype(np.float32)
     om = OM.DenseGaussian(P.astype(np.float32), None, const)
     oq, oi = OH.HMC(step_size=0.15, n_leapfrogs=L).step([q0], om.logp, om.grad, [npz], u)
-    for impl in (0, 1, 2, 3):
+    for impl in (0, 1, 2, 3, 5):
         x = T(q0)
         h = zs.HMC(step_size=0.15, n_leapfrogs=L, dense_impl=impl)
         op, info = h.sample(zs.fused.GaussianLogJoint(P), {}, {"x": x})
@@ -555,7 +554,7 @@ def test_single_chain_and_tiny_shapes(zs):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("path", ["diag", "dense0", "dense1", "dense2"])
+@pytest.mark.parametrize("path", ["diag", "dense0", "dense1", "dense2", "dense5"])
 def test_cuda_graph_replay_is_bitwise_eager(zs, path):
     """Device-driven iterations replayed from a CUDA graph (use_cuda_graph=True)
     give bit-identical chains, step sizes and mass estimates to the eager

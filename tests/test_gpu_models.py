@@ -138,3 +138,56 @@ def test_ais_recovers_analytic_marginal_likelihood(zs):
     truth = stats.norm.logpdf(N(x), 0, np.sqrt(1 + s * s)).sum(-1).mean()
     assert abs(est - truth) < 0.1, (est, truth)
     assert tuple(ais.log_weights.shape) == (n_chains, n_data)
+
+
+def test_ais_device_loop_matches_oracle_step_for_step(zs):
+    """evaluation.py:119-172 with every draw injected (prior samples, HMC noise): the device
+    loop's per-chain log-weights and bound equal the oracle restatement (oracle/evaluation.py);
+    a feed_dict given to run() reaches the HMC transitions, not only the prior density."""
+    from oracle import evaluation as OE
+    rng = np.random.RandomState(4)
+    n_chains, n_data, d, s = 8, 3, 2, 0.8
+    nt, na = 12, 3
+    x_np = (rng.standard_normal((n_data, d)) * 1.2).astype(np.float32)
+    x_wrong = torch.zeros(n_data, d, device="cuda")     # construction-time value, replaced
+    obs = {'x': x_wrong}
+
+    def make(include_x):
+        @zs.meta_bayesian_net()
+        def m():
+            bn = zs.BayesianNet()
+            z = bn.normal('z', torch.zeros(n_data, d, device="cuda"), std=1.,
+                          group_ndims=1, n_samples=n_chains)
+            if include_x:
+                bn.normal('x', z.tensor, std=s, group_ndims=1)
+            return bn
+        return m()
+    hmc = zs.HMC(step_size=0.2, n_leapfrogs=3, adapt_step_size=True,
+                 target_acceptance_rate=0.7)
+    z = torch.zeros(n_chains, n_data, d, device="cuda")
+    ais = zs.AIS(make(True), make(False), hmc, observed=obs, latent={'z': z},
+                 n_temperatures=nt, n_adapt=na)
+    init = [rng.standard_normal((n_chains, n_data, d)).astype(np.float32) for _ in range(2)]
+    noises = [(rng.standard_normal((n_chains, n_data, d)).astype(np.float32),
+               rng.random_sample((n_chains, n_data)).astype(np.float32))
+              for _ in range(na + nt)]
+    est = ais.run(feed_dict={'x': T(x_np)},
+                  noise=lambda k: {"p": {"z": T(noises[k][0])}, "u": T(noises[k][1])},
+                  init=[[T(init[0])], [T(init[1])]])
+
+    c = -0.5 * np.log(2 * np.pi)
+    f32 = np.float32
+    lp = lambda q: (c - 0.5 * q[0].astype(np.float64) ** 2).sum(-1).astype(f32)
+    gp = lambda q: [(-q[0]).astype(f32)]
+    lj = lambda q: (lp(q).astype(np.float64) + (c - np.log(s) - 0.5 * (
+        (x_np - q[0].astype(np.float64)) / s) ** 2).sum(-1)).astype(f32)
+    gj = lambda q: [(-q[0] + (x_np - q[0]) / (s * s)).astype(f32)]
+    oh = OH.HMC(step_size=0.2, n_leapfrogs=3, adapt_step_size=True, target_acceptance_rate=0.7)
+    oa = OE.AIS(lp, gp, lj, gj, oh, n_temperatures=nt, n_adapt=na)
+    oest, olw = oa.run([[init[0]], [init[1]]], lambda k: ([noises[k][0]], noises[k][1]),
+                       adapt_flags=(True, False))
+    np.testing.assert_allclose(N(ais.log_weights), olw, rtol=2e-4, atol=2e-4)
+    assert abs(est - oest) < 2e-4
+    np.testing.assert_allclose(N(ais._schedule), [oa.schedule(t) for t in range(nt + 1)],
+                               rtol=1e-6, atol=1e-7)
+    assert ais.temperature.is_cuda and float(ais.temperature) == 1.0

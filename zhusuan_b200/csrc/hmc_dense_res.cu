@@ -37,7 +37,7 @@ namespace {
 using CR = Cfg2<32>;                 // 128 x 64-half A tile + own 128 x 64-half B tile, 3 stages
 
 struct ResMaps {
-  CUtensorMap p_hi, p_lo;            // P planes [D, D] fp16
+  CUtensorMap p_hi, p_lo;            // P planes [D, D] fp16; box 128 rows (MC: 64 rows)
   CUtensorMap q_hi[2], q_lo[2];      // state planes, buffers 0 / 1: [chains, D] fp16 each
 };
 
@@ -60,6 +60,23 @@ __device__ __forceinline__ void flag_wait(const int* f, int target) {
       __trap();
     }
   }
+}
+
+// 2-CTA TMA load multicast to the CTAs of `mask` (same CTA-relative smem offset in each; the
+// complete_tx lands on the mbarrier of each destination CTA's pair leader)
+__device__ __forceinline__ void tma_load_2d_2sm_mc(uint32_t dst, const CUtensorMap* map,
+                                                   uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mask(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+      " [%0], %1;"
+      ::"r"(bar), "h"(mask) : "memory");
 }
 
 struct ResEpi {
@@ -212,8 +229,12 @@ __device__ __forceinline__ void epilogue_planes(const ResEpi& a, uint32_t trow, 
   }
 }
 
-template <int DC>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+// MC = 1: clusters of 4 CTAs = two pairs working on the SAME dimension tile and two adjacent chain
+// blocks; each CTA loads half of its 128 P rows and multicasts it to its counterpart in the other
+// pair, so a P tile is read from the L2 once per two pairs (the kernel is bound by L2 read
+// throughput: 6.5 kB/clk chip-wide measured = the ~6.3 kB/clk LTS cap).
+template <int DC, int MC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ planes0,
                  __half* __restrict__ planes1, const float* __restrict__ p0,
                  float* __restrict__ pw, const float* __restrict__ bvec,
@@ -237,19 +258,24 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();                 // 0 = leader
+  const uint32_t crank = cluster_ctarank();                // 0..1 (MC: 0..3)
+  const uint32_t rank = crank & 1u;                        // rank inside the CTA pair
+  const uint32_t pidx = crank >> 1;                        // pair inside the cluster (MC only)
+  const uint32_t leader_rank = crank & ~1u;
   const bool leader = rank == 0;
+  const uint16_t pair_mask = (uint16_t)(3u << leader_rank);
   const int n_blk = (D + BM - 1) / BM;
   const int n_pair = (n_blk + 1) / 2;                      // dimension tiles (M = 256) per block
   const int64_t c_blk = (chains + BN - 1) / BN;            // 256-chain blocks
-  const int64_t my = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  constexpr int CL = MC ? 4 : 2;
+  const int64_t my = blockIdx.x / CL, n_clusters = gridDim.x / CL;
   const int n_kb = D / 64;
   const int flag_per_pass = n_pair * 2 * NUM_EPI_WARPS;    // arrivals on flags[c] per pass
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar + 8 * s, 1);
-      mbar_init(empty_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, MC ? 2 : 1);    // MC: both pairs' MMAs free a slot
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
@@ -267,8 +293,16 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Work decomposition of one pass of a group of `gb` chain blocks.  MC = 0: pair `my` takes the
+  // units u = my, my + n_clusters, ... with (block, tile) = (u / n_pair, u % n_pair).  MC = 1: the
+  // cluster takes v = my, my + n_clusters, ... with (block pair, tile) = (v / n_pair, v % n_pair)
+  // and its pair `pidx` the block 2 * (v / n_pair) + pidx -- a phantom (skipped in the epilogue,
+  // zero-filled by TMA) when that block lies beyond the group.
+#define ZSB_RES_UNITS(gb) (MC ? (((gb) + 1) / 2) * n_pair : (gb) * n_pair)
+#define ZSB_RES_BLOCK(g0, u) ((g0) + (MC ? 2 * ((u) / n_pair) + (int64_t)pidx : (u) / n_pair))
+
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
+    // ===================== TMA producer (every CTA) =====================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.p_hi) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.p_lo) : "memory");
@@ -276,14 +310,15 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
       uint32_t phase = 0;
       for (int64_t g0 = 0; g0 < c_blk; g0 += group_blocks) {
         const int64_t gb = (c_blk - g0 < group_blocks) ? (c_blk - g0) : group_blocks;
-        const int64_t units = gb * n_pair;
+        const int64_t units = ZSB_RES_UNITS(gb);
         for (int i = 0; i <= L; ++i) {
           const int buf = i & 1;
           for (int64_t u = my; u < units; u += n_clusters) {
-            const int64_t cb = g0 + u / n_pair;
+            const int64_t cb = ZSB_RES_BLOCK(g0, u);
+            const bool valid = cb < g0 + gb;
             const int n0 = ((int)(u % n_pair) * 2 + (int)rank) * BM;         // own dimension rows
             const int c0 = (int)(cb * BN) + (int)rank * (BN / 2);            // own chain half
-            if (i > 0 && !(dbg & 4)) {      // every tile of block cb finished pass i-1
+            if (i > 0 && valid && !(dbg & 4)) {  // every tile of block cb finished pass i-1
               flag_wait(flags + cb, i * flag_per_pass);
               asm volatile("fence.proxy.async;" ::: "memory");
             }
@@ -292,8 +327,17 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
               const uint32_t fb = full_bar + 8 * stage;
               const uint32_t sa = smem_base + stage * C::STAGE;
               if (leader) mbar_expect_tx(fb, 2 * C::STAGE);
-              tma_load_2d_2sm(sa, &maps.p_hi, fb, kb * 64, n0);
-              tma_load_2d_2sm(sa + C::A_TILE, &maps.p_lo, fb, kb * 64, n0);
+              if (MC) {     // own half (64 rows = 8 KB) of the P tile, to both pairs
+                const uint16_t mm = (uint16_t)(5u << rank);
+                const uint32_t ho = pidx * (uint32_t)(C::A_TILE / 2);
+                tma_load_2d_2sm_mc(sa + ho, &maps.p_hi, fb, kb * 64, n0 + (int)pidx * (BM / 2),
+                                   mm);
+                tma_load_2d_2sm_mc(sa + C::A_TILE + ho, &maps.p_lo, fb, kb * 64,
+                                   n0 + (int)pidx * (BM / 2), mm);
+              } else {
+                tma_load_2d_2sm(sa, &maps.p_hi, fb, kb * 64, n0);
+                tma_load_2d_2sm(sa + C::A_TILE, &maps.p_lo, fb, kb * 64, n0);
+              }
               tma_load_2d_2sm(sa + 2 * C::A_TILE, &maps.q_hi[buf], fb, kb * 64, c0);
               tma_load_2d_2sm(sa + 2 * C::A_TILE + C::B_TILE, &maps.q_lo[buf], fb, kb * 64, c0);
               if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -312,7 +356,7 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
       uint32_t acc_phase = 0;
       for (int64_t g0 = 0; g0 < c_blk; g0 += group_blocks) {
         const int64_t gb = (c_blk - g0 < group_blocks) ? (c_blk - g0) : group_blocks;
-        const int64_t units = gb * n_pair;
+        const int64_t units = ZSB_RES_UNITS(gb);
         for (int i = 0; i <= L; ++i) {
           for (int64_t u = my; u < units; u += n_clusters) {
             mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
@@ -338,10 +382,10 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
                   umma_f16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
                 }
               }
-              umma_commit_2sm(empty_bar + 8 * stage);
+              umma_commit_mask(empty_bar + 8 * stage, MC ? (uint16_t)0xF : pair_mask);
               if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit_2sm(tfull_bar + 8 * acc);
+            umma_commit_mask(tfull_bar + 8 * acc, pair_mask);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           }
         }
@@ -359,13 +403,14 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
     uint32_t acc_phase = 0;
     for (int64_t g0 = 0; g0 < c_blk; g0 += group_blocks) {
       const int64_t gb = (c_blk - g0 < group_blocks) ? (c_blk - g0) : group_blocks;
-      const int64_t units = gb * n_pair;
+      const int64_t units = ZSB_RES_UNITS(gb);
       for (int i = 0; i <= L; ++i) {
         const bool last = i == L;
         const float s2 = mul(eps, (i > 0 && !last) ? 1.f : 0.5f);
         const int buf = i & 1;
         for (int64_t u = my; u < units; u += n_clusters) {
-          const int64_t cb = g0 + u / n_pair;
+          const int64_t cb = ZSB_RES_BLOCK(g0, u);
+          const bool valid = cb < g0 + gb;
           const int nb = (int)(u % n_pair) * 2 + (int)rank;
           const int n = nb * BM + quarter * 32 + lane;
           const int64_t c0 = cb * BN + half * (BN / 2);
@@ -383,7 +428,7 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
           const ResEpi ea{pl[buf], pl[buf] + plane, pl[buf ^ 1], pl[buf ^ 1] + plane,
                           i == 0 ? p0 : pw, pw, i == 0 ? lp0_part : lp1_part, k_part,
                           chains, D, sq, fdiv(1.f, sq), scales[1]};
-          const bool skip = (dbg & 1) != 0;
+          const bool skip = (dbg & 1) != 0 || !valid;
           if (last)
             epilogue_planes<2, 0, DC>(ea, trow, n, n_ok, nb < n_blk, c0, part_row, lane, s2,
                                       eps_over_m_sq, inv_m, b_n, mu_n, skip);
@@ -395,8 +440,8 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
                                       eps_over_m_sq, inv_m, b_n, mu_n, skip);
           tc_fence_before();
           if (leader) mbar_arrive(tempty_bar + 8 * acc);
-          else mbar_arrive_remote(tempty_bar + 8 * acc, 0);
-          if (!last) {
+          else mbar_arrive_remote(tempty_bar + 8 * acc, leader_rank);
+          if (!last && valid) {
             // publish this warp's planes of (cb, pass i) to the TMA producers of pass i+1
             __threadfence();
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -409,6 +454,8 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
     }
   }
 
+#undef ZSB_RES_UNITS
+#undef ZSB_RES_BLOCK
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) {
@@ -438,17 +485,41 @@ __global__ void __launch_bounds__(256) select_planes_kernel(float* __restrict__ 
   }
 }
 
-template <int DC>
+template <int DC, int MC>
 cudaError_t res_prepare() {
   static const cudaError_t e = cudaFuncSetAttribute(
-      dense_res_kernel<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, CR::SMEM);
+      dense_res_kernel<DC, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, CR::SMEM);
   return e;
+}
+
+int res_mc_mode() {          // 1: clusters of 4 with P-tile multicast (ZSB_RES_MC, default 0)
+  static const int mc = getenv("ZSB_RES_MC") ? atoi(getenv("ZSB_RES_MC")) : 0;
+  return mc;
+}
+
+// co-resident clusters of `cl` CTAs of this kernel (one CTA per SM)
+template <int DC, int MC>
+int res_max_clusters(int cl, int sms) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(cl * (sms / cl)));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = CR::SMEM;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, dense_res_kernel<DC, MC>, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = sms / cl;
+  }
+  return n;
 }
 
 }  // namespace
 
 int zsb_dense_res_group_blocks(int D) {
-  // chain blocks per L2-resident group: two units per CTA pair per pass
+  // chain blocks per group: two units per CTA pair per pass (an even count in multicast mode)
   static const int env = getenv("ZSB_RES_GROUP") ? atoi(getenv("ZSB_RES_GROUP")) : 0;
   if (env > 0) return env;
   int dev = 0, sms = ZSB_NUM_SMS;
@@ -456,6 +527,7 @@ int zsb_dense_res_group_blocks(int D) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int n_pair = ((D + BM - 1) / BM + 1) / 2;
   int g = (2 * (sms / 2)) / n_pair;
+  if (res_mc_mode()) g = 2 * ((2 * (sms / 4)) / n_pair);
   return g < 1 ? 1 : g;
 }
 
@@ -474,8 +546,10 @@ int zsb_dense_res_h16_launch(void* planes0, void* planes1, const float* p0, floa
   }
   ResMaps m;
   int rc;
-  if ((rc = make_map(&m.p_hi, P_h16, (uint64_t)D, (uint64_t)D, BM, 32, 1))) return rc;
-  if ((rc = make_map(&m.p_lo, P_l16, (uint64_t)D, (uint64_t)D, BM, 32, 1))) return rc;
+  const int mc = res_mc_mode() ? 1 : 0;
+  const uint32_t a_rows = mc ? BM / 2 : BM;
+  if ((rc = make_map(&m.p_hi, P_h16, (uint64_t)D, (uint64_t)D, a_rows, 32, 1))) return rc;
+  if ((rc = make_map(&m.p_lo, P_l16, (uint64_t)D, (uint64_t)D, a_rows, 32, 1))) return rc;
   const __half* pl[2] = {reinterpret_cast<const __half*>(planes0),
                          reinterpret_cast<const __half*>(planes1)};
   for (int b = 0; b < 2; ++b) {
@@ -492,30 +566,45 @@ int zsb_dense_res_h16_launch(void* planes0, void* planes1, const float* p0, floa
   const int64_t c_blk = (chains + BN - 1) / BN;
   int group = zsb_dense_res_group_blocks(D);
   if (group > c_blk) group = (int)c_blk;
-  int64_t pairs = sms / 2;
-  if ((int64_t)group * n_pair < pairs) pairs = (int64_t)group * n_pair;
   static const int env_dbg = getenv("ZSB_RES_DBG") ? atoi(getenv("ZSB_RES_DBG")) : 0;
   cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)c_blk, st);
   if (e != cudaSuccess) {
     zsb_set_error("dense_res: cudaMemsetAsync: %s", cudaGetErrorString(e));
     return ZSB_ERR_CUDA;
   }
-  const unsigned grid = (unsigned)(2 * pairs);
-  cudaError_t prep;
-#define ZSB_RES_LAUNCH(DC)                                                                      \
+  const int cl = mc ? 4 : 2;
+  cudaError_t prep = cudaSuccess, le = cudaSuccess;
+  __half* pl0 = reinterpret_cast<__half*>(planes0);
+  __half* pl1 = reinterpret_cast<__half*>(planes1);
+  int Di = D, Li = L, dbg = env_dbg;
+#define ZSB_RES_LAUNCH(DC, MCV)                                                                 \
   do {                                                                                          \
-    prep = res_prepare<DC>();                                                                   \
-    if (prep == cudaSuccess)                                                                    \
-      dense_res_kernel<DC><<<grid, NUM_THREADS, CR::SMEM, st>>>(                                \
-          m, reinterpret_cast<__half*>(planes0), reinterpret_cast<__half*>(planes1), p0, pw,    \
-          bvec, mu, mass, state, lp0_part, lp1_part, k_part, chains, D, L, scales, flags,       \
-          group, env_dbg);                                                                      \
+    prep = res_prepare<DC, MCV>();                                                              \
+    if (prep != cudaSuccess) break;                                                             \
+    static const int max_cl = res_max_clusters<DC, MCV>(cl, sms);                               \
+    int64_t clusters = max_cl;                                                                  \
+    const int64_t units = MCV ? (int64_t)((group + 1) / 2) * n_pair : (int64_t)group * n_pair;  \
+    if (units < clusters) clusters = units;                                                     \
+    cudaLaunchConfig_t cfg = {};                                                                \
+    cfg.gridDim = dim3((unsigned)(cl * clusters));                                              \
+    cfg.blockDim = dim3(NUM_THREADS);                                                           \
+    cfg.dynamicSmemBytes = CR::SMEM;                                                            \
+    cfg.stream = st;                                                                            \
+    cudaLaunchAttribute at[1];                                                                  \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                             \
+    at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1;                          \
+    at[0].val.clusterDim.z = 1;                                                                 \
+    cfg.attrs = at; cfg.numAttrs = 1;                                                           \
+    le = cudaLaunchKernelEx(&cfg, dense_res_kernel<DC, MCV>, m, pl0, pl1, p0, pw, bvec, mu,     \
+                            mass, state, lp0_part, lp1_part, k_part, chains, Di, Li, scales,    \
+                            flags, group, dbg);                                                 \
   } while (0)
-  if (D == 1024) ZSB_RES_LAUNCH(1024);
-  else ZSB_RES_LAUNCH(0);
+  if (mc) { if (D == 1024) ZSB_RES_LAUNCH(1024, 1); else ZSB_RES_LAUNCH(0, 1); }
+  else { if (D == 1024) ZSB_RES_LAUNCH(1024, 0); else ZSB_RES_LAUNCH(0, 0); }
 #undef ZSB_RES_LAUNCH
-  if (prep != cudaSuccess) {
-    zsb_set_error("dense_res: cudaFuncSetAttribute: %s", cudaGetErrorString(prep));
+  if (prep != cudaSuccess || le != cudaSuccess) {
+    zsb_set_error("dense_res: launch setup: %s",
+                  cudaGetErrorString(prep != cudaSuccess ? prep : le));
     return ZSB_ERR_CUDA;
   }
   return zsb_check_launch("hmc_dense_resident");

@@ -540,7 +540,8 @@ class HMC(object):
         if impl is None:
             impl = f.get("impl")
         if impl is None:               # default: fastest legal tensor-core path
-            impl = 2 if D % 64 == 0 else (1 if D % 32 == 0 else 0)
+            impl = (5 if self.n_leapfrogs >= 1 else 2) if D % 64 == 0 else \
+                (1 if D % 32 == 0 else 0)
         if int(impl) in (2, 3, 5) and D % 64 != 0:
             raise ValueError("dense_impl=2/3/5 (fp16 split) needs D % 64 == 0")
         # impl 5: L2-resident whole-trajectory kernel (hmc_dense_res.cu).  The state of q inside
