@@ -290,7 +290,8 @@ int zsb_hmc_dense_trajectory_h16_f32(const float* q0, const void* planes0, float
  * Inside the trajectory the state of q is its fp16 hi/lo plane pair (planes0 from
  * zsb_hmc_dense_h16_prepare_f32; planes1 = work buffer, same size); the proposal's planes end in
  * buffer (n_leapfrogs & 1) and zsb_hmc_dense_select_planes_f32 assigns them to the accepted
- * chains (the `tf.where` + assign of hmc.py:488-497).  D % 64 == 0, n_leapfrogs >= 1. */
+ * chains (the `tf.where` + assign of hmc.py:488-497).  planes1 == planes0 selects the in-place
+ * variant (proposal in planes0; smaller L2 footprint).  D % 64 == 0, n_leapfrogs >= 1. */
 int zsb_hmc_dense_resident_flags(int64_t chains);
 int zsb_hmc_dense_resident_group(int64_t D);
 int zsb_hmc_dense_resident_h16_f32(void* planes0, void* planes1, const float* p0, float* pw,

@@ -445,7 +445,8 @@ def test_univariate_more_contract_and_sampling():
         np.testing.assert_allclose(s.float().mean(0).cpu().numpy(), mean.cpu().numpy(), rtol=0.08)
         assert torch.isfinite(d.log_prob(s)).all()
     s = D.BinConcrete(torch.tensor(0.5, device=dev), torch.zeros(4, device=dev)).sample(100)
-    assert tuple(s.shape) == (100, 4) and bool(((s > 0) & (s < 1)).all())
+    # sigmoid((logit + logistic noise) / T) saturates to exactly 0 / 1 in float32 for |noise| > ~8 T
+    assert tuple(s.shape) == (100, 4) and bool(((s >= 0) & (s <= 1)).all())
     # BayesianNet factories
     bn = zs.BayesianNet(observed={"g": torch.tensor([1.0, 2.0], device=dev)})
     g = bn.gamma("g", a, b, group_ndims=1)

@@ -377,27 +377,45 @@ __global__ void __launch_bounds__(256) diag_normal_traj_kernel(
   for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < chains;
        row += (int64_t)gridDim.x * 8) {
     float q0[E], qc[E], pc[E], mu[E], prec[E], ls[E], ms[E];
-    // Philox blocks are 4 consecutive columns; lane owns columns c = (j*32 + lane) for j<E
-    // in the noise-injected layout, so draw per element from block c/4, word c%4.
+    // Philox blocks are 4 consecutive columns; lane owns columns c = j*32 + lane (coalesced
+    // rows), i.e. word c%4 of block c/4.  Each block is generated ONCE per row -- lane l draws
+    // blocks l, l+32, ... -- and its four normals are handed to the four lanes that own its
+    // columns with warp shuffles (round 1 drew the full block in every one of them: 4x the
+    // Philox + Box-Muller work in the hot loop of config 1').
+    constexpr int NBLK = (E + 3) / 4;
+    float zb[NBLK][4];
+    if (!noise) {
+#pragma unroll
+      for (int t = 0; t < NBLK; ++t) {
+        const int64_t blk = (int64_t)t * 32 + lane;
+        if (blk * 4 < D)
+          philox_normal4(seed, ZSB_STREAM_MOMENTUM, iter, (uint32_t)(row0 + row), (uint32_t)blk,
+                         zb[t]);
+        else
+          zb[t][0] = zb[t][1] = zb[t][2] = zb[t][3] = 0.f;
+      }
+    }
     float lp0 = 0.f, k0 = 0.f;
 #pragma unroll
     for (int j = 0; j < E; ++j) {
       const int64_t c = (int64_t)j * 32 + lane;
+      float zsh = 0.f;
+      if (!noise) {           // all lanes take part in the shuffles (no divergence on c < D)
+        const int src = (j & 3) * 8 + (lane >> 2);          // lane holding block c / 4
+        const float a0 = __shfl_sync(0xffffffffu, zb[j >> 2][0], src);
+        const float a1 = __shfl_sync(0xffffffffu, zb[j >> 2][1], src);
+        const float a2 = __shfl_sync(0xffffffffu, zb[j >> 2][2], src);
+        const float a3 = __shfl_sync(0xffffffffu, zb[j >> 2][3], src);
+        const int w = lane & 3;
+        zsh = w == 0 ? a0 : w == 1 ? a1 : w == 2 ? a2 : a3;
+      }
       if (c < D) {
         q0[j] = q[row * D + c];
         mu[j] = mean[c % mean_n];
         ls[j] = logstd[c % logstd_n];
         ms[j] = mass[c % mass_n];
         prec[j] = expf(mul(-2.f, ls[j]));                       // univariate.py:177
-        float z;
-        if (noise) {
-          z = noise[row * D + c];
-        } else {
-          float z4[4];
-          philox_normal4(seed, ZSB_STREAM_MOMENTUM, iter, (uint32_t)(row0 + row),
-                         (uint32_t)(c >> 2), z4);
-          z = z4[c & 3];
-        }
+        const float z = noise ? noise[row * D + c] : zsh;
         pc[j] = mul(z, sqrtf(ms[j]));                           // hmc.py:22
         if (p0_out) p0_out[row * D + c] = pc[j];
         qc[j] = q0[j];

@@ -334,7 +334,7 @@ int zsb_hmc_dense_trajectory_h16_f32(const float* q0, const void* planes0, float
 // of zsb_hmc_dense_resident_flags(chains) words.  On return the proposal's planes are in buffer
 // (n_leapfrogs & 1) -- zsb_hmc_dense_select_planes_f32 assigns them to the accepted chains -- and
 // pw holds the final momentum.  D % 64 == 0, n_leapfrogs >= 1.
-int zsb_hmc_dense_resident_flags(int64_t chains) { return (int)zsb_ceil_div(chains, 256); }
+int zsb_hmc_dense_resident_flags(int64_t chains) { return 2 * (int)zsb_ceil_div(chains, 256); }
 int zsb_hmc_dense_resident_group(int64_t D) { return zsb_dense_res_group_blocks((int)D); }
 int zsb_hmc_dense_resident_h16_f32(void* planes0, void* planes1, const float* p0, float* pw,
                                    const void* P_h16, const void* P_l16, const float* scales,
@@ -345,7 +345,7 @@ int zsb_hmc_dense_resident_h16_f32(void* planes0, void* planes1, const float* p0
   ZSB_REQUIRE(planes0 && planes1 && p0 && pw && P_h16 && P_l16 && scales && mass && state &&
                   lp0_part && lp1_part && k_part && flags,
               "zsb_hmc_dense_resident_h16_f32: null arg");
-  ZSB_REQUIRE(planes0 != planes1 && p0 != pw, "zsb_hmc_dense_resident_h16_f32: aliased buffers");
+  ZSB_REQUIRE(p0 != pw, "zsb_hmc_dense_resident_h16_f32: aliased buffers");
   return zsb_dense_res_h16_launch(planes0, planes1, p0, pw, P_h16, P_l16, scales, bvec, mu, mass,
                                   state, lp0_part, lp1_part, k_part, flags, chains, (int)D,
                                   n_leapfrogs, (cudaStream_t)stream);

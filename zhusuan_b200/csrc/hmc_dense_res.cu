@@ -242,7 +242,7 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
                  const float* __restrict__ state, float* __restrict__ lp0_part,
                  float* __restrict__ lp1_part, float* __restrict__ k_part, int64_t chains,
                  int D_rt, int L, const float* __restrict__ scales, int* __restrict__ flags,
-                 int group_blocks, int dbg) {
+                 int group_blocks, int dbg, int inplace) {
   using C = CR;
   const int D = DC ? DC : D_rt;
   extern __shared__ uint8_t smem_raw[];
@@ -312,7 +312,7 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
         const int64_t gb = (c_blk - g0 < group_blocks) ? (c_blk - g0) : group_blocks;
         const int64_t units = ZSB_RES_UNITS(gb);
         for (int i = 0; i <= L; ++i) {
-          const int buf = i & 1;
+          const int buf = inplace ? 0 : (i & 1);
           for (int64_t u = my; u < units; u += n_clusters) {
             const int64_t cb = ZSB_RES_BLOCK(g0, u);
             const bool valid = cb < g0 + gb;
@@ -398,7 +398,7 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
     const float eps = state[ZSB_ST_EPS_USED];
     const float sq = scales[0];
     const int64_t plane = chains * (int64_t)D;
-    __half* pl[2] = {planes0, planes1};
+    __half* pl[2] = {planes0, inplace ? planes0 : planes1};
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t g0 = 0; g0 < c_blk; g0 += group_blocks) {
@@ -422,6 +422,15 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
           const float mu_n = (n_ok && mu) ? mu[n] : 0.f;
           mbar_wait(tfull_bar + 8 * acc, acc_phase);
           tc_fence_after();
+          if (inplace && valid && !last) {
+            // single plane buffer: q_next's planes overwrite q's.  This pair's MMAs of (cb, i)
+            // have completed (tfull) -> count it; nobody may overwrite the planes of block cb
+            // before EVERY dimension tile's MMAs of pass i have read them.
+            int* mma_done = flags + c_blk;
+            if (leader && warp == 2 && lane == 0) flag_add_release(mma_done + cb, 1);
+            if (lane == 0) flag_wait(mma_done + cb, (i + 1) * n_pair);
+            __syncwarp();
+          }
           const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                 (uint32_t)(acc * BN + half * (BN / 2));
           const int64_t part_row = (int64_t)(nb * 4 + quarter) * chains;
@@ -492,8 +501,9 @@ cudaError_t res_prepare() {
   return e;
 }
 
-int res_mc_mode() {          // 1: clusters of 4 with P-tile multicast (ZSB_RES_MC, default 0)
-  static const int mc = getenv("ZSB_RES_MC") ? atoi(getenv("ZSB_RES_MC")) : 0;
+// ZSB_RES_MC: 1 / 0 force the P-tile multicast variant (clusters of 4) on / off; unset = auto
+int res_mc_env() {
+  static const int mc = getenv("ZSB_RES_MC") ? atoi(getenv("ZSB_RES_MC")) : -1;
   return mc;
 }
 
@@ -518,23 +528,48 @@ int res_max_clusters(int cl, int sms) {
 
 }  // namespace
 
-int zsb_dense_res_group_blocks(int D) {
-  // chain blocks per group: two units per CTA pair per pass (an even count in multicast mode)
-  static const int env = getenv("ZSB_RES_GROUP") ? atoi(getenv("ZSB_RES_GROUP")) : 0;
-  if (env > 0) return env;
+// Variant + group size for a problem.  Multicast (clusters of 4 CTAs = two pairs sharing a P tile:
+// 20 % fewer L2 reads per MAC, but only 33 such clusters = 132 of the 148 SMs are co-resident on
+// B200; measured 19.4 vs 20.1 ms per iteration at 65 536 x 1024) when the group still fills two
+// units per pair; chain blocks per group = two units per CTA pair per pass.
+void res_choose(int D, int64_t chains, int* mc_out, int* group_out) {
+  static const int env_group = getenv("ZSB_RES_GROUP") ? atoi(getenv("ZSB_RES_GROUP")) : 0;
   int dev = 0, sms = ZSB_NUM_SMS;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int n_pair = ((D + BM - 1) / BM + 1) / 2;
-  int g = (2 * (sms / 2)) / n_pair;
-  if (res_mc_mode()) g = 2 * ((2 * (sms / 4)) / n_pair);
-  return g < 1 ? 1 : g;
+  const int64_t c_blk = (chains + BN - 1) / BN;
+  int mc = res_mc_env();
+  int max_cl4 = 0;
+  if (mc != 0 && res_prepare<0, 1>() == cudaSuccess) {
+    static const int cached = res_max_clusters<0, 1>(4, sms);
+    max_cl4 = cached;
+  }
+  if (mc < 0) mc = (max_cl4 > 0 && c_blk * n_pair >= 4 * (int64_t)max_cl4) ? 1 : 0;
+  if (mc && max_cl4 <= 0) mc = 0;
+  int g = mc ? 2 * ((2 * max_cl4) / n_pair) : (2 * (sms / 2)) / n_pair;
+  if (env_group > 0) g = env_group;
+  if (g < 1) g = 1;
+  if (getenv("ZSB_RES_VERBOSE"))
+    fprintf(stderr, "zsb dense_res: multicast %d (%d co-resident clusters of 4), group = %d blocks\n",
+            mc, max_cl4, g);
+  *mc_out = mc;
+  *group_out = g;
+}
+
+int zsb_dense_res_group_blocks(int D) {
+  int mc, g;
+  res_choose(D, 1LL << 30, &mc, &g);
+  return g;
 }
 
 // One launch = the L+1 passes of a trajectory for every chain (D % 64 == 0, L >= 1).
 //   planes0: fp16 hi/lo planes of q * sq (zsb_hmc_dense_h16_prepare_f32), planes1: work buffer;
 //   on return the proposal's planes are in buffer (L & 1); p0 -> pw (final momentum);
-//   lp0_part / lp1_part / k_part as the per-pass kernel writes them; flags: int32[ceil(chains/256)].
+//   lp0_part / lp1_part / k_part as the per-pass kernel writes them; flags: int32[2*ceil(chains/256)].
+//   planes1 == planes0 selects the IN-PLACE variant (8 instead of 12 bytes of L2 footprint per
+//   element): an epilogue then waits until every dimension tile's MMAs of the pass have read the
+//   block's planes before it overwrites them; the proposal's planes end in planes0.
 int zsb_dense_res_h16_launch(void* planes0, void* planes1, const float* p0, float* pw,
                              const void* P_h16, const void* P_l16, const float* scales,
                              const float* bvec, const float* mu, const float* mass,
@@ -546,7 +581,8 @@ int zsb_dense_res_h16_launch(void* planes0, void* planes1, const float* p0, floa
   }
   ResMaps m;
   int rc;
-  const int mc = res_mc_mode() ? 1 : 0;
+  int mc = 0, group = 1;
+  res_choose(D, chains, &mc, &group);
   const uint32_t a_rows = mc ? BM / 2 : BM;
   if ((rc = make_map(&m.p_hi, P_h16, (uint64_t)D, (uint64_t)D, a_rows, 32, 1))) return rc;
   if ((rc = make_map(&m.p_lo, P_l16, (uint64_t)D, (uint64_t)D, a_rows, 32, 1))) return rc;
@@ -564,10 +600,10 @@ int zsb_dense_res_h16_launch(void* planes0, void* planes1, const float* p0, floa
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int n_pair = ((D + BM - 1) / BM + 1) / 2;
   const int64_t c_blk = (chains + BN - 1) / BN;
-  int group = zsb_dense_res_group_blocks(D);
   if (group > c_blk) group = (int)c_blk;
   static const int env_dbg = getenv("ZSB_RES_DBG") ? atoi(getenv("ZSB_RES_DBG")) : 0;
-  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)c_blk, st);
+  const int inplace = planes0 == planes1 ? 1 : 0;
+  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)c_blk * 2, st);
   if (e != cudaSuccess) {
     zsb_set_error("dense_res: cudaMemsetAsync: %s", cudaGetErrorString(e));
     return ZSB_ERR_CUDA;
@@ -597,7 +633,7 @@ int zsb_dense_res_h16_launch(void* planes0, void* planes1, const float* p0, floa
     cfg.attrs = at; cfg.numAttrs = 1;                                                           \
     le = cudaLaunchKernelEx(&cfg, dense_res_kernel<DC, MCV>, m, pl0, pl1, p0, pw, bvec, mu,     \
                             mass, state, lp0_part, lp1_part, k_part, chains, Di, Li, scales,    \
-                            flags, group, dbg);                                                 \
+                            flags, group, dbg, inplace);                                        \
   } while (0)
   if (mc) { if (D == 1024) ZSB_RES_LAUNCH(1024, 1); else ZSB_RES_LAUNCH(0, 1); }
   else { if (D == 1024) ZSB_RES_LAUNCH(1024, 0); else ZSB_RES_LAUNCH(0, 0); }
