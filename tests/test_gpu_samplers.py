@@ -117,3 +117,33 @@ def test_gamma_family_moments(zs):
     np.testing.assert_allclose(x.var(0), alpha / beta ** 2, rtol=0.08)
     y = N(zs.distributions.Beta(T(alpha), T(beta)).sample(n))
     np.testing.assert_allclose(y.mean(0), alpha / (alpha + beta), rtol=0.03, atol=2e-3)
+
+
+def test_gamma_family_sample_shapes(zs):
+    """The broadcast / n_samples shape cases of the reference's test_sample_shape_2parameter
+    (tests/distributions/utils.py) for the distributions that draw on the device sampler."""
+    D = zs.distributions
+    cases = [([2, 3], [], None, [2, 3]), ([2, 3], [], 1, [1, 2, 3]), ([5], [5], 2, [2, 5]),
+             ([2, 1, 4], [1, 2, 4], 3, [3, 2, 2, 4]), ([2, 3], [2, 1], 1, [1, 2, 3]),
+             ([1, 3], [], 2, [2, 1, 3]), ([2, 1, 5], [3, 1], 3, [3, 2, 3, 5])]
+    for make in (D.Gamma, D.Beta, D.InverseGamma):
+        for s1, s2, n, target in cases:
+            x = make(torch.ones(s1, device="cuda") + 1, torch.ones(s2, device="cuda") + 1).sample(n)
+            assert list(x.shape) == target and x.dtype == torch.float32
+            assert bool(torch.isfinite(x).all()) and bool((x > 0).all())
+
+
+def test_vector_valued_sample_shapes(zs):
+    """test_sample_shape_1parameter(is_univariate=False) cases for the distributions whose draws
+    come from the device samplers."""
+    D = zs.distributions
+    makes = {"OnehotCategorical": lambda l: D.OnehotCategorical(l),
+             "Multinomial": lambda l: D.Multinomial(l, 7),
+             "Dirichlet": lambda l: D.Dirichlet(l.abs() + 1),
+             "Categorical": lambda l: D.Categorical(l)}
+    for name, make in makes.items():
+        for shape, n, target in (([2, 4], None, [2, 4]), ([3], 2, [2, 3]),
+                                 ([2, 1, 4], 3, [3, 2, 1, 4])):
+            x = make(torch.zeros(shape, device="cuda")).sample(n)
+            want = target[:-1] if name == "Categorical" else target
+            assert list(x.shape) == want, (name, shape, n, tuple(x.shape))
