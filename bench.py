@@ -323,11 +323,34 @@ def run_iwae(args):
     local_step = step_fn(W, x, K, dev, fused=True)
     unit = "particle-ELBOs/s"
 
-    def step():
+    def eager_step():
         cost, g = local_step()
         if world > 1:
             g, (cost,) = zs.dist.all_reduce_mean_gradients(g, [cost.detach()], n_local=N)
         return cost, g
+
+    step = eager_step
+    launches_per_replay = None
+    if args.cuda_graph:
+        # The step (forward, SGVB backward, gradient all-reduce) captured ONCE and replayed: the
+        # eager step is bound by the host (~170 launches + autograd bookkeeping per step).  The
+        # samplers' Philox counters are frozen by the capture, so the device draw epoch
+        # (zs.random.enable_device_epoch) is bumped at the end of the captured step: every
+        # replay draws fresh eps.
+        zs.random.enable_device_epoch(dev)
+        for _ in range(3):
+            eager_step()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        c0, l0 = zs.random.counter(), lib.launches
+        with torch.cuda.graph(graph):
+            g_cost, g_grads = eager_step()
+            zs.random.bump_device_epoch(max(1, zs.random.counter() - c0))
+        launches_per_replay = lib.launches - l0
+
+        def step():
+            graph.replay()
+            return g_cost, g_grads
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -352,12 +375,14 @@ def run_iwae(args):
     if sampler:
         sampler.mark_end("timed")
     launches = lib.launches - launches0
+    if launches_per_replay is not None:
+        launches = launches_per_replay * args.steps
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         td.all_reduce(ms, op=td.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
     value = world * K * N / (ms_per_step * 1e-3)
-    bound = float(-cost)
+    bound = float(-cost.detach())
 
     # e2e: per step, H2D of the step's batch from pinned memory, the step, D2H of the bound
     e2e = None
@@ -386,9 +411,17 @@ def run_iwae(args):
         e2e = {"value": world * K * N * args.steps / (float(t.item()) * 1e-3), "unit": unit,
                "h2d_bytes_per_step": N * 784 * 4, "d2h_bytes_per_step": 4,
                "steps": args.steps, "sm_mhz": None}
-    if rank != 0:
+
+    def teardown():
+        nonlocal step
         if world > 1:
+            if args.cuda_graph:        # captured NCCL work must go before the communicator
+                step = None
+                graph.reset()
+            torch.cuda.synchronize()
             td.destroy_process_group()
+    if rank != 0:
+        teardown()
         return
     win = sampler.stop() if sampler else {}
     if e2e is not None and "e2e" in win:
@@ -417,14 +450,14 @@ def run_iwae(args):
                         % (K, N, N * world),
             "l2": "activations larger than L2 ([K*N, 500] fp32 = %.0f MB per layer)"
                   % (K * N * 500 * 4 / 1e6),
+            "cuda_graph": bool(args.cuda_graph),
             "parallelism": "batch sharded x%d, particles local, 1 packed gradient "
                            "all-reduce/step" % world},
         "clocks": win.get("timed"), "e2e": e2e, "gpu_launches": launches,
         "roofline": roof, "cpu_baseline": cpu, "bound_value": bound,
     }
-    print(json.dumps(out))
-    if world > 1:
-        td.destroy_process_group()
+    print(json.dumps(out), flush=True)
+    teardown()
 
 
 def run_hmc(args):
@@ -589,6 +622,8 @@ def run_hmc(args):
 
     if rank != 0:
         if world > 1:
+            hmc._graphs.clear()
+            torch.cuda.synchronize()
             td.destroy_process_group()
         return
     win = sampler.stop() if sampler else {}
@@ -669,8 +704,10 @@ def run_hmc(args):
         "roofline": roof, "cpu_baseline": cpu,
         "acceptance_mean": acc_mean, "step_size": step_size,
     }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     if world > 1:
+        hmc._graphs.clear()             # captured NCCL work must go before the communicator
+        torch.cuda.synchronize()
         td.destroy_process_group()
 
 

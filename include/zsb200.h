@@ -38,6 +38,15 @@ int zsb_version(void);
 int zsb_last_error(char* buf, size_t n);       /* host buffer */
 int zsb_device_count(void);
 int zsb_stream_sync(void* stream);
+/* Device-resident draw epoch.  The reference's random ops (tf.random_normal hmc.py:22,
+ * univariate.py:161-172; tf.random_uniform univariate.py:386-396; tf.random.categorical
+ * univariate.py:478-494; tf.random_gamma multivariate.py:660-663) advance a per-op counter on every
+ * sess.run.  Here every sampler call takes (seed, iter) by value; when a step is captured once into
+ * a CUDA graph those values are frozen, so a registered device uint32 `epoch` is ADDED to `iter`
+ * inside the kernels and zsb_random_bump_epoch (captured at the end of the step) advances it:
+ * each replay draws fresh numbers.  NULL unregisters. */
+int zsb_random_set_device_epoch(const uint32_t* epoch);
+int zsb_random_bump_epoch(uint32_t* epoch, uint32_t by, void* stream);
 
 /* ---- sampler state block: 16 float32 in device memory (tf.Variables of hmc.py:258-264,
  *      StepsizeTuner hmc.py:82-87, EWMV.t hmc.py:118) ------------------------------------- */
@@ -167,6 +176,20 @@ int zsb_linear_tc_f32(int epi, const void* w_planes, const float* scale_w, const
                       const float* scale_h, const float* bias, const float* x_obs, int64_t n_x,
                       const float* gout, float* out, float* part, int64_t R, int J, int K,
                       int relu, void* stream);
+/* As zsb_linear_tc_f32, additionally folding max |out| (epi 0 / 2) into amax_scale[2] so that the
+ * consumer's operand split (zsb_split16_dual_f32, have_amax = 1) needs no pass over `out`. */
+int zsb_linear_tc_amax_f32(int epi, const void* w_planes, const float* scale_w,
+                           const void* h_planes, const float* scale_h, const float* bias,
+                           const float* x_obs, int64_t n_x, const float* gout, float* out,
+                           float* part, int64_t R, int J, int K, int relu, float* amax_scale,
+                           void* stream);
+/* Both operand layouts of an activation / gradient matrix in one pass: planes [2][R][Kp] and
+ * planes_t [2][K][Rp] (either may be NULL) of src * scale, optionally times the ReLU mask
+ * (mask_src > 0) -- the `g * (y > 0)` of the dense layer's backward (tf.layers.dense + relu,
+ * iwae.py:23-44) -- and the column sums of the masked matrix (bias gradient) into col_sum. */
+int zsb_split16_dual_f32(const float* src, const float* mask_src, int64_t R, int K, void* planes,
+                         void* planes_t, float* col_sum, float* scale, int have_amax,
+                         void* stream);
 
 /* ---- diagnostics: effective sample size (zhusuan/diagnostics.py:17-64, the Stan estimator) on the
  * device; samples [M, D] row-major with burn-in already dropped -> ess [D].  M >= 2. */
@@ -320,6 +343,19 @@ int zsb_sample_dirichlet_f32(const float* alpha, int64_t alpha_rows, int64_t n_r
 int zsb_sample_gamma_f32(const float* alpha, int64_t alpha_rows, const float* beta,
                          int64_t beta_rows, int64_t n_rows, int64_t row_len, uint64_t seed,
                          uint32_t iter, float* out, void* stream);
+
+/* ---- K8, config 5: Logistic-Normal Topic Model E-step log-joint (csrc/lntm.cu) -----------------
+ * log p = sum_k Normal(eta_k; mean_k, exp(logstd_k)).log_prob + sum_v x[d,v] log(softmax(eta) @ phi)[v]
+ * (examples/topic_models/lntm_mcem.py:33-48, e_obj :97-99; UnnormalizedMultinomial._log_prob,
+ * multivariate.py:435-443 with normalize_logits=False) and its gradient w.r.t. eta, fused and
+ * sparsity-aware: the corpus is CSR, only the words a document contains are formed, the
+ * [chains*docs, V] matrix of the reference never exists.  phi_t = softmax(beta)^T [V, K]. */
+int zsb_lntm_phi_t_f32(const float* beta, int64_t n_topics, int64_t n_vocab, float* phi_t,
+                       void* stream);
+int zsb_lntm_logjoint_f32(const float* eta, const float* eta_mean, const float* eta_logstd,
+                          const float* phi_t, const int64_t* doc_ptr, const int32_t* word_idx,
+                          const float* word_cnt, float* lp_out, float* grad_out, int64_t chains,
+                          int64_t docs, int64_t n_topics, void* stream);
 
 /* ---- K5: SG-MCMC updates (zhusuan/sgmcmc.py) ------------------------------------------------ */
 int zsb_sgmcmc_parts(void);   /* capacity (floats) of every `part` scratch */

@@ -132,6 +132,46 @@ class BNN(object):
         return [gw0.astype(d), gw1.astype(d)]
 
 
+class LNTM(object):
+    """E-step objective of examples/topic_models/lntm_mcem.py:33-48 with log_joint = e_obj
+    (:97-99): Normal prior on eta (group_ndims=1) + UnnormalizedMultinomial(log(softmax(eta) @
+    softmax(beta)), normalize_logits=False).log_prob(x) (multivariate.py:435-443), dense.
+    eta [chains, docs, K]; x [docs, V]; beta [K, V]."""
+
+    def __init__(self, x, beta, eta_mean, eta_logstd, dtype=np.float64):
+        self.dtype = dtype
+        self.x = np.asarray(x, dtype)
+        b = np.asarray(beta, np.float64)
+        e = np.exp(b - b.max(-1, keepdims=True))
+        self.phi = (e / e.sum(-1, keepdims=True)).astype(dtype)     # lntm_mcem.py:41
+        self.mean = np.asarray(eta_mean, dtype)
+        self.logstd = np.asarray(eta_logstd, dtype)
+
+    def _theta(self, eta):
+        e = np.exp(eta - eta.max(-1, keepdims=True))
+        return e / e.sum(-1, keepdims=True)
+
+    def logp(self, qs):
+        d = self.dtype
+        eta = np.asarray(qs[0], d)
+        prior = D.normal_log_prob(eta, self.mean, self.logstd, 1, d)
+        doc_word = self._theta(eta) @ self.phi                        # lntm_mcem.py:43-44
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ll = np.where(self.x > 0, self.x * np.log(doc_word), 0).sum(-1)
+        return (prior + ll).astype(d)
+
+    def grad(self, qs):
+        d = self.dtype
+        eta = np.asarray(qs[0], d)
+        th = self._theta(eta)
+        doc_word = th @ self.phi
+        ratio = np.where(self.x > 0, self.x / doc_word, 0)
+        dth = ratio @ self.phi.T
+        g = th * (dth - (th * dth).sum(-1, keepdims=True))
+        g = g - np.exp(d(-2) * self.logstd) * (eta - self.mean)
+        return [g.astype(d)]
+
+
 def make_dense_gaussian_problem(D_, seed=2):
     """Config 2 synthetic target: Sigma = A A^T / D + 0.1 I,
     rescaled to unit diagonal; P = Sigma^-1 computed in float64.

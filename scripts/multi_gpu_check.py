@@ -18,18 +18,21 @@ import torch.distributed as td
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import zhusuan_b200 as zs                               # noqa: E402
-from oracle.models import make_dense_gaussian_problem   # noqa: E402  (synthetic target only)
+from bench import make_dense_gaussian_problem          # noqa: E402  (synthetic target)
 
 
-def run(model_fn, q, n_iters, group, chain_offset, dense):
+def run(model_fn, q, n_iters, group, chain_offset, dense, graph=False):
     kw = dict(step_size=0.05 if dense else 1e-3, n_leapfrogs=6,
               adapt_step_size=True, adapt_mass=True, mass_collect_iters=4,
-              seed=99, process_group=group, chain_offset=chain_offset)
+              seed=99, process_group=group, chain_offset=chain_offset,
+              use_cuda_graph=graph)
     h = zs.HMC(**kw)
     op, info = h.sample(model_fn, {}, {"x": q})
     for i in range(n_iters):
         op(adapt_step_size=True, adapt_mass=True)
     op.synchronize()
+    info.n_collectives = h._pk.n_collectives
+    info.n_search = h.n_search_iters
     return info
 
 
@@ -40,8 +43,11 @@ def main():
     dev = torch.device("cuda", local)
     td.init_process_group("nccl", device_id=dev)
     ok = True
-    for dense in (False, True):
-        D, C = (64, 96 * world) if dense else (100, 64 * world)
+    for case in ("diag", "dense64", "dense1024", "dense1024-graph"):
+        dense = case != "diag"
+        graph = case.endswith("graph")
+        D, C = {"diag": (100, 64 * world), "dense64": (64, 96 * world)}.get(
+            case, (1024, 320 * world))
         g = torch.Generator(device="cpu"); g.manual_seed(5)
         q_all = torch.randn(C, D, generator=g) * 0.5
         if dense:
@@ -58,7 +64,7 @@ def main():
             model = gaussian()
         n_local = C // world
         q = q_all[rank * n_local:(rank + 1) * n_local].to(dev).contiguous()
-        info = run(model, q, 12, None, None, dense)          # sharded (default group)
+        info = run(model, q, 12, None, None, dense, graph)   # sharded (default group)
         gathered = [torch.empty_like(q) for _ in range(world)]
         td.all_gather(gathered, q)
         accs = [torch.empty_like(info.acceptance_rate) for _ in range(world)]
@@ -75,10 +81,14 @@ def main():
             d = (qs - q1).abs().max().item()
             same_rows = ((qs - q1).abs().amax(1) < 1e-3).float().mean().item()
             ss = abs(float(info.updated_step_size) - float(info1.updated_step_size)) / float(info1.updated_step_size)
-            print("%s: max|dq| %.3e  rows equal %.4f  step-size rel diff %.2e  acc mean %.4f vs %.4f"
-                  % ("dense" if dense else "diag", d, same_rows, ss,
-                     torch.cat(accs).mean().item(), info1.acceptance_rate.mean().item()))
-            ok &= same_rows > 0.98 and ss < 1e-4
+            # ONE packed all-reduce per iteration (+1 for the very first mass update, + the
+            # acceptance-only reductions inside the two step-size searches)
+            want = 12 + 1 + info.n_search
+            print("%s: max|dq| %.3e  rows equal %.4f  step-size rel diff %.2e  acc mean %.4f vs "
+                  "%.4f  collectives %d (expected %d)"
+                  % (case, d, same_rows, ss, torch.cat(accs).mean().item(),
+                     info1.acceptance_rate.mean().item(), info.n_collectives, want))
+            ok &= same_rows > 0.98 and ss < 1e-4 and info.n_collectives == want
         td.barrier()
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")

@@ -659,3 +659,64 @@ def test_resident_kernel_shapes_vs_oracle(zs, D, C, L):
     np.testing.assert_allclose(N(info.acceptance_rate), oi.acceptance_rate, rtol=2e-4, atol=1e-4)
     near = np.abs(u - oi.acceptance_rate) < 1e-3
     np.testing.assert_allclose(N(x)[~near], oq[0][~near], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["diag", "dense5", "generic"])
+def test_hmc_state_dict_round_trip_resumes_bitwise(zs, path):
+    """HMC.state_dict() / load_state_dict(): a sampler rebuilt from a checkpoint (latents +
+    state dict) continues EXACTLY like the uninterrupted one -- step size, dual-averaging state,
+    EWMV mean / variance, iteration counter (Philox stream) -- across a mass_collect_iters
+    boundary.  The check_numerics flag is not part of the checkpoint."""
+    rng = np.random.RandomState(5)
+    if path == "dense5":
+        D, C = 64, 80
+        P, _ = OM.make_dense_gaussian_problem(D, seed=2)
+        model = lambda: zs.fused.GaussianLogJoint(P)
+        kw = {"dense_impl": 5}
+    else:
+        D, C = 24, 40
+        std = (0.5 + rng.random_sample(D)).astype(np.float32)
+
+        def model():
+            if path == "generic":
+                return lambda o: zs.distributions.Normal(
+                    torch.zeros(D, device="cuda"), std=T(std), group_ndims=1).log_prob(o['x'])
+
+            @zs.meta_bayesian_net()
+            def gaussian():
+                bn = zs.BayesianNet()
+                bn.normal('x', torch.zeros(D, device="cuda"), std=T(std), group_ndims=1)
+                return bn
+            return gaussian()
+        kw = {}
+    q0 = rng.standard_normal((C, D)).astype(np.float32)
+
+    def build(x):
+        h = zs.HMC(step_size=0.05, n_leapfrogs=5, adapt_step_size=True, adapt_mass=True,
+                   mass_collect_iters=6, seed=21, **kw)
+        op, info = h.sample(model(), {}, {"x": x})
+        return h, op, info
+    xa = T(q0)
+    ha, opa, _ = build(xa)
+    for _ in range(4):
+        opa(adapt_step_size=True, adapt_mass=True)
+    opa.synchronize()
+    ckpt, x_ckpt = ha.state_dict(), xa.clone()
+    ha._state[9] = float("nan")                 # a raised flag must not travel in a checkpoint
+    assert float(ha.state_dict()["state"][9]) == 0.0
+    ha._state[9] = 0.0
+    for _ in range(5):
+        opa(adapt_step_size=True, adapt_mass=True)
+    opa.synchronize()
+    xb = x_ckpt.clone()
+    hb, opb, _ = build(xb)
+    hb.load_state_dict(ckpt)
+    for _ in range(5):
+        opb(adapt_step_size=True, adapt_mass=True)
+    opb.synchronize()
+    assert (ha._t, ha._ewmv_t) == (hb._t, hb._ewmv_t) == (9, 9)
+    np.testing.assert_array_equal(N(xa), N(xb))
+    np.testing.assert_array_equal(N(ha._state)[:9], N(hb._state)[:9])
+    np.testing.assert_array_equal(N(ha._mass[0]), N(hb._mass[0]))
+    np.testing.assert_array_equal(N(ha._ew_var[0]), N(hb._ew_var[0]))

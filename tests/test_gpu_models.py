@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from oracle import hmc as OH
+from oracle import models as OM
 
 pytestmark = pytest.mark.gpu
 
@@ -191,3 +192,59 @@ def test_ais_device_loop_matches_oracle_step_for_step(zs):
     np.testing.assert_allclose(N(ais._schedule), [oa.schedule(t) for t in range(nt + 1)],
                                rtol=1e-6, atol=1e-7)
     assert ais.temperature.is_cuda and float(ais.temperature) == 1.0
+
+
+@pytest.mark.parametrize("K,V,C,Dn", [(16, 50, 5, 3), (32, 200, 70, 4), (128, 1000, 130, 7)])
+def test_lntm_fused_kernel_matches_oracle(zs, K, V, C, Dn):
+    """zs.fused.LNTMLogJoint (sparsity-aware fused kernel, csrc/lntm.cu) vs the dense float64
+    oracle restatement of lntm_mcem.py:33-48 / e_obj: log-joint values and d/d eta, including an
+    empty (padding) document, counts > 1, and a chain count that is not a multiple of the block's
+    64; the dense torch restatement (the object as a callable) agrees as well."""
+    rng = np.random.RandomState(K + V)
+    x = rng.poisson(0.08, (Dn, V)).astype(np.float32)
+    x[0] = 0                                             # padding document (lntm_mcem.py:71-74)
+    x[1, :5] += 3
+    beta = rng.standard_normal((K, V)).astype(np.float32)
+    mean = (0.3 * rng.standard_normal(K)).astype(np.float32)
+    logstd = (0.2 * rng.standard_normal(K)).astype(np.float32)
+    eta = rng.standard_normal((C, Dn, K)).astype(np.float32)
+    om = OM.LNTM(x, beta, mean, logstd)
+    lj = zs.fused.LNTMLogJoint(T(x), T(beta), T(mean), T(logstd))
+    assert int(lj.doc_ptr[-1]) == int((x != 0).sum()) and int(lj.doc_ptr[1]) == 0
+    lp = N(lj.logp([T(eta)]))
+    g = N(lj.grad([T(eta)])[0])
+    ref_lp, ref_g = om.logp([eta]), om.grad([eta])[0]
+    np.testing.assert_allclose(lp, ref_lp, rtol=2e-5, atol=1e-3)
+    np.testing.assert_allclose(g, ref_g, rtol=2e-4, atol=2e-4 * np.abs(ref_g).max())
+    dense = N(lj({"eta": T(eta)}))
+    np.testing.assert_allclose(dense, ref_lp, rtol=5e-5, atol=5e-3)
+
+
+def test_lntm_fused_hmc_matches_oracle(zs):
+    """HMC on the fused LNTM provider (two chain axes [chains, docs], lntm_mcem.py:69-70,
+    99-105) vs the oracle HMC on the dense oracle model, injected noise, adaptive step size."""
+    rng = np.random.RandomState(9)
+    K, V, C, Dn = 32, 120, 6, 5
+    x = rng.poisson(0.1, (Dn, V)).astype(np.float32)
+    beta = rng.standard_normal((K, V)).astype(np.float32)
+    mean = np.zeros(K, np.float32)
+    logstd = np.zeros(K, np.float32)
+    om = OM.LNTM(x, beta, mean, logstd, dtype=np.float32)
+    lj = zs.fused.LNTMLogJoint(T(x), T(beta), T(mean), T(logstd))
+    eta0 = (0.1 * rng.standard_normal((C, Dn, K))).astype(np.float32)
+    eta = T(eta0)
+    h = zs.HMC(step_size=0.02, n_leapfrogs=6, adapt_step_size=True, target_acceptance_rate=0.6)
+    op, info = h.sample(lj, {}, {"eta": eta})
+    assert h._provider is lj and tuple(info.acceptance_rate.shape) == (C, Dn)
+    oh = OH.HMC(step_size=0.02, n_leapfrogs=6, adapt_step_size=True, target_acceptance_rate=0.6)
+    oq = [eta0]
+    for i in range(4):
+        npz = rng.standard_normal(eta0.shape).astype(np.float32)
+        u = rng.random_sample((C, Dn)).astype(np.float32)
+        with np.errstate(all="ignore"):
+            oq, oi = oh.step(oq, om.logp, om.grad, [npz], u, True, False)
+        op(adapt_step_size=True, noise={"p": {"eta": T(npz)}, "u": T(u)})
+        np.testing.assert_allclose(N(info.acceptance_rate), oi.acceptance_rate, rtol=2e-3,
+                                   atol=2e-4)
+        near = np.abs(u - oi.acceptance_rate) < 1e-3
+        np.testing.assert_allclose(N(eta)[~near], oq[0][~near], rtol=1e-3, atol=1e-4)

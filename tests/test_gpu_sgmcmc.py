@@ -185,3 +185,40 @@ def test_bnn_fused_matches_generic_path_with_philox(zs):
     np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-3)
+
+
+@pytest.mark.parametrize("name", ["sgld", "psgld", "sghmc", "sgnht_vector", "sgnht_scalar"])
+def test_sgmcmc_state_dict_round_trip_resumes_bitwise(zs, name):
+    """SGMCMC.state_dict() / load_state_dict(): a sampler rebuilt from (latents, state dict)
+    continues exactly like the uninterrupted one (iteration counter = Philox stream position,
+    momenta, RMSprop accumulator, thermostats), across a momentum-resampling boundary."""
+    rng = np.random.RandomState(2)
+    D, C = 10, 12
+    std = torch.tensor((0.5 + rng.random_sample(D)).astype(np.float32), device="cuda")
+    lj = lambda o: zs.distributions.Normal(torch.zeros(D, device="cuda"), std=std,
+                                           group_ndims=1).log_prob(o['w'])
+    make = {"sgld": lambda: zs.SGLD(0.01, seed=3),
+            "psgld": lambda: zs.PSGLD(0.01, seed=3),
+            "sghmc": lambda: zs.SGHMC(0.01, friction=0.3, n_iter_resample_v=4, seed=3),
+            "sgnht_vector": lambda: zs.SGNHT(0.01, variance_extra=0.1, n_iter_resample_v=4,
+                                             seed=3),
+            "sgnht_scalar": lambda: zs.SGNHT(0.01, variance_extra=0.1, use_vector_alpha=False,
+                                             seed=3)}[name]
+    q0 = torch.tensor(rng.standard_normal((C, D)).astype(np.float32), device="cuda")
+    wa = q0.clone()
+    sa = make()
+    opa, _ = sa.sample(lj, {}, {"w": wa})
+    for _ in range(3):
+        opa()
+    ckpt, w_ckpt = sa.state_dict(), wa.clone()
+    for _ in range(5):
+        opa()
+    wb = w_ckpt.clone()
+    sb = make()
+    opb, _ = sb.sample(lj, {}, {"w": wb})
+    sb.load_state_dict(ckpt)
+    for _ in range(5):
+        opb()
+    torch.cuda.synchronize()
+    assert sa.t == sb.t == 8
+    np.testing.assert_array_equal(wa.cpu().numpy(), wb.cpu().numpy())

@@ -13,6 +13,7 @@
 
 void zsb_set_error(const char* fmt, ...);
 int zsb_check_launch(const char* what);
+const uint32_t* zsb_epoch_ptr();   // device draw epoch (api.cu), NULL when not registered
 
 #define ZSB_REQUIRE(cond, ...)                    \
   do {                                            \

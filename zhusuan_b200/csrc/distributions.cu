@@ -495,13 +495,15 @@ int zsb_reparam_normal_f32(const float* mean, int64_t mean_n, const float* logst
   ZSB_REQUIRE(mean_n > 0 && logstd_n > 0 && group > 0 && n_out >= 0 && z_out,
               "zsb_reparam_normal_f32: bad sizes");
   Ops3 ops{{mean, logstd, nullptr}, {mean_n, logstd_n, 1}};
+  const uint32_t* ep = zsb_epoch_ptr();
   auto f = [=] __device__(float mu, float ls, float, int64_t i, int64_t) -> float {
     float e;
     if (eps) {
       e = eps[i];
     } else {
       float z4[4];
-      philox_normal4(seed, ZSB_STREAM_SAMPLE, iter, (uint32_t)((uint64_t)i >> 34),
+      philox_normal4(seed, ZSB_STREAM_SAMPLE, iter + (ep ? *ep : 0u),
+                     (uint32_t)((uint64_t)i >> 34),
                      (uint32_t)(i >> 2), z4);
       e = z4[i & 3];
     }
@@ -519,12 +521,14 @@ int zsb_reparam_normal_f32(const float* mean, int64_t mean_n, const float* logst
 int zsb_sample_bernoulli_i32(const float* logits, int64_t logits_n, const float* u, uint64_t seed,
                              uint32_t iter, int32_t* out, int64_t n, void* stream) {
   ZSB_REQUIRE(logits_n > 0 && n >= 0, "zsb_sample_bernoulli_i32: bad sizes");
+  const uint32_t* ep = zsb_epoch_ptr();
   auto f = [=] __device__(int64_t i) {
     float uu;
     if (u) {
       uu = u[i];
     } else {
-      const Philox4 r = philox4x32_10((uint32_t)(i >> 2), (uint32_t)((uint64_t)i >> 34), iter,
+      const Philox4 r = philox4x32_10((uint32_t)(i >> 2), (uint32_t)((uint64_t)i >> 34),
+                                      iter + (ep ? *ep : 0u),
                                       ZSB_STREAM_SAMPLE, (uint32_t)seed, (uint32_t)(seed >> 32));
       const uint32_t w = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
       uu = u32_to_uniform(w);

@@ -38,7 +38,7 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
                   const float* __restrict__ x_obs, int64_t n_x, const float* __restrict__ gout,
                   float* __restrict__ out, float* __restrict__ part, int64_t R, int J, int Kp,
                   int relu, const float* __restrict__ scale_w, const float* __restrict__ scale_h,
-                  int k_slices) {
+                  int k_slices, float* __restrict__ amax_scale) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + GC::STAGES * GC::STAGE;
@@ -158,6 +158,7 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
     const float acc_scale = 1.f / (scale_w[0] * scale_h[0]);   // powers of two: exact
     int acc = 0;
     uint32_t acc_phase = 0;
+    float amax = 0.f;        // max |stored output| (EPI 0 / 2): the consumer's fp16-split scale
     for (int64_t uu = unit0; uu < n_units; uu += unit_step) {
       const int64_t u = uu % n_tiles;
       const int slice = (int)(uu / n_tiles);
@@ -208,12 +209,14 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
           const bool ok = full || (j_ok && rbase + jj < R);
           const float l = empty_slice ? b_use : fmaf(__uint_as_float(v[jj]), acc_scale, b_use);
           if (EPI == 0) {
-            if (ok) *po = relu ? fmaxf(l, 0.f) : l;
+            const float y = relu ? fmaxf(l, 0.f) : l;
+            if (ok) { *po = y; amax = fmaxf(amax, fabsf(y)); }
           } else if (EPI == 1) {
             lpv[jj] = ok ? bern_lp(xe[jj], l) : 0.f;
           } else {
             const float g = __shfl_sync(0xffffffffu, ge, jj);
-            if (ok) *po = g * (xe[jj] - __fdividef(1.f, 1.f + __expf(-l)));
+            const float y = g * (xe[jj] - __fdividef(1.f, 1.f + __expf(-l)));
+            if (ok) { *po = y; amax = fmaxf(amax, fabsf(y)); }
           }
           if (EPI != 1) po += J;
         }
@@ -244,6 +247,11 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
       else mbar_arrive_remote(tempty_bar + 8 * acc, 0);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (EPI != 1 && amax_scale) {       // NaN / inf never win the max (fmaxf drops NaN)
+      amax = warp_max(amax <= 3.0e38f ? amax : 0.f);
+      if (lane == 0 && amax > 0.f)
+        atomicMax(reinterpret_cast<unsigned int*>(amax_scale) + 2, __float_as_uint(amax));
+    }
   }
 
   tc_fence_before();
@@ -252,6 +260,81 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
                  ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// One pass over an activation / gradient matrix that produces BOTH operand layouts of the dense
+// layers: src [R, K] fp32 (optionally times the ReLU mask (mask_src > 0)) ->
+//   planes   [2][R][Kp]  fp16 hi/lo of src * scale   (forward / input-gradient products)
+//   planes_t [2][K][Rp]  fp16 hi/lo of (src * scale)^T (weight-gradient product, contraction over R)
+//   col_sum  [K] += sum_r src[r, k] * mask           (the bias gradient; float atomics)
+// 64 x 64 tiles through shared memory; float2 loads, half2 stores in both layouts.
+__global__ void __launch_bounds__(256) split16_dual_kernel(
+    const float* __restrict__ src, const float* __restrict__ mask_src, int64_t R, int K, int Kp,
+    int64_t Rp, __half* __restrict__ planes, __half* __restrict__ planes_t,
+    float* __restrict__ col_sum, const float* __restrict__ scale) {
+  __shared__ float tile[64][65];
+  __shared__ float csum[8][64];
+  const float s = scale[0];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
+  const int64_t r_tiles = (Rp + 63) / 64;
+  const int c_tiles = (Kp + 63) / 64;
+  const int64_t n_pl = R * (int64_t)Kp, n_plt = (int64_t)K * Rp;
+  for (int64_t t = blockIdx.x; t < r_tiles * c_tiles; t += gridDim.x) {
+    const int64_t r0 = (t / c_tiles) * 64;
+    const int c0 = (int)(t % c_tiles) * 64;
+    const int c = c0 + 2 * tx;
+    float cs0 = 0.f, cs1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = ty + 8 * i;
+      const int64_t r = r0 + rl;
+      float2 v = make_float2(0.f, 0.f);
+      if (r < R && c < K) {                      // K is even: c + 1 < K as well
+        v = *reinterpret_cast<const float2*>(src + r * K + c);
+        if (mask_src) {
+          const float2 m = *reinterpret_cast<const float2*>(mask_src + r * K + c);
+          v.x = m.x > 0.f ? v.x : 0.f;
+          v.y = m.y > 0.f ? v.y : 0.f;
+        }
+      }
+      cs0 += v.x; cs1 += v.y;
+      v.x *= s; v.y *= s;
+      tile[rl][2 * tx] = v.x;
+      tile[rl][2 * tx + 1] = v.y;
+      if (planes && r < R && c < Kp) {
+        const __half2 h = __floats2half2_rn(v.x, v.y);
+        const float2 hf = __half22float2(h);
+        *reinterpret_cast<__half2*>(planes + r * Kp + c) = h;
+        *reinterpret_cast<__half2*>(planes + n_pl + r * Kp + c) =
+            __floats2half2_rn(v.x - hf.x, v.y - hf.y);
+      }
+    }
+    if (col_sum) { csum[ty][2 * tx] = cs0; csum[ty][2 * tx + 1] = cs1; }
+    __syncthreads();
+    if (col_sum && threadIdx.x < 64 && c0 + (int)threadIdx.x < K) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a += csum[i][threadIdx.x];
+      atomicAdd(col_sum + c0 + threadIdx.x, a);
+    }
+    if (planes_t) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int kl = ty + 8 * i;
+        const int k = c0 + kl;
+        const int64_t r = r0 + 2 * tx;
+        if (k < K && r < Rp) {                   // Rp is a multiple of 64: r + 1 < Rp as well
+          const float x0 = tile[2 * tx][kl], x1 = tile[2 * tx + 1][kl];
+          const __half2 h = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(h);
+          *reinterpret_cast<__half2*>(planes_t + (int64_t)k * Rp + r) = h;
+          *reinterpret_cast<__half2*>(planes_t + n_plt + (int64_t)k * Rp + r) =
+              __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -405,6 +488,33 @@ int zsb_split16_pad_t_f32(const float* src, int64_t R, int C, void* planes, floa
   return zsb_check_launch("split16_pad_t");
 }
 
+// Both operand layouts of one matrix in ONE pass (see split16_dual_kernel): planes [2][R][Kp]
+// and / or planes_t [2][K][Rp] (either may be NULL), optional ReLU mask source, optional column
+// sums (bias gradient; col_sum must be zeroed by the caller).  have_amax = 1: scale[2] already
+// holds max |src| (written by zsb_linear_tc_amax_f32), so no max pass is run.  K must be even.
+int zsb_split16_dual_f32(const float* src, const float* mask_src, int64_t R, int K, void* planes,
+                         void* planes_t, float* col_sum, float* scale, int have_amax,
+                         void* stream) {
+  ZSB_REQUIRE(src && scale && R > 0 && K > 0 && K % 2 == 0 && (planes || planes_t),
+              "zsb_split16_dual_f32: bad args (K must be even)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kp = zsb_linear_tc_kpad(K);
+  const int64_t Rp = ((R + 63) / 64) * 64;
+  if (!have_amax) {
+    const int64_t n = R * (int64_t)K;
+    int64_t blocks = zsb_ceil_div(n, 256 * 8);
+    if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
+    absmax2_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n, scale);
+  }
+  pow2_scale_kernel<<<1, 32, 0, st>>>(scale);
+  int64_t tiles = ((Rp + 63) / 64) * ((Kp + 63) / 64);
+  if (tiles > ZSB_NUM_SMS * 16) tiles = ZSB_NUM_SMS * 16;
+  split16_dual_kernel<<<(unsigned)tiles, 256, 0, st>>>(
+      src, mask_src, R, K, Kp, Rp, reinterpret_cast<__half*>(planes),
+      reinterpret_cast<__half*>(planes_t), col_sum, scale);
+  return zsb_check_launch("split16_dual");
+}
+
 // Fused dense layer on the tensor cores.  w_planes [2][J][Kp], h_planes [2][R][Kp] (fp16 planes
 // from zsb_split16_pad_f32 with their scales); bias [J] or NULL.
 //   epi 0: out [R, J] = h W^T + bias (ReLU if relu != 0)
@@ -425,10 +535,26 @@ int zsb_linear_tc_slices(int64_t R, int J, int K) {
   const int kb_per = (int)((n_kb + want - 1) / want);
   return (n_kb + kb_per - 1) / kb_per;                       // no empty slice
 }
+int zsb_linear_tc_amax_f32(int epi, const void* w_planes, const float* scale_w,
+                           const void* h_planes, const float* scale_h, const float* bias,
+                           const float* x_obs, int64_t n_x, const float* gout, float* out,
+                           float* part, int64_t R, int J, int K, int relu, float* amax_scale,
+                           void* stream);
 int zsb_linear_tc_f32(int epi, const void* w_planes, const float* scale_w, const void* h_planes,
                       const float* scale_h, const float* bias, const float* x_obs, int64_t n_x,
                       const float* gout, float* out, float* part, int64_t R, int J, int K,
                       int relu, void* stream) {
+  return zsb_linear_tc_amax_f32(epi, w_planes, scale_w, h_planes, scale_h, bias, x_obs, n_x, gout,
+                                out, part, R, J, K, relu, nullptr, stream);
+}
+// As zsb_linear_tc_f32; additionally the running max |out| (epi 0 / 2, not with split-K) is
+// folded into amax_scale[2] (uint bits, atomicMax): the scale slot zsb_split16_dual_f32 consumes
+// with have_amax = 1, so the consumer's operand split needs no separate max pass over `out`.
+int zsb_linear_tc_amax_f32(int epi, const void* w_planes, const float* scale_w,
+                           const void* h_planes, const float* scale_h, const float* bias,
+                           const float* x_obs, int64_t n_x, const float* gout, float* out,
+                           float* part, int64_t R, int J, int K, int relu, float* amax_scale,
+                           void* stream) {
   ZSB_REQUIRE(epi >= 0 && epi <= 2, "zsb_linear_tc_f32: unknown epilogue");
   ZSB_REQUIRE(w_planes && h_planes && scale_w && scale_h && out && R > 0 && J > 0 && K > 0,
               "zsb_linear_tc_f32: bad args");
@@ -473,7 +599,8 @@ int zsb_linear_tc_f32(int epi, const void* w_planes, const float* scale_w, const
     if (prep == cudaSuccess)                                                                   \
       linear_tc2_kernel<EPI><<<grid, NUM_THREADS, GC::SMEM, st>>>(                             \
           m_whi, m_wlo, m_hhi, m_hlo, bias, x_obs, n_x, gout, epi == 1 ? nullptr : out_k,      \
-          part, R, J, Kp, relu, scale_w, scale_h, k_slices);                                   \
+          part, R, J, Kp, relu, scale_w, scale_h, k_slices,                                    \
+          k_slices > 1 ? nullptr : amax_scale);                                                \
   } while (0)
   if (epi == 0) ZSB_LIN(0);
   else if (epi == 1) ZSB_LIN(1);

@@ -25,7 +25,8 @@ namespace {
 __global__ void __launch_bounds__(256) categorical_sample_kernel(
     const float* __restrict__ logits, int64_t logit_rows, int64_t rows, int C,
     const float* __restrict__ u_in, uint64_t seed, uint32_t iter, int32_t* __restrict__ out,
-    int64_t n_draws) {
+    int64_t n_draws, const uint32_t* __restrict__ epoch) {
+  if (epoch) iter += *epoch;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -120,7 +121,8 @@ __device__ __forceinline__ float gamma_mt(float alpha, uint32_t elem_lo, uint32_
 __global__ void __launch_bounds__(256) gamma_rows_kernel(
     const float* __restrict__ alpha, int64_t alpha_rows, const float* __restrict__ beta,
     int64_t beta_rows, const float* __restrict__ gam_in, int64_t n_rows, int C, int normalise,
-    uint64_t seed, uint32_t iter, float* __restrict__ out) {
+    uint64_t seed, uint32_t iter, float* __restrict__ out, const uint32_t* __restrict__ epoch) {
+  if (epoch) iter += *epoch;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -166,7 +168,7 @@ int zsb_sample_categorical_i32(const float* logits, int64_t logit_rows, int64_t 
   const int64_t n = n_samples * rows;
   if (n == 0) return ZSB_OK;
   categorical_sample_kernel<<<warp_grid(n), 256, 0, (cudaStream_t)stream>>>(
-      logits, logit_rows, rows, (int)n_categories, u, seed, iter, out, n);
+      logits, logit_rows, rows, (int)n_categories, u, seed, iter, out, n, zsb_epoch_ptr());
   return zsb_check_launch("sample_categorical");
 }
 
@@ -180,7 +182,8 @@ int zsb_sample_dirichlet_f32(const float* alpha, int64_t alpha_rows, int64_t n_r
               "zsb_sample_dirichlet_f32: bad args");
   if (n_rows == 0) return ZSB_OK;
   gamma_rows_kernel<<<warp_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(
-      alpha, alpha_rows, nullptr, 1, gammas, n_rows, (int)n_categories, 1, seed, iter, out);
+      alpha, alpha_rows, nullptr, 1, gammas, n_rows, (int)n_categories, 1, seed, iter, out,
+      zsb_epoch_ptr());
   return zsb_check_launch("sample_dirichlet");
 }
 
@@ -194,7 +197,7 @@ int zsb_sample_gamma_f32(const float* alpha, int64_t alpha_rows, const float* be
   if (n_rows == 0) return ZSB_OK;
   gamma_rows_kernel<<<warp_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(
       alpha, alpha_rows, beta, beta ? beta_rows : 1, nullptr, n_rows, (int)row_len, 0, seed, iter,
-      out);
+      out, zsb_epoch_ptr());
   return zsb_check_launch("sample_gamma");
 }
 

@@ -7,7 +7,7 @@ import math
 import numpy as np
 import torch
 
-__all__ = ["GaussianLogJoint", "BNNRegressionLogJoint", "linear",
+__all__ = ["GaussianLogJoint", "BNNRegressionLogJoint", "LNTMLogJoint", "linear",
            "linear_bernoulli_log_prob", "LinearBernoulli"]
 
 
@@ -130,6 +130,89 @@ class BNNRegressionLogJoint(object):
 
 
 
+class LNTMLogJoint(object):
+    """E-step objective of the Logistic-Normal Topic Model, examples/topic_models/
+    lntm_mcem.py:33-48 with ``model.log_joint = e_obj`` (:97-99):
+
+        eta [chains, docs, K] ~ Normal(eta_mean, exp(eta_logstd)), group_ndims=1
+        log p = cond_log_prob('eta') + UnnormalizedMultinomial(log(softmax(eta) @ softmax(beta)),
+                                                                normalize_logits=False).log_prob(x)
+
+    ``zs.HMC.sample`` recognises it (``_zsb_fused`` kind "provider") and takes log-joint values
+    and gradients from ONE fused, sparsity-aware kernel (zsb_lntm_logjoint_f32): the corpus is held
+    in CSR, only the words a document contains are formed, and the [chains*docs, V] matrix
+    ``doc_word`` of the reference never exists (335 TB at BASELINE config 5).  As a plain callable
+    it is the dense torch restatement of the reference graph (small shapes / cross-check).
+
+    x: dense [docs, V] counts (any float/int tensor); beta: [K, V] (fixed during the E-step; call
+    ``set_beta`` after every M-step); K in {16, 32, 64, 128}.
+    """
+
+    def __init__(self, x, beta, eta_mean, eta_logstd, name="eta"):
+        from ._lib import lib  # noqa: F401  (fail early without the library)
+        self.name = name
+        dev = beta.device
+        x = torch.as_tensor(x, device=dev)
+        self.x = x.to(torch.float32)
+        self.n_docs, self.n_vocab = int(x.shape[0]), int(x.shape[1])
+        nz = (self.x != 0)
+        per_doc = nz.sum(1)
+        self.doc_ptr = torch.zeros(self.n_docs + 1, dtype=torch.int64, device=dev)
+        self.doc_ptr[1:] = torch.cumsum(per_doc, 0)
+        idx = nz.nonzero(as_tuple=False)                  # row-major: sorted by document
+        self.word_idx = idx[:, 1].to(torch.int32).contiguous()
+        self.word_cnt = self.x[idx[:, 0], idx[:, 1]].contiguous()
+        self.eta_mean = eta_mean.detach().to(torch.float32).contiguous()
+        self.eta_logstd = eta_logstd.detach().to(torch.float32).contiguous()
+        self.n_topics = int(beta.shape[0])
+        if self.n_topics not in (16, 32, 64, 128):
+            raise ValueError("LNTMLogJoint: n_topics must be 16, 32, 64 or 128")
+        self.phi_t = torch.empty((self.n_vocab, self.n_topics), dtype=torch.float32, device=dev)
+        self.set_beta(beta)
+        self._zsb_fused = {"kind": "provider", "obj": self}
+
+    def set_beta(self, beta):
+        from ._lib import lib, ptr, stream
+        self.beta = beta.detach().to(torch.float32).contiguous()
+        lib.call("zsb_lntm_phi_t_f32", ptr(self.beta), self.n_topics, self.n_vocab,
+                 ptr(self.phi_t), stream())
+
+    def _launch(self, eta, want_lp, want_grad):
+        from ._lib import lib, ptr, stream
+        eta = eta.detach()
+        if eta.dim() != 3 or int(eta.shape[1]) != self.n_docs or \
+                int(eta.shape[2]) != self.n_topics:
+            raise ValueError("eta must be [chains, %d, %d]" % (self.n_docs, self.n_topics))
+        eta = eta.to(torch.float32).contiguous()
+        chains = int(eta.shape[0])
+        lp = torch.empty((chains, self.n_docs), dtype=torch.float32, device=eta.device) \
+            if want_lp else None
+        g = torch.empty_like(eta) if want_grad else None
+        lib.call("zsb_lntm_logjoint_f32", ptr(eta), ptr(self.eta_mean), ptr(self.eta_logstd),
+                 ptr(self.phi_t), ptr(self.doc_ptr), ptr(self.word_idx), ptr(self.word_cnt),
+                 ptr(lp), ptr(g), chains, self.n_docs, self.n_topics, stream())
+        return lp, g
+
+    # provider interface used by HMC's generic path instead of autograd
+    def logp(self, var_list):
+        return self._launch(var_list[0], True, False)[0]
+
+    def grad(self, var_list):
+        return [self._launch(var_list[0], False, True)[1]]
+
+    def __call__(self, observed):
+        """Dense restatement of the reference graph in torch (lntm_mcem.py:33-48)."""
+        eta = observed[self.name]
+        theta = torch.softmax(eta, -1)
+        phi = torch.softmax(self.beta, -1)
+        doc_word = theta.reshape(-1, self.n_topics) @ phi
+        doc_word = doc_word.reshape(tuple(eta.shape[:-1]) + (self.n_vocab,))
+        prec = torch.exp(-2 * self.eta_logstd)
+        prior = (-0.5 * math.log(2 * math.pi) - self.eta_logstd
+                 - 0.5 * prec * (eta - self.eta_mean) ** 2).sum(-1)
+        return prior + (self.x * torch.log(doc_word)).sum(-1)
+
+
 # ---------------------------------------------------------------------------
 # K8: dense layers of a VAE / BNN log-joint on tcgen05 (gemm_logjoint_tc.cu)
 # ---------------------------------------------------------------------------
@@ -160,25 +243,81 @@ def _tc_split_t(t2d):
     return planes, scale
 
 
-def _tc_grad_input(g, W):
-    """dh [R, K] = g [R, J] @ W [J, K] on the tensor cores."""
+class _Planes(object):
+    """fp16 hi/lo operand planes of one [rows, K] matrix times a power-of-two scale: row-major
+    ``planes`` [2, rows, Kp] (forward / input-gradient products) and transposed ``planes_t``
+    [2, K, Rp] (weight-gradient product, contraction over the rows); ``scale`` = device float[4]."""
+    __slots__ = ("planes", "planes_t", "scale", "rows", "K")
+
+    def __init__(self, planes, planes_t, scale, rows, K):
+        self.planes, self.planes_t, self.scale, self.rows, self.K = planes, planes_t, scale, rows, K
+
+
+def _tc_split_dual(t2d, mask=None, want=(True, True), amax=None, col_sum=None):
+    """One pass over fp32 ``t2d`` [R, K] (times the ReLU mask ``mask > 0``) -> _Planes with the
+    layouts asked for in ``want`` = (row-major, transposed); ``amax`` = scale slot whose max-|.|
+    word a producing GEMM already filled (no max pass then); ``col_sum`` [K] += column sums."""
+    from ._lib import lib, ptr, stream
+    t2d = t2d.detach().to(torch.float32).contiguous()
+    R, K = int(t2d.shape[0]), int(t2d.shape[1])
+    dev = t2d.device
+    if K % 2:                      # odd widths: the two single-layout kernels (same max|.| in
+        if mask is not None:       # both -> the same power-of-two scale)
+            t2d = t2d * (mask > 0)
+        if col_sum is not None:
+            col_sum += t2d.sum(0)
+        pl, sc = _tc_split(t2d) if want[0] else (None, None)
+        plt, sct = _tc_split_t(t2d) if want[1] else (None, None)
+        return _Planes(pl, plt, sc if sc is not None else sct, R, K)
+    Kp = lib.load().zsb_linear_tc_kpad(K)
+    Rp = lib.load().zsb_linear_tc_kpad(R)
+    planes = torch.empty((2, R, Kp), dtype=torch.float16, device=dev) if want[0] else None
+    planes_t = torch.empty((2, K, Rp), dtype=torch.float16, device=dev) if want[1] else None
+    scale = amax if amax is not None else torch.zeros(4, dtype=torch.float32, device=dev)
+    m = None if mask is None else mask.detach().to(torch.float32).contiguous()
+    lib.call("zsb_split16_dual_f32", ptr(t2d), ptr(m), R, K, ptr(planes), ptr(planes_t),
+             ptr(col_sum), ptr(scale), int(amax is not None), stream())
+    return _Planes(planes, planes_t, scale, R, K)
+
+
+def _planes_of(h2, src, need_t):
+    """Operand planes of activation ``h2`` (= ``src`` flattened to 2-D), cached on ``src``: the
+    producing GEMM left the max |.| in ``src._zsb_amax`` (no max pass), and every consumer of the
+    same activation (e.g. the two heads of the encoder) shares one split."""
+    R, K = int(h2.shape[0]), int(h2.shape[1])
+    pl = getattr(src, "_zsb_pl", None)
+    if (pl is not None and pl.rows == R and pl.K == K and pl.planes is not None
+            and (not need_t or pl.planes_t is not None)):
+        return pl
+    amax = getattr(src, "_zsb_amax", None)
+    pl = _tc_split_dual(h2, want=(True, need_t), amax=None if K % 2 else amax)
+    try:
+        src._zsb_pl = pl
+        if amax is not None:
+            del src._zsb_amax
+    except (AttributeError, RuntimeError):
+        pass
+    return pl
+
+
+def _tc_grad_input(gpl, W, R):
+    """dh [R, K] = g [R, J] @ W [J, K] on the tensor cores (+ the scale slot holding max|dh|)."""
     wtp, wts = _tc_split(W.detach().t())
-    gp, gs = _tc_split(g)
-    return _tc_linear(0, wtp, wts, gp, gs, None, None, None, int(g.shape[0]),
-                      int(W.shape[1]), int(W.shape[0]))
+    amax = torch.zeros(4, dtype=torch.float32, device=W.device)
+    dh = _tc_linear(0, wtp, wts, gpl.planes, gpl.scale, None, None, None, R,
+                    int(W.shape[1]), int(W.shape[0]), amax=amax)
+    return dh, amax
 
 
-def _tc_grad_weight(g, h2):
-    """dW [J, K] = g^T [J, R] @ h [R, K]: contraction over the rows, split-K
-    over the CTA pairs."""
-    htp, hts = _tc_split_t(h2)
-    gtp, gts = _tc_split_t(g)
-    return _tc_linear(0, htp, hts, gtp, gts, None, None, None, int(g.shape[1]),
-                      int(h2.shape[1]), int(h2.shape[0]), split_k=True)
+def _tc_grad_weight(gpl, hpl, R):
+    """dW [J, K] = g^T [J, R] @ h [R, K]: contraction over the rows, split-K over the CTA pairs;
+    both operands in the transposed plane layout."""
+    return _tc_linear(0, hpl.planes_t, hpl.scale, gpl.planes_t, gpl.scale, None, None, None,
+                      gpl.K, hpl.K, R, split_k=True)
 
 
 def _tc_linear(epi, wp, ws, hp, hs, bias, x, gout, R, J, K, relu=False,
-               split_k=False):
+               split_k=False, amax=None):
     from ._lib import lib, ptr, stream
     dev = hp.device
     part = None
@@ -192,43 +331,60 @@ def _tc_linear(epi, wp, ws, hp, hs, bias, x, gout, R, J, K, relu=False,
                            dtype=torch.float32, device=dev)
     else:
         out = torch.empty((R, J), dtype=torch.float32, device=dev)
-    lib.call("zsb_linear_tc_f32", epi, ptr(wp), ptr(ws), ptr(hp), ptr(hs),
+    lib.call("zsb_linear_tc_amax_f32", epi, ptr(wp), ptr(ws), ptr(hp), ptr(hs),
              ptr(bias), ptr(x), int(x.shape[0]) if x is not None else 0,
-             ptr(gout), ptr(out), ptr(part), R, J, K, int(bool(relu)), stream())
+             ptr(gout), ptr(out), ptr(part), R, J, K, int(bool(relu)), ptr(amax), stream())
     return out
 
 
+def _tag(t, amax):
+    try:
+        t._zsb_amax = amax
+    except (AttributeError, RuntimeError):
+        pass
+    return t
+
+
 class _Linear(torch.autograd.Function):
-    """y = relu?(h W^T + b): forward and both backward products on the
-    tcgen05 kernel at fp32 accuracy (epi 0; the weight gradient uses the
-    transposed operand planes and split-K)."""
+    """y = relu?(h W^T + b): forward and both backward products on the tcgen05 kernel at fp32
+    accuracy (epi 0; the weight gradient uses the transposed operand planes and split-K).
+    Memory passes around the GEMMs are fused (round 2): every GEMM leaves max|out| for its
+    consumer's scale, ONE pass (zsb_split16_dual_f32) turns an activation / gradient into both
+    operand layouts, applies the ReLU mask and accumulates the bias gradient."""
 
     @staticmethod
     def forward(ctx, h, W, b, relu):
         lead = h.shape[:-1]
-        h2 = h.reshape(-1, h.shape[-1])
+        h2 = h if h.dim() == 2 else h.reshape(-1, h.shape[-1])
         R, K, J = int(h2.shape[0]), int(h2.shape[1]), int(W.shape[0])
+        need_dw = bool(ctx.needs_input_grad[1])
+        hpl = _planes_of(h2, h, need_dw)
         wp, ws = _tc_split(W)
-        hp, hs = _tc_split(h2)
         bias = b.detach().to(torch.float32).contiguous() if b is not None else None
-        y = _tc_linear(0, wp, ws, hp, hs, bias, None, None, R, J, K, relu)
-        ctx.save_for_backward(h2, W, y if relu else None)
-        ctx.meta = (lead, relu, b is not None)
-        return y.reshape(tuple(lead) + (J,))
+        amax = torch.zeros(4, dtype=torch.float32, device=h2.device)
+        y = _tc_linear(0, wp, ws, hpl.planes, hpl.scale, bias, None, None, R, J, K, relu,
+                       amax=amax)
+        ctx.save_for_backward(W, y if relu else None)
+        ctx.hpl = hpl
+        ctx.meta = (lead, relu, b is not None, R, K, J)
+        return _tag(y.reshape(tuple(lead) + (J,)), amax)
 
     @staticmethod
     def backward(ctx, gy):
-        h2, W, y = ctx.saved_tensors
-        lead, relu, has_b = ctx.meta
-        g = gy.reshape(-1, gy.shape[-1])
-        if relu:
-            g = g * (y > 0)
-        g = g.to(torch.float32).contiguous()
+        W, y = ctx.saved_tensors
+        lead, relu, has_b, R, K, J = ctx.meta
         need = ctx.needs_input_grad
-        dh = _tc_grad_input(g, W).reshape(tuple(lead) + (W.shape[1],)) \
-            if need[0] else None
-        dW = _tc_grad_weight(g, h2) if need[1] else None
-        db = g.sum(0) if (has_b and need[2]) else None
+        g = gy.reshape(-1, J)
+        db = torch.zeros(J, dtype=torch.float32, device=g.device) \
+            if (has_b and need[2]) else None
+        gpl = _tc_split_dual(g, mask=y if relu else None, want=(bool(need[0]), bool(need[1])),
+                             amax=getattr(gy, "_zsb_amax", None), col_sum=db)
+        dh = None
+        if need[0]:
+            dh2, amax = _tc_grad_input(gpl, W, R)
+            dh = _tag(dh2.reshape(tuple(lead) + (K,)), amax)
+        dW = _tc_grad_weight(gpl, ctx.hpl, R) if need[1] else None
+        ctx.hpl = None
         return dh, dW, db, None
 
 
@@ -246,31 +402,39 @@ class _LinearBernoulliLogProb(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, W, b, x):
         lead = h.shape[:-1]
-        h2 = h.reshape(-1, h.shape[-1])
+        h2 = h if h.dim() == 2 else h.reshape(-1, h.shape[-1])
         R, K, J = int(h2.shape[0]), int(h2.shape[1]), int(W.shape[0])
         x2 = x.reshape(-1, J).to(torch.float32).contiguous()
         if R % int(x2.shape[0]) != 0:
             raise ValueError("rows of the observation (%d) must divide the rows "
                              "of the activations (%d)" % (x2.shape[0], R))
         wp, ws = _tc_split(W)
-        hp, hs = _tc_split(h2)
+        hpl = _planes_of(h2, h, bool(ctx.needs_input_grad[1]))
         bias = b.detach().to(torch.float32).contiguous() if b is not None else None
-        lp = _tc_linear(1, wp, ws, hp, hs, bias, x2, None, R, J, K)
-        ctx.save_for_backward(h2, W, bias, x2, wp, ws, hp, hs)
+        lp = _tc_linear(1, wp, ws, hpl.planes, hpl.scale, bias, x2, None, R, J, K)
+        ctx.save_for_backward(W, bias, x2, wp, ws)
+        ctx.hpl = hpl
         ctx.meta = (lead, R, J, K, b is not None)
         return lp.reshape(tuple(lead))
 
     @staticmethod
     def backward(ctx, glp):
-        h2, W, bias, x2, wp, ws, hp, hs = ctx.saved_tensors
+        W, bias, x2, wp, ws = ctx.saved_tensors
         lead, R, J, K, has_b = ctx.meta
-        g = glp.reshape(-1).to(torch.float32).contiguous()
-        dl = _tc_linear(2, wp, ws, hp, hs, bias, x2, g, R, J, K)
+        hpl = ctx.hpl
         need = ctx.needs_input_grad
-        dh = _tc_grad_input(dl, W).reshape(tuple(lead) + (K,)) \
-            if need[0] else None
-        dW = _tc_grad_weight(dl, h2) if need[1] else None
-        db = dl.sum(0) if (has_b and need[2]) else None
+        g = glp.reshape(-1).to(torch.float32).contiguous()
+        amax = torch.zeros(4, dtype=torch.float32, device=g.device)
+        dl = _tc_linear(2, wp, ws, hpl.planes, hpl.scale, bias, x2, g, R, J, K, amax=amax)
+        db = torch.zeros(J, dtype=torch.float32, device=g.device) \
+            if (has_b and need[2]) else None
+        dlpl = _tc_split_dual(dl, want=(bool(need[0]), bool(need[1])), amax=amax, col_sum=db)
+        dh = None
+        if need[0]:
+            dh2, a2 = _tc_grad_input(dlpl, W, R)
+            dh = _tag(dh2.reshape(tuple(lead) + (K,)), a2)
+        dW = _tc_grad_weight(dlpl, hpl, R) if need[1] else None
+        ctx.hpl = None
         return dh, dW, db, None
 
 

@@ -128,6 +128,7 @@ class HMC(object):
         self._dense_impl = dense_impl
         self._use_graph = bool(use_cuda_graph)
         self._graphs = {}
+        self._graph_launches = {}
         self._dev_mode = False   # True while capturing / replaying a graph
         self._t = 0              # host mirror of hmc.py:264 (deterministic)
         self._ewmv_t = 0         # host mirror of hmc.py:118
@@ -163,6 +164,12 @@ class HMC(object):
         fused = getattr(meta_bn, "_zsb_fused", None)
         if fused is None and not callable(meta_bn):
             fused = _detect_diag_normal(meta_bn, self._observed, latent)
+        # kind "provider": the log-joint object computes its own values / gradients with a
+        # fused kernel (e.g. zs.fused.LNTMLogJoint); everything else runs on the generic path
+        self._provider = None
+        if fused is not None and fused["kind"] == "provider":
+            self._provider = fused["obj"]
+            fused = None
         self._fused = fused
 
         if fused is not None and fused["kind"] == "dense_gaussian":
@@ -251,11 +258,15 @@ class HMC(object):
 
     # ---------------------------------------------------------------- helpers
     def _get_log_posterior(self, var_list):                   # hmc.py:426-428
+        if self._provider is not None:
+            return self._provider.logp(var_list)
         joint_obs = merge_dicts(dict(zip(self._latent_k, var_list)),
                                 self._observed)
         return self._log_joint(joint_obs)
 
     def _get_gradient(self, var_list):                        # hmc.py:430-432
+        if self._provider is not None:
+            return self._provider.grad(var_list)
         xs = [v.detach().requires_grad_(True) for v in var_list]
         with torch.enable_grad():
             lp = self._get_log_posterior(xs)
@@ -346,6 +357,7 @@ class HMC(object):
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             self._dev_mode = True
+            l0 = lib.launches
             try:
                 with torch.cuda.graph(g):
                     self._iterate_eager(adapt_step, adapt_m, None, self._t,
@@ -353,9 +365,12 @@ class HMC(object):
             finally:
                 self._dev_mode = False
             self._graphs[key] = g
+            self._graph_launches[key] = lib.launches - l0
+            lib.launches = l0              # capturing launched nothing
         if adapt_m and self._has_mass:
             self._ewmv_t += 1
         g.replay()
+        lib.launches += self._graph_launches[key]   # kernels the replay launches
         if self._world > 1:
             self._pk.n_collectives += 1        # the all-reduce captured in the graph
         self._pk.mass_valid = bool(adapt_m and self._has_mass)

@@ -124,6 +124,28 @@ class SGMCMC(object):
         self.t += 1                                        # sgmcmc.py:107-108
         return None
 
+    # ----------------------------------------------------------- checkpointing
+    _STATE_LISTS = ("vs", "alphas", "_alpha1", "_mean_k")
+
+    def state_dict(self):
+        """All sampler state besides the latents themselves: the iteration counter ``t``
+        (sgmcmc.py:73) and the auxiliary variables of the update rule -- PSGLD's second-moment
+        accumulator, SGHMC / SGNHT momenta, SGNHT thermostats (sgmcmc.py:225-226, 320-324,
+        450-458).  The reference keeps them in tf.Variables and has no checkpoint API."""
+        d = {"t": int(self.t), "lr": float(self.lr)}
+        for name in self._STATE_LISTS:
+            if hasattr(self, name):
+                d[name] = [x.clone() for x in getattr(self, name)]
+        return d
+
+    def load_state_dict(self, d):
+        self.t = int(d["t"])
+        self.lr = float(d.get("lr", self.lr))
+        for name in self._STATE_LISTS:
+            if name in d:
+                for dst, src in zip(getattr(self, name), d[name]):
+                    dst.copy_(src)
+
     def _noise(self, noise, key, k):
         n = noise.get(key)
         return None if n is None else ptr(n[self._latent_k[k]].contiguous())

@@ -23,6 +23,11 @@ def convert_to_tensor(x, dtype=None, device=None):
         device = "cuda" if torch.cuda.is_available() else "cpu"
     if dtype is None and isinstance(x, float):
         dtype = torch.float32
+    if isinstance(x, (bool, int, float)):
+        # a device-side fill, not a host-to-device copy: legal inside CUDA-graph capture
+        dt = dtype or (torch.bool if isinstance(x, bool) else
+                       torch.int32 if isinstance(x, int) else torch.float32)
+        return torch.full((), x, dtype=dt, device=device)
     t = torch.as_tensor(x, device=device)
     if dtype is not None:
         t = t.to(dtype)
