@@ -47,34 +47,39 @@ def step_fn(W, x, K, dev, fused=False):
         lin = lambda h, w, b, relu=False: (F.relu(F.linear(h, w, b)) if relu
                                            else F.linear(h, w, b))
 
-    @zs.meta_bayesian_net(scope="gen", reuse_variables=True)
-    def build_gen(n, n_particles):                                   # iwae.py:23-32
-        bn = zs.BayesianNet()
-        z = bn.normal("z", torch.zeros(n, z_dim, device=dev), std=1., group_ndims=1,
-                      n_samples=n_particles)
-        hh = lin(z.tensor, W["d1"], W["d1_b"], True)
-        hh = lin(hh, W["d2"], W["d2_b"], True)
-        if fused:
-            bn.stochastic("x", zs.fused.LinearBernoulli(hh, W["d3"], W["d3_b"]))
-        else:
-            bn.bernoulli("x", F.linear(hh, W["d3"], W["d3_b"]), group_ndims=1)
-        return bn
-
-    def build_q_net(x, n_particles):                                 # iwae.py:35-44
-        bn = zs.BayesianNet()
-        hh = lin(x.float(), W["e1"], W["e1_b"], True)
-        hh = lin(hh, W["e2"], W["e2_b"], True)
-        bn.normal("z", lin(hh, W["em"], W["em_b"]), logstd=lin(hh, W["es"], W["es_b"]),
-                  group_ndims=1, n_samples=n_particles)
-        return bn
-
     def step():
+        # fresh leaves every step (views of the parameters, no copy): under CUDA-graph capture the
+        # autograd engine then works on the capturing stream only (a leaf created on the legacy
+        # stream would make that stream depend on the capture)
+        Wd = {k: v.detach().requires_grad_(True) for k, v in W.items()}
+
+        @zs.meta_bayesian_net(scope="gen", reuse_variables=True)
+        def build_gen(n, n_particles):                                   # iwae.py:23-32
+            bn = zs.BayesianNet()
+            z = bn.normal("z", torch.zeros(n, z_dim, device=dev), std=1., group_ndims=1,
+                          n_samples=n_particles)
+            hh = lin(z.tensor, Wd["d1"], Wd["d1_b"], True)
+            hh = lin(hh, Wd["d2"], Wd["d2_b"], True)
+            if fused:
+                bn.stochastic("x", zs.fused.LinearBernoulli(hh, Wd["d3"], Wd["d3_b"]))
+            else:
+                bn.bernoulli("x", F.linear(hh, Wd["d3"], Wd["d3_b"]), group_ndims=1)
+            return bn
+
+        def build_q_net(x, n_particles):                                 # iwae.py:35-44
+            bn = zs.BayesianNet()
+            hh = lin(x.float(), Wd["e1"], Wd["e1_b"], True)
+            hh = lin(hh, Wd["e2"], Wd["e2_b"], True)
+            bn.normal("z", lin(hh, Wd["em"], Wd["em_b"]), logstd=lin(hh, Wd["es"], Wd["es_b"]),
+                      group_ndims=1, n_samples=n_particles)
+            return bn
+
         model = build_gen(n, K)
         variational = build_q_net(x, K)
         lb = zs.variational.iw_objective(model, {'x': x}, variational=variational, axis=0)
-        cost = torch.mean(lb.sgvb())                                 # iwae.py:72-75
-        grads = torch.autograd.grad(cost, list(W.values()))
-        return cost, grads
+        cost = torch.mean(lb.sgvb())                                     # iwae.py:72-75
+        grads = torch.autograd.grad(cost, list(Wd.values()))
+        return cost.detach(), grads
     return step
 
 
