@@ -76,8 +76,11 @@ def parse():
                          "--total-chains split over the GPUs")
     ap.add_argument("--total-chains", type=int, default=65536)
     ap.add_argument("--chains-per-gpu", type=int, default=65536)
-    ap.add_argument("--cuda-graph", action="store_true",
-                    help="replay the HMC iteration (incl. its all-reduce) from a CUDA graph")
+    ap.add_argument("--cuda-graph", action="store_true", default=None,
+                    help="replay the step (incl. its all-reduce) from a CUDA graph; default: on "
+                         "for --workload iwae (the eager step is host-bound: ~80 launches + "
+                         "autograd bookkeeping), off for hmc")
+    ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
     ap.add_argument("--iwae-batch", type=int, default=4096)
     ap.add_argument("--iwae-particles", type=int, default=64)
     ap.add_argument("--cpu-batch", type=int, default=128)
@@ -282,6 +285,8 @@ def main():
     if args.scaling == "strong":
         w = int(os.environ.get("WORLD_SIZE", "1")) if args.impl != "reference" else args.gpus
         args.chains_per_gpu = args.total_chains // max(1, w)
+    if args.cuda_graph is None:
+        args.cuda_graph = args.workload == "iwae"
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "iwae":
