@@ -170,6 +170,21 @@ def test_reinforce_reference_test(zs, x_mean, x_std, rtol, atol):
     c3, bc = lb2.reinforce(baseline=b)
     assert torch.isfinite(c3) and torch.isfinite(bc)
     assert torch.autograd.grad(bc, [b])[0] is not None
+    # the moving-mean baseline is ONE persistent variable (tf.get_variable('moving_mean'),
+    # exclusive_kl.py:209-216): it keeps averaging across objective instances / training steps
+    from zhusuan_b200.variational import exclusive_kl as EK
+    EK.reset_moving_mean()
+    signal = float((log_joint({'x': qx}) - log_qx).mean())
+    mm, decay = 0.0, 0.8
+    for step in range(4):
+        with pytest.warns(FutureWarning):
+            lbk = zs.variational.elbo(log_joint, observed={}, latent={'x': [qx, log_qx]}, axis=0)
+        lbk.reinforce(decay=decay)
+        mm = mm - (1 - decay) * (mm - signal)
+        np.testing.assert_allclose(float(lbk._moving_mean), mm, rtol=1e-5)
+    own = torch.zeros((), device="cuda")
+    lbk.reinforce(decay=decay, moving_mean=own)              # caller-held variable, in place
+    np.testing.assert_allclose(float(own), 0.2 * signal, rtol=1e-5)
 
 
 def test_effective_sample_size_vs_oracle(zs):

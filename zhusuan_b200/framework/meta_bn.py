@@ -1,6 +1,17 @@
-"""MetaBayesianNet / meta_bayesian_net (zhusuan/framework/meta_bn.py:29-148)."""
-import copy
-from functools import wraps
+"""Deferred model construction: ``MetaBayesianNet`` / ``@meta_bayesian_net``.
+
+Contract mirrored from zhusuan/framework/meta_bn.py:29-148: a model is a *function* that builds a
+``BayesianNet``; the decorator captures the call (function + arguments) instead of running it, and
+every ``observe(**{name: value})`` replays the call with the observations published to the nodes
+being built, so that ``bn.stochastic(name, ...)`` picks its value up by name (bn.py:348-371).
+``meta_bn.log_joint = fn`` overrides the default sum of conditional log-probs (bn.py:454-465).
+
+How the observations reach the net under construction: a build *frame* (who is building, with
+which observations) is pushed on a per-class stack for the duration of the builder call;
+``_BayesianNet.__init__`` looks at the innermost frame.  ``Local`` is that frame type -- the name
+the reference uses and the one bn.py imports.
+"""
+import functools
 
 from .utils import Context
 
@@ -8,54 +19,59 @@ __all__ = ["MetaBayesianNet", "meta_bayesian_net"]
 
 
 class Local(Context):
-    def __getattr__(self, item):
-        return self.__dict__.get(item, None)
+    """One build frame: ``observations`` (dict name -> value) and ``meta_bn`` (the owner)."""
 
-    def __setattr__(self, key, value):
-        self.__dict__[key] = value
+    def __init__(self, meta_bn=None, observations=None):
+        self.meta_bn = meta_bn
+        self.observations = dict(observations or {})
+
+
+class _DeferredCall(object):
+    """``fn(*args, **kwargs)`` frozen for later replays (shallow copies, as the reference takes)."""
+
+    __slots__ = ("fn", "args", "kwargs")
+
+    def __init__(self, fn, args, kwargs):
+        self.fn = fn
+        self.args = tuple(args or ())
+        self.kwargs = dict(kwargs or {})
+
+    def __call__(self):
+        return self.fn(*self.args, **self.kwargs)
 
 
 class MetaBayesianNet(object):
-    """A lazily-built Bayesian net: ``observe(**obs)`` re-runs the builder
-    under a Local context carrying the observations (meta_bn.py:87-106)."""
+    """A Bayesian net that is (re)built on demand.
 
-    def __init__(self, f, args=None, kwargs=None, scope=None,
-                 reuse_variables=False):
+    :param f: the builder; must return a ``BayesianNet``.
+    :param args / kwargs: its arguments (meta_bn.py:50-56).
+    :param scope / reuse_variables: TF variable-scope options of the reference.  Parameters
+        here are explicit tensors owned by the caller, so they only keep their validation:
+        ``reuse_variables`` without a ``scope`` is an error (meta_bn.py:57-60).
+    """
+
+    def __init__(self, f, args=None, kwargs=None, scope=None, reuse_variables=False):
         if reuse_variables and scope is None:
-            raise ValueError("Cannot reuse tensorflow Variables when `scope` "
-                             "is not provided.")
-        self._f = f
-        self._args = copy.copy(args) or ()
-        self._kwargs = copy.copy(kwargs) or {}
-        self._scope = scope
-        self._reuse_variables = reuse_variables
-        self._log_joint = None
+            raise ValueError("Cannot reuse tensorflow Variables when `scope` is not provided.")
+        self._build = _DeferredCall(f, args, kwargs)
+        self._scope, self._reuse_variables = scope, bool(reuse_variables)
+        self.log_joint = None       # None: sum of cond_log_p; else a callable bn -> log joint
 
-    @property
-    def log_joint(self):
-        return self._log_joint
-
-    @log_joint.setter
-    def log_joint(self, value):
-        self._log_joint = value
-
-    def _run_with_observations(self, func, observations):
-        with Local() as local_cxt:
-            local_cxt.observations = observations
-            local_cxt.meta_bn = self
-            return func(*self._args, **self._kwargs)
-
-    def observe(self, **kwargs):
-        return self._run_with_observations(self._f, kwargs)
+    def observe(self, **observations):
+        """Build the net with the named stochastic nodes fixed to the given values
+        (meta_bn.py:87-106) and return it."""
+        with Local(meta_bn=self, observations=observations):
+            return self._build()
 
 
 def meta_bayesian_net(scope=None, reuse_variables=False):
-    """Decorator turning a BayesianNet-building function into a
-    MetaBayesianNet factory (meta_bn.py:109-148)."""
-    def wrapper(f):
-        @wraps(f)
-        def _wrapped(*args, **kwargs):
-            return MetaBayesianNet(f, args=args, kwargs=kwargs, scope=scope,
+    """``@zs.meta_bayesian_net(scope=..., reuse_variables=...)``: calling the decorated function
+    no longer builds the net but returns the ``MetaBayesianNet`` holding that call
+    (meta_bn.py:109-148)."""
+    def decorate(builder):
+        @functools.wraps(builder)
+        def make(*args, **kwargs):
+            return MetaBayesianNet(builder, args=args, kwargs=kwargs, scope=scope,
                                    reuse_variables=reuse_variables)
-        return _wrapped
-    return wrapper
+        return make
+    return decorate

@@ -27,9 +27,16 @@ class EvidenceLowerBoundObjective(VariationalObjective):
     def sgvb(self):                                # exclusive_kl.py:139-159
         return -self.tensor
 
-    def reinforce(self, variance_reduction=True, baseline=None, decay=0.8):
+    def reinforce(self, variance_reduction=True, baseline=None, decay=0.8,
+                  moving_mean=None):
         """exclusive_kl.py:161-231 (score-function estimator; host-composed
-        from the same kernels -- a "next" row)."""
+        from the same kernels -- a "next" row).
+
+        The reference keeps the moving-mean baseline in ``tf.get_variable('moving_mean')``
+        (exclusive_kl.py:209-216): ONE variable that persists across ``sess.run`` steps.  Here an
+        objective is rebuilt every step, so the variable lives in a module-level registry
+        (one per device, ``reset_moving_mean()`` clears it) or in the 0-d tensor passed as
+        ``moving_mean`` (updated in place) -- not on the short-lived objective instance."""
         l_signal = self._log_joint_term() + self._entropy_term()
         baseline_cost = None
         if variance_reduction:
@@ -41,12 +48,15 @@ class EvidenceLowerBoundObjective(VariationalObjective):
                                                     ops.OP_MEAN, self._axis)
                 l_signal = l_signal - baseline
             bc = l_signal.detach().mean()
-            if not hasattr(self, "_moving_mean"):
-                self._moving_mean = torch.zeros((), device=bc.device)
-            # assign_moving_average: mm -= (1 - decay) * (mm - bc)
-            self._moving_mean = self._moving_mean - (1 - decay) * (
-                self._moving_mean - bc)
-            l_signal = l_signal - self._moving_mean
+            mm = moving_mean
+            if mm is None:
+                mm = _MOVING_MEAN.get(bc.device)
+                if mm is None:
+                    mm = _MOVING_MEAN[bc.device] = torch.zeros((), device=bc.device)
+            # assign_moving_average: mm -= (1 - decay) * (mm - bc), in place on the variable
+            mm.sub_((1 - decay) * (mm - bc))
+            self._moving_mean = mm
+            l_signal = l_signal - mm
         cost = -self._log_joint_term()
         if self._entropy_term() is not None:
             cost = cost + l_signal.detach() * self._entropy_term()
@@ -55,6 +65,14 @@ class EvidenceLowerBoundObjective(VariationalObjective):
         if baseline_cost is not None:
             return cost, baseline_cost
         return cost
+
+
+_MOVING_MEAN = {}      # the 'moving_mean' variable of exclusive_kl.py:209-212, one per device
+
+
+def reset_moving_mean():
+    """Forget the REINFORCE moving-mean baseline (a fresh ``tf.global_variables_initializer``)."""
+    _MOVING_MEAN.clear()
 
 
 def elbo(meta_bn, observed, latent=None, axis=None, variational=None):
