@@ -343,6 +343,17 @@ int zsb_sample_dirichlet_f32(const float* alpha, int64_t alpha_rows, int64_t n_r
 int zsb_sample_gamma_f32(const float* alpha, int64_t alpha_rows, const float* beta,
                          int64_t beta_rows, int64_t n_rows, int64_t row_len, uint64_t seed,
                          uint32_t iter, float* out, void* stream);
+/* Base noise (kind 0: U[0,1), kind 1: N(0,1)) for the samplers whose transform is composed on the
+ * host side (tf.random_uniform / tf.random_normal of univariate.py:306-317, 622-640, 1246-1265,
+ * 1363-1379): Philox block (i / 4, 0, iter, 9), word i % 4. */
+int zsb_sample_base_noise_f32(int kind, float* out, int64_t n, uint64_t seed, uint32_t iter,
+                              void* stream);
+/* Poisson._sample (univariate.py:915-920) / Binomial._sample (univariate.py:1025-1045): kind 0 =
+ * Poisson(rate = param), 1 = Binomial(n_experiments, sigmoid(param)); one uniform per draw
+ * (injected u [n] or Philox), inverse transform enumerating the support outwards from the mode. */
+int zsb_sample_count_i32(int kind, const float* param, int64_t param_n, int64_t n_experiments,
+                         const float* u, uint64_t seed, uint32_t iter, int32_t* out, int64_t n,
+                         void* stream);
 
 /* ---- K8, config 5: Logistic-Normal Topic Model E-step log-joint (csrc/lntm.cu) -----------------
  * log p = sum_k Normal(eta_k; mean_k, exp(logstd_k)).log_prob + sum_v x[d,v] log(softmax(eta) @ phi)[v]

@@ -90,3 +90,60 @@ def dirichlet(alpha, n_samples, seed, it):
     full = np.broadcast_to(a, (n_samples,) + a.shape).reshape(-1)
     g = gamma_marsaglia_tsang(full, seed, it).reshape(-1, C)
     return (g / g.sum(-1, keepdims=True)).reshape((n_samples,) + a.shape)
+
+
+STREAM_COUNT = 8
+
+
+def count_uniforms(seed, it, n):
+    """The uniform of draw i: word i % 4 of Philox block (i // 4, 0, it, STREAM_COUNT)."""
+    i = np.arange(n, dtype=np.uint64)
+    key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], np.uint32)
+    ctr = PH.counter(STREAM_COUNT, it, np.uint32(0), (i >> np.uint64(2)).astype(np.uint32))
+    w = PH.philox4x32_10(ctr, key)
+    return PH.u32_to_uniform(w[np.arange(n), (i & np.uint64(3)).astype(np.int64)])
+
+
+def _invert_from_mode(u, mode, pmf, kmax):
+    """Inverse transform visiting mode, mode+1, mode-1, mode+2, ... (float64 pmf callable)."""
+    s = pmf(mode)
+    if u < s:
+        return mode
+    lo = hi = mode
+    for _ in range(10 * (kmax if kmax < 10 ** 8 else 10 ** 5) + 100):
+        if hi < kmax:
+            hi += 1
+            s += pmf(hi)
+            if u < s:
+                return hi
+        if lo > 0:
+            lo -= 1
+            s += pmf(lo)
+            if u < s:
+                return lo
+        if hi >= kmax and lo <= 0:
+            break
+    return hi
+
+
+def poisson_inverse(rate, u):
+    """Poisson draws from uniforms, the kernel's enumeration order (float64 pmf)."""
+    from scipy import stats
+    rate, u = np.broadcast_arrays(np.asarray(rate, np.float64), np.asarray(u, np.float64))
+    out = np.empty(u.shape, np.int32)
+    for idx in np.ndindex(u.shape):
+        lam = rate[idx]
+        out[idx] = _invert_from_mode(u[idx], int(np.floor(lam)),
+                                     lambda k: stats.poisson.pmf(k, lam), 10 ** 9) if lam > 0 else 0
+    return out
+
+
+def binomial_inverse(logits, n, u):
+    from scipy import stats
+    logits, u = np.broadcast_arrays(np.asarray(logits, np.float64), np.asarray(u, np.float64))
+    out = np.empty(u.shape, np.int32)
+    for idx in np.ndindex(u.shape):
+        p = 1.0 / (1.0 + np.exp(-logits[idx]))
+        m = min(n, int(np.floor((n + 1) * p)))
+        out[idx] = _invert_from_mode(u[idx], m, lambda k: stats.binom.pmf(k, n, p), n)
+    return out

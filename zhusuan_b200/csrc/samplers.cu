@@ -145,6 +145,107 @@ __global__ void __launch_bounds__(256) gamma_rows_kernel(
   }
 }
 
+#define ZSB_STREAM_COUNT 8u
+
+// Inverse transform of a unimodal integer distribution with ONE uniform, visiting the outcomes in
+// the order mode, mode+1, mode-1, mode+2, ... (any fixed enumeration of the support with running
+// sums is a valid inverse CDF; this one needs O(std) steps).  pm = pmf(mode); up(k) = pmf(k+1) /
+// pmf(k); down(k) = pmf(k-1) / pmf(k); support [0, kmax].
+template <class Up, class Down>
+__device__ __forceinline__ int invert_from_mode(float u, int mode, float pm, int kmax, int max_steps,
+                                                Up up, Down down) {
+  float s = pm;
+  if (u < s) return mode;
+  int lo = mode, hi = mode;
+  float plo = pm, phi = pm;
+  for (int it = 0; it < max_steps; ++it) {
+    if (hi < kmax) {
+      phi *= up(hi); ++hi; s += phi;
+      if (u < s) return hi;
+    }
+    if (lo > 0) {
+      plo *= down(lo); --lo; s += plo;
+      if (u < s) return lo;
+    }
+    if (hi >= kmax && lo <= 0) break;
+  }
+  return hi;          // u within float round-off of 1: the far tail
+}
+
+// kind 0: Poisson(rate = a[i % a_n]);  kind 1: Binomial(n, p = sigmoid(a[i % a_n])).
+__global__ void __launch_bounds__(256) count_sample_kernel(
+    int kind, const float* __restrict__ a, int64_t a_n, int n_exp, const float* __restrict__ u_in,
+    uint64_t seed, uint32_t iter, int32_t* __restrict__ out, int64_t n,
+    const uint32_t* __restrict__ epoch) {
+  if (epoch) iter += *epoch;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float u;
+    if (u_in) {
+      u = u_in[i];
+    } else {
+      const Philox4 r = philox4x32_10((uint32_t)(i >> 2), (uint32_t)((uint64_t)i >> 34), iter,
+                                      ZSB_STREAM_COUNT, (uint32_t)seed, (uint32_t)(seed >> 32));
+      const uint32_t w = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
+      u = u32_to_uniform(w);
+    }
+    const float par = a[i % a_n];
+    int k;
+    if (kind == 0) {
+      const float lam = par;
+      if (!(lam > 0.f)) { out[i] = 0; continue; }
+      const int m = (int)floorf(lam);
+      const float pm = expf((float)m * logf(lam) - lam - lgammaf((float)m + 1.f));
+      const int steps = (int)(12.f * sqrtf(lam) + 64.f);
+      k = invert_from_mode(u, m, pm, 0x7fffffff, steps,
+                           [=](int j) { return lam / (float)(j + 1); },
+                           [=](int j) { return (float)j / lam; });
+    } else {
+      const float p = 1.f / (1.f + expf(-par));
+      const float q = 1.f - p;
+      if (p <= 0.f) { out[i] = 0; continue; }
+      if (q <= 0.f) { out[i] = n_exp; continue; }
+      int m = (int)floorf((float)(n_exp + 1) * p);
+      m = m > n_exp ? n_exp : m;
+      const float pm = expf(lgammaf((float)n_exp + 1.f) - lgammaf((float)m + 1.f) -
+                            lgammaf((float)(n_exp - m) + 1.f) + (float)m * logf(p) +
+                            (float)(n_exp - m) * log1pf(-p));
+      const float odds = p / q;
+      k = invert_from_mode(u, m, pm, n_exp, n_exp + 1,
+                           [=](int j) { return (float)(n_exp - j) / (float)(j + 1) * odds; },
+                           [=](int j) { return (float)j / (float)(n_exp - j + 1) / odds; });
+    }
+    out[i] = k;
+  }
+}
+
+#define ZSB_STREAM_BASE 9u
+
+// out[i] = uniform [0, 1) (kind 0) or standard normal (kind 1): the base noise of the
+// reparameterised samplers; one Philox block per 4 consecutive elements.
+__global__ void __launch_bounds__(256) base_noise_kernel(int kind, float* __restrict__ out,
+                                                         int64_t n, uint64_t seed, uint32_t iter,
+                                                         const uint32_t* __restrict__ epoch) {
+  if (epoch) iter += *epoch;
+  const int64_t n4 = (n + 3) / 4;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n4;
+       b += (int64_t)gridDim.x * blockDim.x) {
+    const Philox4 r = philox4x32_10((uint32_t)b, (uint32_t)((uint64_t)b >> 32), iter,
+                                    ZSB_STREAM_BASE, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float v[4];
+    if (kind == 0) {
+      v[0] = u32_to_uniform(r.x); v[1] = u32_to_uniform(r.y);
+      v[2] = u32_to_uniform(r.z); v[3] = u32_to_uniform(r.w);
+    } else {
+      box_muller(r.x, r.y, v[0], v[1]);
+      box_muller(r.z, r.w, v[2], v[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * b + j < n) out[4 * b + j] = v[j];
+  }
+}
+
 inline unsigned warp_grid(int64_t n_warps) {
   int64_t blocks = zsb_ceil_div(n_warps, 8);
   if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
@@ -199,6 +300,39 @@ int zsb_sample_gamma_f32(const float* alpha, int64_t alpha_rows, const float* be
       alpha, alpha_rows, beta, beta ? beta_rows : 1, nullptr, n_rows, (int)row_len, 0, seed, iter,
       out, zsb_epoch_ptr());
   return zsb_check_launch("sample_gamma");
+}
+
+// Base noise of the reparameterised samplers whose transform is composed on the host side
+// (Uniform / Laplace / FoldNormal / (Bin)Concrete / MatrixVariateNormal: tf.random_uniform /
+// tf.random_normal in univariate.py:306-317, 622-640, 1246-1265, 1363-1379): kind 0 = U[0, 1),
+// kind 1 = N(0, 1); element i = word i % 4 of Philox block (i / 4, 0, iter, 9).
+int zsb_sample_base_noise_f32(int kind, float* out, int64_t n, uint64_t seed, uint32_t iter,
+                              void* stream) {
+  ZSB_REQUIRE((kind == 0 || kind == 1) && out && n >= 0, "zsb_sample_base_noise_f32: bad args");
+  if (n == 0) return ZSB_OK;
+  int64_t blocks = zsb_ceil_div((n + 3) / 4, 256);
+  if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
+  base_noise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(kind, out, n, seed, iter,
+                                                                        zsb_epoch_ptr());
+  return zsb_check_launch("sample_base_noise");
+}
+
+// Poisson._sample (univariate.py:915-920, tf.random_poisson) / Binomial._sample (univariate.py:
+// 1025-1045: n_experiments categorical draws summed): out[i] for i < n, parameter broadcast by
+// i % param_n; kind 0 = Poisson(rate), 1 = Binomial(n_experiments, sigmoid(logits)); one uniform per
+// draw (injected `u` [n] or Philox), inverse transform from the mode.
+int zsb_sample_count_i32(int kind, const float* param, int64_t param_n, int64_t n_experiments,
+                         const float* u, uint64_t seed, uint32_t iter, int32_t* out, int64_t n,
+                         void* stream) {
+  ZSB_REQUIRE((kind == 0 || kind == 1) && param && out && param_n > 0 && n >= 0 &&
+                  (kind == 0 || (n_experiments > 0 && n_experiments < (1LL << 30))),
+              "zsb_sample_count_i32: bad args");
+  if (n == 0) return ZSB_OK;
+  int64_t blocks = zsb_ceil_div(n, 256);
+  if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
+  count_sample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      kind, param, param_n, (int)n_experiments, u, seed, iter, out, n, zsb_epoch_ptr());
+  return zsb_check_launch("sample_count");
 }
 
 }  // extern "C"

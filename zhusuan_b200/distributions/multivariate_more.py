@@ -61,8 +61,9 @@ class ExpConcrete(Distribution):
         logits, temperature = self._logits, self._temperature
         if not self.is_reparameterized:
             logits, temperature = logits.detach(), temperature.detach()
-        u = torch.rand((int(n_samples),) + tuple(logits.shape),
-                       dtype=self.dtype, device=logits.device)
+        from .. import ops
+        u = ops.base_noise(0, (int(n_samples),) + tuple(logits.shape), logits.device,
+                           *self._next_rng())
         u = u.clamp(1e-7, 1.0 - 1e-7)                 # open interval (0, 1)
         gumbel = -torch.log(-torch.log(u))
         return (logits + gumbel) / temperature
@@ -164,8 +165,9 @@ class MatrixVariateNormalCholesky(Distribution):
         mean, lu, lv = self._mean, self._u_tril, self._v_tril
         if not self.is_reparameterized:
             mean, lu, lv = mean.detach(), lu.detach(), lv.detach()
-        noise = torch.randn((int(n_samples),) + tuple(mean.shape),
-                            dtype=self.dtype, device=mean.device)
+        from .. import ops
+        noise = ops.base_noise(1, (int(n_samples),) + tuple(mean.shape), mean.device,
+                               *self._next_rng())
         return mean + lu @ noise @ lv.transpose(-1, -2)
 
     def _log_prob(self, given):

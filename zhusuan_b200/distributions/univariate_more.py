@@ -109,8 +109,8 @@ class FoldNormal(_TwoParam):
         mean, std = self._mean, self._std
         if not self.is_reparameterized:
             mean, std = mean.detach(), std.detach()
-        eps = torch.randn(_sample_shape(n_samples, self._get_batch_shape()),
-                          dtype=self.dtype, device=mean.device)
+        eps = ops.base_noise(1, _sample_shape(n_samples, self._get_batch_shape()), mean.device,
+                             *self._next_rng())
         return eps * std + mean
 
 
@@ -135,8 +135,8 @@ class Uniform(_TwoParam):
         lo, hi = self._a, self._b
         if not self.is_reparameterized:
             lo, hi = lo.detach(), hi.detach()
-        u = torch.rand(_sample_shape(n_samples, self._get_batch_shape()),
-                       dtype=self.dtype, device=lo.device)
+        u = ops.base_noise(0, _sample_shape(n_samples, self._get_batch_shape()), lo.device,
+                           *self._next_rng())
         return u * (hi - lo) + lo
 
 
@@ -209,8 +209,8 @@ class Laplace(_TwoParam):
         if not self.is_reparameterized:
             loc, scale = loc.detach(), scale.detach()
         # u in (-1, 1): inverse-CDF draw (univariate.py:1246-1265)
-        u = torch.rand(_sample_shape(n_samples, self._get_batch_shape()),
-                       dtype=self.dtype, device=loc.device)
+        u = ops.base_noise(0, _sample_shape(n_samples, self._get_batch_shape()), loc.device,
+                           *self._next_rng())
         u = (2.0 * u - 1.0).clamp(min=-1.0 + 2.0 ** -24)
         return loc - scale * torch.sign(u) * torch.log1p(-torch.abs(u))
 
@@ -252,8 +252,8 @@ class BinConcrete(_TwoParam):
         logits, temperature = self._logits, self._temperature
         if not self.is_reparameterized:
             logits, temperature = logits.detach(), temperature.detach()
-        u = torch.rand(_sample_shape(n_samples, logits.shape), dtype=self.dtype,
-                       device=logits.device).clamp(1e-7, 1.0 - 1e-7)
+        u = ops.base_noise(0, _sample_shape(n_samples, logits.shape), logits.device,
+                           *self._next_rng()).clamp(1e-7, 1.0 - 1e-7)
         logistic = torch.log(u) - torch.log1p(-u)
         return torch.sigmoid((logits + logistic) / temperature)
 
@@ -283,10 +283,13 @@ class Poisson(Distribution):
     def _get_batch_shape(self):
         return self._rate.shape
 
-    def _sample(self, n_samples):
-        r = self._rate.detach().expand(
-            _sample_shape(n_samples, self._rate.shape)).contiguous()
-        return torch.poisson(r).to(self.dtype)
+    def _sample(self, n_samples, u=None):
+        # tf.random_poisson (univariate.py:915-920) -> device sampler (inverse transform from the
+        # mode, one Philox uniform per draw; ``u``: injected uniforms for parity)
+        seed, it = self._next_rng()
+        out = ops.sample_count(0, self._rate, 0, _sample_shape(n_samples, self._rate.shape),
+                               u=u, seed=seed, it=it)
+        return out if self.dtype == torch.int32 else out.to(self.dtype)
 
     def _log_prob(self, given):
         lp = ops.univariate_log_prob(ops.UNI_POISSON, given, self._rate, None,
@@ -333,11 +336,13 @@ class Binomial(Distribution):
     def _get_batch_shape(self):
         return self._logits.shape
 
-    def _sample(self, n_samples):
-        shape = _sample_shape(n_samples, self._logits.shape)
-        p = torch.sigmoid(self._logits.detach()).expand(shape).contiguous()
-        count = torch.full(shape, float(self._n_experiments), device=p.device)
-        return torch.binomial(count, p).to(self.dtype)
+    def _sample(self, n_samples, u=None):
+        # univariate.py:1025-1045 (n categorical draws summed) -> device sampler: the count itself
+        # by inverse transform from the mode, one Philox uniform per draw
+        seed, it = self._next_rng()
+        out = ops.sample_count(1, self._logits, self._n_experiments,
+                               _sample_shape(n_samples, self._logits.shape), u=u, seed=seed, it=it)
+        return out if self.dtype == torch.int32 else out.to(self.dtype)
 
     def _log_prob(self, given):
         lp = ops.univariate_log_prob(ops.UNI_BINOMIAL, given, self._logits,

@@ -597,4 +597,26 @@ def sample_gamma(alpha, beta, shape, seed=0, it=0):
     return out
 
 
+def base_noise(kind, shape, device, seed=0, it=0):
+    """U[0,1) (``kind`` 0) or N(0,1) (1) float32 noise of ``shape`` from the in-kernel Philox."""
+    out = torch.empty(tuple(shape), dtype=_F32, device=device)
+    lib.call("zsb_sample_base_noise_f32", int(kind), ptr(out), out.numel(), int(seed), int(it),
+             stream())
+    return out
+
+
+def sample_count(kind, param, n_experiments, shape, u=None, seed=0, it=0):
+    """Poisson (kind 0, param = rate) / Binomial (kind 1, param = logits) draws of ``shape``
+    (the parameter broadcast against it): int32, one uniform per draw."""
+    p = _f32c(param.detach().to(_F32).expand(shape))
+    out = torch.empty(tuple(shape), dtype=torch.int32, device=p.device)
+    n = out.numel()
+    if n == 0:
+        return out
+    uu = None if u is None else _f32c(u.expand(shape)).reshape(-1)
+    lib.call("zsb_sample_count_i32", int(kind), ptr(p.reshape(-1)), n, int(n_experiments),
+             ptr(uu), int(seed), int(it), ptr(out), n, stream())
+    return out
+
+
 LOG_2PI = math.log(2.0 * math.pi)
