@@ -30,10 +30,17 @@ Pinning status:
     literal of tests/distributions/test_univariate.py and test_multivariate.py
     (SciPy targets as the reference computes them), tests/cases.py.
   * effective sample size: PINNED to the properties of tests/test_diagnostics.py.
-  * HMC trajectory / accept decision / step-size + mass adaptation, SG-MCMC
-    updates: the reference has NO golden vectors (tests/test_mcmc.py is
-    statistical only) and TensorFlow is not installable here, so these are
-    "parity unpinned" by the reference; the oracle itself is the pin
-    (tests/golden/*.npz generated by tests/golden/make_golden.py) and the
-    reference's statistical harness is re-run against it.
+  * HMC trajectory / accept decision / step-size search / dual averaging / mass
+    adaptation and the eight SG-MCMC update rules: PINNED to outputs of the
+    reference's own zhusuan/hmc.py and zhusuan/sgmcmc.py, imported unmodified
+    and executed on the NumPy stand-in for the TF-1.x graph API in
+    oracle/tf_shim/ (TensorFlow itself is not installable here).  Vectors:
+    tests/golden/ref_*.npz, written by oracle/tf_shim/make_ref_golden.py;
+    checked by tests/test_ref_pins.py (bit-exact on element-wise models,
+    float32 matmul-order rounding on dense ones) and regenerated + compared
+    whenever /root/reference is present.  The reference's statistical harness
+    (tests/test_mcmc.py) is re-run against the oracle as well.
+  * device sampler streams (oracle/samplers.py) and AIS (oracle/evaluation.py):
+    "parity unpinned" by the reference (it tests moments / an analytic marginal
+    only); the restatement is the pin there.
 """

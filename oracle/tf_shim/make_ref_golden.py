@@ -1,0 +1,219 @@
+"""Golden vectors produced by THE REFERENCE'S OWN SOURCE (zhusuan/hmc.py, zhusuan/sgmcmc.py),
+executed unmodified on the NumPy TensorFlow stand-in of this directory (TEST INFRASTRUCTURE ONLY).
+
+    python oracle/tf_shim/make_ref_golden.py        ->  tests/golden/ref_*.npz
+
+Needs /root/reference (it is not on the GPU box: the fixtures are committed).  Every random draw
+of the reference (tf.random_normal hmc.py:22 / sgmcmc.py:196-365, tf.random_uniform hmc.py:485) is
+replaced by injected arrays, which are stored next to the outputs; the per-iteration booleans are
+fed through placeholders exactly as the reference's examples do (hmc.py:228-231).
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("ZHUSUAN_REFERENCE", "/root/reference")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def load_reference():
+    """Register the shim as `tensorflow`, then import zhusuan.hmc / zhusuan.sgmcmc from the
+    reference checkout WITHOUT running zhusuan/__init__.py (which pulls in the whole package)."""
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    for m in [k for k in sys.modules if k == "tensorflow" or k.startswith("tensorflow.")]:
+        del sys.modules[m]
+    tf = importlib.import_module("tensorflow")
+    assert tf.__version__.endswith("numpy-shim")
+    pkg = types.ModuleType("zhusuan")
+    pkg.__path__ = [os.path.join(REF, "zhusuan")]
+    for m in [k for k in sys.modules if k == "zhusuan" or k.startswith("zhusuan.")]:
+        del sys.modules[m]
+    sys.modules["zhusuan"] = pkg
+    hmc = importlib.import_module("zhusuan.hmc")
+    sgmcmc = importlib.import_module("zhusuan.sgmcmc")
+    assert os.path.realpath(hmc.__file__).startswith(os.path.realpath(REF))
+    return tf, hmc, sgmcmc
+
+
+def dense_problem(D, seed):
+    """Sigma = A A^T / D + 0.1 I rescaled to unit diagonal (the benchmark's target family)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    A = rng.standard_normal((D, D))
+    S = A @ A.T / D + 0.1 * np.eye(D)
+    d = 1.0 / np.sqrt(np.diag(S))
+    S = S * d[:, None] * d[None, :]
+    P = np.linalg.inv(S)
+    P = 0.5 * (P + P.T)
+    _, logdet = np.linalg.slogdet(S)
+    return P, -0.5 * (D * np.log(2 * np.pi) + logdet)
+
+
+def run_reference_hmc(kind, D, C, cfg, n_iters, n_adapt, seed):
+    tf, hmc_mod, _ = load_reference()
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = {}
+    if kind == "dense":
+        P, const = dense_problem(D, seed=2)
+        mu = (0.5 * rng.standard_normal(D)).astype(np.float32)
+        P32 = P.astype(np.float32)
+        Pt, mut = tf.constant(P32), tf.constant(mu)
+
+        def log_joint(obs):                      # a callable log-joint (hmc.py:412-416)
+            xc = obs["x"] - mut
+            return -0.5 * tf.reduce_sum(xc * tf.matmul(xc, Pt), axis=-1) + np.float32(const)
+        q0 = rng.standard_normal((C, D)).astype(np.float32)
+        out.update(P=P, mu=mu, const=np.float64(const))
+    else:
+        std = (1.0 / (1.0 + np.arange(D))).astype(np.float32)      # gaussian.py:29
+        logstd = np.log(std).astype(np.float32)
+        ls = tf.constant(logstd)
+
+        def log_joint(obs):        # Normal._log_prob, univariate.py:174-181, group_ndims = 1
+            x = obs["x"]
+            c = np.float32(-0.5 * np.log(2 * np.pi))
+            precision = tf.exp(-2 * ls)
+            return tf.reduce_sum(c - ls - 0.5 * precision * tf.square(x - 0.0), axis=-1)
+        q0 = (0.1 * rng.standard_normal((C, D))).astype(np.float32)
+        out.update(std=std)
+    adapt_step = tf.placeholder(tf.bool, shape=[], name="adapt_step_size")
+    adapt_mass = tf.placeholder(tf.bool, shape=[], name="adapt_mass")
+    x = tf.Variable(q0, name="x", dtype=tf.float32)
+    sampler = hmc_mod.HMC(step_size=cfg["step_size"], n_leapfrogs=cfg["n_leapfrogs"],
+                          adapt_step_size=adapt_step,
+                          target_acceptance_rate=cfg["target_acceptance_rate"],
+                          adapt_mass=adapt_mass, mass_collect_iters=cfg["mass_collect_iters"],
+                          mass_decay=cfg["mass_decay"])
+    sample_op, info = sampler.sample(log_joint, observed={}, latent={"x": x})
+    sess = tf.Session()
+    rec = {k: [] for k in ("noise_p", "noise_u", "q", "acc", "accept", "step_size", "lp", "h0",
+                           "h1", "lp0", "p0")}
+    for i in range(n_iters):
+        npz = rng.standard_normal((C, D)).astype(np.float32)
+        nu = rng.random(C).astype(np.float32)
+        tf.set_noise(normal=[npz], uniform=[nu])
+        adapt = i < n_adapt
+        _, r = sess.run([sample_op, info], feed_dict={adapt_step: adapt, adapt_mass: adapt})
+        rec["noise_p"].append(npz)
+        rec["noise_u"].append(nu)
+        rec["q"].append(np.array(x.value))
+        rec["acc"].append(r.acceptance_rate)
+        rec["accept"].append((nu < r.acceptance_rate).astype(np.int32))
+        rec["step_size"].append(np.float32(r.updated_step_size))
+        rec["lp"].append(r.log_prob)
+        rec["h0"].append(r.orig_hamiltonian)
+        rec["h1"].append(r.hamiltonian)
+        rec["lp0"].append(r.orig_log_prob)
+        rec["p0"].append(r.init_momentum["x"])
+        np.testing.assert_array_equal(r.samples["x"], x.value)
+    out.update({k: np.stack(v) for k, v in rec.items()})
+    out.update(q0=q0, n_adapt=np.int32(n_adapt),
+               **{"cfg_" + k: np.float32(v) for k, v in cfg.items()})
+    return out
+
+
+def run_reference_sgmcmc(seed=303):
+    """The eight SG-MCMC configurations of tests/golden/make_golden.py, on the reference classes."""
+    tf, _, sg = load_reference()
+    rng = np.random.Generator(np.random.PCG64(seed))
+    D, C, T = 8, 6, 5
+    std = (0.5 + 0.1 * np.arange(D)).astype(np.float32)
+    mean = np.linspace(-1, 1, D).astype(np.float32)
+    q0 = rng.standard_normal((C, D)).astype(np.float32)
+    nz = lambda: rng.standard_normal((C, D)).astype(np.float32)
+    out = {"q0": q0, "std": std, "mean": mean}
+    ls, mu = np.log(std).astype(np.float32), mean
+    configs = {
+        "sgld": (sg.SGLD, dict(learning_rate=0.01)),
+        "psgld": (sg.PSGLD, dict(learning_rate=0.01)),
+        "sghmc1": (sg.SGHMC, dict(learning_rate=0.01, friction=0.3, variance_estimate=0.02,
+                                  n_iter_resample_v=3, second_order=False)),
+        "sghmc2": (sg.SGHMC, dict(learning_rate=0.01, friction=0.3, variance_estimate=0.02,
+                                  n_iter_resample_v=3, second_order=True)),
+        "sgnht1v": (sg.SGNHT, dict(learning_rate=0.01, variance_extra=0.1, tune_rate=2.,
+                                   n_iter_resample_v=4, second_order=False,
+                                   use_vector_alpha=True)),
+        "sgnht2v": (sg.SGNHT, dict(learning_rate=0.01, variance_extra=0.1, tune_rate=2.,
+                                   n_iter_resample_v=4, second_order=True,
+                                   use_vector_alpha=True)),
+        "sgnht1s": (sg.SGNHT, dict(learning_rate=0.01, variance_extra=0.1, tune_rate=2.,
+                                   n_iter_resample_v=None, second_order=False,
+                                   use_vector_alpha=False)),
+        "sgnht2s": (sg.SGNHT, dict(learning_rate=0.01, variance_extra=0.1, tune_rate=2.,
+                                   n_iter_resample_v=None, second_order=True,
+                                   use_vector_alpha=False)),
+    }
+    for name, (cls, kw) in configs.items():
+        lst, mut = tf.constant(ls), tf.constant(mu)
+
+        def log_joint(obs):
+            x = obs["x"]
+            c = np.float32(-0.5 * np.log(2 * np.pi))
+            return tf.reduce_sum(c - lst - 0.5 * tf.exp(-2 * lst) * tf.square(x - mut), axis=-1)
+        x = tf.Variable(q0.copy(), name="x", dtype=tf.float32)
+        v0 = nz()
+        tf.set_noise(normal=[v0] * 4)          # the momentum initialisers (Variable initial values)
+        sampler = cls(**kw)
+        sample_op, info = sampler.sample(log_joint, observed={}, latent={"x": x})
+        sess = tf.Session()
+        qs, draws, mk, al = [], [], [], []
+        for t in range(T):
+            pool = [nz() for _ in range(4)]          # consumed in evaluation order
+            tf.set_noise(normal=list(pool))
+            _, r = sess.run([sample_op, info])
+            used = 4 - len(tf._NOISE["normal"])
+            qs.append(np.array(x.value))
+            draws.append(np.stack(pool))
+            out.setdefault(name + "_n_used", []).append(used)
+            if hasattr(r, "mean_k"):
+                mk.append(np.asarray(r.mean_k["x"], np.float32))
+            if hasattr(r, "alpha"):
+                al.append(np.asarray(r.alpha["x"], np.float32))
+        out[name + "_v0"] = v0
+        out[name + "_q"] = np.stack(qs)
+        draws = np.stack(draws)
+        used = np.asarray(out.pop(name + "_n_used"), np.int32)
+        # consumption order inside one run: the momentum re-draw (sgmcmc.py:306-309, 446-449)
+        # is evaluated before the injected noise of the update, so a 2-draw step is
+        # (resample, noise) and a 1-draw step is (noise,)
+        two = (used == 2)[:, None, None]
+        out[name + "_resample"] = np.where(two, draws[:, 0], 0).astype(np.float32)
+        out[name + "_noise"] = np.where(two, draws[:, 1], draws[:, 0]).astype(np.float32)
+        out[name + "_n_used"] = used
+        if mk:
+            out[name + "_mean_k"] = np.stack(mk)
+        if al:
+            out[name + "_alpha"] = np.stack(al)
+    return out
+
+
+HMC_CASES = {
+    "ref_hmc_diag": ("diag", 12, 16, dict(step_size=1e-3, n_leapfrogs=5,
+                                          target_acceptance_rate=0.9, mass_collect_iters=4,
+                                          mass_decay=0.99), 14, 9, 101),
+    "ref_hmc_dense32": ("dense", 32, 24, dict(step_size=0.05, n_leapfrogs=4,
+                                              target_acceptance_rate=0.8, mass_collect_iters=3,
+                                              mass_decay=0.99), 12, 10, 202),
+    "ref_hmc_dense64": ("dense", 64, 40, dict(step_size=0.05, n_leapfrogs=6,
+                                              target_acceptance_rate=0.8, mass_collect_iters=3,
+                                              mass_decay=0.99), 16, 12, 404),
+}
+
+
+def main():
+    for name, (kind, D, C, cfg, n_iters, n_adapt, seed) in HMC_CASES.items():
+        out = run_reference_hmc(kind, D, C, cfg, n_iters, n_adapt, seed)
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+        print(name, "acc mean per iteration", np.round(out["acc"].mean(1), 3).tolist())
+    out = run_reference_sgmcmc()
+    np.savez_compressed(os.path.join(GOLD, "ref_sgmcmc.npz"), **out)
+    print("ref_sgmcmc draws per step", {k: out[k].tolist() for k in out if k.endswith("_n_used")})
+
+
+if __name__ == "__main__":
+    main()

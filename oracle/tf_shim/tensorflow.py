@@ -1,0 +1,795 @@
+"""A NumPy stand-in for the TensorFlow-1.x graph API, just large enough to EXECUTE THE REFERENCE'S
+OWN SOURCE FILES ``zhusuan/hmc.py`` and ``zhusuan/sgmcmc.py`` unmodified (TEST INFRASTRUCTURE ONLY).
+
+Why it exists.  TensorFlow cannot be installed here (no wheel, no network), so round 1 could only
+restate hmc.py / sgmcmc.py in NumPy (oracle/hmc.py, oracle/sgmcmc.py) -- "parity unpinned by the
+reference".  With this module registered as ``tensorflow`` the reference files themselves run:
+their control flow, variable updates, quirks (``mu = 10 * eps0``, the EWMV update order, the
+step-size search loop, ...) are then the reference's, not a restatement.  oracle/tf_shim/
+make_ref_golden.py drives them and writes tests/golden/ref_*.npz; tests/test_ref_pins.py checks the
+oracle (and, on the GPU, the CUDA path) against those vectors.
+
+What it is.  A lazily evaluated dataflow graph with TF-1.x semantics:
+  * every op builds a ``Tensor`` holding a closure; ``Session.run(fetches, feed_dict)`` evaluates
+    the fetches in order with per-run memoisation (an op executes at most once per run) after its
+    control dependencies (``tf.control_dependencies``);
+  * ``Variable`` reads return the value at the moment of the FIRST read in a run (the reference
+    only relies on orders that its data / control dependencies enforce; every use of an updated
+    value goes through the assign op's output);
+  * ``tf.cond`` traces both branches at graph-construction time and executes only the taken one;
+    ``tf.while_loop`` re-traces its body on concrete loop values at run time;
+  * ``tf.gradients`` is reverse-mode differentiation over the recorded ops (the handful the
+    test log-joints use);
+  * ``tf.random_normal`` / ``tf.random_uniform`` pop arrays injected with ``set_noise`` (TF's own
+    Philox streams are irrelevant to parity: all parity runs inject noise);
+  * arithmetic is NumPy float32 (IEEE +,-,*,/ and sqrt are bit-identical to TF-CPU's; exp / pow /
+    reductions may differ from Eigen's kernels in the last ulp).
+Nothing outside hmc.py / sgmcmc.py's needs is implemented; an unknown attribute raises.
+"""
+import contextlib
+
+import numpy as np
+
+__version__ = "1.x-numpy-shim"
+
+float32, float64, int32, int64, bool = np.float32, np.float64, np.int32, np.int64, np.bool_
+_SERIAL = [0]
+_CTRL_STACK = [[]]
+
+
+# ------------------------------------------------------------------------------------------------
+class TensorShape(object):
+    def __init__(self, dims):
+        self._dims = None if dims is None else [None if d is None else int(d) for d in dims]
+
+    @property
+    def ndims(self):
+        return None if self._dims is None else len(self._dims)
+
+    def as_list(self):
+        return list(self._dims)
+
+    def concatenate(self, other):
+        return TensorShape(self._dims + TensorShape(other)._dims if not isinstance(
+            other, TensorShape) else self._dims + other._dims)
+
+    def __len__(self):
+        return len(self._dims)
+
+    def __iter__(self):
+        return iter(self._dims)
+
+    def __getitem__(self, k):
+        return TensorShape(self._dims[k]) if isinstance(k, slice) else self._dims[k]
+
+    def __bool__(self):                      # TF 1.x: unknown rank is falsy, any known shape truthy
+        return self._dims is not None
+
+    __nonzero__ = __bool__
+
+    def __eq__(self, other):
+        return list(self._dims) == list(TensorShape(other)._dims if not isinstance(
+            other, TensorShape) else other._dims)
+
+    def __repr__(self):
+        return "TensorShape(%r)" % (self._dims,)
+
+
+class _Ctx(object):
+    """One Session.run: memo of evaluated tensors, the feed, variable snapshots."""
+
+    def __init__(self, feed, parent=None, floor=None):
+        self.feed = feed
+        self.memo = {}
+        self.parent = parent
+        self.floor = floor          # tensors created before `floor` belong to the parent
+
+    def _home(self, t):
+        c = self
+        while c.parent is not None and t.serial < c.floor:
+            c = c.parent
+        return c
+
+    def eval(self, t):
+        t = convert_to_tensor(t)
+        home = self._home(t)
+        if id(t) in home.memo:
+            return home.memo[id(t)][1]
+        for d in t.deps:
+            self.eval(d)
+        v = t.fn(self)
+        home.memo[id(t)] = (t, v)
+        return v
+
+
+class Tensor(object):
+    __array_priority__ = 1000
+
+    def __init__(self, fn, inputs=(), op="op", vjp=None, dtype=None, name=None):
+        self.fn = fn
+        self.inputs = tuple(inputs)
+        self.op = op
+        self.vjp = vjp              # (cotangent Tensor) -> list of cotangent Tensors / None per input
+        self._dtype = dtype
+        self.name = name
+        _SERIAL[0] += 1
+        self.serial = _SERIAL[0]
+        self.deps = tuple(_CTRL_STACK[-1])
+
+    # --- static information (computed by a throw-away evaluation: only used on pure tensors) ---
+    def _peek(self):
+        return _Ctx({}).eval(self)
+
+    def get_shape(self):
+        return TensorShape(np.shape(self._peek()))
+
+    shape = property(get_shape)
+
+    @property
+    def dtype(self):
+        return self._dtype if self._dtype is not None else np.float32
+
+    def eval(self, feed_dict=None, session=None):
+        return Session().run(self, feed_dict)
+
+    # --- operators ---
+    def __add__(self, o): return add(self, o)
+    def __radd__(self, o): return add(o, self)
+    def __sub__(self, o): return subtract(self, o)
+    def __rsub__(self, o): return subtract(o, self)
+    def __mul__(self, o): return multiply(self, o)
+    def __rmul__(self, o): return multiply(o, self)
+    def __truediv__(self, o): return divide(self, o)
+    def __rtruediv__(self, o): return divide(o, self)
+    __div__, __rdiv__ = __truediv__, __rtruediv__
+    def __neg__(self): return negative(self)
+    def __pow__(self, o): return pow(self, o)
+    def __rpow__(self, o): return pow(o, self)
+    def __abs__(self): return abs(self)
+    def __lt__(self, o): return less(self, o)
+    def __gt__(self, o): return greater(self, o)
+    def __le__(self, o): return _cmp(np.less_equal, self, o)
+    def __ge__(self, o): return _cmp(np.greater_equal, self, o)
+    def __getitem__(self, k): return _unary(lambda a: a[k], self, "getitem")
+    __hash__ = object.__hash__
+
+    def __bool__(self):
+        raise TypeError("a graph Tensor has no truth value (use tf.cond)")
+
+    __nonzero__ = __bool__
+
+
+def _like(value, ref):
+    """Python scalars take the dtype of the tensor they meet (TF constant conversion)."""
+    if isinstance(value, Tensor):
+        return value
+    if isinstance(ref, Tensor) and isinstance(value, (int, float, np.floating, np.integer)) \
+            and not isinstance(value, (np.bool_, type(True))):
+        dt = ref._dtype               # (never evaluated: dtypes are inferred structurally)
+        if dt is not None and dt is not np.bool_:
+            return constant(value, dtype=dt)
+    return convert_to_tensor(value)
+
+
+def _dt(*ts):
+    """Result dtype of an op from its inputs' declared dtypes (None when unknown)."""
+    ds = [t._dtype for t in ts if isinstance(t, Tensor) and t._dtype is not None]
+    if not ds:
+        return None
+    return np.result_type(*ds).type
+
+
+def _f32(a):
+    a = np.asarray(a)
+    return a.astype(np.float32) if a.dtype == np.float64 else a
+
+
+def convert_to_tensor(value, dtype=None, name=None, preferred_dtype=None):
+    if isinstance(value, Tensor):
+        if dtype is not None and value._dtype is not None and value._dtype is not dtype:
+            return cast(value, dtype)
+        return value
+    if isinstance(value, TensorShape):
+        value = value.as_list()
+    return constant(value, dtype=dtype, name=name)
+
+
+def constant(value, dtype=None, shape=None, name=None):
+    if dtype is None:
+        a = np.asarray(value)
+        if a.dtype == np.float64:
+            a = a.astype(np.float32)
+        elif a.dtype == np.int64:
+            a = a.astype(np.int32)
+    else:
+        a = np.asarray(value, dtype=dtype)
+    if shape is not None:
+        a = np.broadcast_to(a, tuple(shape)).copy()
+    return Tensor(lambda c, a=a: a, op="const", dtype=a.dtype.type, name=name)
+
+
+def placeholder(dtype, shape=None, name=None):
+    t = Tensor(None, op="placeholder", dtype=dtype, name=name)
+
+    def fn(c, t=t):
+        cc = c
+        while cc is not None:
+            if t in cc.feed:
+                return np.asarray(cc.feed[t], dtype=dtype)
+            cc = cc.parent
+        raise ValueError("placeholder %r was not fed" % (name,))
+    t.fn = fn
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+class Variable(Tensor):
+    def __init__(self, initial_value, name=None, trainable=True, dtype=None):
+        if isinstance(initial_value, Tensor):
+            v = np.array(initial_value._peek())
+        else:
+            v = np.array(initial_value)
+        if dtype is not None:
+            v = v.astype(dtype)
+        elif v.dtype == np.float64:
+            v = v.astype(np.float32)
+        elif v.dtype == np.int64:
+            v = v.astype(np.int32)
+        self.value = v
+        Tensor.__init__(self, lambda c: self.value, op="variable", dtype=v.dtype.type, name=name)
+        self.deps = ()
+
+    def assign(self, value, use_locking=None):
+        return assign(self, value)
+
+    def assign_add(self, delta, use_locking=None):
+        return assign(self, self + _like(delta, self))
+
+    def load(self, value, session=None):
+        self.value = np.array(value, dtype=self.value.dtype)
+
+    def _peek(self):
+        return self.value
+
+    @property
+    def initializer(self):
+        return no_op()
+
+
+def assign(ref, value, validate_shape=None, use_locking=None):
+    value = _like(value, ref)
+
+    def fn(c):
+        v = np.array(c.eval(value), dtype=ref.value.dtype)
+        c.eval(ref)                        # pin the pre-assignment snapshot for this run
+        ref.value = v.reshape(ref.value.shape) if v.shape != ref.value.shape else v
+        return ref.value
+    return Tensor(fn, inputs=(value,), op="assign", dtype=ref._dtype)
+
+
+def global_variables_initializer():
+    return no_op()
+
+
+def no_op(name=None):
+    return Tensor(lambda c: None, op="no_op")
+
+
+def group(*ops, **kw):
+    ops = [o for o in ops if o is not None]
+
+    def fn(c):
+        for o in ops:
+            c.eval(o)
+        return None
+    return Tensor(fn, inputs=tuple(ops), op="group")
+
+
+@contextlib.contextmanager
+def control_dependencies(deps):
+    deps = [d for d in (deps or []) if isinstance(d, Tensor)]
+    _CTRL_STACK.append(_CTRL_STACK[-1] + deps)
+    try:
+        yield
+    finally:
+        _CTRL_STACK.pop()
+
+
+@contextlib.contextmanager
+def name_scope(name=None, default_name=None, values=None):
+    yield name
+
+
+variable_scope = name_scope
+
+
+# ------------------------------------------------------------------------------------------------
+def _unbroadcast(g, like):
+    """Sum the cotangent `g` (Tensor) back to the shape of input `like` (Tensor)."""
+    def fn(c):
+        gv, shape = np.asarray(c.eval(g)), np.shape(c.eval(like))
+        while gv.ndim > len(shape):
+            gv = gv.sum(0)
+        for ax, n in enumerate(shape):
+            if n == 1 and gv.shape[ax] != 1:
+                gv = gv.sum(ax, keepdims=True)
+        return gv.astype(np.asarray(c.eval(like)).dtype, copy=False)
+    return Tensor(fn, inputs=(g, like), op="unbroadcast", dtype=like._dtype)
+
+
+def _binary(npf, a, b, op, vjp=None):
+    a, b = _like(a, b), _like(b, a)
+    return Tensor(lambda c: npf(c.eval(a), c.eval(b)), inputs=(a, b), op=op, vjp=vjp,
+                  dtype=_dt(a, b))
+
+
+def _unary(npf, a, op, vjp=None, dtype=None):
+    a = convert_to_tensor(a)
+    return Tensor(lambda c: npf(c.eval(a)), inputs=(a,), op=op, vjp=vjp,
+                  dtype=dtype if dtype is not None else a._dtype)
+
+
+def add(a, b, name=None):
+    a, b = _like(a, b), _like(b, a)
+    return _binary(np.add, a, b, "add", lambda g: [_unbroadcast(g, a), _unbroadcast(g, b)])
+
+
+def subtract(a, b, name=None):
+    a, b = _like(a, b), _like(b, a)
+    return _binary(np.subtract, a, b, "sub",
+                   lambda g: [_unbroadcast(g, a), _unbroadcast(negative(g), b)])
+
+
+def multiply(a, b, name=None):
+    a, b = _like(a, b), _like(b, a)
+    return _binary(np.multiply, a, b, "mul",
+                   lambda g: [_unbroadcast(g * b, a), _unbroadcast(g * a, b)])
+
+
+def divide(a, b, name=None):
+    a, b = _like(a, b), _like(b, a)
+    return _binary(np.true_divide, a, b, "div",
+                   lambda g: [_unbroadcast(g / b, a), _unbroadcast(negative(g * a / (b * b)), b)])
+
+
+div = truediv = realdiv = divide
+
+
+def negative(a, name=None):
+    return _unary(np.negative, a, "neg", lambda g: [negative(g)])
+
+
+def square(a, name=None):
+    a = convert_to_tensor(a)
+    return _unary(np.square, a, "square", lambda g: [g * (a * 2.0)])
+
+
+def sqrt(a, name=None):
+    a = convert_to_tensor(a)
+    out = _unary(np.sqrt, a, "sqrt")
+    out.vjp = lambda g: [g * 0.5 / out]
+    return out
+
+
+def exp(a, name=None):
+    a = convert_to_tensor(a)
+    out = _unary(lambda x: np.exp(x).astype(np.asarray(x).dtype, copy=False), a, "exp")
+    out.vjp = lambda g: [g * out]
+    return out
+
+
+def log(a, name=None):
+    a = convert_to_tensor(a)
+    return _unary(np.log, a, "log", lambda g: [g / a])
+
+
+def abs(a, name=None):                                         # noqa: A001
+    a = convert_to_tensor(a)
+    return _unary(np.abs, a, "abs", lambda g: [g * sign(a)])
+
+
+def sign(a, name=None):
+    return _unary(np.sign, a, "sign")
+
+
+def pow(a, b, name=None):                                      # noqa: A001
+    a, b = _like(a, b), _like(b, a)
+    return _binary(lambda x, y: np.power(x, y).astype(np.result_type(x, y), copy=False), a, b, "pow")
+
+
+def mod(a, b, name=None):
+    return _binary(np.mod, a, b, "mod")
+
+
+floormod = mod
+
+
+def minimum(a, b, name=None):
+    a, b = _like(a, b), _like(b, a)
+    return _binary(np.minimum, a, b, "minimum")
+
+
+def maximum(a, b, name=None):
+    a, b = _like(a, b), _like(b, a)
+    return _binary(np.maximum, a, b, "maximum")
+
+
+def _cmp(npf, a, b):
+    a, b = _like(a, b), _like(b, a)
+    return Tensor(lambda c: npf(c.eval(a), c.eval(b)), inputs=(a, b), op="cmp", dtype=np.bool_)
+
+
+def less(a, b, name=None): return _cmp(np.less, a, b)
+def greater(a, b, name=None): return _cmp(np.greater, a, b)
+def equal(a, b, name=None): return _cmp(np.equal, a, b)
+def logical_and(a, b, name=None): return _cmp(np.logical_and, a, b)
+def logical_or(a, b, name=None): return _cmp(np.logical_or, a, b)
+def logical_xor(a, b, name=None): return _cmp(np.logical_xor, a, b)
+def logical_not(a, name=None): return _unary(np.logical_not, a, "not", dtype=np.bool_)
+def is_finite(a, name=None): return _unary(np.isfinite, a, "is_finite", dtype=np.bool_)
+
+
+def identity(a, name=None):
+    return _unary(lambda x: x, a, "identity", lambda g: [g])
+
+
+def stop_gradient(a, name=None):
+    return _unary(lambda x: x, a, "stop_gradient", lambda g: [None])
+
+
+def cast(a, dtype, name=None):
+    a = convert_to_tensor(a)
+    return _unary(lambda x: np.asarray(x).astype(dtype), a, "cast", lambda g: [g], dtype=dtype)
+
+
+to_float = lambda a, name=None: cast(a, np.float32)            # noqa: E731
+to_int32 = lambda a, name=None: cast(a, np.int32)              # noqa: E731
+
+
+def check_numerics(a, message, name=None):
+    a = convert_to_tensor(a)
+
+    def f(x):
+        if not np.all(np.isfinite(x)):
+            raise errors.InvalidArgumentError(None, None, message)
+        return x
+    return _unary(f, a, "check_numerics", lambda g: [g])
+
+
+def _shape_arg(c, shape):
+    if isinstance(shape, Tensor):
+        return tuple(int(s) for s in np.atleast_1d(c.eval(shape)))
+    if isinstance(shape, TensorShape):
+        return tuple(shape.as_list())
+    return tuple(int(c.eval(s)) if isinstance(s, Tensor) else int(s) for s in shape)
+
+
+def zeros(shape, dtype=np.float32, name=None):
+    return Tensor(lambda c: np.zeros(_shape_arg(c, shape), dtype), op="zeros", dtype=dtype)
+
+
+def ones(shape, dtype=np.float32, name=None):
+    return Tensor(lambda c: np.ones(_shape_arg(c, shape), dtype), op="ones", dtype=dtype)
+
+
+def zeros_like(a, dtype=None, name=None):
+    a = convert_to_tensor(a)
+    return _unary(lambda x: np.zeros(np.shape(x), dtype or np.asarray(x).dtype), a, "zeros_like",
+                  dtype=dtype)
+
+
+def ones_like(a, dtype=None, name=None):
+    a = convert_to_tensor(a)
+    return _unary(lambda x: np.ones(np.shape(x), dtype or np.asarray(x).dtype), a, "ones_like",
+                  dtype=dtype)
+
+
+def shape(a, name=None, out_type=np.int32):                    # noqa: F811
+    a = convert_to_tensor(a)
+    return _unary(lambda x: np.asarray(np.shape(x), np.int32), a, "shape", dtype=np.int32)
+
+
+def range(*args, **kw):                                        # noqa: A001
+    ts = [convert_to_tensor(a) for a in args]
+    return Tensor(lambda c: np.arange(*[int(c.eval(t)) for t in ts], dtype=np.int32),
+                  inputs=tuple(ts), op="range", dtype=np.int32)
+
+
+def expand_dims(a, axis=None, name=None, dim=None):
+    a = convert_to_tensor(a)
+    ax = axis if axis is not None else dim
+    return _unary(lambda x: np.expand_dims(x, ax), a, "expand_dims",
+                  lambda g: [reshape(g, shape(a))])
+
+
+def reshape(a, shp, name=None):
+    a = convert_to_tensor(a)
+    return Tensor(lambda c: np.reshape(c.eval(a), _shape_arg(c, shp)), inputs=(a,), op="reshape",
+                  vjp=lambda g: [reshape(g, shape(a))], dtype=a._dtype)
+
+
+def tile(a, multiples, name=None):
+    a = convert_to_tensor(a)
+    return Tensor(lambda c: np.tile(c.eval(a), _shape_arg(c, multiples)), inputs=(a,), op="tile",
+                  dtype=a._dtype)
+
+
+def where(cond, x=None, y=None, name=None):
+    cond, x, y = convert_to_tensor(cond), convert_to_tensor(x), convert_to_tensor(y)
+
+    def fn(c):
+        cv, xv, yv = c.eval(cond), c.eval(x), c.eval(y)
+        if np.ndim(cv) == 1 and np.ndim(xv) > 1:         # TF: a vector condition selects rows
+            cv = cv.reshape((-1,) + (1,) * (np.ndim(xv) - 1))
+        return np.where(cv, xv, yv)
+    return Tensor(fn, inputs=(cond, x, y), op="where", dtype=_dt(x, y))
+
+
+def _axes(c, axis, ndim):
+    if axis is None:
+        return None
+    if isinstance(axis, Tensor):
+        axis = c.eval(axis)
+    ax = tuple(int(a) for a in np.atleast_1d(axis))
+    return tuple(a % ndim for a in ax) if ndim else ax
+
+
+def _reduce(npf, a, axis, keepdims, op, vjp_scale):
+    a = convert_to_tensor(a)
+
+    def fn(c):
+        x = np.asarray(c.eval(a))
+        ax = _axes(c, axis, x.ndim)
+        if ax is not None and len(ax) == 0:
+            return x
+        return npf(x, axis=ax, keepdims=(True if keepdims else False), dtype=x.dtype if x.dtype.kind == "f" else None)
+    out = Tensor(fn, inputs=(a,), op=op, dtype=a._dtype)
+
+    def vjp(g):
+        def gfn(c):
+            x = np.asarray(c.eval(a))
+            gv = np.asarray(c.eval(g))
+            ax = _axes(c, axis, x.ndim)
+            n = 1.0
+            if ax is None:
+                ax = tuple(np.arange(x.ndim))
+            if not keepdims:
+                for d in sorted(ax):
+                    gv = np.expand_dims(gv, d)
+            for d in ax:
+                n *= x.shape[d]
+            gv = np.broadcast_to(gv, x.shape)
+            return (gv / x.dtype.type(n) if vjp_scale else gv).astype(x.dtype, copy=False)
+        return [Tensor(gfn, inputs=(g, a), op=op + "_grad", dtype=a._dtype)]
+    out.vjp = vjp
+    return out
+
+
+def reduce_sum(a, axis=None, keepdims=False, name=None, reduction_indices=None, keep_dims=None):
+    axis = axis if axis is not None else reduction_indices
+    return _reduce(np.sum, a, axis, keepdims or keep_dims, "reduce_sum", False)
+
+
+def reduce_mean(a, axis=None, keepdims=False, name=None, reduction_indices=None, keep_dims=None):
+    axis = axis if axis is not None else reduction_indices
+    return _reduce(np.mean, a, axis, keepdims or keep_dims, "reduce_mean", True)
+
+
+def add_n(inputs, name=None):
+    out = inputs[0]
+    for t in inputs[1:]:
+        out = add(out, t)
+    return out
+
+
+def matmul(a, b, transpose_a=False, transpose_b=False, name=None):
+    a, b = convert_to_tensor(a), convert_to_tensor(b)
+    ta = (lambda x: np.swapaxes(x, -1, -2)) if transpose_a else (lambda x: x)
+    tb = (lambda x: np.swapaxes(x, -1, -2)) if transpose_b else (lambda x: x)
+    out = Tensor(lambda c: np.matmul(ta(c.eval(a)), tb(c.eval(b))), inputs=(a, b), op="matmul",
+                 dtype=_dt(a, b))
+    if not transpose_a and not transpose_b:
+        out.vjp = lambda g: [matmul(g, b, transpose_b=True), matmul(a, g, transpose_a=True)]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def cond(pred, true_fn=None, false_fn=None, name=None, fn1=None, fn2=None, strict=False):
+    """Both branches are traced now (graph construction); only the taken one ever executes, so
+    side effects created inside a branch (assigns) are conditional, as in TF."""
+    true_fn, false_fn = true_fn or fn1, false_fn or fn2
+    pred = convert_to_tensor(pred)
+    t_out, f_out = true_fn(), false_fn()
+    is_list = isinstance(t_out, (list, tuple))
+    t_list = [convert_to_tensor(x) for x in (t_out if is_list else [t_out])]
+    f_list = [convert_to_tensor(x) for x in (f_out if is_list else [f_out])]
+    outs = []
+    for tt, ff in zip(t_list, f_list):
+        def fn(c, tt=tt, ff=ff):
+            return c.eval(tt) if builtins_bool(c.eval(pred)) else c.eval(ff)
+        outs.append(Tensor(fn, inputs=(pred, tt, ff), op="cond", dtype=_dt(tt, ff)))
+    return outs if is_list else outs[0]
+
+
+def builtins_bool(x):
+    return True if np.asarray(x).item() else False
+
+
+def while_loop(cond, body, loop_vars, shape_invariants=None, parallel_iterations=10,   # noqa: F811
+               back_prop=True, swap_memory=False, name=None, maximum_iterations=None):
+    flat = []
+
+    def flatten(v):
+        if isinstance(v, (list, tuple)):
+            return [flatten(x) for x in v]
+        flat.append(convert_to_tensor(v))
+        return len(flat) - 1
+    structure = flatten(list(loop_vars))
+    n = len(flat)
+
+    def rebuild(struct, vals):
+        return [rebuild(s, vals) if isinstance(s, list) else vals[s] for s in struct]
+
+    def run(c):
+        vals = [c.eval(t) for t in flat]
+        it = 0
+        while True:
+            floor = _SERIAL[0] + 1
+            sub = _Ctx(c.feed, parent=c, floor=floor)     # this iteration's temporaries
+            consts = [Tensor(lambda cc, v=v: v, op="loop_var",
+                             dtype=np.asarray(v).dtype.type) for v in vals]
+            args = rebuild(structure, consts)
+            if not builtins_bool(sub.eval(convert_to_tensor(cond(*args)))):
+                break
+            if maximum_iterations is not None and it >= maximum_iterations:
+                break
+            out = body(*args)
+            out_flat = []
+
+            def fl(v):
+                if isinstance(v, (list, tuple)):
+                    for x in v:
+                        fl(x)
+                else:
+                    out_flat.append(convert_to_tensor(v))
+            fl(list(out))
+            assert len(out_flat) == n, "while_loop: body changed the structure"
+            vals = [sub.eval(t) for t in out_flat]
+            it += 1
+        return vals
+    all_out = Tensor(run, inputs=tuple(flat), op="while_all")
+    outs = [Tensor(lambda c, k=k: c.eval(all_out)[k], inputs=(all_out,), op="while",
+                   dtype=flat[k]._dtype) for k in np.arange(n)]
+    rebuilt = rebuild(structure, outs)
+    return rebuilt if isinstance(loop_vars, (list, tuple)) else rebuilt[0]
+
+
+def gradients(ys, xs, grad_ys=None, name=None, **kw):
+    """Reverse-mode differentiation of sum(ys) with respect to the tensors `xs`."""
+    ys = list(ys) if isinstance(ys, (list, tuple)) else [ys]
+    xs = [convert_to_tensor(x) for x in xs]
+    y = ys[0] if len(ys) == 1 else add_n(ys)
+    # topological order of the sub-graph between xs and y
+    order, seen = [], set()
+    xset = {id(x) for x in xs}
+
+    def visit(t):
+        if id(t) in seen:
+            return
+        seen.add(id(t))
+        if id(t) not in xset:
+            for i in t.inputs:
+                if isinstance(i, Tensor):
+                    visit(i)
+        order.append(t)
+    visit(y)
+    cot = {id(y): ones_like(y)}
+    for t in reversed(order):
+        g = cot.get(id(t))
+        if g is None or id(t) in xset or t.vjp is None:
+            if g is not None and id(t) not in xset and t.vjp is None and t.op not in (
+                    "const", "variable", "placeholder", "loop_var", "zeros", "ones", "cmp",
+                    "shape", "range", "zeros_like", "ones_like"):
+                raise NotImplementedError("tf.gradients through op %r" % t.op)
+            continue
+        for inp, gi in zip(t.inputs, t.vjp(g)):
+            if gi is None or not isinstance(inp, Tensor):
+                continue
+            cot[id(inp)] = gi if id(inp) not in cot else add(cot[id(inp)], gi)
+    return [cot.get(id(x)) for x in xs]
+
+
+# ------------------------------------------------------------------------------------------------
+_NOISE = {"normal": [], "uniform": []}
+
+
+def set_noise(normal=(), uniform=()):
+    """Arrays handed out, in evaluation order, by the tf.random_normal / tf.random_uniform ops of
+    the next Session.run."""
+    _NOISE["normal"] = list(normal)
+    _NOISE["uniform"] = list(uniform)
+
+
+def _noise_op(kind, shp, extra):
+    def fn(c):
+        want = _shape_arg(c, shp)
+        if not _NOISE[kind]:
+            raise RuntimeError("tf.random_%s evaluated but no injected noise is left" % kind)
+        a = np.asarray(_NOISE[kind].pop(0), np.float32)
+        assert tuple(a.shape) == want, (kind, a.shape, want)
+        return extra(a)
+    return Tensor(fn, op="random_" + kind, dtype=np.float32)
+
+
+def random_normal(shape, mean=0.0, stddev=1.0, dtype=np.float32, seed=None, name=None):   # noqa
+    m, s = np.float32(mean), stddev
+    if isinstance(s, Tensor):
+        base = _noise_op("normal", shape, lambda a: a)
+        return base * s + m if mean != 0.0 else base * s
+    s = np.float32(s)
+    return _noise_op("normal", shape, lambda a: (a * s + m) if (s != 1 or m != 0) else a)
+
+
+def random_uniform(shape, minval=0, maxval=None, dtype=np.float32, seed=None, name=None):  # noqa
+    return _noise_op("uniform", shape, lambda a: a)
+
+
+class random(object):                                          # tf.random.*
+    normal = staticmethod(random_normal)
+    uniform = staticmethod(random_uniform)
+
+
+def set_random_seed(seed):
+    pass
+
+
+# ------------------------------------------------------------------------------------------------
+class Session(object):
+    def __init__(self, *a, **k):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def run(self, fetches, feed_dict=None):
+        ctx = _Ctx(dict(feed_dict or {}))
+
+        def ev(f):
+            if f is None:
+                return None
+            if isinstance(f, Tensor):
+                v = ctx.eval(f)
+                return None if v is None else np.array(v)
+            if isinstance(f, dict):
+                return {k: ev(v) for k, v in f.items()}
+            if isinstance(f, (list, tuple)):
+                out = [ev(x) for x in f]
+                if hasattr(f, "_fields"):
+                    return type(f)(*out)
+                return out if isinstance(f, list) else tuple(out)
+            if hasattr(f, "__dict__"):              # plain result structs (HMCInfo)
+                import copy
+                o = copy.copy(f)
+                o.__dict__ = {k: ev(v) for k, v in f.__dict__.items()}
+                return o
+            return f
+        return ev(fetches)
+
+
+class errors(object):
+    class InvalidArgumentError(Exception):
+        def __init__(self, node_def=None, op=None, message=""):
+            Exception.__init__(self, message)
+            self.message = message
+
+
+class train(object):
+    pass
+
+
+def __getattr__(name):
+    raise AttributeError("the NumPy TensorFlow shim (oracle/tf_shim) does not implement tf.%s"
+                         % name)

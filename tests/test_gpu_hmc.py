@@ -66,13 +66,43 @@ def _replay(zs, g, model, expect_kind, q_tol=2e-5, **hmc_kw):
         np.testing.assert_allclose(N(x), g["q"][i], rtol=q_tol, atol=q_tol)
         np.testing.assert_allclose(float(info.updated_step_size),
                                    g["step_size"][i], rtol=1e-4)
-        np.testing.assert_allclose(float(h._state[7]), g["eps_used"][i],
-                                   rtol=1e-5)
-        np.testing.assert_allclose(N(h._mass[0]), g["mass"][i], rtol=1e-3)
+        if "eps_used" in g.files:       # internals the reference's HMCInfo does not expose
+            np.testing.assert_allclose(float(h._state[7]), g["eps_used"][i],
+                                       rtol=1e-5)
+            np.testing.assert_allclose(N(h._mass[0]), g["mass"][i], rtol=1e-3)
     op.synchronize()
     assert n_mismatch == 0
-    assert h.n_search_iters == int(g["n_search_iters"])
+    if "n_search_iters" in g.files:
+        assert h.n_search_iters == int(g["n_search_iters"])
     return h
+
+
+# ---- vectors written by the reference's own hmc.py (oracle/tf_shim/make_ref_golden.py) ----------
+def test_reference_run_diag_fused(zs):
+    g = np.load(os.path.join(GOLD, "ref_hmc_diag.npz"))
+    D = g["std"].shape[0]
+
+    @zs.meta_bayesian_net()
+    def gaussian(n_x, stdev, n_particles):
+        bn = zs.BayesianNet()
+        bn.normal('x', torch.zeros(n_x, device="cuda"), std=stdev,
+                  n_samples=n_particles, group_ndims=1)
+        return bn
+    _replay(zs, g, gaussian(D, T(g["std"]), g["q0"].shape[0]), "diag_normal")
+
+
+@pytest.mark.parametrize("name,impl,q_tol", [
+    ("ref_hmc_dense32", 0, 5e-5), ("ref_hmc_dense32", 1, 5e-5),
+    ("ref_hmc_dense64", 0, 5e-5), ("ref_hmc_dense64", 1, 5e-5),
+    ("ref_hmc_dense64", 2, 1e-4), ("ref_hmc_dense64", 5, 1e-4)])
+def test_reference_run_dense(zs, name, impl, q_tol):
+    """16 chained adaptive iterations of the reference's HMC (step-size search, dual averaging,
+    mass adaptation, diverging and healthy iterations) replayed on each dense kernel."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    lj = zs.fused.GaussianLogJoint(g["P"], mean=g["mu"],
+                                   log_det_cov=-2 * float(g["const"])
+                                   - g["P"].shape[0] * np.log(2 * np.pi))
+    _replay(zs, g, lj, "dense_gaussian", q_tol=q_tol, dense_impl=impl)
 
 
 def test_golden_diag_fused_through_bayesian_net(zs):

@@ -48,9 +48,12 @@ CONFIGS = {
 }
 
 
+# sgmcmc.npz: written by the oracle; ref_sgmcmc.npz: written by the reference's own sgmcmc.py
+# (oracle/tf_shim/make_ref_golden.py) -- same configurations, same keys
+@pytest.mark.parametrize("fixture", ["sgmcmc.npz", "ref_sgmcmc.npz"])
 @pytest.mark.parametrize("name", sorted(CONFIGS))
-def test_golden_replay(zs, name):
-    g = np.load(os.path.join(GOLD, "sgmcmc.npz"))
+def test_golden_replay(zs, name, fixture):
+    g = np.load(os.path.join(GOLD, fixture))
     cls, kw = CONFIGS[name]
     mean, std = T(g["mean"]), T(g["std"])
 

@@ -1,0 +1,158 @@
+"""The CPU oracle against vectors produced by the reference's OWN source.
+
+tests/golden/ref_*.npz were written by oracle/tf_shim/make_ref_golden.py: zhusuan/hmc.py and
+zhusuan/sgmcmc.py of the reference checkout, imported unmodified and executed on the NumPy
+stand-in for the TF-1.x graph API (oracle/tf_shim/tensorflow.py), with every random draw
+injected.  The state machine (step-size search hmc.py:279-333, dual averaging hmc.py:56-90, mass
+estimator hmc.py:93-158, the SG-MCMC update rules sgmcmc.py:183-470) therefore comes from the
+reference's code, not from the restatement in oracle/.  Here:
+
+* oracle/hmc.py and oracle/sgmcmc.py must reproduce those vectors (float32: bit-exact for the
+  element-wise models, rounding of the matmul summation order for the dense one);
+* where the reference checkout is present (this container, not the GPU box) the vectors are
+  regenerated and must equal the committed files bit for bit.
+
+CPU only.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import hmc as OH
+from oracle import models as OM
+from oracle import sgmcmc as OS
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+SHIM = os.path.join(os.path.dirname(HERE), "oracle", "tf_shim")
+REF = os.environ.get("ZHUSUAN_REFERENCE", "/root/reference")
+have_ref = os.path.isfile(os.path.join(REF, "zhusuan", "hmc.py"))
+
+
+def _model(g):
+    if "P" in g.files:
+        return OM.DenseGaussian(g["P"].astype(np.float32), g["mu"], float(g["const"]))
+    return OM.DiagGaussian(np.zeros_like(g["std"]), g["std"])
+
+
+@pytest.mark.parametrize("name,tol", [("ref_hmc_diag", 0.0), ("ref_hmc_dense32", 3e-5),
+                                      ("ref_hmc_dense64", 3e-5)])
+def test_oracle_hmc_reproduces_reference_run(name, tol):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    model = _model(g)
+    h = OH.HMC(step_size=float(g["cfg_step_size"]), n_leapfrogs=int(g["cfg_n_leapfrogs"]),
+               adapt_step_size=True, target_acceptance_rate=float(g["cfg_target_acceptance_rate"]),
+               adapt_mass=True, mass_collect_iters=int(g["cfg_mass_collect_iters"]),
+               mass_decay=float(g["cfg_mass_decay"]))
+    q = [g["q0"].copy()]
+    n_live = 0
+    for i in range(g["q"].shape[0]):
+        adapt = i < int(g["n_adapt"])
+        q, info = h.step(q, model.logp, model.grad, [g["noise_p"][i]], g["noise_u"][i],
+                         adapt_step_size=adapt, adapt_mass=adapt)
+        cmp = lambda a, b, what: np.testing.assert_allclose(
+            a, b, rtol=tol, atol=tol * 1e-1, err_msg="%s iteration %d %s" % (name, i, what))
+        np.testing.assert_array_equal(info.if_accept.astype(np.int32), g["accept"][i])
+        cmp(info.init_momentum[0], g["p0"][i], "p0")
+        cmp(info.orig_log_prob, g["lp0"][i], "lp0")
+        cmp(info.orig_hamiltonian, g["h0"][i], "h0")
+        cmp(info.acceptance_rate, g["acc"][i], "acc")
+        cmp(info.log_prob, g["lp"][i], "lp")
+        cmp(np.float32(info.updated_step_size), g["step_size"][i], "step_size")
+        np.testing.assert_allclose(q[0], g["q"][i], rtol=tol * 30, atol=tol,
+                                   err_msg="%s iteration %d q" % (name, i))
+        live = g["acc"][i] > 1e-6        # a diverged proposal's energy is chaotic in float32
+        cmp(info.hamiltonian[live], g["h1"][i][live], "h1")
+        n_live += int(live.sum())
+    # the fixture exercises both regimes: diverging step-size overshoots and healthy iterations
+    assert 0.3 * g["acc"].size < n_live < g["acc"].size
+
+
+SG = {
+    "sgld": (OS.SGLD, dict(learning_rate=0.01)),
+    "psgld": (OS.PSGLD, dict(learning_rate=0.01)),
+    "sghmc1": (OS.SGHMC, dict(learning_rate=0.01, friction=0.3, variance_estimate=0.02,
+                              n_iter_resample_v=3, second_order=False)),
+    "sghmc2": (OS.SGHMC, dict(learning_rate=0.01, friction=0.3, variance_estimate=0.02,
+                              n_iter_resample_v=3, second_order=True)),
+    "sgnht1v": (OS.SGNHT, dict(learning_rate=0.01, variance_extra=0.1, tune_rate=2.,
+                               n_iter_resample_v=4, second_order=False, use_vector_alpha=True)),
+    "sgnht2v": (OS.SGNHT, dict(learning_rate=0.01, variance_extra=0.1, tune_rate=2.,
+                               n_iter_resample_v=4, second_order=True, use_vector_alpha=True)),
+    "sgnht1s": (OS.SGNHT, dict(learning_rate=0.01, variance_extra=0.1, tune_rate=2.,
+                               n_iter_resample_v=None, second_order=False,
+                               use_vector_alpha=False)),
+    "sgnht2s": (OS.SGNHT, dict(learning_rate=0.01, variance_extra=0.1, tune_rate=2.,
+                               n_iter_resample_v=None, second_order=True,
+                               use_vector_alpha=False)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SG))
+def test_oracle_sgmcmc_reproduces_reference_run(name):
+    g = np.load(os.path.join(GOLD, "ref_sgmcmc.npz"))
+    model = OM.DiagGaussian(g["mean"], g["std"])
+    cls, kw = SG[name]
+    s = cls(**kw)
+    q = [g["q0"].copy()]
+    if hasattr(s, "init_v"):
+        s.init_v([g[name + "_v0"]])
+    tol = 1e-6 if name == "psgld" else 0.0      # x**2 (reference) vs x*x: one rounding
+    for t in range(g[name + "_q"].shape[0]):
+        if hasattr(s, "init_v"):
+            q, info = s.step(q, model.grad, [g[name + "_resample"][t]], [g[name + "_noise"][t]])
+        else:
+            q, info = s.step(q, model.grad, [g[name + "_noise"][t]])
+        np.testing.assert_allclose(q[0], g[name + "_q"][t], rtol=tol, atol=tol)
+        if name + "_mean_k" in g.files:
+            np.testing.assert_allclose(np.asarray(info["mean_k"][0], np.float32),
+                                       g[name + "_mean_k"][t], rtol=1e-6)
+        if name + "_alpha" in g.files:
+            np.testing.assert_allclose(np.asarray(info["alpha"][0], np.float32).reshape(-1),
+                                       g[name + "_alpha"][t].reshape(-1), rtol=1e-6)
+    # the schedule of momentum re-draws is the reference's own (t % n == 0, counted from 0)
+    n = kw.get("n_iter_resample_v")
+    want = [2 if (n and t % n == 0) else 1 for t in range(g[name + "_q"].shape[0])]
+    assert g[name + "_n_used"].tolist() == want
+
+
+def test_reference_run_equals_oracle_made_fixtures():
+    """The round-1 fixtures (written by the oracle) and the reference-run ones share seeds and
+    configurations: same inputs, same outputs."""
+    for a, b, tol in (("hmc_diag", "ref_hmc_diag", 0.0), ("hmc_dense", "ref_hmc_dense32", 3e-5)):
+        o, r = np.load(os.path.join(GOLD, a + ".npz")), np.load(os.path.join(GOLD, b + ".npz"))
+        np.testing.assert_array_equal(o["noise_p"], r["noise_p"])
+        np.testing.assert_array_equal(o["q0"], r["q0"])
+        np.testing.assert_array_equal(o["accept"], r["accept"])
+        for k in ("acc", "step_size", "lp", "lp0", "h0", "p0"):
+            np.testing.assert_allclose(o[k], r[k], rtol=tol, atol=tol * 1e-1, err_msg=a + " " + k)
+        np.testing.assert_allclose(o["q"], r["q"], rtol=tol * 30, atol=tol)
+
+
+@pytest.mark.skipif(not have_ref, reason="reference checkout not present (GPU box)")
+def test_committed_vectors_are_what_the_reference_code_produces():
+    sys.path.insert(0, SHIM)
+    saved = {k: sys.modules.get(k) for k in ("tensorflow", "zhusuan")}
+    try:
+        import make_ref_golden as M
+        name = "ref_hmc_dense32"
+        kind, D, C, cfg, n_iters, n_adapt, seed = M.HMC_CASES[name]
+        out = M.run_reference_hmc(kind, D, C, cfg, n_iters, n_adapt, seed)
+        g = np.load(os.path.join(GOLD, name + ".npz"))
+        for k in ("q", "acc", "step_size", "lp", "h0", "h1", "lp0", "p0", "accept", "noise_p"):
+            np.testing.assert_array_equal(out[k], g[k], err_msg=k)
+        out = M.run_reference_sgmcmc()
+        g = np.load(os.path.join(GOLD, "ref_sgmcmc.npz"))
+        for k in g.files:
+            np.testing.assert_array_equal(out[k], g[k], err_msg=k)
+        import zhusuan.hmc
+        assert os.path.realpath(zhusuan.hmc.__file__).startswith(os.path.realpath(REF))
+    finally:
+        sys.path.remove(SHIM)
+        for k in [m for m in sys.modules if m == "tensorflow" or m.startswith("zhusuan")]:
+            del sys.modules[k]
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
