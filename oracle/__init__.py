@@ -40,7 +40,9 @@ Pinning status:
     float32 matmul-order rounding on dense ones) and regenerated + compared
     whenever /root/reference is present.  The reference's statistical harness
     (tests/test_mcmc.py) is re-run against the oracle as well.
-  * device sampler streams (oracle/samplers.py) and AIS (oracle/evaluation.py):
-    "parity unpinned" by the reference (it tests moments / an analytic marginal
-    only); the restatement is the pin there.
+  * AIS (oracle/evaluation.py): PINNED the same way -- class AIS of
+    zhusuan/evaluation.py:57-172 run on the stand-in, tests/golden/ref_ais.npz.
+  * device sampler streams (oracle/samplers.py): "parity unpinned" by the
+    reference (TF's generators; it tests shapes and moments only); the
+    restatement of the published algorithms is the pin there.
 """

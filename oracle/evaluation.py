@@ -1,9 +1,10 @@
 """NumPy restatement of zhusuan/evaluation.py:57-172 (AIS) on the HMC oracle
 (TEST ORACLE ONLY -- see oracle/__init__).  Every random draw is injected: the two prior
 samples (evaluation.py:87, 100-101, 138) and the HMC noise of each adaptation / temperature
-iteration.  "Parity unpinned" by the reference (tests/test_evaluation.py only checks the
-estimate of a known marginal likelihood statistically); tests/test_gpu_models.py re-runs that
-check and compares the device loop with this restatement step for step."""
+iteration.  Pinned to the reference's own class AIS run on the NumPy TF stand-in
+(oracle/tf_shim/make_ref_golden.py -> tests/golden/ref_ais.npz, tests/test_ref_pins.py);
+tests/test_gpu_models.py also re-runs the reference's statistical check (known marginal) and
+compares the device loop with this restatement and with that fixture step for step."""
 import numpy as np
 
 from . import hmc as OH

@@ -192,6 +192,62 @@ def run_reference_sgmcmc(seed=303):
     return out
 
 
+def run_reference_ais(seed=4):
+    """zhusuan/evaluation.py:57-172 (class AIS) driving the reference's HMC: z ~ N(0, I),
+    x | z ~ N(z, s^2 I).  `zhusuan.variational` (imported by evaluation.py for
+    is_loglikelihood only) is stubbed: AIS does not touch it."""
+    tf, hmc_mod, _ = load_reference()
+    stub = types.ModuleType("zhusuan.variational")
+    stub.ImportanceWeightedObjective = None
+    sys.modules["zhusuan.variational"] = stub
+    ev = importlib.import_module("zhusuan.evaluation")
+    assert os.path.realpath(ev.__file__).startswith(os.path.realpath(REF))
+    rng = np.random.RandomState(seed)
+    n_chains, n_data, d, s = 8, 3, 2, 0.8
+    nt, na = 12, 3
+    x_np = (rng.standard_normal((n_data, d)) * 1.2).astype(np.float32)
+    init = [rng.standard_normal((n_chains, n_data, d)).astype(np.float32) for _ in range(2)]
+    noises = [(rng.standard_normal((n_chains, n_data, d)).astype(np.float32),
+               rng.random_sample((n_chains, n_data)).astype(np.float32))
+              for _ in range(na + nt)]
+    c = np.float32(-0.5 * np.log(2 * np.pi))
+    xt = tf.constant(x_np)
+
+    def normal_lp(x, mean, std):        # Normal._log_prob (univariate.py:174-181), group_ndims 1
+        logstd = np.float32(np.log(std))
+        return tf.reduce_sum(c - logstd - np.float32(0.5 * np.exp(-2 * np.log(std)))
+                             * tf.square(x - mean), axis=-1)
+
+    class _Net(object):                 # the two BayesianNet methods AIS calls
+        def __init__(self, obs): self.obs = obs
+        def log_joint(self): return normal_lp(self.obs["z"], 0.0, 1.0)
+        def get(self, names): return [tf.random_normal([n_chains, n_data, d]) for _ in names]
+
+    class _Proposal(object):
+        def observe(self, **obs): return _Net(obs)
+
+    def log_joint(obs):
+        return normal_lp(obs["z"], 0.0, 1.0) + normal_lp(obs["x"], obs["z"], s)
+    z = tf.Variable(np.zeros((n_chains, n_data, d), np.float32), name="z", dtype=tf.float32)
+    hmc = hmc_mod.HMC(step_size=0.2, n_leapfrogs=3, adapt_step_size=True,
+                      target_acceptance_rate=0.7)
+    ais = ev.AIS(log_joint, _Proposal(), hmc, observed={"x": xt}, latent={"z": z},
+                 n_temperatures=nt, n_adapt=na)
+    # consumption order of AIS.run: prior draw, n_adapt x (p, u), prior draw, nt x (p, u)
+    normal = [init[0]] + [n[0] for n in noises[:na]] + [init[1]] + [n[0] for n in noises[na:]]
+    tf.set_noise(normal=normal, uniform=[n[1] for n in noises])
+    captured = {}
+    orig = ais._get_lower_bound
+    ais._get_lower_bound = lambda lw: captured.setdefault("lw", np.array(lw)) is None or orig(lw)
+    est = ais.run(tf.Session(), {})
+    assert not tf._NOISE["normal"] and not tf._NOISE["uniform"]
+    return dict(x=x_np, s=np.float32(s), init=np.stack(init),
+                noise_p=np.stack([n[0] for n in noises]), noise_u=np.stack([n[1] for n in noises]),
+                log_weights=captured["lw"].astype(np.float32), bound=np.float64(est),
+                z_final=np.array(z.value), n_temperatures=np.int32(nt), n_adapt=np.int32(na),
+                schedule=np.array([ais._get_schedule_t(t) for t in range(nt + 1)]))
+
+
 HMC_CASES = {
     "ref_hmc_diag": ("diag", 12, 16, dict(step_size=1e-3, n_leapfrogs=5,
                                           target_acceptance_rate=0.9, mass_collect_iters=4,
@@ -210,6 +266,9 @@ def main():
         out = run_reference_hmc(kind, D, C, cfg, n_iters, n_adapt, seed)
         np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
         print(name, "acc mean per iteration", np.round(out["acc"].mean(1), 3).tolist())
+    out = run_reference_ais()
+    np.savez_compressed(os.path.join(GOLD, "ref_ais.npz"), **out)
+    print("ref_ais bound", float(out["bound"]))
     out = run_reference_sgmcmc()
     np.savez_compressed(os.path.join(GOLD, "ref_sgmcmc.npz"), **out)
     print("ref_sgmcmc draws per step", {k: out[k].tolist() for k in out if k.endswith("_n_used")})

@@ -78,8 +78,9 @@ class TensorShape(object):
 class _Ctx(object):
     """One Session.run: memo of evaluated tensors, the feed, variable snapshots."""
 
-    def __init__(self, feed, parent=None, floor=None):
+    def __init__(self, feed, parent=None, floor=None, peek=False):
         self.feed = feed
+        self.peek = peek            # static-shape inference: unfed placeholders read as zeros
         self.memo = {}
         self.parent = parent
         self.floor = floor          # tensors created before `floor` belong to the parent
@@ -118,7 +119,7 @@ class Tensor(object):
 
     # --- static information (computed by a throw-away evaluation: only used on pure tensors) ---
     def _peek(self):
-        return _Ctx({}).eval(self)
+        return _Ctx({}, peek=True).eval(self)
 
     def get_shape(self):
         return TensorShape(np.shape(self._peek()))
@@ -216,6 +217,8 @@ def placeholder(dtype, shape=None, name=None):
         while cc is not None:
             if t in cc.feed:
                 return np.asarray(cc.feed[t], dtype=dtype)
+            if cc.peek and cc.parent is None:
+                return np.zeros(tuple(shape) if shape is not None else (), dtype=dtype)
             cc = cc.parent
         raise ValueError("placeholder %r was not fed" % (name,))
     t.fn = fn

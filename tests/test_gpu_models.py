@@ -194,6 +194,38 @@ def test_ais_device_loop_matches_oracle_step_for_step(zs):
     assert ais.temperature.is_cuda and float(ais.temperature) == 1.0
 
 
+def test_ais_device_loop_matches_reference_run(zs):
+    """tests/golden/ref_ais.npz: the reference's own class AIS (evaluation.py:57-172) and HMC,
+    executed on the NumPy TF stand-in (oracle/tf_shim/make_ref_golden.py) with every draw
+    injected; the device loop must reproduce its per-chain log-weights and bound."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_ais.npz"))
+    s = float(g["s"])
+    n_chains, n_data, d = g["init"].shape[1:]
+    nt, na = int(g["n_temperatures"]), int(g["n_adapt"])
+
+    def make(include_x):
+        @zs.meta_bayesian_net()
+        def m():
+            bn = zs.BayesianNet()
+            z = bn.normal('z', torch.zeros(n_data, d, device="cuda"), std=1.,
+                          group_ndims=1, n_samples=n_chains)
+            if include_x:
+                bn.normal('x', z.tensor, std=s, group_ndims=1)
+            return bn
+        return m()
+    hmc = zs.HMC(step_size=0.2, n_leapfrogs=3, adapt_step_size=True,
+                 target_acceptance_rate=0.7)
+    z = torch.zeros(n_chains, n_data, d, device="cuda")
+    ais = zs.AIS(make(True), make(False), hmc, observed={'x': T(g["x"])}, latent={'z': z},
+                 n_temperatures=nt, n_adapt=na)
+    est = ais.run(noise=lambda k: {"p": {"z": T(g["noise_p"][k])}, "u": T(g["noise_u"][k])},
+                  init=[[T(g["init"][0])], [T(g["init"][1])]])
+    np.testing.assert_allclose(N(ais.log_weights), g["log_weights"], rtol=2e-4, atol=2e-4)
+    assert abs(est - float(g["bound"])) < 2e-4
+    np.testing.assert_allclose(N(z), g["z_final"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(N(ais._schedule), g["schedule"], rtol=1e-6, atol=1e-7)
+
+
 @pytest.mark.parametrize("K,V,C,Dn", [(16, 50, 5, 3), (32, 200, 70, 4), (128, 1000, 130, 7)])
 def test_lntm_fused_kernel_matches_oracle(zs, K, V, C, Dn):
     """zs.fused.LNTMLogJoint (sparsity-aware fused kernel, csrc/lntm.cu) vs the dense float64

@@ -118,6 +118,28 @@ def test_oracle_sgmcmc_reproduces_reference_run(name):
     assert g[name + "_n_used"].tolist() == want
 
 
+def test_oracle_ais_reproduces_reference_run():
+    """class AIS of zhusuan/evaluation.py:57-172 driving the reference's HMC (prior draws, HMC noise
+    injected): per-chain log-weights and the bound."""
+    from oracle import evaluation as OE
+    g = np.load(os.path.join(GOLD, "ref_ais.npz"))
+    x, s = g["x"], float(g["s"])
+    c, f32 = -0.5 * np.log(2 * np.pi), np.float32
+    lp = lambda q: (c - 0.5 * q[0].astype(np.float64) ** 2).sum(-1).astype(f32)
+    gp = lambda q: [(-q[0]).astype(f32)]
+    lj = lambda q: (lp(q).astype(np.float64) + (c - np.log(s) - 0.5 * (
+        (x - q[0].astype(np.float64)) / s) ** 2).sum(-1)).astype(f32)
+    gj = lambda q: [(-q[0] + (x - q[0]) / (s * s)).astype(f32)]
+    oh = OH.HMC(step_size=0.2, n_leapfrogs=3, adapt_step_size=True, target_acceptance_rate=0.7)
+    nt, na = int(g["n_temperatures"]), int(g["n_adapt"])
+    oa = OE.AIS(lp, gp, lj, gj, oh, n_temperatures=nt, n_adapt=na)
+    est, lw = oa.run([[g["init"][0]], [g["init"][1]]],
+                     lambda k: ([g["noise_p"][k]], g["noise_u"][k]), adapt_flags=(True, False))
+    np.testing.assert_allclose(lw, g["log_weights"], rtol=1e-5, atol=5e-6)
+    assert abs(est - float(g["bound"])) < 5e-6
+    np.testing.assert_allclose([oa.schedule(t) for t in range(nt + 1)], g["schedule"], rtol=1e-12)
+
+
 def test_reference_run_equals_oracle_made_fixtures():
     """The round-1 fixtures (written by the oracle) and the reference-run ones share seeds and
     configurations: same inputs, same outputs."""
@@ -145,6 +167,10 @@ def test_committed_vectors_are_what_the_reference_code_produces():
             np.testing.assert_array_equal(out[k], g[k], err_msg=k)
         out = M.run_reference_sgmcmc()
         g = np.load(os.path.join(GOLD, "ref_sgmcmc.npz"))
+        for k in g.files:
+            np.testing.assert_array_equal(out[k], g[k], err_msg=k)
+        out = M.run_reference_ais()
+        g = np.load(os.path.join(GOLD, "ref_ais.npz"))
         for k in g.files:
             np.testing.assert_array_equal(out[k], g[k], err_msg=k)
         import zhusuan.hmc
