@@ -2,6 +2,8 @@
 log-joint (config 5, examples/topic_models/lntm_mcem.py:33-48, 97-105) through
 the BayesianNet contract incl. a two-chain-axis HMC run vs the oracle, and AIS
 (evaluation.py:57-172) against an analytic marginal likelihood."""
+import os
+
 import numpy as np
 import pytest
 import torch
