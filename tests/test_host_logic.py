@@ -458,3 +458,32 @@ def test_top_level_names_of_the_reference_package():
         deco = zs.reuse("scope")
     assert deco(lambda: 3)() == 3
     assert zs.merge_dicts({"a": 1}, {"b": 2}, {"a": 3}) == {"a": 3, "b": 2}
+
+
+def test_context_frames_are_per_thread():
+    """framework/utils.py Context: frames nest per class and per thread."""
+    import threading
+    from zhusuan_b200.framework.utils import Context
+
+    class A(Context):
+        pass
+
+    class B(Context):
+        pass
+    seen = {}
+    with A() as a:
+        with B() as b:
+            assert A.get_context() is a and B.get_context() is b
+
+            def other():
+                try:
+                    A.get_context()
+                    seen["other"] = "found"
+                except RuntimeError as e:
+                    seen["other"] = str(e)
+            t = threading.Thread(target=other)
+            t.start()
+            t.join()
+        with pytest.raises(RuntimeError, match="No contexts on the stack"):
+            B.get_context()
+    assert seen["other"] == "No contexts on the stack."

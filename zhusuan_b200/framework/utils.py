@@ -1,32 +1,40 @@
 """Context stack (zhusuan/framework/utils.py:20-46) and ``reuse_variables``."""
+import threading
 from functools import wraps
 
 __all__ = ["Context", "reuse_variables", "reuse"]
 
 
 class Context(object):
-    """Context stack; class-level lists, one per subclass, NOT thread-safe
-    (same as the reference, framework/utils.py:35-46)."""
-    _contexts = {}
+    """Scoped "who is building right now" frames (the role of zhusuan/framework/utils.py:20-46).
+
+    ``with frame:`` makes ``frame`` the innermost one of its class until the block ends;
+    ``Cls.get_context()`` returns the innermost frame of ``Cls`` or raises ``RuntimeError``.
+    Unlike the reference's class-level lists the stacks are PER THREAD (one dict of stacks in a
+    ``threading.local``), so two host threads can build nets concurrently."""
+
+    _tls = threading.local()
+
+    @classmethod
+    def get_contexts(cls):
+        stacks = Context._tls.__dict__.setdefault("stacks", {})
+        return stacks.setdefault(cls, [])       # Local and BayesianNet frames never mix
+
+    @classmethod
+    def get_context(cls):
+        frames = cls.get_contexts()
+        if not frames:
+            raise RuntimeError("No contexts on the stack.")
+        return frames[-1]
 
     def __enter__(self):
         type(self).get_contexts().append(self)
         return self
 
     def __exit__(self, exc_type, exc_val, exc_tb):
-        type(self).get_contexts().pop()
-
-    @classmethod
-    def get_contexts(cls):
-        # one stack per class (Local and BayesianNet do not share a stack)
-        return Context._contexts.setdefault(cls, [])
-
-    @classmethod
-    def get_context(cls):
-        try:
-            return cls.get_contexts()[-1]
-        except IndexError:
-            raise RuntimeError("No contexts on the stack.")
+        frames = type(self).get_contexts()
+        assert frames and frames[-1] is self, "context frames must nest"
+        frames.pop()
 
 
 def reuse_variables(scope):
