@@ -113,7 +113,10 @@ def main():
     op, info = h.sample(gaussian(), {}, {"x": xq})
     ms = timeit(lambda: op(), n=10)
     report("fused diag HMC iteration C1' (1M x 100, L=10)", 12 * C1 * D1, ms,
-           "read q, write q + init_momentum; %.3e chain-steps/s" % (C1 * L / (ms * 1e-3)))
+           "actual traffic: read q, write q + init_momentum; %.3e chain-steps/s; ALGORITHMIC "
+           "(SURVEY 8d: 16 D B per chain-step) %.0f GB/s = %.3f of the HBM peak" % (
+               C1 * L / (ms * 1e-3), 16 * D1 * C1 * L / (ms * 1e-3) / 1e9,
+               16 * D1 * C1 * L / (ms * 1e-3) / 1e9 / PEAK))
     # config 1 proper: 64 chains x 100, L=10 (launch-latency bound)
     xq2 = torch.zeros(64, D1, device=dev)
     h2 = zs.HMC(step_size=1e-3, n_leapfrogs=10, adapt_step_size=True, adapt_mass=True,
@@ -135,8 +138,8 @@ def main():
     report("config 1 via CUDA graph", 12 * 64 * D1, ms,
            "%.3e chain-steps/s, %.1f us per iteration" % (64 * 10 / (ms * 1e-3), ms * 1e3))
     # dense D=64, 4096 chains, L=10: small-problem regime for the dense path
-    import oracle.models as OM
-    P, _ = OM.make_dense_gaussian_problem(64, seed=2)
+    from bench import make_dense_gaussian_problem
+    P, _ = make_dense_gaussian_problem(64, seed=2)
     for graph in (False, True):
         xd = torch.randn(4096, 64, device=dev)
         hd = zs.HMC(step_size=0.05, n_leapfrogs=10, adapt_step_size=True, seed=3,

@@ -1,0 +1,8 @@
+#!/bin/bash
+# BNN SGHMC kernel rewrite: parity tests, config-4 bench, round-2 microbenchmarks, ncu of the kernel
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_sgmcmc.py tests/test_gpu_models.py -q -m gpu 2>&1 | tail -8 > gpurun_out/r2_call17_tests.log
+cat gpurun_out/r2_call17_tests.log
+timeout 300 python scripts/bench_bnn.py > gpurun_out/r2_call17_bnn.jsonl 2> gpurun_out/r2_call17_bnn.err; cat gpurun_out/r2_call17_bnn.jsonl; tail -3 gpurun_out/r2_call17_bnn.err
+timeout 600 python scripts/bench_kernels.py > gpurun_out/r2_call17_kernels.jsonl 2> gpurun_out/r2_call17_kernels.err; cat gpurun_out/r2_call17_kernels.jsonl; tail -3 gpurun_out/r2_call17_kernels.err
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sghmc_bnn -s 5 -c 1 -o gpurun_out/r2_call17_bnn python scripts/bench_bnn.py > gpurun_out/r2_call17_ncu.log 2>&1; tail -3 gpurun_out/r2_call17_ncu.log
