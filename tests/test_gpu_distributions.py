@@ -584,3 +584,70 @@ def test_plugin_distribution_subclass_group_sum_on_device():
     bn = zs.BayesianNet(observed={"y": x})
     node = bn.stochastic("y", Scaled(scale, group_ndims=3))
     assert tuple(node.cond_log_p.shape) == (5,) and tuple(bn.log_joint().shape) == (5,)
+
+
+@pytest.mark.parametrize("rows,group,pn", [(4096, 16, "row"), (1000, 40, "tile"), (64, 784, "full"),
+                                           (333, 12, "scalar"), (50, 100, "row")])
+def test_vec4_row_kernels_match_scalar_path(rows, group, pn):
+    """csrc/distributions.cu: the 128-bit row-reduce path (aligned operands, group % 4 == 0) and
+    the scalar path (forced here by operands whose device pointer is 4 bytes off a 16-byte
+    boundary) evaluate the same log-probs, gradients and reparameterised samples -- the latter
+    bit for bit, Philox block i >> 2 feeding elements 4 (i >> 2) .. + 3 in both."""
+    from zhusuan_b200._lib import lib, ptr, stream
+    rng = np.random.RandomState(rows + group)
+    n = rows * group
+    pshape = {"row": (group,), "tile": (rows // 8 if rows % 8 == 0 else rows, group),
+              "full": (rows, group), "scalar": (1,)}[pn]
+
+    def both(a):
+        """(aligned copy, copy whose data_ptr is 4 bytes past a 16-byte boundary)"""
+        al = T(a).contiguous()
+        buf = torch.empty(al.numel() + 4, device="cuda", dtype=al.dtype)
+        off = buf[1:1 + al.numel()].view(al.shape)
+        off.copy_(al)
+        assert al.data_ptr() % 16 == 0 and off.data_ptr() % 16 == 4
+        return al, off
+    x = both(rng.standard_normal((rows, group)).astype(np.float32))
+    mu = both(rng.standard_normal(pshape).astype(np.float32))
+    ls = both((0.3 * rng.standard_normal(pshape)).astype(np.float32))
+    lg = both(rng.standard_normal((rows, group)).astype(np.float32))
+    xb = both((rng.random_sample(pshape if pn != "scalar" else (rows, group)) < 0.3)
+              .astype(np.float32))
+    gout = T(rng.standard_normal(rows).astype(np.float32))
+    res = []
+    for v in (0, 1):
+        out = torch.empty(rows, device="cuda")
+        lib.call("zsb_logprob_normal_f32", ptr(x[v]), n, ptr(mu[v]), mu[v].numel(), ptr(ls[v]),
+                 ls[v].numel(), ptr(out), rows, group, stream())
+        d = [both(np.zeros((rows, group), np.float32))[v] for _ in range(3)]
+        lib.call("zsb_logprob_normal_bwd_f32", ptr(x[v]), n, ptr(mu[v]), mu[v].numel(),
+                 ptr(ls[v]), ls[v].numel(), ptr(gout), rows, group, ptr(d[0]), ptr(d[1]),
+                 ptr(d[2]), stream())
+        ob = torch.empty(rows, device="cuda")
+        lib.call("zsb_logprob_bernoulli_f32", ptr(xb[v]), xb[v].numel(), ptr(lg[v]), n, ptr(ob),
+                 rows, group, stream())
+        dl = both(np.zeros((rows, group), np.float32))[v]
+        lib.call("zsb_logprob_bernoulli_bwd_f32", ptr(xb[v]), xb[v].numel(), ptr(lg[v]), n,
+                 ptr(gout), rows, group, ptr(dl), stream())
+        gs = torch.empty(rows, device="cuda")
+        lib.call("zsb_group_sum_f32", ptr(x[v]), ptr(gs), rows, group, stream())
+        z = both(np.zeros((rows, group), np.float32))[v]
+        e = both(np.zeros((rows, group), np.float32))[v]
+        lq = torch.empty(rows, device="cuda")
+        lib.call("zsb_reparam_normal_f32", ptr(mu[v]), mu[v].numel(), ptr(ls[v]), ls[v].numel(),
+                 None, 77, 3, ptr(z), ptr(e), ptr(lq), rows, group, stream())
+        z1 = both(np.zeros((rows, group), np.float32))[v]
+        lib.call("zsb_reparam_normal_f32", ptr(mu[v]), mu[v].numel(), ptr(ls[v]), ls[v].numel(),
+                 None, 77, 3, ptr(z1), None, None, n, 1, stream())
+        res.append([N(t) for t in (out, d[0], d[1], d[2], ob, dl, gs, z, e, lq, z1)])
+    names = "lp dgiven dmean dlogstd lp_b dlogits gsum z eps logq z_flat".split()
+    for name, a, b in zip(names, *res):
+        if name in ("z", "eps", "z_flat"):
+            np.testing.assert_array_equal(a, b, err_msg=name)
+        else:
+            np.testing.assert_allclose(a, b, rtol=2e-5, atol=2e-5 * group ** 0.5, err_msg=name)
+    np.testing.assert_array_equal(res[0][7], res[0][10])       # grouped and flat draws agree
+    ref = OD.normal_log_prob(N(x[0]), N(mu[0]).reshape(pshape), N(ls[0]).reshape(pshape), 1,
+                             np.float64) if pn != "tile" else None
+    if ref is not None:
+        np.testing.assert_allclose(res[0][0], ref, rtol=RTOL, atol=1e-4)
