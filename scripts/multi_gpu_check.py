@@ -31,7 +31,12 @@ def run(model_fn, q, n_iters, group, chain_offset, dense, graph=False):
     for i in range(n_iters):
         op(adapt_step_size=True, adapt_mass=True)
     op.synchronize()
-    info.n_collectives = h._pk.n_collectives
+    c_adapt = h._pk.n_collectives
+    for i in range(3):                      # sampling phase: nothing adapts, nothing to exchange
+        op(adapt_step_size=False, adapt_mass=False)
+    op.synchronize()
+    info.n_collectives = c_adapt
+    info.n_collectives_sampling = h._pk.n_collectives - c_adapt
     info.n_search = h.n_search_iters
     return info
 
@@ -89,6 +94,9 @@ def main():
                   % (case, d, same_rows, ss, torch.cat(accs).mean().item(),
                      info1.acceptance_rate.mean().item(), info.n_collectives, want))
             ok &= same_rows > 0.98 and ss < 1e-4 and info.n_collectives == want
+            ok &= info.n_collectives_sampling == 0      # 3 non-adapting iterations: no all-reduce
+            print("   + 3 non-adapting iterations: %d collectives (expected 0)"
+                  % info.n_collectives_sampling)
         td.barrier()
     if rank == 0:
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")

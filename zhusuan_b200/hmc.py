@@ -341,6 +341,10 @@ class HMC(object):
             return self._iterate_graph(adapt_step, adapt_m)
         return self._iterate_eager(adapt_step, adapt_m, noise, t, init)
 
+    def _needs_acc_exchange(self, adapt_step):
+        """Does this iteration's tuner update read the GLOBAL mean acceptance?"""
+        return bool(self._has_step and adapt_step)
+
     def _iterate_graph(self, adapt_step, adapt_m):
         """Replay (or first capture) the iteration as a CUDA graph.  All
         per-iteration scalars (t / Philox iteration, EWMV count, ones-vs-
@@ -371,7 +375,8 @@ class HMC(object):
             self._ewmv_t += 1
         g.replay()
         lib.launches += self._graph_launches[key]   # kernels the replay launches
-        if self._world > 1:
+        if self._world > 1 and ((adapt_m and self._has_mass) or
+                                self._needs_acc_exchange(adapt_step)):
             self._pk.n_collectives += 1        # the all-reduce captured in the graph
         self._pk.mass_valid = bool(adapt_m and self._has_mass)
         self._q_versions = [q._version for q in self._q]
@@ -435,11 +440,18 @@ class HMC(object):
         prefetch = bool(self._has_mass and adapt_m)
         if prefetch:
             self._mass_stats_into_packed(s)
+        # The global mean acceptance only feeds the dual-averaging update (hmc.py:89-112 inside
+        # tf.cond(adapt_step_size)); an iteration that adapts neither step size nor mass has no
+        # exchange step at all, its ranks run unsynchronised (state[ACC_MEAN] is then rank-local).
+        exchange = prefetch or self._needs_acc_exchange(adapt_step)
         if dev:
-            if self._world > 1:                # captured into the graph
+            if self._world > 1 and exchange:   # captured into the graph
                 zdist.all_reduce_sum(self._pk.buf if prefetch else self._pk.acc, self._group)
         else:
-            self._pk.reduce_all(prefetch)      # the ONE collective of the iteration
+            if exchange:
+                self._pk.reduce_all(prefetch)  # the ONE collective of the iteration
+            else:
+                self._pk.mass_valid = False
             self._q_versions = [q._version for q in self._q]
         lib.call("zsb_hmc_tune_f32", ptr(self._state), ptr(self._stats),
                  int(self._has_step), int(adapt_step), 1.0 if init else 0.0,
