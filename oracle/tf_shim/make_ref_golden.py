@@ -70,15 +70,18 @@ def run_reference_hmc(kind, D, C, cfg, n_iters, n_adapt, seed):
         q0 = rng.standard_normal((C, D)).astype(np.float32)
         out.update(P=P, mu=mu, const=np.float64(const))
     else:
+        # the model of examples/toy_examples/gaussian.py:15-20, built with the REFERENCE'S OWN
+        # meta_bayesian_net / BayesianNet.normal / Normal.log_prob (framework/bn.py,
+        # framework/meta_bn.py, distributions/univariate.py run on the stand-in too)
+        fw = importlib.import_module("zhusuan.framework")
         std = (1.0 / (1.0 + np.arange(D))).astype(np.float32)      # gaussian.py:29
-        logstd = np.log(std).astype(np.float32)
-        ls = tf.constant(logstd)
 
-        def log_joint(obs):        # Normal._log_prob, univariate.py:174-181, group_ndims = 1
-            x = obs["x"]
-            c = np.float32(-0.5 * np.log(2 * np.pi))
-            precision = tf.exp(-2 * ls)
-            return tf.reduce_sum(c - ls - 0.5 * precision * tf.square(x - 0.0), axis=-1)
+        @fw.meta_bayesian_net()
+        def gaussian(n_x, stdev, n_particles):
+            bn = fw.BayesianNet()
+            bn.normal('x', tf.zeros([n_x]), std=stdev, n_samples=n_particles, group_ndims=1)
+            return bn
+        log_joint = gaussian(D, std, C)
         q0 = (0.1 * rng.standard_normal((C, D))).astype(np.float32)
         out.update(std=std)
     adapt_step = tf.placeholder(tf.bool, shape=[], name="adapt_step_size")

@@ -33,6 +33,7 @@ import numpy as np
 __version__ = "1.x-numpy-shim"
 
 float32, float64, int32, int64, bool = np.float32, np.float64, np.int32, np.int64, np.bool_
+float16, int16, int8, uint8 = np.float16, np.int16, np.int8, np.uint8
 _SERIAL = [0]
 _CTRL_STACK = [[]]
 
@@ -80,7 +81,7 @@ class _Ctx(object):
 
     def __init__(self, feed, parent=None, floor=None, peek=False):
         self.feed = feed
-        self.peek = peek            # static-shape inference: unfed placeholders read as zeros
+        self.peek = peek            # static-shape inference, see _is_peek()
         self.memo = {}
         self.parent = parent
         self.floor = floor          # tensors created before `floor` belong to the parent
@@ -101,6 +102,18 @@ class _Ctx(object):
         v = t.fn(self)
         home.memo[id(t)] = (t, v)
         return v
+
+
+def _is_peek(c):
+    """Static-shape inference (`Tensor.get_shape`) evaluates a tensor in a scratch context.  There
+    the graph must be free of side effects and cheap: random ops yield zeros without consuming
+    injected noise, assigns do not write, unfed placeholders read as zeros, `cond` takes its first
+    branch and `while_loop` returns its initial loop variables (both shape-preserving in TF)."""
+    while c is not None:
+        if c.peek:
+            return True
+        c = c.parent
+    return False
 
 
 class Tensor(object):
@@ -186,6 +199,9 @@ def _f32(a):
 
 
 def convert_to_tensor(value, dtype=None, name=None, preferred_dtype=None):
+    for typ, conv in _TENSOR_CONVERSIONS:          # Tensor-likes registered by the reference
+        if isinstance(value, typ):
+            return convert_to_tensor(conv(value, dtype=dtype, name=name, as_ref=False), dtype)
     if isinstance(value, Tensor):
         if dtype is not None and value._dtype is not None and value._dtype is not dtype:
             return cast(value, dtype)
@@ -229,7 +245,8 @@ def placeholder(dtype, shape=None, name=None):
 class Variable(Tensor):
     def __init__(self, initial_value, name=None, trainable=True, dtype=None):
         if isinstance(initial_value, Tensor):
-            v = np.array(initial_value._peek())
+            # a real evaluation (initialisers draw from the injected noise), not a shape peek
+            v = np.array(_Ctx({}).eval(initial_value))
         else:
             v = np.array(initial_value)
         if dtype is not None:
@@ -264,6 +281,8 @@ def assign(ref, value, validate_shape=None, use_locking=None):
 
     def fn(c):
         v = np.array(c.eval(value), dtype=ref.value.dtype)
+        if _is_peek(c):
+            return v.reshape(ref.value.shape) if v.shape != ref.value.shape else v
         c.eval(ref)                        # pin the pre-assignment snapshot for this run
         ref.value = v.reshape(ref.value.shape) if v.shape != ref.value.shape else v
         return ref.value
@@ -609,6 +628,8 @@ def cond(pred, true_fn=None, false_fn=None, name=None, fn1=None, fn2=None, stric
     outs = []
     for tt, ff in zip(t_list, f_list):
         def fn(c, tt=tt, ff=ff):
+            if _is_peek(c):
+                return c.eval(tt)
             return c.eval(tt) if builtins_bool(c.eval(pred)) else c.eval(ff)
         outs.append(Tensor(fn, inputs=(pred, tt, ff), op="cond", dtype=_dt(tt, ff)))
     return outs if is_list else outs[0]
@@ -636,7 +657,7 @@ def while_loop(cond, body, loop_vars, shape_invariants=None, parallel_iterations
     def run(c):
         vals = [c.eval(t) for t in flat]
         it = 0
-        while True:
+        while not _is_peek(c):
             floor = _SERIAL[0] + 1
             sub = _Ctx(c.feed, parent=c, floor=floor)     # this iteration's temporaries
             consts = [Tensor(lambda cc, v=v: v, op="loop_var",
@@ -716,6 +737,8 @@ def set_noise(normal=(), uniform=()):
 def _noise_op(kind, shp, extra):
     def fn(c):
         want = _shape_arg(c, shp)
+        if _is_peek(c):
+            return extra(np.zeros(want, np.float32))
         if not _NOISE[kind]:
             raise RuntimeError("tf.random_%s evaluated but no injected noise is left" % kind)
         a = np.asarray(_NOISE[kind].pop(0), np.float32)
@@ -773,6 +796,10 @@ class Session(object):
                 if hasattr(f, "_fields"):
                     return type(f)(*out)
                 return out if isinstance(f, list) else tuple(out)
+            for typ, fetch_fn in _RUN_CONVERSIONS:  # e.g. StochasticTensor (bn.py:311-316)
+                if isinstance(f, typ):
+                    tensors, contraction = fetch_fn(f)
+                    return contraction([ev(t) for t in tensors])
             if hasattr(f, "__dict__"):              # plain result structs (HMCInfo)
                 import copy
                 o = copy.copy(f)
@@ -791,6 +818,123 @@ class errors(object):
 
 class train(object):
     pass
+
+
+# ---- what zhusuan/framework/bn.py and zhusuan/distributions/{base,utils,univariate}.py add -------
+def rank(a, name=None):
+    a = convert_to_tensor(a)
+    return Tensor(lambda c: np.int32(np.ndim(c.eval(a))), inputs=(a,), op="rank", dtype=np.int32)
+
+
+def _assert(check, what):
+    def build(x, y=None, message=None, data=None, summarize=None, name=None):
+        x = convert_to_tensor(x)
+        y_t = None if y is None else (y if isinstance(y, Tensor) else None)
+
+        def fn(c):
+            yv = c.eval(y_t) if y_t is not None else y
+            if not check(np.asarray(c.eval(x)), yv):
+                raise errors.InvalidArgumentError(None, None, message or ("assert_%s failed" % what))
+            return None
+        return Tensor(fn, inputs=(x,) + ((y_t,) if y_t is not None else ()), op="assert_" + what)
+    return build
+
+
+assert_rank = _assert(lambda x, r: x.ndim == int(r), "rank")
+assert_rank_at_least = _assert(lambda x, r: x.ndim >= int(r), "rank_at_least")
+assert_greater_equal = _assert(lambda x, y: np.all(x >= y), "greater_equal")
+assert_greater = _assert(lambda x, y: np.all(x > y), "greater")
+assert_less_equal = _assert(lambda x, y: np.all(x <= y), "less_equal")
+assert_positive = _assert(lambda x, y: np.all(x > 0), "positive")
+
+
+def squeeze(a, axis=None, name=None, squeeze_dims=None):
+    axis = squeeze_dims if axis is None else axis
+    ax = None if axis is None else (tuple(axis) if isinstance(axis, (list, tuple)) else axis)
+    a = convert_to_tensor(a)
+    return Tensor(lambda c: np.squeeze(c.eval(a), axis=ax), inputs=(a,), op="squeeze",
+                  vjp=lambda g: [reshape(g, shape(a))], dtype=a._dtype)
+
+
+def concat(values, axis, name=None):
+    vals = [convert_to_tensor(v) for v in values]
+    return Tensor(lambda c: np.concatenate([np.atleast_1d(c.eval(v)) for v in vals],
+                                           axis=int(c.eval(axis)) if isinstance(axis, Tensor)
+                                           else axis),
+                  inputs=tuple(vals), op="concat", dtype=_dt(*vals))
+
+
+def reduce_prod(a, axis=None, keepdims=False, name=None, reduction_indices=None, keep_dims=None):
+    t = _reduce(np.prod, a, axis if axis is not None else reduction_indices,
+                keepdims or (True if keep_dims else False), "prod", None)
+    t.vjp = None                                   # not differentiated by the reference paths run
+    return t
+
+
+def reduce_all(a, axis=None, keepdims=False, name=None):
+    a = convert_to_tensor(a)
+    return Tensor(lambda c: np.all(c.eval(a), axis=axis, keepdims=keepdims), inputs=(a,),
+                  op="reduce_all", dtype=np.bool_)
+
+
+def reduce_max(a, axis=None, keepdims=False, name=None, reduction_indices=None, keep_dims=None):
+    t = _reduce(np.max, a, axis if axis is not None else reduction_indices,
+                keepdims or (True if keep_dims else False), "max", None)
+    t.vjp = None
+    return t
+
+
+def broadcast_static_shape(s1, s2):
+    return TensorShape(np.broadcast_shapes(tuple(TensorShape(s1).as_list()),
+                                           tuple(TensorShape(s2).as_list())))
+
+
+def lgamma(a, name=None):
+    from scipy.special import gammaln
+    return _unary(lambda x: gammaln(x).astype(np.asarray(x).dtype), a, "lgamma")
+
+
+def make_template(name, func, create_scope_now_=False, unique_name_=None, custom_getter_=None,
+                  **kwargs):
+    return func
+
+
+class contrib(object):
+    class distributions(object):
+        pass
+
+
+# ---- `tensorflow.python.client.session` (zhusuan/framework/bn.py:10-11, variational/base.py:12) ---
+_RUN_CONVERSIONS = []       # (type, fetch_function) registered by the reference's Tensor-likes
+_TENSOR_CONVERSIONS = []    # (type, conversion function)
+
+
+def register_tensor_conversion_function(base_type, conversion_func, priority=100):
+    _TENSOR_CONVERSIONS.append((base_type, conversion_func))
+
+
+def _register_session_run_conversion_functions(tensor_type, fetch_function, feed_function=None,
+                                               feed_function_for_partial_run=None):
+    _RUN_CONVERSIONS.append((tensor_type, fetch_function))
+
+
+def _install_submodules():
+    import sys
+    import types
+    me = sys.modules[__name__]
+    me.__path__ = []                                    # importable as a package
+    py = types.ModuleType(__name__ + ".python")
+    client = types.ModuleType(__name__ + ".python.client")
+    sess = types.ModuleType(__name__ + ".python.client.session")
+    sess.register_session_run_conversion_functions = _register_session_run_conversion_functions
+    py.client, client.session = client, sess
+    py.__path__, client.__path__ = [], []
+    for m in (py, client, sess):
+        sys.modules[m.__name__] = m
+    me.python = py
+
+
+_install_submodules()
 
 
 def __getattr__(name):

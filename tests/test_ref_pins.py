@@ -159,12 +159,15 @@ def test_committed_vectors_are_what_the_reference_code_produces():
     saved = {k: sys.modules.get(k) for k in ("tensorflow", "zhusuan")}
     try:
         import make_ref_golden as M
-        name = "ref_hmc_dense32"
-        kind, D, C, cfg, n_iters, n_adapt, seed = M.HMC_CASES[name]
-        out = M.run_reference_hmc(kind, D, C, cfg, n_iters, n_adapt, seed)
-        g = np.load(os.path.join(GOLD, name + ".npz"))
-        for k in ("q", "acc", "step_size", "lp", "h0", "h1", "lp0", "p0", "accept", "noise_p"):
-            np.testing.assert_array_equal(out[k], g[k], err_msg=k)
+        # ref_hmc_diag: the model of examples/toy_examples/gaussian.py built with the reference's
+        # own meta_bayesian_net / BayesianNet.normal / Normal.log_prob; dense32: a callable
+        for name in ("ref_hmc_diag", "ref_hmc_dense32"):
+            kind, D, C, cfg, n_iters, n_adapt, seed = M.HMC_CASES[name]
+            out = M.run_reference_hmc(kind, D, C, cfg, n_iters, n_adapt, seed)
+            g = np.load(os.path.join(GOLD, name + ".npz"))
+            for k in ("q", "acc", "step_size", "lp", "h0", "h1", "lp0", "p0", "accept",
+                      "noise_p"):
+                np.testing.assert_array_equal(out[k], g[k], err_msg=name + " " + k)
         out = M.run_reference_sgmcmc()
         g = np.load(os.path.join(GOLD, "ref_sgmcmc.npz"))
         for k in g.files:
