@@ -251,6 +251,95 @@ def run_reference_ais(seed=4):
                 schedule=np.array([ais._get_schedule_t(t) for t in range(nt + 1)]))
 
 
+def run_reference_variational(seed=77):
+    """The VAE of examples/variational_autoencoders/iwae.py:23-44 (smaller layers) on the
+    REFERENCE'S OWN framework + distributions + variational code: importance_weighted_objective /
+    elbo with .sgvb() (iwae.py:72-75), and elbo(...).reinforce() over three steps (moving-mean
+    baseline state).  tf.layers.dense weights are Glorot-uniform draws of the given generator."""
+    tf, _, _ = load_reference()
+    fw = importlib.import_module("zhusuan.framework")
+    var = importlib.import_module("zhusuan.variational")
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tf.reset_default_graph()
+    tf.set_init_rng(rng)
+    N, x_dim, z_dim, H, K = 6, 10, 4, 8, 5
+
+    @fw.meta_bayesian_net(scope="gen", reuse_variables=True)
+    def build_gen(n, x_dim, z_dim, n_particles):
+        bn = fw.BayesianNet()
+        z_mean = tf.zeros([n, z_dim])
+        z = bn.normal("z", z_mean, std=1., group_ndims=1, n_samples=n_particles)
+        h = tf.layers.dense(z, H, activation=tf.nn.relu)
+        h = tf.layers.dense(h, H, activation=tf.nn.relu)
+        x_logits = tf.layers.dense(h, x_dim)
+        bn.bernoulli("x", x_logits, group_ndims=1)
+        return bn
+
+    def q_net(reparameterized):
+        @fw.reuse_variables(scope="q_net")
+        def build_q_net(x, z_dim, n_particles):
+            bn = fw.BayesianNet()
+            h = tf.layers.dense(tf.cast(x, tf.float32), H, activation=tf.nn.relu)
+            h = tf.layers.dense(h, H, activation=tf.nn.relu)
+            z_mean = tf.layers.dense(h, z_dim)
+            z_logstd = tf.layers.dense(h, z_dim)
+            bn.normal("z", z_mean, logstd=z_logstd, group_ndims=1, n_samples=n_particles,
+                      is_reparameterized=reparameterized)
+            return bn
+        return build_q_net
+    x_np = (rng.random((N, x_dim)) < 0.4).astype(np.int32)
+    x = tf.constant(x_np)
+    model = build_gen(N, x_dim, z_dim, K)
+    build_q = q_net(True)
+    variational = build_q(x, z_dim, K)
+    iw = var.importance_weighted_objective(model, {'x': x}, variational=variational, axis=0)
+    el = var.elbo(model, {'x': x}, variational=variational, axis=0)
+    q_vars = tf.trainable_variables()                 # the four q-net layers (built first)
+    iw_cost, el_cost = tf.reduce_mean(iw.sgvb()), tf.reduce_mean(el.sgvb())
+    lj, ent = iw._log_joint_term(), iw._entropy_term()        # builds the generator
+    all_vars = tf.trainable_variables()
+    names = ["q%d_%s" % (i // 2, "wb"[i % 2]) for i in range(len(q_vars))] + \
+            ["g%d_%s" % (i // 2, "wb"[i % 2]) for i in range(len(all_vars) - len(q_vars))]
+    eps = rng.standard_normal((K, N, z_dim)).astype(np.float32)
+    sess = tf.Session()
+    out = {"x": x_np, "eps": eps, "names": np.array(names)}
+    for nme, v in zip(names, all_vars):
+        out["w_" + nme] = np.array(v.value)
+    tf.set_noise(normal=[eps])
+    r = sess.run([iw, iw_cost, lj, ent] + tf.gradients(iw_cost, all_vars))
+    out.update(iw_bound=r[0], iw_cost=r[1], log_joint=r[2], entropy=r[3])
+    for nme, g in zip(names, r[4:]):
+        out["iw_grad_" + nme] = g
+    tf.set_noise(normal=[eps])
+    r = sess.run([el, el_cost] + tf.gradients(el_cost, all_vars))
+    out.update(elbo_bound=r[0], elbo_cost=r[1])
+    for nme, g in zip(names, r[2:]):
+        out["elbo_grad_" + nme] = g
+    # ---- score-function estimator with the moving-mean baseline, three consecutive steps -------
+    variational_sf = q_net(False)
+    # the SAME q-net weights: reuse_variables templates own their variables, so copy them over
+    bn_sf = variational_sf(x, z_dim, K)
+    sf_vars = tf.trainable_variables()[len(all_vars):]
+    for dst, src in zip(sf_vars, q_vars):
+        dst.load(src.value)
+    el_sf = var.elbo(model, {'x': x}, variational=bn_sf, axis=0)
+    rf_cost = tf.reduce_mean(el_sf.reinforce())
+    rf_grads = tf.gradients(rf_cost, sf_vars)
+    mm = tf.get_variable('moving_mean')
+    eps_sf = rng.standard_normal((3, K, N, z_dim)).astype(np.float32)
+    costs, mms, grads = [], [], []
+    for t in range(3):
+        tf.set_noise(normal=[eps_sf[t]])
+        r = sess.run([rf_cost] + rf_grads)
+        costs.append(r[0])
+        grads.append(r[1:])
+        mms.append(np.array(mm.value))
+    out.update(rf_eps=eps_sf, rf_cost=np.array(costs), rf_moving_mean=np.array(mms))
+    for i, nme in enumerate(names[:len(q_vars)]):
+        out["rf_grad_" + nme] = np.stack([g[i] for g in grads])
+    return out
+
+
 HMC_CASES = {
     "ref_hmc_diag": ("diag", 12, 16, dict(step_size=1e-3, n_leapfrogs=5,
                                           target_acceptance_rate=0.9, mass_collect_iters=4,
@@ -269,6 +358,10 @@ def main():
         out = run_reference_hmc(kind, D, C, cfg, n_iters, n_adapt, seed)
         np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
         print(name, "acc mean per iteration", np.round(out["acc"].mean(1), 3).tolist())
+    out = run_reference_variational()
+    np.savez_compressed(os.path.join(GOLD, "ref_vae.npz"), **out)
+    print("ref_vae iw bound", out["iw_bound"].tolist(), "reinforce costs", out["rf_cost"].tolist(),
+          "moving mean", out["rf_moving_mean"].tolist())
     out = run_reference_ais()
     np.savez_compressed(os.path.join(GOLD, "ref_ais.npz"), **out)
     print("ref_ais bound", float(out["bound"]))

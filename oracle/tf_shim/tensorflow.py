@@ -50,6 +50,16 @@ class TensorShape(object):
     def as_list(self):
         return list(self._dims)
 
+    def is_fully_defined(self):
+        return self._dims is not None and all(d is not None for d in self._dims)
+
+    def is_compatible_with(self, other):
+        o = other if isinstance(other, TensorShape) else TensorShape(other)
+        if self._dims is None or o._dims is None:
+            return True
+        return len(self._dims) == len(o._dims) and all(
+            a is None or b is None or a == b for a, b in zip(self._dims, o._dims))
+
     def concatenate(self, other):
         return TensorShape(self._dims + TensorShape(other)._dims if not isinstance(
             other, TensorShape) else self._dims + other._dims)
@@ -139,6 +149,9 @@ class Tensor(object):
 
     shape = property(get_shape)
 
+    def set_shape(self, shape):                 # static hints carry no information here
+        pass
+
     @property
     def dtype(self):
         return self._dtype if self._dtype is not None else np.float32
@@ -201,7 +214,8 @@ def _f32(a):
 def convert_to_tensor(value, dtype=None, name=None, preferred_dtype=None):
     for typ, conv in _TENSOR_CONVERSIONS:          # Tensor-likes registered by the reference
         if isinstance(value, typ):
-            return convert_to_tensor(conv(value, dtype=dtype, name=name, as_ref=False), dtype)
+            # dtype objects here are NumPy types (no .is_compatible_with): convert, then cast
+            return convert_to_tensor(conv(value, dtype=None, name=name, as_ref=False), dtype)
     if isinstance(value, Tensor):
         if dtype is not None and value._dtype is not None and value._dtype is not dtype:
             return cast(value, dtype)
@@ -461,7 +475,9 @@ def stop_gradient(a, name=None):
 
 def cast(a, dtype, name=None):
     a = convert_to_tensor(a)
-    return _unary(lambda x: np.asarray(x).astype(dtype), a, "cast", lambda g: [g], dtype=dtype)
+    flt = np.dtype(dtype).kind == "f" and (a._dtype is None or np.dtype(a._dtype).kind == "f")
+    return _unary(lambda x: np.asarray(x).astype(dtype), a, "cast",
+                  (lambda g: [cast(g, a._dtype or np.float32)]) if flt else None, dtype=dtype)
 
 
 to_float = lambda a, name=None: cast(a, np.float32)            # noqa: E731
@@ -564,7 +580,10 @@ def _reduce(npf, a, axis, keepdims, op, vjp_scale):
         ax = _axes(c, axis, x.ndim)
         if ax is not None and len(ax) == 0:
             return x
-        return npf(x, axis=ax, keepdims=(True if keepdims else False), dtype=x.dtype if x.dtype.kind == "f" else None)
+        kd = True if keepdims else False
+        if npf in (np.max, np.min):
+            return npf(x, axis=ax, keepdims=kd)
+        return npf(x, axis=ax, keepdims=kd, dtype=x.dtype if x.dtype.kind == "f" else None)
     out = Tensor(fn, inputs=(a,), op=op, dtype=a._dtype)
 
     def vjp(g):
@@ -707,14 +726,21 @@ def gradients(ys, xs, grad_ys=None, name=None, **kw):
                     visit(i)
         order.append(t)
     visit(y)
+    active = {}                     # does the tensor depend on any x?  (order is topological)
+    for t in order:
+        active[id(t)] = id(t) in xset or any(
+            isinstance(i, Tensor) and active.get(id(i), False) for i in t.inputs)
     cot = {id(y): ones_like(y)}
     for t in reversed(order):
         g = cot.get(id(t))
         if g is None or id(t) in xset or t.vjp is None:
-            if g is not None and id(t) not in xset and t.vjp is None and t.op not in (
-                    "const", "variable", "placeholder", "loop_var", "zeros", "ones", "cmp",
-                    "shape", "range", "zeros_like", "ones_like"):
+            if g is not None and id(t) not in xset and t.vjp is None and active[id(t)] and \
+                    t.op not in ("const", "variable", "placeholder", "loop_var", "zeros", "ones",
+                                 "cmp", "shape", "range", "zeros_like", "ones_like",
+                                 "stop_gradient"):
                 raise NotImplementedError("tf.gradients through op %r" % t.op)
+            continue
+        if not active[id(t)]:
             continue
         for inp, gi in zip(t.inputs, t.vjp(g)):
             if gi is None or not isinstance(inp, Tensor):
@@ -878,9 +904,11 @@ def reduce_all(a, axis=None, keepdims=False, name=None):
 
 
 def reduce_max(a, axis=None, keepdims=False, name=None, reduction_indices=None, keep_dims=None):
-    t = _reduce(np.max, a, axis if axis is not None else reduction_indices,
-                keepdims or (True if keep_dims else False), "max", None)
-    t.vjp = None
+    axis = axis if axis is not None else reduction_indices
+    kd = True if (keepdims or keep_dims) else False
+    a = convert_to_tensor(a)
+    t = _reduce(np.max, a, axis, kd, "max", None)
+    t.vjp = _reduce_max_vjp(a, axis, kd, t)
     return t
 
 
@@ -894,14 +922,142 @@ def lgamma(a, name=None):
     return _unary(lambda x: gammaln(x).astype(np.asarray(x).dtype), a, "lgamma")
 
 
-def make_template(name, func, create_scope_now_=False, unique_name_=None, custom_getter_=None,
-                  **kwargs):
-    return func
-
-
 class contrib(object):
     class distributions(object):
         pass
+
+
+# ---- what the VAE of examples/variational_autoencoders/iwae.py adds ------------------------------
+def _reduce_max_vjp(a, axis, keepdims, out):
+    def vjp(g):
+        def gfn(c):
+            x = np.asarray(c.eval(a))
+            gv = np.asarray(c.eval(g))
+            ax = _axes(c, axis, x.ndim)
+            if ax is None:
+                ax = tuple(np.arange(x.ndim))
+            m = np.max(x, axis=ax, keepdims=True)
+            if not keepdims:
+                for d in sorted(ax):
+                    gv = np.expand_dims(gv, d)
+            ind = (x == m).astype(x.dtype)
+            return (ind / ind.sum(axis=ax, keepdims=True) * gv).astype(x.dtype, copy=False)
+        return [Tensor(gfn, inputs=(g, a), op="max_grad", dtype=a._dtype)]
+    return vjp
+
+
+def sigmoid(a, name=None):
+    a = convert_to_tensor(a)
+    f = lambda x: (1.0 / (1.0 + np.exp(-x))).astype(np.asarray(x).dtype)       # noqa: E731
+    out = _unary(f, a, "sigmoid")
+    out.vjp = lambda g: [g * out * (1.0 - out)]
+    return out
+
+
+def _dense_matmul(x, w):
+    """x [..., in] . w [in, out] (tf.layers.dense contracts the last axis)."""
+    x, w = convert_to_tensor(x), convert_to_tensor(w)
+    out = Tensor(lambda c: np.matmul(c.eval(x), c.eval(w)), inputs=(x, w), op="dense_matmul",
+                 dtype=_dt(x, w))
+
+    def vjp(g):
+        dx = Tensor(lambda c: np.matmul(c.eval(g), np.asarray(c.eval(w)).T), inputs=(g, w),
+                    op="dense_dx", dtype=x._dtype)
+
+        def dw(c):
+            xv, gv = np.asarray(c.eval(x)), np.asarray(c.eval(g))
+            return np.matmul(xv.reshape(-1, xv.shape[-1]).T, gv.reshape(-1, gv.shape[-1]))
+        return [dx, Tensor(dw, inputs=(x, g), op="dense_dw", dtype=w._dtype)]
+    out.vjp = vjp
+    return out
+
+
+_TEMPLATES = []          # stack of variable stores (tf.make_template / zs.reuse_variables)
+_DEFAULT_STORE = {"vars": {}, "count": 0}
+_TRAINABLE = []
+_INIT = {"rng": None}
+
+
+def set_init_rng(rng):
+    """numpy Generator the Glorot-uniform initialiser of tf.layers.dense draws from."""
+    _INIT["rng"] = rng
+
+
+def trainable_variables(scope=None):
+    return list(_TRAINABLE)
+
+
+def reset_default_graph():
+    del _TRAINABLE[:]
+    _DEFAULT_STORE["vars"].clear()
+    _DEFAULT_STORE["count"] = 0
+
+
+class _Template(object):
+    """tf.make_template: variables are created by the first call and reused by later ones."""
+
+    def __init__(self, name, func):
+        self.name, self.func = name, func
+        self.store = {"vars": {}, "count": 0}
+
+    def __call__(self, *args, **kwargs):
+        self.store["count"] = 0
+        _TEMPLATES.append(self.store)
+        try:
+            return self.func(*args, **kwargs)
+        finally:
+            _TEMPLATES.pop()
+
+
+def make_template(name, func, create_scope_now_=False, unique_name_=None, custom_getter_=None,
+                  **kwargs):
+    return _Template(name, func)
+
+
+class nn(object):
+    @staticmethod
+    def relu(a, name=None):
+        a = convert_to_tensor(a)
+        out = _unary(lambda x: np.maximum(x, 0).astype(np.asarray(x).dtype), a, "relu")
+        out.vjp = lambda g: [g * cast(greater(a, 0.0), a._dtype or np.float32)]
+        return out
+
+    @staticmethod
+    def sigmoid_cross_entropy_with_logits(_sentinel=None, labels=None, logits=None, name=None):
+        # max(x, 0) - x z + log(1 + exp(-|x|)), TF's numerically stable form
+        z, x = convert_to_tensor(labels), convert_to_tensor(logits)
+
+        def f(c):
+            xv, zv = np.asarray(c.eval(x)), np.asarray(c.eval(z))
+            return (np.maximum(xv, 0) - xv * zv + np.log1p(np.exp(-np.abs(xv)))).astype(xv.dtype)
+        out = Tensor(f, inputs=(z, x), op="sigmoid_xent", dtype=x._dtype)
+        out.vjp = lambda g: [_unbroadcast(negative(g * x), z), _unbroadcast(g * (sigmoid(x) - z), x)]
+        return out
+
+    sigmoid = staticmethod(sigmoid)
+
+
+class layers(object):
+    @staticmethod
+    def dense(inputs, units, activation=None, use_bias=True, name=None, **kw):
+        store = _TEMPLATES[-1] if _TEMPLATES else _DEFAULT_STORE
+        k = store["count"]
+        store["count"] += 1
+        key = name or ("dense" if k == 0 else "dense_%d" % k)
+        inputs = convert_to_tensor(inputs)
+        if key not in store["vars"]:
+            fan_in = int(inputs.get_shape().as_list()[-1])
+            limit = np.sqrt(6.0 / (fan_in + units))                 # glorot_uniform, TF's default
+            w0 = _INIT["rng"].uniform(-limit, limit, (fan_in, units)).astype(np.float32)
+            kern = Variable(w0, name=key + "/kernel")
+            bias = Variable(np.zeros(units, np.float32), name=key + "/bias")
+            store["vars"][key] = (kern, bias)
+            _TRAINABLE.extend([kern, bias])
+        kern, bias = store["vars"][key]
+        y = _dense_matmul(inputs, kern)
+        if use_bias:
+            y = y + bias
+        return activation(y) if activation is not None else y
 
 
 # ---- `tensorflow.python.client.session` (zhusuan/framework/bn.py:10-11, variational/base.py:12) ---
@@ -918,6 +1074,55 @@ def _register_session_run_conversion_functions(tensor_type, fetch_function, feed
     _RUN_CONVERSIONS.append((tensor_type, fetch_function))
 
 
+def constant_initializer(value=0, dtype=np.float32):
+    return lambda shape=(): np.full(tuple(shape), value, dtype)
+
+
+def zeros_initializer(dtype=np.float32):
+    return lambda shape=(): np.zeros(tuple(shape), dtype)
+
+
+def get_variable(name, shape=None, dtype=None, initializer=None, trainable=True, **kw):
+    """Variables are keyed by name inside the innermost template (else globally): a second
+    `get_variable` of the same name returns the same variable (the reference relies on that for
+    REINFORCE's 'moving_mean', exclusive_kl.py:209-212)."""
+    store = _TEMPLATES[-1] if _TEMPLATES else _DEFAULT_STORE
+    key = "var:" + name
+    if key not in store["vars"]:
+        init = initializer if initializer is not None else zeros_initializer()
+        v0 = init(tuple(shape or ())) if callable(init) else np.asarray(init)
+        store["vars"][key] = Variable(np.asarray(v0, dtype or np.float32), name=name,
+                                      trainable=trainable)
+        if trainable:
+            _TRAINABLE.append(store["vars"][key])
+    return store["vars"][key]
+
+
+def _assign_moving_average(variable, value, decay, zero_debias=True, name=None):
+    """tensorflow/python/training/moving_averages.py (TF 1.13, the reference's pinned minimum:
+    requirements-dev.txt:2), restated -- TensorFlow is a third-party dependency that is not in
+    the reference checkout:
+
+        d = 1 - decay
+        zero_debias (the DEFAULT):  biased -= (biased - value) * d;  local_step += 1
+                                    variable -= variable - biased / (1 - (1 - d) ** local_step)
+        else:                       variable -= (variable - value) * d
+    """
+    d = np.float32(1.0) - np.float32(decay)
+    value = convert_to_tensor(value)
+    if not zero_debias:
+        return assign(variable, variable - (variable - value) * d)
+    if not hasattr(variable, "_zd"):
+        variable._zd = (Variable(np.zeros_like(variable.value), name="biased", trainable=False),
+                        Variable(np.zeros((), variable.value.dtype), name="local_step",
+                                 trainable=False))
+    biased, step = variable._zd
+    upd_b = assign(biased, biased - (biased - value) * d)
+    upd_s = assign(step, step + np.float32(1.0))
+    return assign(variable, variable - (variable - upd_b / (np.float32(1.0)
+                                                            - pow(np.float32(1.0) - d, upd_s))))
+
+
 def _install_submodules():
     import sys
     import types
@@ -927,9 +1132,13 @@ def _install_submodules():
     client = types.ModuleType(__name__ + ".python.client")
     sess = types.ModuleType(__name__ + ".python.client.session")
     sess.register_session_run_conversion_functions = _register_session_run_conversion_functions
-    py.client, client.session = client, sess
-    py.__path__, client.__path__ = [], []
-    for m in (py, client, sess):
+    training = types.ModuleType(__name__ + ".python.training")
+    mavg = types.ModuleType(__name__ + ".python.training.moving_averages")
+    mavg.assign_moving_average = _assign_moving_average
+    training.moving_averages = mavg
+    py.client, client.session, py.training = client, sess, training
+    py.__path__, client.__path__, training.__path__ = [], [], []
+    for m in (py, client, sess, training, mavg):
         sys.modules[m.__name__] = m
     me.python = py
 

@@ -133,3 +133,16 @@ def reinforce_grad_logq(log_joint, log_q, axis, dtype=np.float32):
     lj, lq = np.asarray(log_joint, dtype), np.asarray(log_q, dtype)
     k = lq.shape[axis] if axis is not None else 1
     return (-(lj - lq) / dtype(k)).astype(dtype)
+
+
+def zero_debiased_moving_average(state, value, decay):
+    """``moving_averages.assign_moving_average(var, value, decay)`` of TensorFlow 1.x with its
+    default ``zero_debias=True`` (tensorflow/python/training/moving_averages.py; TF is a third-party
+    dependency absent from the reference checkout -- pinned version: requirements-dev.txt:2), as
+    exclusive_kl.py:215-216 calls it for REINFORCE's baseline:
+        biased -= (biased - value) * (1 - decay);  step += 1;  var = biased / (1 - decay ** step)
+    state = (biased, step) or None.  Returns (var, state)."""
+    biased, step = state if state is not None else (0.0, 0)
+    biased = biased - (biased - value) * (1.0 - decay)
+    step += 1
+    return biased / (1.0 - decay ** step), (biased, step)

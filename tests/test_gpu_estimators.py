@@ -3,6 +3,7 @@ VIMCO (monte_carlo.py:166-227), importance / RWS (inclusive_kl.py:119-151) and
 REINFORCE (exclusive_kl.py:161-231) -- against the CPU oracle and the reference's
 own seeded gradient tests (tests/variational/test_monte_carlo.py:104-142,
 test_inclusive_kl.py:26-92, test_exclusive_kl.py:80-122)."""
+import os
 import warnings
 
 import numpy as np
@@ -174,17 +175,20 @@ def test_reinforce_reference_test(zs, x_mean, x_std, rtol, atol):
     # exclusive_kl.py:209-216): it keeps averaging across objective instances / training steps
     from zhusuan_b200.variational import exclusive_kl as EK
     EK.reset_moving_mean()
+    # update rule: TF's assign_moving_average with its default zero_debias=True (restated in
+    # oracle/variational.py::zero_debiased_moving_average); pinned to the reference's own
+    # exclusive_kl.py run on the TF stand-in by test_vae_objectives_match_reference_run below
     signal = float((log_joint({'x': qx}) - log_qx).mean())
-    mm, decay = 0.0, 0.8
+    decay, state = 0.8, None
     for step in range(4):
         with pytest.warns(FutureWarning):
             lbk = zs.variational.elbo(log_joint, observed={}, latent={'x': [qx, log_qx]}, axis=0)
         lbk.reinforce(decay=decay)
-        mm = mm - (1 - decay) * (mm - signal)
+        mm, state = OV.zero_debiased_moving_average(state, signal * (1 + 0.0 * step), decay)
         np.testing.assert_allclose(float(lbk._moving_mean), mm, rtol=1e-5)
     own = torch.zeros((), device="cuda")
     lbk.reinforce(decay=decay, moving_mean=own)              # caller-held variable, in place
-    np.testing.assert_allclose(float(own), 0.2 * signal, rtol=1e-5)
+    np.testing.assert_allclose(float(own), signal, rtol=1e-5)   # first debiased update = the value
 
 
 def test_effective_sample_size_vs_oracle(zs):
@@ -208,3 +212,101 @@ def test_effective_sample_size_vs_oracle(zs):
     got = N(zs.diagnostics.effective_sample_size_per_dim(T(x), burn_in=0))
     np.testing.assert_allclose(got, OG.ess_per_dim(x, 0), rtol=2e-3)
     assert abs(zs.diagnostics.effective_sample_size_1d(T(x[:, 3])) - OG.ess_1d(x[:, 3])) < 1.0
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_vae_objectives_match_reference_run(zs, fused):
+    """tests/golden/ref_vae.npz: the VAE of examples/variational_autoencoders/iwae.py:23-44 run on
+    the REFERENCE'S OWN BayesianNet / Normal / Bernoulli / importance_weighted_objective / elbo /
+    .sgvb() / .reinforce() (executed on the NumPy TF stand-in, oracle/tf_shim/make_ref_golden.py).
+    The same model written against this package -- generic path (registry kernels + torch linear)
+    and the K8 path (tcgen05 dense layers, Bernoulli epilogue) -- must reproduce the per-datum
+    bounds, the costs and the gradient of every weight; the injected eps enters through a
+    user-defined Distribution subclass (the plugin contract, bn.stochastic)."""
+    import torch.nn.functional as F
+    from zhusuan_b200.variational import exclusive_kl as EK
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vae.npz"))
+    names = [str(n) for n in g["names"]]
+    K, N, z_dim = g["eps"].shape
+    x = T(g["x"]).to(torch.int32)
+
+    def weights():
+        # TF kernels are [in, out]; torch linear weights [out, in]
+        return {n: (T(g["w_" + n].T.copy()) if n.endswith("_w") else T(g["w_" + n]))
+                .requires_grad_(True) for n in names}
+
+    class InjectedNormal(zs.distributions.Normal):
+        def __init__(self, *a, **kw):
+            self._eps = kw.pop("eps")
+            super(InjectedNormal, self).__init__(*a, **kw)
+
+        def _sample(self, n_samples):
+            return super(InjectedNormal, self)._sample(n_samples, eps=self._eps)
+
+    if fused:
+        lin = lambda h, w, b, relu=False: zs.fused.linear(h, w, b, relu=relu)
+    else:
+        lin = lambda h, w, b, relu=False: (F.relu(F.linear(h, w, b)) if relu
+                                           else F.linear(h, w, b))
+
+    def nets(W, eps, reparameterized=True):
+        @zs.meta_bayesian_net(scope="gen", reuse_variables=True)
+        def build_gen(n, n_particles):
+            bn = zs.BayesianNet()
+            z = bn.normal("z", torch.zeros(n, z_dim, device="cuda"), std=1., group_ndims=1,
+                          n_samples=n_particles)
+            h = lin(z.tensor, W["g0_w"], W["g0_b"], True)
+            h = lin(h, W["g1_w"], W["g1_b"], True)
+            if fused:
+                bn.stochastic("x", zs.fused.LinearBernoulli(h, W["g2_w"], W["g2_b"]))
+            else:
+                bn.bernoulli("x", F.linear(h, W["g2_w"], W["g2_b"]), group_ndims=1)
+            return bn
+
+        def build_q_net(xx, n_particles):
+            bn = zs.BayesianNet()
+            h = lin(xx.float(), W["q0_w"], W["q0_b"], True)
+            h = lin(h, W["q1_w"], W["q1_b"], True)
+            bn.stochastic("z", InjectedNormal(lin(h, W["q2_w"], W["q2_b"]),
+                                              logstd=lin(h, W["q3_w"], W["q3_b"]), group_ndims=1,
+                                              is_reparameterized=reparameterized, eps=T(eps)),
+                          n_samples=n_particles)
+            return bn
+        return build_gen(N, K), build_q_net(x, K)
+
+    def check_grads(cost, W, key, which, rtol, atol, t=None):
+        grads = torch.autograd.grad(cost, [W[n] for n in which], allow_unused=True)
+        for n, gr in zip(which, grads):
+            want = g[key + n] if t is None else g[key + n][t]
+            want = want.T if n.endswith("_w") else want
+            np.testing.assert_allclose(N_(gr), want, rtol=rtol, atol=atol,
+                                       err_msg="%s%s fused=%s" % (key, n, fused))
+
+    N_ = lambda t: t.detach().cpu().numpy()
+    tol = 2e-4 if fused else 5e-5
+    W = weights()
+    model, variational = nets(W, g["eps"])
+    lb = zs.variational.iw_objective(model, {'x': x}, variational=variational, axis=0)
+    np.testing.assert_allclose(N_(lb.tensor), g["iw_bound"], rtol=1e-5, atol=1e-5)
+    cost = torch.mean(lb.sgvb())
+    np.testing.assert_allclose(float(cost.detach()), float(g["iw_cost"]), rtol=1e-5)
+    check_grads(cost, W, "iw_grad_", names, tol * 5, tol)
+    W = weights()
+    model, variational = nets(W, g["eps"])
+    el = zs.variational.elbo(model, {'x': x}, variational=variational, axis=0)
+    np.testing.assert_allclose(N_(el.tensor), g["elbo_bound"], rtol=1e-5, atol=1e-5)
+    cost = torch.mean(el.sgvb())
+    np.testing.assert_allclose(float(cost.detach()), float(g["elbo_cost"]), rtol=1e-5)
+    check_grads(cost, W, "elbo_grad_", names, tol * 5, tol)
+    # REINFORCE with the moving-mean baseline over three steps (exclusive_kl.py:161-231)
+    EK.reset_moving_mean()
+    for t in range(3):
+        W = weights()
+        model, variational = nets(W, g["rf_eps"][t], reparameterized=False)
+        el = zs.variational.elbo(model, {'x': x}, variational=variational, axis=0)
+        cost = torch.mean(el.reinforce())
+        np.testing.assert_allclose(float(cost.detach()), float(g["rf_cost"][t]), rtol=5e-5)
+        np.testing.assert_allclose(float(el._moving_mean), float(g["rf_moving_mean"][t]),
+                                   rtol=1e-5)
+        check_grads(cost, W, "rf_grad_", names[:8], 2e-3, 2e-4, t)
+    EK.reset_moving_mean()

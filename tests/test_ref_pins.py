@@ -176,6 +176,10 @@ def test_committed_vectors_are_what_the_reference_code_produces():
         g = np.load(os.path.join(GOLD, "ref_ais.npz"))
         for k in g.files:
             np.testing.assert_array_equal(out[k], g[k], err_msg=k)
+        out = M.run_reference_variational()
+        g = np.load(os.path.join(GOLD, "ref_vae.npz"))
+        for k in g.files:
+            np.testing.assert_array_equal(out[k], g[k], err_msg=k)
         import zhusuan.hmc
         assert os.path.realpath(zhusuan.hmc.__file__).startswith(os.path.realpath(REF))
     finally:
@@ -185,3 +189,71 @@ def test_committed_vectors_are_what_the_reference_code_produces():
         for k, v in saved.items():
             if v is not None:
                 sys.modules[k] = v
+
+
+def _vae_terms_torch(g, eps, reparameterized, dtype):
+    """An independent restatement (torch autograd, CPU) of the VAE the fixture was produced on
+    (iwae.py:23-44): returns the weights (leaf tensors), log_joint [K, N] and log q [K, N]."""
+    import torch
+    names = [str(n) for n in g["names"]]
+    w = {n: torch.tensor(g["w_" + n], dtype=dtype, requires_grad=True) for n in names}
+    x = torch.tensor(g["x"], dtype=dtype)
+    e = torch.tensor(eps, dtype=dtype)
+    c = -0.5 * np.log(2 * np.pi)
+    relu = torch.relu
+    h = relu(x @ w["q0_w"] + w["q0_b"])
+    h = relu(h @ w["q1_w"] + w["q1_b"])
+    mean, logstd = h @ w["q2_w"] + w["q2_b"], h @ w["q3_w"] + w["q3_b"]
+    if reparameterized:
+        z = mean + torch.exp(logstd) * e
+    else:                                   # Normal._sample with stop_gradient (univariate.py:163-165)
+        z = (mean + torch.exp(logstd) * e).detach()
+    log_q = (c - logstd - 0.5 * torch.exp(-2 * logstd) * (z - mean) ** 2).sum(-1)
+    log_pz = (c - 0.5 * z ** 2).sum(-1)
+    h = relu(z @ w["g0_w"] + w["g0_b"])
+    h = relu(h @ w["g1_w"] + w["g1_b"])
+    logits = h @ w["g2_w"] + w["g2_b"]
+    log_px = -(torch.clamp(logits, min=0) - logits * x +
+               torch.log1p(torch.exp(-logits.abs()))).sum(-1)
+    return w, log_pz + log_px, log_q
+
+
+def test_reference_run_vae_objectives_against_independent_autograd():
+    """tests/golden/ref_vae.npz = the reference's own framework / distributions / variational code
+    (importance_weighted_objective, elbo, .sgvb(), .reinforce()) on the NumPy TF stand-in.  Its
+    values AND its tf.gradients results must agree with torch autograd on a restatement of the
+    same model -- this vouches for the stand-in's reverse-mode differentiation."""
+    import torch
+    g = np.load(os.path.join(GOLD, "ref_vae.npz"))
+    names = [str(n) for n in g["names"]]
+    K = g["eps"].shape[0]
+    w, lj, lq = _vae_terms_torch(g, g["eps"], True, torch.float64)
+    np.testing.assert_allclose(lj.detach().numpy(), g["log_joint"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(-lq.detach().numpy(), g["entropy"], rtol=2e-6, atol=2e-6)
+    bound = torch.logsumexp(lj - lq, 0) - np.log(K)
+    np.testing.assert_allclose(bound.detach().numpy(), g["iw_bound"], rtol=2e-6)
+    cost = -bound.mean()
+    grads = torch.autograd.grad(cost, [w[n] for n in names], retain_graph=True)
+    for n, gr in zip(names, grads):
+        np.testing.assert_allclose(gr.numpy(), g["iw_grad_" + n], rtol=2e-4, atol=2e-6, err_msg=n)
+    ecost = -(lj - lq).mean(0).mean()
+    np.testing.assert_allclose(float(ecost), float(g["elbo_cost"]), rtol=2e-6)
+    grads = torch.autograd.grad(ecost, [w[n] for n in names])
+    for n, gr in zip(names, grads):
+        np.testing.assert_allclose(gr.numpy(), g["elbo_grad_" + n], rtol=2e-4, atol=2e-6,
+                                   err_msg=n)
+    # REINFORCE, three steps: baseline = the moving mean BEFORE the step's update; update =
+    # TF's zero-debiased assign_moving_average (oracle/variational.py)
+    from oracle import variational as OV
+    state, mm_prev = None, 0.0
+    for t in range(3):
+        w, lj, lq = _vae_terms_torch(g, g["rf_eps"][t], False, torch.float64)
+        signal = (lj - lq).detach()
+        cost = (-lj - (signal - mm_prev) * lq).mean(0).mean()
+        np.testing.assert_allclose(float(cost), float(g["rf_cost"][t]), rtol=2e-5)
+        grads = torch.autograd.grad(cost, [w[n] for n in names[:8]])
+        for n, gr in zip(names[:8], grads):
+            np.testing.assert_allclose(gr.numpy(), g["rf_grad_" + n][t], rtol=5e-4, atol=5e-5,
+                                       err_msg="step %d %s" % (t, n))
+        mm_prev, state = OV.zero_debiased_moving_average(state, float(signal.mean()), 0.8)
+        np.testing.assert_allclose(mm_prev, float(g["rf_moving_mean"][t]), rtol=2e-6)
