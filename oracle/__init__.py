@@ -40,6 +40,11 @@ Pinning status:
     float32 matmul-order rounding on dense ones) and regenerated + compared
     whenever /root/reference is present.  The reference's statistical harness
     (tests/test_mcmc.py) is re-run against the oracle as well.
+  * ELBO / IWAE .sgvb(), REINFORCE with its moving-mean baseline, VIMCO and the
+    inclusive-KL importance estimator: additionally PINNED to the reference's
+    own framework/ + distributions/ + variational/ code run on the stand-in
+    on the VAE of examples/variational_autoencoders/iwae.py
+    (tests/golden/ref_vae.npz: bounds, costs, tf.gradients of every weight).
   * AIS (oracle/evaluation.py): PINNED the same way -- class AIS of
     zhusuan/evaluation.py:57-172 run on the stand-in, tests/golden/ref_ais.npz.
   * device sampler streams (oracle/samplers.py): "parity unpinned" by the

@@ -337,6 +337,23 @@ def run_reference_variational(seed=77):
     out.update(rf_eps=eps_sf, rf_cost=np.array(costs), rf_moving_mean=np.array(mms))
     for i, nme in enumerate(names[:len(q_vars)]):
         out["rf_grad_" + nme] = np.stack([g[i] for g in grads])
+    # ---- VIMCO (monte_carlo.py:166-227) and the self-normalised importance estimator of the
+    # inclusive KL (inclusive_kl.py:119-151) on the same non-reparameterised q-net ----------------
+    gen_vars = all_vars[len(q_vars):]
+    iw_sf = var.importance_weighted_objective(model, {'x': x}, variational=bn_sf, axis=0)
+    vm_cost = tf.reduce_mean(iw_sf.vimco())
+    kl_sf = var.klpq(model, {'x': x}, variational=bn_sf, axis=0)
+    im_cost = tf.reduce_mean(kl_sf.importance())
+    tf.set_noise(normal=[eps])
+    r = sess.run([vm_cost] + tf.gradients(vm_cost, sf_vars + gen_vars))
+    out["vimco_cost"] = r[0]
+    for nme, gr in zip(names, r[1:]):
+        out["vimco_grad_" + nme] = gr
+    tf.set_noise(normal=[eps])
+    r = sess.run([im_cost] + tf.gradients(im_cost, sf_vars))
+    out["importance_cost"] = r[0]
+    for nme, gr in zip(names[:len(q_vars)], r[1:]):
+        out["importance_grad_" + nme] = gr
     return out
 
 

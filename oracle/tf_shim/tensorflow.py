@@ -39,9 +39,14 @@ _CTRL_STACK = [[]]
 
 
 # ------------------------------------------------------------------------------------------------
+class Dimension(int):
+    """tf.Dimension: an int whose `.value` is itself (monte_carlo.py:173 reads `.value`)."""
+    value = property(lambda self: int(self))
+
+
 class TensorShape(object):
     def __init__(self, dims):
-        self._dims = None if dims is None else [None if d is None else int(d) for d in dims]
+        self._dims = None if dims is None else [None if d is None else Dimension(d) for d in dims]
 
     @property
     def ndims(self):
@@ -222,6 +227,11 @@ def convert_to_tensor(value, dtype=None, name=None, preferred_dtype=None):
         return value
     if isinstance(value, TensorShape):
         value = value.as_list()
+    if isinstance(value, (list, tuple)) and any(isinstance(v, Tensor) for v in value):
+        parts = [convert_to_tensor(v) for v in value]            # tf.stack (auto-packing)
+        out = Tensor(lambda c: np.stack([np.asarray(c.eval(p)) for p in parts]),
+                     inputs=tuple(parts), op="pack", dtype=_dt(*parts))
+        return cast(out, dtype) if dtype is not None and out._dtype is not dtype else out
     return constant(value, dtype=dtype, name=name)
 
 
@@ -536,6 +546,10 @@ def range(*args, **kw):                                        # noqa: A001
 def expand_dims(a, axis=None, name=None, dim=None):
     a = convert_to_tensor(a)
     ax = axis if axis is not None else dim
+    if isinstance(ax, Tensor):
+        return Tensor(lambda c: np.expand_dims(c.eval(a), int(c.eval(ax))), inputs=(a, ax),
+                      op="expand_dims", vjp=lambda g: [reshape(g, shape(a)), None],
+                      dtype=a._dtype)
     return _unary(lambda x: np.expand_dims(x, ax), a, "expand_dims",
                   lambda g: [reshape(g, shape(a))])
 
@@ -925,6 +939,43 @@ def lgamma(a, name=None):
 class contrib(object):
     class distributions(object):
         pass
+
+
+# ---- what ImportanceWeightedObjective.vimco (monte_carlo.py:166-227) adds -----------------------
+def one_hot(indices, depth, on_value=None, off_value=None, axis=None, dtype=np.float32, name=None):
+    def fn(c):
+        i = np.asarray(c.eval(indices) if isinstance(indices, Tensor) else indices)
+        d = int(c.eval(depth) if isinstance(depth, Tensor) else depth)
+        return (np.arange(d) == i[..., None]).astype(dtype)
+    ins = tuple(t for t in (indices, depth) if isinstance(t, Tensor))
+    return Tensor(fn, inputs=ins, op="one_hot", dtype=dtype)
+
+
+def transpose(a, perm=None, name=None):
+    a = convert_to_tensor(a)
+
+    def fn(c):
+        p = None if perm is None else tuple(int(v) for v in np.asarray(
+            c.eval(perm) if isinstance(perm, Tensor) else perm))
+        return np.transpose(c.eval(a), p)
+
+    def vjp(g):
+        def gfn(c):
+            p = None if perm is None else tuple(int(v) for v in np.asarray(
+                c.eval(perm) if isinstance(perm, Tensor) else perm))
+            return np.transpose(c.eval(g), None if p is None else tuple(np.argsort(p)))
+        return [Tensor(gfn, inputs=(g,), op="transpose_grad", dtype=a._dtype)]
+    ins = (a,) + ((perm,) if isinstance(perm, Tensor) else ())
+    return Tensor(fn, inputs=ins, op="transpose", vjp=vjp, dtype=a._dtype)
+
+
+def matrix_diag(a, name=None):
+    a = convert_to_tensor(a)
+
+    def fn(c):
+        x = np.asarray(c.eval(a))
+        return x[..., None] * np.eye(x.shape[-1], dtype=x.dtype)
+    return Tensor(fn, inputs=(a,), op="matrix_diag", dtype=a._dtype)
 
 
 # ---- what the VAE of examples/variational_autoencoders/iwae.py adds ------------------------------

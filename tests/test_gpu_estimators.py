@@ -310,3 +310,17 @@ def test_vae_objectives_match_reference_run(zs, fused):
                                    rtol=1e-5)
         check_grads(cost, W, "rf_grad_", names[:8], 2e-3, 2e-4, t)
     EK.reset_moving_mean()
+    # VIMCO (monte_carlo.py:166-227) and the inclusive-KL importance estimator
+    # (inclusive_kl.py:119-151) on the non-reparameterised q-net
+    W = weights()
+    model, variational = nets(W, g["eps"], reparameterized=False)
+    lb = zs.variational.iw_objective(model, {'x': x}, variational=variational, axis=0)
+    cost = torch.mean(lb.vimco())
+    np.testing.assert_allclose(float(cost.detach()), float(g["vimco_cost"]), rtol=2e-5)
+    check_grads(cost, W, "vimco_grad_", names, 2e-3, 2e-4)
+    W = weights()
+    model, variational = nets(W, g["eps"], reparameterized=False)
+    kl = zs.variational.klpq(model, {'x': x}, variational=variational, axis=0)
+    cost = torch.mean(kl.importance())
+    np.testing.assert_allclose(float(cost.detach()), float(g["importance_cost"]), rtol=2e-5)
+    check_grads(cost, W, "importance_grad_", names[:8], 2e-3, 2e-4)

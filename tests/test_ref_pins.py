@@ -257,3 +257,27 @@ def test_reference_run_vae_objectives_against_independent_autograd():
                                        err_msg="step %d %s" % (t, n))
         mm_prev, state = OV.zero_debiased_moving_average(state, float(signal.mean()), 0.8)
         np.testing.assert_allclose(mm_prev, float(g["rf_moving_mean"][t]), rtol=2e-6)
+    # VIMCO (monte_carlo.py:166-227) and self-normalised importance (inclusive_kl.py:119-151)
+    w, lj, lq = _vae_terms_torch(g, g["eps"], False, torch.float64)
+    lw = lj - lq
+    lwd = lw.detach()
+    mean_except = (lwd.sum(0, keepdim=True) - lwd) / (K - 1)
+    x_ex = lwd.t().unsqueeze(1).repeat(1, K, 1)                       # [N, k, j] = lw[j, n]
+    idx = torch.arange(K)
+    x_ex[:, idx, idx] = mean_except.t()
+    control = (torch.logsumexp(x_ex, -1) - np.log(K)).t()             # [K, N]
+    lme = torch.logsumexp(lw, 0) - np.log(K)
+    signal = lme.detach().unsqueeze(0) - control
+    cost = (-(lq * signal).sum(0) - lme).mean()
+    np.testing.assert_allclose(float(cost.detach()), float(g["vimco_cost"]), rtol=2e-6)
+    grads = torch.autograd.grad(cost, [w[n] for n in names], retain_graph=True)
+    for n, gr in zip(names, grads):
+        np.testing.assert_allclose(gr.numpy(), g["vimco_grad_" + n], rtol=5e-4, atol=5e-6,
+                                   err_msg="vimco " + n)
+    wt = torch.softmax(lwd, 0)
+    cost = (-(wt * lq).sum(0)).mean()
+    np.testing.assert_allclose(float(cost.detach()), float(g["importance_cost"]), rtol=2e-6)
+    grads = torch.autograd.grad(cost, [w[n] for n in names[:8]])
+    for n, gr in zip(names[:8], grads):
+        np.testing.assert_allclose(gr.numpy(), g["importance_grad_" + n], rtol=5e-4, atol=5e-6,
+                                   err_msg="importance " + n)
