@@ -357,6 +357,84 @@ def run_reference_variational(seed=77):
     return out
 
 
+def run_reference_bnn_sghmc(seed=707):
+    """Config 4's model, examples/bayesian_neural_nets/bnn_sgmcmc.py:19-35 + its log_joint
+    override (74-77), on the reference's BayesianNet and SGHMC classes: per-weight prior
+    log-stddevs, second-order SGHMC with a momentum re-draw at t = 0 and t = 3, five steps."""
+    tf, _, sg = load_reference()
+    fw = importlib.import_module("zhusuan.framework")
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tf.reset_default_graph()
+    C, n_in, H, B, n_train = 9, 4, 37, 23, 500
+    x_np = rng.standard_normal((B, n_in)).astype(np.float32)
+    y_np = rng.standard_normal(B).astype(np.float32)
+    layer_sizes = [n_in, H, 1]
+    ls_np = [(0.1 * rng.standard_normal((H, n_in + 1))).astype(np.float32),
+             (0.1 * rng.standard_normal((1, H + 1))).astype(np.float32)]
+    w_np = [rng.uniform(-2, 2, (C, H, n_in + 1)).astype(np.float32),
+            rng.uniform(-2, 2, (C, 1, H + 1)).astype(np.float32)]
+
+    @fw.meta_bayesian_net(scope="bnn", reuse_variables=True)
+    def build_bnn(x, layer_sizes, logstds, n_particles):
+        bn = fw.BayesianNet()
+        h = tf.tile(x[None, ...], [n_particles, 1, 1])
+        for i, (n_i, n_o) in enumerate(zip(layer_sizes[:-1], layer_sizes[1:])):
+            w = bn.normal("w" + str(i), tf.zeros([n_o, n_i + 1]),
+                          logstd=logstds[i], group_ndims=2, n_samples=n_particles)
+            h = tf.concat([h, tf.ones(tf.shape(h)[:-1])[..., None]], -1)
+            h = tf.einsum("imk,ijk->ijm", w, h) / tf.sqrt(
+                tf.cast(tf.shape(h)[2], tf.float32))
+            if i < len(layer_sizes) - 2:
+                h = tf.nn.relu(h)
+        y_mean = bn.deterministic("y_mean", tf.squeeze(h, 2))
+        y_logstd = -0.95
+        bn.normal("y", y_mean, logstd=y_logstd)
+        return bn
+    x, y = tf.constant(x_np), tf.constant(y_np)
+    w_names = ["w0", "w1"]
+    wv = [tf.Variable(w, name=n) for w, n in zip(w_np, w_names)]
+    logstds = [tf.constant(a) for a in ls_np]
+    model = build_bnn(x, layer_sizes, logstds, C)
+
+    def log_joint(bn):                                            # bnn_sgmcmc.py:74-77
+        log_pws = bn.cond_log_prob(w_names)
+        log_py_xw = bn.cond_log_prob('y')
+        return tf.add_n(log_pws) + tf.reduce_mean(log_py_xw, 1) * n_train
+    model.log_joint = log_joint
+    kw = dict(learning_rate=1e-4, friction=0.2, variance_estimate=0.01, n_iter_resample_v=3,
+              second_order=True)
+    v0 = [rng.standard_normal(w.shape).astype(np.float32) for w in w_np]
+    tf.set_noise(normal=[v0[0], v0[1]] * 2)
+    sgmcmc = sg.SGHMC(**kw)
+    sample_op, info = sgmcmc.sample(model, observed={'y': y}, latent=dict(zip(w_names, wv)))
+    sess = tf.Session()
+    out = dict(x=x_np, y=y_np, logstd0=ls_np[0], logstd1=ls_np[1], w0_init=w_np[0],
+               w1_init=w_np[1], n_train=np.int32(n_train), v0_0=v0[0], v0_1=v0[1],
+               **{"cfg_" + k: np.float32(v) for k, v in kw.items()})
+    rec = {k: [] for k in ("w0", "w1", "noise0", "noise1", "resample0", "resample1", "mean_k0",
+                           "mean_k1", "n_used")}
+    for t in range(5):
+        pool = [rng.standard_normal(w_np[k % 2].shape).astype(np.float32) for k in range(4)]
+        tf.set_noise(normal=list(pool))
+        _, r = sess.run([sample_op, info])
+        used = 4 - len(tf._NOISE["normal"])
+        # consumption order inside a run: [re-draw of v for w0, w1,] then the update noise of
+        # w0, w1 (latents are visited in dictionary order, sgmcmc.py:105-107)
+        if used == 4:
+            rs, nz = pool[:2], pool[2:]
+        else:
+            assert used == 2
+            rs, nz = [np.zeros_like(pool[0]), np.zeros_like(pool[1])], pool[:2]
+        rec["n_used"].append(used)
+        for k in range(2):
+            rec["w%d" % k].append(np.array(wv[k].value))
+            rec["noise%d" % k].append(nz[k])
+            rec["resample%d" % k].append(rs[k])
+            rec["mean_k%d" % k].append(np.float32(r.mean_k["w%d" % k]))
+    out.update({k: np.stack(v) for k, v in rec.items()})
+    return out
+
+
 HMC_CASES = {
     "ref_hmc_diag": ("diag", 12, 16, dict(step_size=1e-3, n_leapfrogs=5,
                                           target_acceptance_rate=0.9, mass_collect_iters=4,
@@ -379,6 +457,9 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "ref_vae.npz"), **out)
     print("ref_vae iw bound", out["iw_bound"].tolist(), "reinforce costs", out["rf_cost"].tolist(),
           "moving mean", out["rf_moving_mean"].tolist())
+    out = run_reference_bnn_sghmc()
+    np.savez_compressed(os.path.join(GOLD, "ref_bnn_sghmc.npz"), **out)
+    print("ref_bnn_sghmc draws per step", out["n_used"].tolist(), "mean_k", out["mean_k0"].tolist())
     out = run_reference_ais()
     np.savez_compressed(os.path.join(GOLD, "ref_ais.npz"), **out)
     print("ref_ais bound", float(out["bound"]))

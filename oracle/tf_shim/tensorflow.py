@@ -741,9 +741,12 @@ def gradients(ys, xs, grad_ys=None, name=None, **kw):
         order.append(t)
     visit(y)
     active = {}                     # does the tensor depend on any x?  (order is topological)
+    nondiff = ("shape", "rank", "cmp", "not", "is_finite", "one_hot", "range", "zeros_like",
+               "ones_like", "stop_gradient", "reduce_all")
     for t in order:
-        active[id(t)] = id(t) in xset or any(
-            isinstance(i, Tensor) and active.get(id(i), False) for i in t.inputs)
+        cut = t.op in nondiff or t.op.startswith("assert_") or (t.op == "cast" and t.vjp is None)
+        active[id(t)] = id(t) in xset or (not cut and any(
+            isinstance(i, Tensor) and active.get(id(i), False) for i in t.inputs))
     cot = {id(y): ones_like(y)}
     for t in reversed(order):
         g = cot.get(id(t))
@@ -752,7 +755,8 @@ def gradients(ys, xs, grad_ys=None, name=None, **kw):
                     t.op not in ("const", "variable", "placeholder", "loop_var", "zeros", "ones",
                                  "cmp", "shape", "range", "zeros_like", "ones_like",
                                  "stop_gradient"):
-                raise NotImplementedError("tf.gradients through op %r" % t.op)
+                raise NotImplementedError("tf.gradients through op %r (dtype %r, inputs %r)" % (
+                    t.op, t._dtype, [(i.op, i._dtype) for i in t.inputs if isinstance(i, Tensor)]))
             continue
         if not active[id(t)]:
             continue
@@ -898,10 +902,41 @@ def squeeze(a, axis=None, name=None, squeeze_dims=None):
 
 def concat(values, axis, name=None):
     vals = [convert_to_tensor(v) for v in values]
-    return Tensor(lambda c: np.concatenate([np.atleast_1d(c.eval(v)) for v in vals],
-                                           axis=int(c.eval(axis)) if isinstance(axis, Tensor)
-                                           else axis),
-                  inputs=tuple(vals), op="concat", dtype=_dt(*vals))
+    ax_of = lambda c: int(c.eval(axis)) if isinstance(axis, Tensor) else int(axis)   # noqa: E731
+    out = Tensor(lambda c: np.concatenate([np.atleast_1d(c.eval(v)) for v in vals], axis=ax_of(c)),
+                 inputs=tuple(vals), op="concat", dtype=_dt(*vals))
+
+    def vjp(g):
+        def piece(k):
+            def fn(c):
+                sizes = [np.atleast_1d(c.eval(v)).shape[ax_of(c)] for v in vals]
+                lo = int(np.sum(sizes[:k]))
+                return np.take(np.asarray(c.eval(g)), np.arange(lo, lo + sizes[k]), axis=ax_of(c))
+            return Tensor(fn, inputs=(g,) + tuple(vals), op="concat_grad", dtype=vals[k]._dtype)
+        return [piece(k) for k in np.arange(len(vals))]
+    out.vjp = vjp
+    return out
+
+
+def einsum(equation, *operands, **kw):
+    """Two-operand einsum with explicit output (the only form the reference's examples use);
+    the cotangents are einsums with the subscripts permuted."""
+    a, b = [convert_to_tensor(o) for o in operands]
+    lhs, res = equation.replace(" ", "").split("->")
+    sa, sb = lhs.split(",")
+    out = Tensor(lambda c: np.einsum(equation, c.eval(a), c.eval(b)), inputs=(a, b), op="einsum",
+                 dtype=_dt(a, b))
+
+    def vjp(g):
+        def grad(own, other, other_t, own_t):
+            def fn(c):
+                r = np.einsum("%s,%s->%s" % (res, other, own), c.eval(g), c.eval(other_t))
+                return r.astype(np.asarray(c.eval(own_t)).dtype, copy=False)
+            return Tensor(fn, inputs=(g, other_t, own_t), op="einsum_grad", dtype=own_t._dtype)
+        assert set(sa) <= set(res + sb) and set(sb) <= set(res + sa), "einsum vjp: summed-out index"
+        return [grad(sa, sb, b, a), grad(sb, sa, a, b)]
+    out.vjp = vjp
+    return out
 
 
 def reduce_prod(a, axis=None, keepdims=False, name=None, reduction_indices=None, keep_dims=None):

@@ -225,3 +225,28 @@ def test_sgmcmc_state_dict_round_trip_resumes_bitwise(zs, name):
     torch.cuda.synchronize()
     assert sa.t == sb.t == 8
     np.testing.assert_array_equal(wa.cpu().numpy(), wb.cpu().numpy())
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_bnn_sghmc_matches_reference_run(zs, fused):
+    """tests/golden/ref_bnn_sghmc.npz: config 4's model (bnn_sgmcmc.py:19-35, 74-77) run on the
+    reference's own BayesianNet + SGHMC classes (oracle/tf_shim/make_ref_golden.py).  The fused
+    one-launch kernel (csrc/sgmcmc_bnn.cu) and the generic path must follow it step for step."""
+    g = np.load(os.path.join(GOLD, "ref_bnn_sghmc.npz"))
+    lj = zs.fused.BNNRegressionLogJoint(T(g["x"]), T(g["y"]), [T(g["logstd0"]), T(g["logstd1"])],
+                                        int(g["n_train"]))
+    w0, w1 = T(g["w0_init"]), T(g["w1_init"])
+    sg = zs.SGHMC(learning_rate=float(g["cfg_learning_rate"]), friction=float(g["cfg_friction"]),
+                  variance_estimate=float(g["cfg_variance_estimate"]),
+                  n_iter_resample_v=int(g["cfg_n_iter_resample_v"]), second_order=True,
+                  use_fused=fused)
+    op, info = sg.sample(lj, {}, {"w0": w0, "w1": w1})
+    assert (sg._fused_bnn() is lj) == fused
+    sg.init_momentum({"w0": T(g["v0_0"]), "w1": T(g["v0_1"])})
+    for t in range(g["w0"].shape[0]):
+        op(noise={"noise": {"w0": T(g["noise0"][t]), "w1": T(g["noise1"][t])},
+                  "resample": {"w0": T(g["resample0"][t]), "w1": T(g["resample1"][t])}})
+        np.testing.assert_allclose(N(w0), g["w0"][t], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(N(w1), g["w1"][t], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(N(info.mean_k["w0"]), g["mean_k0"][t], rtol=1e-3)
+        np.testing.assert_allclose(N(info.mean_k["w1"]), g["mean_k1"][t], rtol=1e-3)

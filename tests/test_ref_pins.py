@@ -180,6 +180,10 @@ def test_committed_vectors_are_what_the_reference_code_produces():
         g = np.load(os.path.join(GOLD, "ref_vae.npz"))
         for k in g.files:
             np.testing.assert_array_equal(out[k], g[k], err_msg=k)
+        out = M.run_reference_bnn_sghmc()
+        g = np.load(os.path.join(GOLD, "ref_bnn_sghmc.npz"))
+        for k in g.files:
+            np.testing.assert_array_equal(out[k], g[k], err_msg=k)
         import zhusuan.hmc
         assert os.path.realpath(zhusuan.hmc.__file__).startswith(os.path.realpath(REF))
     finally:
@@ -281,3 +285,34 @@ def test_reference_run_vae_objectives_against_independent_autograd():
     for n, gr in zip(names[:8], grads):
         np.testing.assert_allclose(gr.numpy(), g["importance_grad_" + n], rtol=5e-4, atol=5e-6,
                                    err_msg="importance " + n)
+
+
+def test_oracle_bnn_sghmc_reproduces_reference_run():
+    """tests/golden/ref_bnn_sghmc.npz: config 4's model (bnn_sgmcmc.py:19-35, log_joint 74-77) on
+    the reference's BayesianNet + SGHMC classes (second order, momentum re-draws at t = 0, 3).
+    oracle/models.py::BNN (hand-derived gradient) + oracle/sgmcmc.py::SGHMC must follow it."""
+    g = np.load(os.path.join(GOLD, "ref_bnn_sghmc.npz"))
+    ls0, ls1 = g["logstd0"], g["logstd1"]
+
+    class M(OM.BNN):                      # per-weight prior log-stddevs (bnn_sgmcmc.py:71)
+        def grad(self, qs):
+            g0, g1 = OM.BNN.grad(self, qs)
+            g0 = g0 + np.exp(-2 * self.ls0) * qs[0] - np.exp(-2 * ls0) * qs[0]
+            g1 = g1 + np.exp(-2 * self.ls1) * qs[1] - np.exp(-2 * ls1) * qs[1]
+            return [g0, g1]
+    for dtype, tol in ((np.float32, 2e-5), (np.float64, 2e-5)):
+        om = M(g["x"].astype(dtype), g["y"].astype(dtype), int(g["n_train"]), dtype=dtype)
+        s = OS.SGHMC(dtype=dtype, learning_rate=float(g["cfg_learning_rate"]),
+                     friction=float(g["cfg_friction"]),
+                     variance_estimate=float(g["cfg_variance_estimate"]),
+                     n_iter_resample_v=int(g["cfg_n_iter_resample_v"]), second_order=True)
+        s.init_v([g["v0_0"].astype(dtype), g["v0_1"].astype(dtype)])
+        q = [g["w0_init"].astype(dtype), g["w1_init"].astype(dtype)]
+        for t in range(g["w0"].shape[0]):
+            q, info = s.step(q, om.grad, [g["resample0"][t], g["resample1"][t]],
+                             [g["noise0"][t], g["noise1"][t]])
+            np.testing.assert_allclose(q[0], g["w0"][t], rtol=tol * 10, atol=tol)
+            np.testing.assert_allclose(q[1], g["w1"][t], rtol=tol * 10, atol=tol)
+            np.testing.assert_allclose(info["mean_k"][0], g["mean_k0"][t], rtol=1e-3)
+            np.testing.assert_allclose(info["mean_k"][1], g["mean_k1"][t], rtol=1e-3)
+    assert g["n_used"].tolist() == [4, 2, 2, 4, 2]
