@@ -435,6 +435,67 @@ def run_reference_bnn_sghmc(seed=707):
     return out
 
 
+def run_reference_lntm_hmc(seed=909):
+    """Config 5's E-step: the model of examples/topic_models/lntm_mcem.py:33-48 with the e_obj
+    log-joint override (97-98) on the reference's BayesianNet, sampled by the reference's HMC
+    with two chain axes [chains, docs] (69-70, 99-105), adaptive step size, injected noise."""
+    tf, hmc_mod, _ = load_reference()
+    fw = importlib.import_module("zhusuan.framework")
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tf.reset_default_graph()
+    K, V, C, Dn = 32, 120, 6, 5
+    log_delta = 10.0
+    x_np = rng.poisson(0.1, (Dn, V)).astype(np.float32)
+    x_np[0] = 0                                              # a padding document (71-74)
+    beta_np = rng.standard_normal((K, V)).astype(np.float32)
+    mean_np = (0.2 * rng.standard_normal(K)).astype(np.float32)
+    logstd_np = (0.1 * rng.standard_normal(K)).astype(np.float32)
+    eta0 = (0.1 * rng.standard_normal((C, Dn, K))).astype(np.float32)
+
+    @fw.meta_bayesian_net(scope='lntm')
+    def lntm(n_chains, n_docs, n_topics, n_vocab, eta_mean, eta_logstd):
+        bn = fw.BayesianNet()
+        eta_mean = tf.tile(tf.expand_dims(eta_mean, 0), [n_docs, 1])
+        eta = bn.normal('eta', eta_mean, logstd=eta_logstd, n_samples=n_chains, group_ndims=1)
+        theta = tf.nn.softmax(eta)
+        beta = bn.normal('beta', tf.zeros([n_topics, n_vocab]), logstd=log_delta, group_ndims=1)
+        phi = tf.nn.softmax(beta)
+        doc_word = tf.matmul(tf.reshape(theta, [-1, n_topics]), phi)
+        doc_word = tf.reshape(doc_word, [n_chains, n_docs, n_vocab])
+        bn.unnormalized_multinomial('x', tf.log(doc_word), normalize_logits=False,
+                                    dtype=tf.float32)
+        return bn
+
+    def e_obj(bn):
+        return bn.cond_log_prob('eta') + bn.cond_log_prob('x')
+    cfg = dict(step_size=0.02, n_leapfrogs=6, target_acceptance_rate=0.6)
+    hmc = hmc_mod.HMC(adapt_step_size=True, **cfg)
+    eta = tf.Variable(eta0, name='eta')
+    model = lntm(C, Dn, K, V, tf.constant(mean_np), tf.constant(logstd_np))
+    model.log_joint = e_obj
+    sample_op, info = hmc.sample(model, observed={'x': tf.constant(x_np),
+                                                  'beta': tf.constant(beta_np)},
+                                 latent={'eta': eta})
+    sess = tf.Session()
+    rec = {k: [] for k in ("noise_p", "noise_u", "eta", "acc", "step_size", "lp", "lp0", "h0",
+                           "h1")}
+    for i in range(8):
+        npz = rng.standard_normal(eta0.shape).astype(np.float32)
+        nu = rng.random((C, Dn)).astype(np.float32)
+        tf.set_noise(normal=[npz], uniform=[nu])
+        with np.errstate(all="ignore"):
+            _, r = sess.run([sample_op, info])
+        rec["noise_p"].append(npz); rec["noise_u"].append(nu)
+        rec["eta"].append(np.array(eta.value)); rec["acc"].append(r.acceptance_rate)
+        rec["step_size"].append(np.float32(r.updated_step_size))
+        rec["lp"].append(r.log_prob); rec["lp0"].append(r.orig_log_prob)
+        rec["h0"].append(r.orig_hamiltonian); rec["h1"].append(r.hamiltonian)
+    out = {k: np.stack(v) for k, v in rec.items()}
+    out.update(x=x_np, beta=beta_np, eta_mean=mean_np, eta_logstd=logstd_np, eta0=eta0,
+               **{"cfg_" + k: np.float32(v) for k, v in cfg.items()})
+    return out
+
+
 HMC_CASES = {
     "ref_hmc_diag": ("diag", 12, 16, dict(step_size=1e-3, n_leapfrogs=5,
                                           target_acceptance_rate=0.9, mass_collect_iters=4,
@@ -457,6 +518,10 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "ref_vae.npz"), **out)
     print("ref_vae iw bound", out["iw_bound"].tolist(), "reinforce costs", out["rf_cost"].tolist(),
           "moving mean", out["rf_moving_mean"].tolist())
+    out = run_reference_lntm_hmc()
+    np.savez_compressed(os.path.join(GOLD, "ref_lntm_hmc.npz"), **out)
+    print("ref_lntm_hmc acc mean", np.round(out["acc"].mean((1, 2)), 3).tolist(), "step",
+          out["step_size"].tolist())
     out = run_reference_bnn_sghmc()
     np.savez_compressed(os.path.join(GOLD, "ref_bnn_sghmc.npz"), **out)
     print("ref_bnn_sghmc draws per step", out["n_used"].tolist(), "mean_k", out["mean_k0"].tolist())

@@ -1122,6 +1122,18 @@ class nn(object):
 
     sigmoid = staticmethod(sigmoid)
 
+    @staticmethod
+    def softmax(logits, axis=-1, name=None, dim=None):
+        a = convert_to_tensor(logits)
+        ax = dim if dim is not None else axis
+
+        def f(x):
+            e = np.exp(x - np.max(x, axis=ax, keepdims=True))
+            return (e / e.sum(axis=ax, keepdims=True)).astype(np.asarray(x).dtype)
+        out = _unary(f, a, "softmax")
+        out.vjp = lambda g: [out * (g - reduce_sum(g * out, axis=ax, keepdims=True))]
+        return out
+
 
 class layers(object):
     @staticmethod

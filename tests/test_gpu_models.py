@@ -282,3 +282,25 @@ def test_lntm_fused_hmc_matches_oracle(zs):
                                    atol=2e-4)
         near = np.abs(u - oi.acceptance_rate) < 1e-3
         np.testing.assert_allclose(N(eta)[~near], oq[0][~near], rtol=1e-3, atol=1e-4)
+
+
+def test_lntm_fused_hmc_follows_reference_run(zs):
+    """tests/golden/ref_lntm_hmc.npz: config 5's E-step on the reference's own BayesianNet /
+    UnnormalizedMultinomial / HMC (oracle/tf_shim/make_ref_golden.py).  HMC on the fused
+    sparsity-aware LNTM kernel (csrc/lntm.cu) follows it iteration by iteration."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                             "ref_lntm_hmc.npz"))
+    lj = zs.fused.LNTMLogJoint(T(g["x"]), T(g["beta"]), T(g["eta_mean"]), T(g["eta_logstd"]))
+    eta = T(g["eta0"])
+    h = zs.HMC(step_size=float(g["cfg_step_size"]), n_leapfrogs=int(g["cfg_n_leapfrogs"]),
+               adapt_step_size=True, target_acceptance_rate=float(g["cfg_target_acceptance_rate"]))
+    op, info = h.sample(lj, {}, {"eta": eta})
+    assert h._provider is lj
+    for i in range(g["eta"].shape[0]):
+        op(adapt_step_size=True, noise={"p": {"eta": T(g["noise_p"][i])}, "u": T(g["noise_u"][i])})
+        np.testing.assert_allclose(N(info.orig_log_prob), g["lp0"][i], rtol=2e-5, atol=2e-3)
+        np.testing.assert_allclose(N(info.acceptance_rate), g["acc"][i], rtol=3e-3, atol=3e-4)
+        np.testing.assert_allclose(float(info.updated_step_size), g["step_size"][i], rtol=3e-4)
+        near = np.abs(g["noise_u"][i] - g["acc"][i]) < 2e-3
+        np.testing.assert_allclose(N(eta)[~near], g["eta"][i][~near], rtol=1e-3, atol=2e-4)
+        eta.copy_(T(g["eta"][i]))            # continue from the reference's state

@@ -184,6 +184,10 @@ def test_committed_vectors_are_what_the_reference_code_produces():
         g = np.load(os.path.join(GOLD, "ref_bnn_sghmc.npz"))
         for k in g.files:
             np.testing.assert_array_equal(out[k], g[k], err_msg=k)
+        out = M.run_reference_lntm_hmc()
+        g = np.load(os.path.join(GOLD, "ref_lntm_hmc.npz"))
+        for k in g.files:
+            np.testing.assert_array_equal(out[k], g[k], err_msg=k)
         import zhusuan.hmc
         assert os.path.realpath(zhusuan.hmc.__file__).startswith(os.path.realpath(REF))
     finally:
@@ -316,3 +320,25 @@ def test_oracle_bnn_sghmc_reproduces_reference_run():
             np.testing.assert_allclose(info["mean_k"][0], g["mean_k0"][t], rtol=1e-3)
             np.testing.assert_allclose(info["mean_k"][1], g["mean_k1"][t], rtol=1e-3)
     assert g["n_used"].tolist() == [4, 2, 2, 4, 2]
+
+
+def test_oracle_lntm_hmc_follows_reference_run():
+    """tests/golden/ref_lntm_hmc.npz: config 5's E-step (lntm_mcem.py:33-48, e_obj 97-98) on the
+    reference's BayesianNet, UnnormalizedMultinomial and HMC (two chain axes).  The oracle's dense
+    restatement (oracle/models.py::LNTM, analytic gradient) driving oracle/hmc.py must follow it:
+    identical accept decisions away from u ~ acc, state and step sizes to float32 rounding."""
+    g = np.load(os.path.join(GOLD, "ref_lntm_hmc.npz"))
+    om = OM.LNTM(g["x"], g["beta"], g["eta_mean"], g["eta_logstd"], dtype=np.float32)
+    oh = OH.HMC(step_size=float(g["cfg_step_size"]), n_leapfrogs=int(g["cfg_n_leapfrogs"]),
+                adapt_step_size=True, target_acceptance_rate=float(g["cfg_target_acceptance_rate"]))
+    q = [g["eta0"].copy()]
+    for i in range(g["eta"].shape[0]):
+        with np.errstate(all="ignore"):
+            q, info = oh.step(q, om.logp, om.grad, [g["noise_p"][i]], g["noise_u"][i], True, False)
+        np.testing.assert_allclose(info.orig_log_prob, g["lp0"][i], rtol=2e-5, atol=2e-4)
+        np.testing.assert_allclose(info.acceptance_rate, g["acc"][i], rtol=2e-3, atol=2e-4)
+        np.testing.assert_allclose(np.float32(info.updated_step_size), g["step_size"][i],
+                                   rtol=2e-4)
+        near = np.abs(g["noise_u"][i] - g["acc"][i]) < 1e-3
+        np.testing.assert_allclose(q[0][~near], g["eta"][i][~near], rtol=1e-3, atol=1e-4)
+        q = [g["eta"][i].copy()]             # continue from the reference's state
