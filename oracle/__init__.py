@@ -45,6 +45,10 @@ Pinning status:
     own framework/ + distributions/ + variational/ code run on the stand-in
     on the VAE of examples/variational_autoencoders/iwae.py
     (tests/golden/ref_vae.npz: bounds, costs, tf.gradients of every weight).
+  * the BNN and LNTM log-joints (oracle/models.py, hand-derived gradients): PINNED to
+    bnn_sgmcmc.py:19-35 / lntm_mcem.py:33-48 built on the reference's own
+    BayesianNet and sampled by its SGHMC / HMC on the stand-in
+    (tests/golden/ref_bnn_sghmc.npz, ref_lntm_hmc.npz).
   * AIS (oracle/evaluation.py): PINNED the same way -- class AIS of
     zhusuan/evaluation.py:57-172 run on the stand-in, tests/golden/ref_ais.npz.
   * device sampler streams (oracle/samplers.py): "parity unpinned" by the
