@@ -496,6 +496,45 @@ def run_reference_lntm_hmc(seed=909):
     return out
 
 
+def run_reference_hmc_big(name):
+    """The L = 50 adaptive protocol of tests/golden/make_golden.py (BIG: every iteration starts
+    from a prescribed posterior draw, the sampler's adaptation state carries over) executed by the
+    reference's own HMC -- the source of truth the BIG fixtures (written by the float32 oracle
+    with a float64 re-evaluation) are compared with in tests/test_ref_pins.py.  Returns the
+    per-iteration outputs; nothing is written."""
+    tf, hmc_mod, _ = load_reference()
+    sys.path.insert(0, GOLD)
+    import make_golden as MG
+    cfg = dict(MG.BIG[name])
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    D, C, L = cfg["D"], cfg["C"], cfg["L"]
+    P, const, mu, _ = MG.big_problem(cfg)
+    Pt, mut = tf.constant(P.astype(np.float32)), tf.constant(mu)
+
+    def log_joint(obs):
+        xc = obs["x"] - mut
+        return -0.5 * tf.reduce_sum(xc * tf.matmul(xc, Pt), axis=-1) + np.float32(const)
+    adapt_step = tf.placeholder(tf.bool, shape=[], name="adapt_step_size")
+    adapt_mass = tf.placeholder(tf.bool, shape=[], name="adapt_mass")
+    x = tf.Variable(MG.big_state(cfg, 0), name="x", dtype=tf.float32)
+    sampler = hmc_mod.HMC(step_size=cfg["eps0"], n_leapfrogs=L, adapt_step_size=adapt_step,
+                          adapt_mass=adapt_mass, mass_collect_iters=cfg["mci"])
+    sample_op, info = sampler.sample(log_joint, observed={}, latent={"x": x})
+    sess = tf.Session()
+    rec = {k: [] for k in ("acc", "step_size", "lp", "lp0", "h0", "h1", "q")}
+    for i in range(cfg["iters"]):
+        x.load(MG.big_state(cfg, i))                  # the caller assigns the latent variable
+        tf.set_noise(normal=[MG.big_noise(cfg, i)], uniform=[g["noise_u"][i]])
+        adapt = i < cfg["n_adapt"]
+        with np.errstate(all="ignore"):
+            _, r = sess.run([sample_op, info], feed_dict={adapt_step: adapt, adapt_mass: adapt})
+        rec["acc"].append(r.acceptance_rate); rec["step_size"].append(r.updated_step_size)
+        rec["lp"].append(r.log_prob); rec["lp0"].append(r.orig_log_prob)
+        rec["h0"].append(r.orig_hamiltonian); rec["h1"].append(r.hamiltonian)
+        rec["q"].append(np.array(x.value))
+    return {k: np.stack(v) for k, v in rec.items()}
+
+
 HMC_CASES = {
     "ref_hmc_diag": ("diag", 12, 16, dict(step_size=1e-3, n_leapfrogs=5,
                                           target_acceptance_rate=0.9, mass_collect_iters=4,

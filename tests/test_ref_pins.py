@@ -342,3 +342,38 @@ def test_oracle_lntm_hmc_follows_reference_run():
         near = np.abs(g["noise_u"][i] - g["acc"][i]) < 1e-3
         np.testing.assert_allclose(q[0][~near], g["eta"][i][~near], rtol=1e-3, atol=1e-4)
         q = [g["eta"][i].copy()]             # continue from the reference's state
+
+
+@pytest.mark.skipif(not have_ref, reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize("name", ["hmc_dense64", "hmc_dense1024"])
+def test_reference_hmc_itself_passes_the_l50_protocol(name):
+    """The L = 50 adaptive fixtures the benchmarked CUDA kernels are replayed against
+    (tests/golden/hmc_dense64.npz, hmc_dense1024.npz: written by the float32 oracle, with a
+    float64 re-evaluation of every iteration) versus THE REFERENCE'S OWN hmc.py run on the TF
+    stand-in under the same protocol, at the benchmark's shape (D = 1024, L = 50, both step-size
+    searches, mass != 1): every accept decision, the step-size trajectory exactly, Hamiltonians
+    within 1e-6 of float64."""
+    sys.path.insert(0, SHIM)
+    saved = {k: sys.modules.get(k) for k in ("tensorflow", "zhusuan")}
+    try:
+        import make_ref_golden as M
+        o = M.run_reference_hmc_big(name)
+    finally:
+        sys.path.remove(SHIM)
+        for k in [m for m in sys.modules if m == "tensorflow" or m.startswith("tensorflow.")
+                  or m.startswith("zhusuan")]:
+            del sys.modules[k]
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    accept = (g["noise_u"] < o["acc"]).astype(np.int32)
+    np.testing.assert_array_equal(accept, g["accept"])
+    np.testing.assert_array_equal(np.asarray(o["step_size"], np.float32), g["step_size"])
+    np.testing.assert_allclose(o["h0"], g["h0_64"], rtol=1e-6)
+    live = g["acc64"] > 1e-6
+    assert 0.4 * live.size < live.sum() < live.size      # healthy and diverging iterations
+    np.testing.assert_allclose(o["h1"][live], g["h1_64"][live], rtol=1e-6)
+    np.testing.assert_allclose(o["acc"], g["acc64"], atol=1e-3)
+    np.testing.assert_allclose(o["acc"], g["acc"], atol=1e-3)           # the float32 oracle's
+    np.testing.assert_allclose(o["lp0"], g["lp0"], rtol=1e-6)
