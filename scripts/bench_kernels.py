@@ -69,6 +69,8 @@ def main():
     lo = torch.empty(2, C, D, dtype=torch.float16, device=dev); sc = torch.zeros(4, device=dev); sc[3] = 1.0
     ms = timeit(lambda: lib.call("zsb_hmc_dense_h16_prepare_f32", ptr(q), ptr(lo), ptr(sc), n, s))
     report("dense_h16_prepare (absmax+split)", 12 * n, ms, "read q twice, write 2 fp16 planes")
+    ms = timeit(lambda: lib.call("zsb_hmc_dense_select_planes_f32", ptr(q), ptr(lo), ptr(sc), ptr(acc), C, D, s))
+    report("dense_select_planes", 8 * n, ms, "all accepted: read 2 fp16 planes, write q")
     # sgmcmc
     ms = timeit(lambda: lib.call("zsb_sgmcmc_sgld_f32", ptr(q), ptr(g), None, 1e-6, C, D, 1, 1, 0, s))
     report("sgmcmc_sgld (Philox)", 12 * n, ms)

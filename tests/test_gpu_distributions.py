@@ -293,6 +293,37 @@ def test_kernel_philox_matches_oracle():
     np.testing.assert_array_equal(N(accept), (u_ref < N(acc)).astype(np.int32))
 
 
+@pytest.mark.parametrize("C,D", [(37, 24), (300, 1024), (5, 4), (64, 100)])
+def test_momentum_vec4_path_is_the_scalar_path(C, D):
+    """hmc.py:21-23.  The 128-bit momentum kernel (row_len % 4 == 0, aligned) and the scalar one
+    (taken for a misaligned p) draw the same Philox blocks and do the same arithmetic: identical
+    bits for p and for the kinetic energy; both match the oracle's Philox normals."""
+    from zhusuan_b200._lib import lib, ptr, stream
+    from oracle import philox
+    g = np.random.RandomState(5)
+    mass = torch.tensor(g.uniform(0.3, 3.0, D), dtype=torch.float32, device="cuda")
+    seed, it, row0 = 0xFEEDFACE12345678, 77, 4096
+    buf = torch.zeros(C * D + 4, device="cuda")
+    p_al, p_mis = torch.empty(C, D, device="cuda"), buf[1:1 + C * D].view(C, D)
+    assert p_al.data_ptr() % 16 == 0 and p_mis.data_ptr() % 16 != 0
+    k_al = torch.empty(C, device="cuda")
+    k_mis = torch.empty(C, device="cuda")
+    for p, k in ((p_al, k_al), (p_mis, k_mis)):
+        lib.call("zsb_hmc_momentum_f32", ptr(p), None, ptr(mass), D, C, D, seed, it, 1, row0,
+                 ptr(k), 0, None, stream())
+    np.testing.assert_array_equal(N(p_al), N(p_mis))
+    np.testing.assert_array_equal(N(k_al), N(k_mis))
+    ref = philox.normal_matrix(seed, 1, it, row0, C, D) * np.sqrt(N(mass))[None, :]
+    np.testing.assert_allclose(N(p_al), ref, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(N(k_al), 0.5 * (ref.astype(np.float64) ** 2 / N(mass)).sum(1),
+                               rtol=2e-5)
+    # accumulate = 1 adds to the existing kinetic energy (second latent of a multi-latent model)
+    k2 = k_al.clone()
+    lib.call("zsb_hmc_momentum_f32", ptr(p_al), None, ptr(mass), D, C, D, seed, it, 1, row0,
+             ptr(k2), 1, None, stream())
+    np.testing.assert_allclose(N(k2), 2 * N(k_al), rtol=1e-6)
+
+
 # ---- the nine other elementwise univariate families (univariate_ext.cu) ---------------------
 def _uni_dist(zs, fam, a, b):
     D = zs.distributions

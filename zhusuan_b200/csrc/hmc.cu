@@ -65,32 +65,113 @@ __global__ void __launch_bounds__(256) momentum_kernel(float* __restrict__ p,
   }
 }
 
+// Vectorised form of the same draw (row_len % 4 == 0, one mass entry per column, in-kernel Philox,
+// 16-byte aligned p / mass): the CTA stages mass and sqrt(mass) in shared memory once, a lane turns
+// one Philox block into one 128-bit store.  Same counters, same operation order per element and
+// per kinetic sum as momentum_kernel: the two paths are bit-identical (tests/test_gpu_hmc.py).
+template <int LANES>
+__global__ void __launch_bounds__(256) momentum_vec4_kernel(float* __restrict__ p,
+                                                            const float* __restrict__ mass,
+                                                            int64_t chains, int row_len,
+                                                            uint64_t seed, uint32_t iter_in,
+                                                            uint32_t stream_id, int64_t row0,
+                                                            float* __restrict__ k_out,
+                                                            int accumulate,
+                                                            const float* __restrict__ state) {
+  extern __shared__ float4 mom_sm[];                 // [nblk] mass, [nblk] sqrt(mass)
+  const uint32_t iter = resolve_iter(iter_in, state);
+  const int nblk = row_len >> 2;
+  for (int i = threadIdx.x; i < nblk; i += 256) {
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mass) + i);
+    mom_sm[i] = m;
+    mom_sm[nblk + i] = make_float4(sqrtf(m.x), sqrtf(m.y), sqrtf(m.z), sqrtf(m.w));
+  }
+  __syncthreads();
+  constexpr int rows_per_block = 256 / LANES;
+  const int lane = threadIdx.x % LANES;
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / LANES; row < chains;
+       row += (int64_t)gridDim.x * rows_per_block) {
+    float4* __restrict__ pr = reinterpret_cast<float4*>(p + row * row_len);
+    const uint32_t grow = (uint32_t)(row0 + row);
+    float kin = 0.f;
+#pragma unroll 2
+    for (int b = lane; b < nblk; b += LANES) {
+      float z[4];
+      philox_normal4(seed, stream_id, iter, grow, (uint32_t)b, z);
+      const float4 m = mom_sm[b], sm = mom_sm[nblk + b];
+      float4 pv;
+      pv.x = mul(z[0], sm.x); pv.y = mul(z[1], sm.y);
+      pv.z = mul(z[2], sm.z); pv.w = mul(z[3], sm.w);
+      pr[b] = pv;
+      kin += fdiv(mul(pv.x, pv.x), m.x);
+      kin += fdiv(mul(pv.y, pv.y), m.y);
+      kin += fdiv(mul(pv.z, pv.z), m.z);
+      kin += fdiv(mul(pv.w, pv.w), m.w);
+    }
+    kin = sub_warp_sum<LANES>(kin);
+    if (lane == 0 && k_out) {
+      const float v = mul(0.5f, kin);
+      k_out[row] = accumulate ? add(k_out[row], v) : v;
+    }
+  }
+}
+
 // a5 kinetic (hmc.py:32-34): k[c] (+)= 0.5 * sum_d p^2 / mass
 template <int LANES>
 __global__ void __launch_bounds__(256) kinetic_kernel(const float* __restrict__ p,
                                                       const float* __restrict__ mass,
                                                       int64_t mass_n, int64_t chains,
                                                       int64_t row_len, float* __restrict__ k_out,
-                                                      int accumulate, int vec4) {
+                                                      int accumulate) {
   const int rows_per_block = 256 / LANES;
   const int lane = threadIdx.x % LANES;
   for (int64_t row = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / LANES; row < chains;
        row += (int64_t)gridDim.x * rows_per_block) {
     float kin = 0.f;
-    if (vec4) {            // row_len % 4 == 0, mass_n == row_len, 16-byte aligned
-      const float4* pr = reinterpret_cast<const float4*>(p + row * row_len);
-      const float4* mr = reinterpret_cast<const float4*>(mass);
-      for (int64_t c4 = lane; c4 < row_len / 4; c4 += LANES) {
-        const float4 pv = pr[c4], mv = mr[c4];
-        kin += fdiv(mul(pv.x, pv.x), mv.x);
-        kin += fdiv(mul(pv.y, pv.y), mv.y);
-        kin += fdiv(mul(pv.z, pv.z), mv.z);
-        kin += fdiv(mul(pv.w, pv.w), mv.w);
+    for (int64_t c = lane; c < row_len; c += LANES) {
+      const float pv = p[row * row_len + c];
+      kin += fdiv(mul(pv, pv), mass[c % mass_n]);
+    }
+    kin = sub_warp_sum<LANES>(kin);
+    if (lane == 0) {
+      const float v = mul(0.5f, kin);
+      k_out[row] = accumulate ? add(k_out[row], v) : v;
+    }
+  }
+}
+// 128-bit form (row_len % 4 == 0, mass_n == row_len, 16-byte aligned).  The IEEE division has a
+// slow-path branch per element that keeps the compiler from hoisting loads across it, so four
+// float4 loads per lane are issued explicitly before any of them is consumed; the out-of-range
+// slots of the last batch contribute p = 0 / m = 1, i.e. exactly +0 to a non-negative sum.
+template <int LANES>
+__global__ void __launch_bounds__(256) kinetic_vec4_kernel(const float* __restrict__ p,
+                                                           const float* __restrict__ mass,
+                                                           int64_t chains, int row_len,
+                                                           float* __restrict__ k_out,
+                                                           int accumulate) {
+  constexpr int rows_per_block = 256 / LANES;
+  const int lane = threadIdx.x % LANES;
+  const int n4 = row_len >> 2;
+  const float4* __restrict__ mr = reinterpret_cast<const float4*>(mass);
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / LANES; row < chains;
+       row += (int64_t)gridDim.x * rows_per_block) {
+    const float4* __restrict__ pr = reinterpret_cast<const float4*>(p + row * row_len);
+    float kin = 0.f;
+    for (int c4 = lane; c4 < n4; c4 += 4 * LANES) {
+      float4 pv[4], mv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = c4 + u * LANES;
+        const bool ok = i < n4;
+        pv[u] = ok ? pr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        mv[u] = ok ? __ldg(mr + i) : make_float4(1.f, 1.f, 1.f, 1.f);
       }
-    } else {
-      for (int64_t c = lane; c < row_len; c += LANES) {
-        const float pv = p[row * row_len + c];
-        kin += fdiv(mul(pv, pv), mass[c % mass_n]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        kin += fdiv(mul(pv[u].x, pv[u].x), mv[u].x);
+        kin += fdiv(mul(pv[u].y, pv[u].y), mv[u].y);
+        kin += fdiv(mul(pv[u].z, pv[u].z), mv[u].z);
+        kin += fdiv(mul(pv[u].w, pv[u].w), mv[u].w);
       }
     }
     kin = sub_warp_sum<LANES>(kin);
@@ -338,15 +419,38 @@ __global__ void __launch_bounds__(256) mass_stats4_kernel(const float* __restric
   reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * 2 + 0) * D)[d4] = s1;
   reinterpret_cast<float4*>(part + ((int64_t)blockIdx.x * 2 + 1) * D)[d4] = s2;
 }
+// Stage 2: stats[which][d] = sum_b part[b][which][d] in a fixed order.  A 256-thread block owns 32
+// consecutive columns of the [2*D] output; its 8 warps take the partials b = w, w + 8, ... (four
+// independent 128-byte-coalesced loads in flight per thread), then warp 0 adds the 8 sub-sums in
+// warp order.  (One thread per column walking all n_part partials took as long as stage 1.)
 __global__ void __launch_bounds__(256) mass_stats_final_kernel(const float* __restrict__ part,
                                                                int n_part, int64_t D,
                                                                float* __restrict__ stats) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over 2*D
-  if (j >= 2 * D) return;
-  const int64_t which = j / D, d = j % D;
-  float s = 0.f;
-  for (int b = 0; b < n_part; ++b) s += part[((int64_t)b * 2 + which) * D + d];
-  stats[j] = s;
+  __shared__ float sub[8][32];
+  const int tx = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t j = (int64_t)blockIdx.x * 32 + tx;               // over 2*D
+  const bool ok = j < 2 * D;
+  const int64_t which = ok ? j / D : 0, d = ok ? j % D : 0;
+  const float* __restrict__ src = part + which * D + d;
+  const int64_t stride = 2 * D;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (ok) {
+    int b = w;
+    for (; b + 24 < n_part; b += 32) {
+      const float v0 = src[(int64_t)b * stride], v1 = src[(int64_t)(b + 8) * stride];
+      const float v2 = src[(int64_t)(b + 16) * stride], v3 = src[(int64_t)(b + 24) * stride];
+      s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+    }
+    for (; b < n_part; b += 8) s0 += src[(int64_t)b * stride];
+  }
+  sub[w][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (w == 0 && ok) {
+    float s = sub[0][tx];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s += sub[i][tx];
+    stats[j] = s;
+  }
 }
 // EWMV.update + get_precision + mass gating (hmc.py:130-159, 283-305), per dimension.
 //   w = (1-decay)/(1-decay^tt); delta = S1/C; mean += w*delta;
@@ -550,6 +654,18 @@ int zsb_hmc_momentum_f32(float* p, const float* noise, const float* mass, int64_
   cudaStream_t st = (cudaStream_t)stream;
   const int lanes = pick_lanes((row_len + 3) / 4);
   const unsigned g = rows_grid(chains, lanes);
+  if (!noise && mass_n == row_len && row_len <= 6144 && zsb_vec4_ok(chains, row_len, {p, mass})) {
+    const size_t sm = (size_t)(row_len / 4) * 2 * sizeof(float4);
+#define ZSB_L(LN) momentum_vec4_kernel<LN><<<g, 256, sm, st>>>(p, mass, chains, (int)row_len, seed,  \
+                                                              iter, stream_id, row0, k_out,        \
+                                                              accumulate, iter_state)
+    switch (lanes) {
+      case 1: ZSB_L(1); break; case 2: ZSB_L(2); break; case 4: ZSB_L(4); break;
+      case 8: ZSB_L(8); break; case 16: ZSB_L(16); break; default: ZSB_L(32); break;
+    }
+#undef ZSB_L
+    return zsb_check_launch("hmc_momentum");
+  }
 #define ZSB_L(LN) momentum_kernel<LN><<<g, 256, 0, st>>>(p, noise, mass, mass_n, chains, row_len, \
                                                         seed, iter, stream_id, row0, k_out,      \
                                                         accumulate, iter_state)
@@ -568,9 +684,20 @@ int zsb_hmc_kinetic_f32(const float* p, const float* mass, int64_t mass_n, int64
   cudaStream_t st = (cudaStream_t)stream;
   const int lanes = pick_lanes(row_len);
   const unsigned g = rows_grid(chains, lanes);
-  const int vec4 = (mass_n == row_len && zsb_vec4_ok(chains, row_len, {p, mass})) ? 1 : 0;
+  if (mass_n == row_len && zsb_vec4_ok(chains, row_len, {p, mass})) {
+    const int lanes4 = pick_lanes(row_len / 4);
+    const unsigned g4 = rows_grid(chains, lanes4);
+#define ZSB_L(LN) kinetic_vec4_kernel<LN><<<g4, 256, 0, st>>>(p, mass, chains, (int)row_len, k_out, \
+                                                             accumulate)
+    switch (lanes4) {
+      case 1: ZSB_L(1); break; case 2: ZSB_L(2); break; case 4: ZSB_L(4); break;
+      case 8: ZSB_L(8); break; case 16: ZSB_L(16); break; default: ZSB_L(32); break;
+    }
+#undef ZSB_L
+    return zsb_check_launch("hmc_kinetic");
+  }
 #define ZSB_L(LN) kinetic_kernel<LN><<<g, 256, 0, st>>>(p, mass, mass_n, chains, row_len, k_out, \
-                                                       accumulate, vec4)
+                                                       accumulate)
   switch (lanes) {
     case 1: ZSB_L(1); break; case 2: ZSB_L(2); break; case 4: ZSB_L(4); break;
     case 8: ZSB_L(8); break; case 16: ZSB_L(16); break; default: ZSB_L(32); break;
@@ -685,7 +812,7 @@ int zsb_hmc_mass_stats_f32(const float* q, const float* ewmv_mean, int64_t chain
   }
   int rc = zsb_check_launch("hmc_mass_stats");
   if (rc) return rc;
-  mass_stats_final_kernel<<<(unsigned)zsb_ceil_div(2 * D, 256), 256, 0, st>>>(part, nb, D, stats);
+  mass_stats_final_kernel<<<(unsigned)zsb_ceil_div(2 * D, 32), 256, 0, st>>>(part, nb, D, stats);
   return zsb_check_launch("hmc_mass_stats_final");
 }
 int zsb_hmc_mass_update_f32(float* ewmv_mean, float* ewmv_var, float* mass, const float* stats,

@@ -474,23 +474,50 @@ dense_res_kernel(const __grid_constant__ ResMaps maps, __half* __restrict__ plan
   }
 }
 
-// q[c, :] <- (hi + lo) / sq of the proposal planes where accept[c] (hmc.py:488-497)
+// q[c, :] <- (hi + lo) / sq of the proposal planes where accept[c] (hmc.py:488-497).
+// One warp per chain at a time (the accept flag is warp-uniform: a rejected chain costs one 4-byte
+// load), 8 dimensions per lane and step: two 128-bit plane loads in, two 128-bit stores out, up to
+// four steps' loads issued before the first use.  D % 8 == 0 (the dense kernels need D % 64 == 0).
 __global__ void __launch_bounds__(256) select_planes_kernel(float* __restrict__ q,
                                                             const __half* __restrict__ planes,
                                                             const float* __restrict__ scales,
                                                             const int32_t* __restrict__ accept,
                                                             int64_t chains, int64_t D) {
   const float inv_sq = 1.f / scales[0];
-  const int64_t n2 = chains * D / 2;
-  const __half2* hi = reinterpret_cast<const __half2*>(planes);
-  const __half2* lo = reinterpret_cast<const __half2*>(planes + chains * D);
-  float2* q2 = reinterpret_cast<float2*>(q);
-  const int64_t d2 = D / 2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    if (!accept[i / d2]) continue;
-    const float2 h = __half22float2(hi[i]), l = __half22float2(lo[i]);
-    q2[i] = make_float2((h.x + l.x) * inv_sq, (h.y + l.y) * inv_sq);
+  const int lane = threadIdx.x & 31;
+  const int n8 = (int)(D >> 3);
+  const int64_t wstride = (int64_t)gridDim.x * 8;
+  for (int64_t c = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); c < chains; c += wstride) {
+    if (!accept[c]) continue;
+    const uint4* __restrict__ hi = reinterpret_cast<const uint4*>(planes + c * D);
+    const uint4* __restrict__ lo = reinterpret_cast<const uint4*>(planes + (chains + c) * D);
+    float4* __restrict__ qr = reinterpret_cast<float4*>(q + c * D);
+    for (int i0 = lane; i0 < n8; i0 += 128) {
+      uint4 h[4], l[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + 32 * u;
+        if (i < n8) { h[u] = __ldcs(hi + i); l[u] = __ldcs(lo + i); }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + 32 * u;
+        if (i < n8) {
+          const uint32_t hw[4] = {h[u].x, h[u].y, h[u].z, h[u].w};
+          const uint32_t lw[4] = {l[u].x, l[u].y, l[u].z, l[u].w};
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
+            const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[k]));
+            o[2 * k] = (hf.x + lf.x) * inv_sq;
+            o[2 * k + 1] = (hf.y + lf.y) * inv_sq;
+          }
+          qr[2 * i] = make_float4(o[0], o[1], o[2], o[3]);
+          qr[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
   }
 }
 
@@ -649,7 +676,8 @@ int zsb_dense_res_h16_launch(void* planes0, void* planes1, const float* p0, floa
 int zsb_dense_select_planes_launch(float* q, const void* planes, const float* scales,
                                    const int32_t* accept, int64_t chains, int64_t D,
                                    cudaStream_t st) {
-  int64_t blocks = zsb_ceil_div(chains * D / 2, 256);
+  ZSB_REQUIRE(D % 8 == 0, "zsb_dense_select_planes: D must be a multiple of 8");
+  int64_t blocks = zsb_ceil_div(chains, 8);
   if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
   if (blocks < 1) blocks = 1;
   select_planes_kernel<<<(unsigned)blocks, 256, 0, st>>>(
