@@ -191,6 +191,27 @@ int zsb_split16_dual_f32(const float* src, const float* mask_src, int64_t R, int
                          void* planes_t, float* col_sum, float* scale, int have_amax,
                          void* stream);
 
+/* Backward of the fused Bernoulli likelihood layer (gradient of epi 1 wrt the logits, epi 2)
+ * emitted directly as the operand planes of the two backward products: dl_planes [2][R][kpad(J)]
+ * = fp16 hi/lo of gout[r] * (x - sigmoid(logits)) * scale_out[0], col_sum [J] += its column sums
+ * (bias gradient, may be NULL).  scale_out = device float[4], zeroed once by the caller; the power
+ * of two follows from max|gout| * (1 + max|x_obs|) >= max|dl| BEFORE the GEMM, so the fp32
+ * dl matrix (822 MB at config 3: univariate.py:398-403 differentiated) never exists. */
+int zsb_linear_tc_bern_grad_planes_f32(const void* w_planes, const float* scale_w,
+                                       const void* h_planes, const float* scale_h,
+                                       const float* bias, const float* x_obs, int64_t n_x,
+                                       const float* gout, void* dl_planes, float* col_sum,
+                                       float* scale_out, int64_t R, int J, int K, void* stream);
+/* Weight gradient of the dense layer, dW [J, K] = g^T h = sum_r g[r, j] * h[r, k] (the
+ * tf.gradients of tf.layers.dense w.r.t. its kernel, iwae.py:23-44), read straight from the
+ * ROW-MAJOR planes h_planes [2][R][kpad(K)] and g_planes [2][R][kpad(J)]: the contraction runs
+ * over the rows, so both operands are MN-major tcgen05 operands and no transposed copy of an
+ * activation is ever written.  part = zsb_linear_tc_slices(J, K, R) * J * K floats of split-K
+ * scratch (NULL: one slice). */
+int zsb_linear_tc_wgrad_f32(const void* h_planes, const float* scale_h, int K,
+                            const void* g_planes, const float* scale_g, int J, int64_t R,
+                            float* out, float* part, void* stream);
+
 /* ---- diagnostics: effective sample size (zhusuan/diagnostics.py:17-64, the Stan estimator) on the
  * device; samples [M, D] row-major with burn-in already dropped -> ess [D].  M >= 2. */
 int zsb_effective_sample_size_f32(const float* samples, int64_t M, int64_t D, float* ess,

@@ -9,6 +9,10 @@
 //          = Bernoulli(logits = l).log_prob(x) summed over the feature axis (univariate.py:398-403
 //            + group_ndims = 1, base.py:303-304) once the partial rows are added up
 //   EPI 2  out[r, j] = g[r] * (x - sigmoid(l))                   d(sum_r g[r] * log_prob[r]) / dl
+//   EPI 3  the EPI 2 values, emitted directly as the fp16 hi/lo operand planes [2][R][Jp] of the
+//          two backward products (dh = dl W, dW = dl^T h) plus their column sums (bias gradient):
+//          the fp32 dl matrix (822 MB at config 3) is never written or re-read.  The planes' scale
+//          is known BEFORE the GEMM: |dl| <= max|g| * (1 + max|x|)  (sigmoid in (0, 1)).
 //
 // fp32 accuracy on fp16 tensor cores: both operands are pre-split into scaled fp16 hi + lo planes
 // (zsb_split16_pad_f32), three kind::f16 tcgen05.mma per k-step accumulate hi*hi + hi*lo + lo*hi
@@ -29,7 +33,24 @@ __device__ __forceinline__ float bern_lp(float x, float l) {   // -sigmoid_cross
   return -(fmaxf(l, 0.f) - l * x + __logf(1.f + __expf(-fabsf(l))));
 }
 
-template <int EPI>
+// MN = 1 (weight-gradient product, EPI 0 only): BOTH operands are read in their row-major plane
+// layout [contraction rows, features] -- MN-major for the tensor core (instruction-descriptor bits
+// 15 / 16) -- so dW = g^T h needs no transposed copy of either matrix.  A stage then holds, per
+// plane, two TMA boxes of 64 contraction rows x 64 features (128-byte rows, SWIZZLE_128B): the
+// canonical MN-major tile ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in fp16 elements with
+// SBO = 1 KB (next 8 contraction rows) and LBO = 8 KB (next 64 features); one k-step of 16
+// contraction rows advances the start address by 2 KB.  `Kp` is the padded contraction length.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address       bits [0,14)
+  d |= (uint64_t)(8192 >> 4) << 16;                   // leading byte offset bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset  bits [32,46)
+  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
+template <int EPI, int MN = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
                   const __grid_constant__ CUtensorMap map_wlo,
@@ -106,10 +127,22 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
           const uint32_t fb = full_bar + 8 * stage;
           const uint32_t sa = smem_base + stage * GC::STAGE;
           if (leader) mbar_expect_tx(fb, 2 * GC::STAGE);
-          tma_load_2d_2sm(sa, &map_whi, fb, kb * 2 * GBK, j0);
-          tma_load_2d_2sm(sa + GC::A_TILE, &map_wlo, fb, kb * 2 * GBK, j0);
-          tma_load_2d_2sm(sa + 2 * GC::A_TILE, &map_hhi, fb, kb * 2 * GBK, r0);
-          tma_load_2d_2sm(sa + 2 * GC::A_TILE + GC::B_TILE, &map_hlo, fb, kb * 2 * GBK, r0);
+          if (MN) {       // boxes of 64 features (c0) x 64 contraction rows (c1), 8 KB each
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const uint32_t o = (uint32_t)b * 8192u;
+              tma_load_2d_2sm(sa + o, &map_whi, fb, j0 + 64 * b, kb * 64);
+              tma_load_2d_2sm(sa + GC::A_TILE + o, &map_wlo, fb, j0 + 64 * b, kb * 64);
+              tma_load_2d_2sm(sa + 2 * GC::A_TILE + o, &map_hhi, fb, r0 + 64 * b, kb * 64);
+              tma_load_2d_2sm(sa + 2 * GC::A_TILE + GC::B_TILE + o, &map_hlo, fb, r0 + 64 * b,
+                              kb * 64);
+            }
+          } else {
+            tma_load_2d_2sm(sa, &map_whi, fb, kb * 2 * GBK, j0);
+            tma_load_2d_2sm(sa + GC::A_TILE, &map_wlo, fb, kb * 2 * GBK, j0);
+            tma_load_2d_2sm(sa + 2 * GC::A_TILE, &map_hhi, fb, kb * 2 * GBK, r0);
+            tma_load_2d_2sm(sa + 2 * GC::A_TILE + GC::B_TILE, &map_hlo, fb, kb * 2 * GBK, r0);
+          }
           if (++stage == GC::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -117,7 +150,7 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      const uint32_t idesc = make_idesc_2sm_f16();
+      const uint32_t idesc = make_idesc_2sm_f16() | (MN ? ((1u << 15) | (1u << 16)) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -132,13 +165,16 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * GC::STAGE;
-          const uint64_t a_hi = make_smem_desc<GBK>(sa);
-          const uint64_t a_lo = make_smem_desc<GBK>(sa + GC::A_TILE);
-          const uint64_t b_hi = make_smem_desc<GBK>(sa + 2 * GC::A_TILE);
-          const uint64_t b_lo = make_smem_desc<GBK>(sa + 2 * GC::A_TILE + GC::B_TILE);
+          const uint64_t a_hi = MN ? make_smem_desc_mn(sa) : make_smem_desc<GBK>(sa);
+          const uint64_t a_lo = MN ? make_smem_desc_mn(sa + GC::A_TILE)
+                                   : make_smem_desc<GBK>(sa + GC::A_TILE);
+          const uint64_t b_hi = MN ? make_smem_desc_mn(sa + 2 * GC::A_TILE)
+                                   : make_smem_desc<GBK>(sa + 2 * GC::A_TILE);
+          const uint64_t b_lo = MN ? make_smem_desc_mn(sa + 2 * GC::A_TILE + GC::B_TILE)
+                                   : make_smem_desc<GBK>(sa + 2 * GC::A_TILE + GC::B_TILE);
 #pragma unroll
-          for (int k = 0; k < GBK / 8; ++k) {              // 16 halves = 32 B per k-step
-            const uint64_t ko = (uint64_t)((k * 8 * 4) >> 4);
+          for (int k = 0; k < GBK / 8; ++k) {     // K-major: 16 halves = 32 B; MN-major: 2 KB
+            const uint64_t ko = MN ? (uint64_t)((k * 2048) >> 4) : (uint64_t)((k * 8 * 4) >> 4);
             const uint32_t first = ((kb - kb0) | k) != 0 ? 1u : 0u;
             umma_f16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
             umma_f16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
@@ -156,6 +192,10 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const float acc_scale = 1.f / (scale_w[0] * scale_h[0]);   // powers of two: exact
+    // EPI 3: `out` = the fp16 plane pair [2][R][Jp_out], amax_scale[0] = their (a-priori) scale
+    __half* __restrict__ pl_out = reinterpret_cast<__half*>(out);
+    const int Jp_out = ((J + 63) / 64) * 64;
+    const float s_out = (EPI == 3) ? amax_scale[0] : 1.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     float amax = 0.f;        // max |stored output| (EPI 0 / 2): the consumer's fp16-split scale
@@ -176,6 +216,7 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
       const int64_t part_row = (int64_t)(nb * 4 + quarter) * R;
       const float b_use = (slice == 0) ? b_j : 0.f;           // bias once across the slices
       const bool warp_j_ok = __all_sync(0xffffffffu, j_ok);
+      float csum = 0.f;                                       // EPI 3: column sum of this lane's j
       // observations of one 16-column block (rows rbase .. rbase+15, this lane's feature j); all
       // 16 loads are issued back to back, one block AHEAD of their use (L2 latency ~1 us)
       auto load_x = [&](float* xe, float& ge, int c) {
@@ -196,13 +237,20 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
           }
         }
         // upstream gradient of the 16 rows: lane jj holds gout[rbase + jj]
-        if (EPI == 2) ge = (lane < 16 && rbase + lane < R) ? __ldg(gout + rbase + lane) : 0.f;
+        if (EPI >= 2) ge = (lane < 16 && rbase + lane < R) ? __ldg(gout + rbase + lane) : 0.f;
       };
       auto process = [&](const uint32_t* v, const float* xe, float ge, int c) {
         const int64_t rbase = r0 + c;
         if (rbase >= R) return;                     // warp-uniform
         float lpv[16];
-        float* __restrict__ po = (EPI != 1) ? out_s + rbase * J + j : nullptr;
+        float* __restrict__ po = (EPI == 0 || EPI == 2) ? out_s + rbase * J + j : nullptr;
+        // EPI 3: even lanes store the hi-plane word of the feature pair (j, j + 1), odd lanes
+        // the lo-plane word of (j - 1, j): 64 contiguous bytes per plane, row and instruction
+        uint32_t* __restrict__ pw = nullptr;
+        if (EPI == 3)
+          pw = reinterpret_cast<uint32_t*>(pl_out + ((lane & 1) ? R * (int64_t)Jp_out : 0) +
+                                           rbase * Jp_out + (j & ~1));
+        const bool col_ok = (j & ~1) < Jp_out;
         const bool full = warp_j_ok && rbase + 16 <= R;   // no per-element predicates
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
@@ -213,12 +261,25 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
             if (ok) { *po = y; amax = fmaxf(amax, fabsf(y)); }
           } else if (EPI == 1) {
             lpv[jj] = ok ? bern_lp(xe[jj], l) : 0.f;
-          } else {
+          } else if (EPI == 2) {
             const float g = __shfl_sync(0xffffffffu, ge, jj);
             const float y = g * (xe[jj] - __fdividef(1.f, 1.f + __expf(-l)));
             if (ok) { *po = y; amax = fmaxf(amax, fabsf(y)); }
+          } else {
+            const float g = __shfl_sync(0xffffffffu, ge, jj);
+            const float y = ok ? g * (xe[jj] - __fdividef(1.f, 1.f + __expf(-l))) : 0.f;
+            csum += y;
+            const float ys = y * s_out;
+            const __half hh = __float2half_rn(ys);
+            const __half ll = __float2half_rn(ys - __half2float(hh));
+            const uint32_t mine = (uint32_t)__half_as_ushort(hh) |
+                                  ((uint32_t)__half_as_ushort(ll) << 16);
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+            const uint32_t word = (lane & 1) ? ((other >> 16) | (mine & 0xFFFF0000u))
+                                             : ((mine & 0xFFFFu) | (other << 16));
+            if (col_ok && rbase + jj < R) pw[(size_t)jj * (size_t)(Jp_out >> 1)] = word;
           }
-          if (EPI != 1) po += J;
+          if (EPI == 0 || EPI == 2) po += J;
         }
         if (EPI == 1) {
           const float sum = warp_transpose_sum16(lpv, lane);
@@ -246,8 +307,9 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
       if (leader) mbar_arrive(tempty_bar + 8 * acc);
       else mbar_arrive_remote(tempty_bar + 8 * acc, 0);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (EPI == 3 && part && j_ok) atomicAdd(part + j, csum);   // bias gradient (part = col_sum)
     }
-    if (EPI != 1 && amax_scale) {       // NaN / inf never win the max (fmaxf drops NaN)
+    if ((EPI == 0 || EPI == 2) && amax_scale) {   // NaN / inf never win the max (fmaxf drops NaN)
       amax = warp_max(amax <= 3.0e38f ? amax : 0.f);
       if (lane == 0 && amax > 0.f)
         atomicMax(reinterpret_cast<unsigned int*>(amax_scale) + 2, __float_as_uint(amax));
@@ -351,6 +413,31 @@ __global__ void __launch_bounds__(256) absmax2_kernel(const float* __restrict__ 
   if ((threadIdx.x & 31) == 0)
     atomicMax(reinterpret_cast<unsigned int*>(scale) + 2, __float_as_uint(m));
 }
+// EPI 3 scale, known before the GEMM runs: |g (x - sigmoid(l))| <= max|g| * (1 + max|x|).
+// absmax_slot_kernel folds max|src| into scale[slot] (uint bits); bern_grad_scale_kernel turns
+// slots 2 (g) and 3 (x) into scale[0] = power of two s with bound * s in [2^11, 2^12).
+__global__ void __launch_bounds__(256) absmax_slot_kernel(const float* __restrict__ src, int64_t n,
+                                                          float* __restrict__ scale, int slot) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = fabsf(src[i]);
+    m = (a == a && a <= 3.0e38f) ? fmaxf(m, a) : m;
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0)
+    atomicMax(reinterpret_cast<unsigned int*>(scale) + slot, __float_as_uint(m));
+}
+__global__ void bern_grad_scale_kernel(float* __restrict__ scale) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned int* u = reinterpret_cast<unsigned int*>(scale);
+  const float m = __uint_as_float(u[2]) * (1.f + __uint_as_float(u[3]));
+  int e = 0;
+  if (m > 0.f && m <= 3.0e38f) frexpf(m, &e);
+  scale[0] = ldexpf(1.f, 12 - e);
+  u[2] = 0u;
+  u[3] = 0u;
+}
 __global__ void pow2_scale_kernel(float* __restrict__ scale) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float m = __uint_as_float(reinterpret_cast<unsigned int*>(scale)[2]);
@@ -434,10 +521,10 @@ __global__ void __launch_bounds__(256) part_sum_kernel(const float* __restrict__
   }
 }
 
-template <int EPI>
+template <int EPI, int MN = 0>
 cudaError_t linear_prepare() {
   static const cudaError_t e =
-      cudaFuncSetAttribute(linear_tc2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(linear_tc2_kernel<EPI, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            GC::SMEM);
   return e;
 }
@@ -623,6 +710,112 @@ int zsb_linear_tc_amax_f32(int epi, const void* w_planes, const float* scale_w,
   if (blocks > ZSB_NUM_SMS * 8) blocks = ZSB_NUM_SMS * 8;
   part_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(part, 4 * n_blk, R, out);
   return zsb_check_launch("linear_tc_part_sum");
+}
+
+// Backward of the Bernoulli likelihood layer with the operand split fused into the GEMM epilogue:
+//   dl[r, j] = gout[r] * (x[r % n_x, j] - sigmoid(h W^T + bias))        (the epi-2 values)
+// is written ONLY as its fp16 hi/lo planes dl_planes [2][R][kpad(J)] times scale_out[0] (the
+// operands of dh = dl W and dW = dl^T h) and summed over the rows into col_sum [J] (+=, the bias
+// gradient; may be NULL).  scale_out: device float[4], zeroed once by the caller; its power of two
+// comes from the bound max|gout| * (1 + max|x_obs|) >= max|dl|, so no pass over dl is needed.
+int zsb_linear_tc_bern_grad_planes_f32(const void* w_planes, const float* scale_w,
+                                       const void* h_planes, const float* scale_h,
+                                       const float* bias, const float* x_obs, int64_t n_x,
+                                       const float* gout, void* dl_planes, float* col_sum,
+                                       float* scale_out, int64_t R, int J, int K, void* stream) {
+  ZSB_REQUIRE(w_planes && h_planes && scale_w && scale_h && x_obs && n_x > 0 && gout &&
+                  dl_planes && scale_out && R > 0 && J > 0 && K > 0,
+              "zsb_linear_tc_bern_grad_planes_f32: bad args");
+  ZSB_REQUIRE(R < (1LL << 31), "zsb_linear_tc_bern_grad_planes_f32: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    int64_t bg = zsb_ceil_div(R, 256 * 8), bx = zsb_ceil_div(n_x * (int64_t)J, 256 * 8);
+    if (bg > ZSB_NUM_SMS * 16) bg = ZSB_NUM_SMS * 16;
+    if (bx > ZSB_NUM_SMS * 16) bx = ZSB_NUM_SMS * 16;
+    absmax_slot_kernel<<<(unsigned)bg, 256, 0, st>>>(gout, R, scale_out, 2);
+    absmax_slot_kernel<<<(unsigned)bx, 256, 0, st>>>(x_obs, n_x * (int64_t)J, scale_out, 3);
+    bern_grad_scale_kernel<<<1, 32, 0, st>>>(scale_out);
+  }
+  const int Kp = zsb_linear_tc_kpad(K);
+  const __half* wp = reinterpret_cast<const __half*>(w_planes);
+  const __half* hp = reinterpret_cast<const __half*>(h_planes);
+  CUtensorMap m_whi, m_wlo, m_hhi, m_hlo;
+  int rc;
+  if ((rc = make_map(&m_whi, wp, (uint64_t)J, (uint64_t)Kp, BM, GBK, 1))) return rc;
+  if ((rc = make_map(&m_wlo, wp + (int64_t)J * Kp, (uint64_t)J, (uint64_t)Kp, BM, GBK, 1)))
+    return rc;
+  if ((rc = make_map(&m_hhi, hp, (uint64_t)R, (uint64_t)Kp, BN / 2, GBK, 1))) return rc;
+  if ((rc = make_map(&m_hlo, hp + R * Kp, (uint64_t)R, (uint64_t)Kp, BN / 2, GBK, 1))) return rc;
+  const int n_blk = (J + BM - 1) / BM;
+  const int64_t n_units = ((R + BN - 1) / BN) * ((n_blk + 1) / 2);
+  int dev = 0, sms = ZSB_NUM_SMS;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t pairs = sms / 2;
+  if (n_units < pairs) pairs = n_units;
+  const unsigned grid = (unsigned)(2 * pairs);
+  const cudaError_t prep = linear_prepare<3>();
+  if (prep != cudaSuccess) {
+    zsb_set_error("linear_tc_bern_grad_planes: cudaFuncSetAttribute: %s",
+                  cudaGetErrorString(prep));
+    return ZSB_ERR_CUDA;
+  }
+  linear_tc2_kernel<3><<<grid, NUM_THREADS, GC::SMEM, st>>>(
+      m_whi, m_wlo, m_hhi, m_hlo, bias, x_obs, n_x, gout, reinterpret_cast<float*>(dl_planes),
+      col_sum, R, J, Kp, 0, scale_w, scale_h, 1, scale_out);
+  return zsb_check_launch("linear_tc_bern_grad_planes");
+}
+
+// Weight gradient of a dense layer WITHOUT transposed operands:
+//   out [J, K] = sum_r g[r, j] * h[r, k]            (dW = g^T h, tf.gradients of tf.layers.dense)
+// h_planes [2][R][Kp(K)], g_planes [2][R][Kp(J)]: the row-major fp16 hi/lo planes the forward /
+// input-gradient products already use (zsb_split16_pad_f32 / zsb_split16_dual_f32).  The contraction
+// runs over the rows, so both operands are MN-major for tcgen05 (see linear_tc2_kernel<0, 1>);
+// split-K over the CTA pairs as in zsb_linear_tc_f32 (part = zsb_linear_tc_slices(J, K, R) * J * K
+// floats, or NULL for a single slice).
+int zsb_linear_tc_wgrad_f32(const void* h_planes, const float* scale_h, int K,
+                            const void* g_planes, const float* scale_g, int J, int64_t R,
+                            float* out, float* part, void* stream) {
+  ZSB_REQUIRE(h_planes && g_planes && scale_h && scale_g && out && R > 0 && J > 0 && K > 0,
+              "zsb_linear_tc_wgrad_f32: bad args");
+  ZSB_REQUIRE(R < (1LL << 31) - 64, "zsb_linear_tc_wgrad_f32: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kp_h = zsb_linear_tc_kpad(K), Jp_g = zsb_linear_tc_kpad(J);
+  const int Rp = zsb_linear_tc_kpad((int)R);                 // padded contraction length
+  const __half* hp = reinterpret_cast<const __half*>(h_planes);
+  const __half* gp = reinterpret_cast<const __half*>(g_planes);
+  CUtensorMap m_whi, m_wlo, m_hhi, m_hlo;                    // "w" = h (lanes = k), "h" = g
+  int rc;
+  if ((rc = make_map(&m_whi, hp, (uint64_t)R, (uint64_t)Kp_h, 64, GBK, 1))) return rc;
+  if ((rc = make_map(&m_wlo, hp + R * Kp_h, (uint64_t)R, (uint64_t)Kp_h, 64, GBK, 1))) return rc;
+  if ((rc = make_map(&m_hhi, gp, (uint64_t)R, (uint64_t)Jp_g, 64, GBK, 1))) return rc;
+  if ((rc = make_map(&m_hlo, gp + R * Jp_g, (uint64_t)R, (uint64_t)Jp_g, 64, GBK, 1))) return rc;
+  const int n_blk = (K + BM - 1) / BM;
+  const int64_t n_units = (((int64_t)J + BN - 1) / BN) * ((n_blk + 1) / 2);
+  int dev = 0, sms = ZSB_NUM_SMS;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int k_slices = part ? zsb_linear_tc_slices(J, K, (int)R) : 1;
+  int64_t pairs = sms / 2;
+  if (n_units * k_slices < pairs) pairs = n_units * k_slices;
+  const unsigned grid = (unsigned)(2 * pairs);
+  const cudaError_t prep = linear_prepare<0, 1>();
+  if (prep != cudaSuccess) {
+    zsb_set_error("linear_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(prep));
+    return ZSB_ERR_CUDA;
+  }
+  linear_tc2_kernel<0, 1><<<grid, NUM_THREADS, GC::SMEM, st>>>(
+      m_whi, m_wlo, m_hhi, m_hlo, nullptr, nullptr, 0, nullptr, k_slices > 1 ? part : out, part,
+      (int64_t)J, K, Rp, 0, scale_h, scale_g, k_slices, nullptr);
+  rc = zsb_check_launch("linear_tc_wgrad");
+  if (rc == ZSB_OK && k_slices > 1) {
+    const int64_t n = (int64_t)J * K;
+    int64_t blocks = zsb_ceil_div(n, 256);
+    if (blocks > ZSB_NUM_SMS * 8) blocks = ZSB_NUM_SMS * 8;
+    slice_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(part, k_slices, n, out);
+    return zsb_check_launch("linear_tc_wgrad_slice_sum");
+  }
+  return rc;
 }
 
 }  // extern "C"

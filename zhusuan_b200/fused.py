@@ -3,6 +3,7 @@ kernels.  Each is also a plain ``log_joint(observed_dict)`` callable built
 from torch ops, so it works on the generic path and as its own cross-check.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -309,11 +310,30 @@ def _tc_grad_input(gpl, W, R):
     return dh, amax
 
 
+# ZSB_WGRAD_T=1: the weight gradient reads TRANSPOSED operand planes (the round-2 scheme, kept as a
+# cross-check); default: MN-major operands straight from the row-major planes.
+_WGRAD_T = os.environ.get("ZSB_WGRAD_T", "0") == "1"
+# ZSB_BERN_UNFUSED=1: the Bernoulli layer's backward writes fp32 dlogits and splits them in a second
+# pass (cross-check of zsb_linear_tc_bern_grad_planes_f32)
+_BERN_UNFUSED = os.environ.get("ZSB_BERN_UNFUSED", "0") == "1"
+
+
 def _tc_grad_weight(gpl, hpl, R):
-    """dW [J, K] = g^T [J, R] @ h [R, K]: contraction over the rows, split-K over the CTA pairs;
-    both operands in the transposed plane layout."""
-    return _tc_linear(0, hpl.planes_t, hpl.scale, gpl.planes_t, gpl.scale, None, None, None,
-                      gpl.K, hpl.K, R, split_k=True)
+    """dW [J, K] = g^T [J, R] @ h [R, K]: contraction over the rows, split-K over the CTA pairs.
+    Both operands are the row-major planes of g and h (MN-major tcgen05 operands,
+    zsb_linear_tc_wgrad_f32); with ZSB_WGRAD_T=1 the transposed plane layout instead."""
+    if _WGRAD_T:
+        return _tc_linear(0, hpl.planes_t, hpl.scale, gpl.planes_t, gpl.scale, None, None, None,
+                          gpl.K, hpl.K, R, split_k=True)
+    from ._lib import lib, ptr, stream
+    J, K = gpl.K, hpl.K
+    dev = gpl.planes.device
+    slices = lib.load().zsb_linear_tc_slices(J, K, R)
+    part = torch.empty(slices * J * K, dtype=torch.float32, device=dev) if slices > 1 else None
+    out = torch.empty((J, K), dtype=torch.float32, device=dev)
+    lib.call("zsb_linear_tc_wgrad_f32", ptr(hpl.planes), ptr(hpl.scale), K, ptr(gpl.planes),
+             ptr(gpl.scale), J, R, ptr(out), ptr(part), stream())
+    return out
 
 
 def _tc_linear(epi, wp, ws, hp, hs, bias, x, gout, R, J, K, relu=False,
@@ -358,7 +378,7 @@ class _Linear(torch.autograd.Function):
         h2 = h if h.dim() == 2 else h.reshape(-1, h.shape[-1])
         R, K, J = int(h2.shape[0]), int(h2.shape[1]), int(W.shape[0])
         need_dw = bool(ctx.needs_input_grad[1])
-        hpl = _planes_of(h2, h, need_dw)
+        hpl = _planes_of(h2, h, need_dw and _WGRAD_T)
         wp, ws = _tc_split(W)
         bias = b.detach().to(torch.float32).contiguous() if b is not None else None
         amax = torch.zeros(4, dtype=torch.float32, device=h2.device)
@@ -377,7 +397,9 @@ class _Linear(torch.autograd.Function):
         g = gy.reshape(-1, J)
         db = torch.zeros(J, dtype=torch.float32, device=g.device) \
             if (has_b and need[2]) else None
-        gpl = _tc_split_dual(g, mask=y if relu else None, want=(bool(need[0]), bool(need[1])),
+        gpl = _tc_split_dual(g, mask=y if relu else None,
+                             want=(bool(need[0]) or (bool(need[1]) and not _WGRAD_T),
+                                   bool(need[1]) and _WGRAD_T),
                              amax=getattr(gy, "_zsb_amax", None), col_sum=db)
         dh = None
         if need[0]:
@@ -409,7 +431,7 @@ class _LinearBernoulliLogProb(torch.autograd.Function):
             raise ValueError("rows of the observation (%d) must divide the rows "
                              "of the activations (%d)" % (x2.shape[0], R))
         wp, ws = _tc_split(W)
-        hpl = _planes_of(h2, h, bool(ctx.needs_input_grad[1]))
+        hpl = _planes_of(h2, h, bool(ctx.needs_input_grad[1]) and _WGRAD_T)
         bias = b.detach().to(torch.float32).contiguous() if b is not None else None
         lp = _tc_linear(1, wp, ws, hpl.planes, hpl.scale, bias, x2, None, R, J, K)
         ctx.save_for_backward(W, bias, x2, wp, ws)
@@ -424,11 +446,22 @@ class _LinearBernoulliLogProb(torch.autograd.Function):
         hpl = ctx.hpl
         need = ctx.needs_input_grad
         g = glp.reshape(-1).to(torch.float32).contiguous()
-        amax = torch.zeros(4, dtype=torch.float32, device=g.device)
-        dl = _tc_linear(2, wp, ws, hpl.planes, hpl.scale, bias, x2, g, R, J, K, amax=amax)
         db = torch.zeros(J, dtype=torch.float32, device=g.device) \
             if (has_b and need[2]) else None
-        dlpl = _tc_split_dual(dl, want=(bool(need[0]), bool(need[1])), amax=amax, col_sum=db)
+        if _WGRAD_T or _BERN_UNFUSED:        # round-2 scheme: fp32 dl, then one split pass
+            amax = torch.zeros(4, dtype=torch.float32, device=g.device)
+            dl = _tc_linear(2, wp, ws, hpl.planes, hpl.scale, bias, x2, g, R, J, K, amax=amax)
+            dlpl = _tc_split_dual(dl, want=(bool(need[0]) or (bool(need[1]) and not _WGRAD_T),
+                                            bool(need[1]) and _WGRAD_T), amax=amax, col_sum=db)
+        else:                                # dl leaves the GEMM epilogue as operand planes
+            from ._lib import lib, ptr, stream
+            Jp = lib.load().zsb_linear_tc_kpad(J)
+            planes = torch.empty((2, R, Jp), dtype=torch.float16, device=g.device)
+            scale = torch.zeros(4, dtype=torch.float32, device=g.device)
+            lib.call("zsb_linear_tc_bern_grad_planes_f32", ptr(wp), ptr(ws), ptr(hpl.planes),
+                     ptr(hpl.scale), ptr(bias), ptr(x2), int(x2.shape[0]), ptr(g), ptr(planes),
+                     ptr(db), ptr(scale), R, J, K, stream())
+            dlpl = _Planes(planes, None, scale, R, J)
         dh = None
         if need[0]:
             dh2, a2 = _tc_grad_input(dlpl, W, R)
