@@ -144,13 +144,14 @@ def test_bernoulli_gradient_planes_from_the_epilogue(zs, R, Nb, K, J, xmax):
     g = (rng.standard_normal(R) * 1e-4).astype(np.float32)
     wp, ws = fused._tc_split(T(W))
     hp, hs = fused._tc_split(T(h))
-    dl = fused._tc_linear(2, wp, ws, hp, hs, T(b), T(x), T(g), R, J, K)       # fp32 epi 2
+    tb, tx, tg = T(b), T(x), T(g)          # kept alive: the ABI takes raw device pointers
+    dl = fused._tc_linear(2, wp, ws, hp, hs, tb, tx, tg, R, J, K)             # fp32 epi 2
     Jp = lib.load().zsb_linear_tc_kpad(J)
     planes = torch.full((2, R, Jp), float("nan"), dtype=torch.float16, device="cuda")
     scale = torch.zeros(4, device="cuda")
     db = torch.zeros(J, device="cuda")
-    lib.call("zsb_linear_tc_bern_grad_planes_f32", ptr(wp), ptr(ws), ptr(hp), ptr(hs), ptr(T(b)),
-             ptr(T(x)), Nb, ptr(T(g)), ptr(planes), ptr(db), ptr(scale), R, J, K, stream())
+    lib.call("zsb_linear_tc_bern_grad_planes_f32", ptr(wp), ptr(ws), ptr(hp), ptr(hs), ptr(tb),
+             ptr(tx), Nb, ptr(tg), ptr(planes), ptr(db), ptr(scale), R, J, K, stream())
     s = float(scale[0])
     bound = float(np.abs(g).max()) * (1.0 + float(np.abs(x).max()))
     assert 2.0 ** 11 <= bound * s < 2.0 ** 12 and np.log2(s) == np.round(np.log2(s))

@@ -50,7 +50,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
   return d;
 }
 
-template <int EPI, int MN = 0>
+template <int EPI, int MN = 0, int GL = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
                   const __grid_constant__ CUtensorMap map_wlo,
@@ -236,21 +236,17 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
             if (++xr == n_x) { xr = 0; xp = x_obs + j; } else xp += J;
           }
         }
-        // upstream gradient of the 16 rows: lane jj holds gout[rbase + jj]
-        if (EPI >= 2) ge = (lane < 16 && rbase + lane < R) ? __ldg(gout + rbase + lane) : 0.f;
+        // upstream gradient of the 16 rows: lane jj holds gout[rbase + jj] (GL = 0: broadcast by
+        // shuffle in process(); GL = 1: process() loads it itself, warp-uniform addresses)
+        if (EPI >= 2 && !GL) ge = (lane < 16 && rbase + lane < R) ? __ldg(gout + rbase + lane) : 0.f;
       };
       auto process = [&](const uint32_t* v, const float* xe, float ge, int c) {
+        // NO early return for rbase >= R: every access below is predicated on the row anyway, and
+        // a return here (uniform, but not provably so) makes the compiler wrap each warp shuffle of
+        // the row sums in a WARPSYNC.COLLECTIVE sequence (125 SHFL + 70 WARPSYNC -> 63 SHFL)
         const int64_t rbase = r0 + c;
-        if (rbase >= R) return;                     // warp-uniform
         float lpv[16];
         float* __restrict__ po = (EPI == 0 || EPI == 2) ? out_s + rbase * J + j : nullptr;
-        // EPI 3: even lanes store the hi-plane word of the feature pair (j, j + 1), odd lanes
-        // the lo-plane word of (j - 1, j): 64 contiguous bytes per plane, row and instruction
-        uint32_t* __restrict__ pw = nullptr;
-        if (EPI == 3)
-          pw = reinterpret_cast<uint32_t*>(pl_out + ((lane & 1) ? R * (int64_t)Jp_out : 0) +
-                                           rbase * Jp_out + (j & ~1));
-        const bool col_ok = (j & ~1) < Jp_out;
         const bool full = warp_j_ok && rbase + 16 <= R;   // no per-element predicates
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
@@ -262,24 +258,39 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
           } else if (EPI == 1) {
             lpv[jj] = ok ? bern_lp(xe[jj], l) : 0.f;
           } else if (EPI == 2) {
-            const float g = __shfl_sync(0xffffffffu, ge, jj);
+            const float g = GL ? ((full || rbase + jj < R) ? __ldg(gout + rbase + jj) : 0.f)
+                               : __shfl_sync(0xffffffffu, ge, jj);
             const float y = g * (xe[jj] - __fdividef(1.f, 1.f + __expf(-l)));
             if (ok) { *po = y; amax = fmaxf(amax, fabsf(y)); }
           } else {
-            const float g = __shfl_sync(0xffffffffu, ge, jj);
+            const float g = GL ? ((full || rbase + jj < R) ? __ldg(gout + rbase + jj) : 0.f)
+                               : __shfl_sync(0xffffffffu, ge, jj);
             const float y = ok ? g * (xe[jj] - __fdividef(1.f, 1.f + __expf(-l))) : 0.f;
             csum += y;
-            const float ys = y * s_out;
-            const __half hh = __float2half_rn(ys);
-            const __half ll = __float2half_rn(ys - __half2float(hh));
-            const uint32_t mine = (uint32_t)__half_as_ushort(hh) |
-                                  ((uint32_t)__half_as_ushort(ll) << 16);
-            const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
-            const uint32_t word = (lane & 1) ? ((other >> 16) | (mine & 0xFFFF0000u))
-                                             : ((mine & 0xFFFFu) | (other << 16));
-            if (col_ok && rbase + jj < R) pw[(size_t)jj * (size_t)(Jp_out >> 1)] = word;
+            lpv[jj] = y * s_out;
           }
           if (EPI == 0 || EPI == 2) po += J;
+        }
+        if (EPI == 3) {
+          // fp16 hi/lo planes of this lane's feature column, two rows per packed conversion;
+          // a warp instruction stores 64 contiguous bytes of one plane row
+          __half* __restrict__ ph = pl_out + rbase * Jp_out + j;
+          __half* __restrict__ pq = ph + R * (int64_t)Jp_out;
+          const bool col_ok = j < Jp_out;
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 2) {
+            const __half2 h2 = __floats2half2_rn(lpv[jj], lpv[jj + 1]);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(lpv[jj] - hf.x, lpv[jj + 1] - hf.y);
+            if (col_ok && (full || rbase + jj < R)) {
+              ph[(size_t)jj * (size_t)Jp_out] = __low2half(h2);
+              pq[(size_t)jj * (size_t)Jp_out] = __low2half(l2);
+            }
+            if (col_ok && (full || rbase + jj + 1 < R)) {
+              ph[(size_t)(jj + 1) * (size_t)Jp_out] = __high2half(h2);
+              pq[(size_t)(jj + 1) * (size_t)Jp_out] = __high2half(l2);
+            }
+          }
         }
         if (EPI == 1) {
           const float sum = warp_transpose_sum16(lpv, lane);
@@ -521,12 +532,17 @@ __global__ void __launch_bounds__(256) part_sum_kernel(const float* __restrict__
   }
 }
 
-template <int EPI, int MN = 0>
+template <int EPI, int MN = 0, int GL = 0>
 cudaError_t linear_prepare() {
-  static const cudaError_t e =
-      cudaFuncSetAttribute(linear_tc2_kernel<EPI, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           GC::SMEM);
+  static const cudaError_t e = cudaFuncSetAttribute(
+      linear_tc2_kernel<EPI, MN, GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GC::SMEM);
   return e;
+}
+// ZSB_EPI_GLOAD=1: the epi 2 / 3 epilogues load the upstream gradient per row (warp-uniform loads)
+// instead of broadcasting it by shuffle (A/B switch of an experiment; default = shuffle)
+int epi_gload() {
+  static const int v = getenv("ZSB_EPI_GLOAD") ? atoi(getenv("ZSB_EPI_GLOAD")) : 0;
+  return v;
 }
 
 }  // namespace
@@ -691,7 +707,14 @@ int zsb_linear_tc_amax_f32(int epi, const void* w_planes, const float* scale_w,
   } while (0)
   if (epi == 0) ZSB_LIN(0);
   else if (epi == 1) ZSB_LIN(1);
-  else ZSB_LIN(2);
+  else if (!epi_gload()) ZSB_LIN(2);
+  else {
+    prep = linear_prepare<2, 0, 1>();
+    if (prep == cudaSuccess)
+      linear_tc2_kernel<2, 0, 1><<<grid, NUM_THREADS, GC::SMEM, st>>>(
+          m_whi, m_wlo, m_hhi, m_hlo, bias, x_obs, n_x, gout, out_k, part, R, J, Kp, relu, scale_w,
+          scale_h, k_slices, amax_scale);
+  }
 #undef ZSB_LIN
   if (prep != cudaSuccess) {
     zsb_set_error("linear_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(prep));
@@ -754,15 +777,20 @@ int zsb_linear_tc_bern_grad_planes_f32(const void* w_planes, const float* scale_
   int64_t pairs = sms / 2;
   if (n_units < pairs) pairs = n_units;
   const unsigned grid = (unsigned)(2 * pairs);
-  const cudaError_t prep = linear_prepare<3>();
+  const cudaError_t prep = epi_gload() ? linear_prepare<3, 0, 1>() : linear_prepare<3>();
   if (prep != cudaSuccess) {
     zsb_set_error("linear_tc_bern_grad_planes: cudaFuncSetAttribute: %s",
                   cudaGetErrorString(prep));
     return ZSB_ERR_CUDA;
   }
-  linear_tc2_kernel<3><<<grid, NUM_THREADS, GC::SMEM, st>>>(
-      m_whi, m_wlo, m_hhi, m_hlo, bias, x_obs, n_x, gout, reinterpret_cast<float*>(dl_planes),
-      col_sum, R, J, Kp, 0, scale_w, scale_h, 1, scale_out);
+  if (epi_gload())
+    linear_tc2_kernel<3, 0, 1><<<grid, NUM_THREADS, GC::SMEM, st>>>(
+        m_whi, m_wlo, m_hhi, m_hlo, bias, x_obs, n_x, gout, reinterpret_cast<float*>(dl_planes),
+        col_sum, R, J, Kp, 0, scale_w, scale_h, 1, scale_out);
+  else
+    linear_tc2_kernel<3><<<grid, NUM_THREADS, GC::SMEM, st>>>(
+        m_whi, m_wlo, m_hhi, m_hlo, bias, x_obs, n_x, gout, reinterpret_cast<float*>(dl_planes),
+        col_sum, R, J, Kp, 0, scale_w, scale_h, 1, scale_out);
   return zsb_check_launch("linear_tc_bern_grad_planes");
 }
 

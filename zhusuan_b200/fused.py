@@ -313,9 +313,11 @@ def _tc_grad_input(gpl, W, R):
 # ZSB_WGRAD_T=1: the weight gradient reads TRANSPOSED operand planes (the round-2 scheme, kept as a
 # cross-check); default: MN-major operands straight from the row-major planes.
 _WGRAD_T = os.environ.get("ZSB_WGRAD_T", "0") == "1"
-# ZSB_BERN_UNFUSED=1: the Bernoulli layer's backward writes fp32 dlogits and splits them in a second
-# pass (cross-check of zsb_linear_tc_bern_grad_planes_f32)
-_BERN_UNFUSED = os.environ.get("ZSB_BERN_UNFUSED", "0") == "1"
+# ZSB_BERN_FUSED=1: the Bernoulli layer's backward emits d/dlogits directly as operand planes from
+# the GEMM epilogue (zsb_linear_tc_bern_grad_planes_f32, epi 3).  Correct (tests) but MEASURED SLOWER
+# than fp32 dlogits + one split pass (1.47 vs 0.75 + 0.5 ms at config 3: the longer epilogue is no
+# longer hidden behind the next unit's MMAs), so it is opt-in.
+_BERN_UNFUSED = os.environ.get("ZSB_BERN_FUSED", "0") != "1"
 
 
 def _tc_grad_weight(gpl, hpl, R):
