@@ -507,7 +507,15 @@ __global__ void __launch_bounds__(256) diag_normal_traj_kernel(
   const float eps = state[ZSB_ST_EPS_USED];
   float local_acc = 0.f;
   bool any_bad = false;
-  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < chains;
+  // warp index through a shuffle: provably warp-uniform, so the row loop's exit is uniform and the
+  // shuffles inside it compile to plain SHFL (not WARPSYNC.COLLECTIVE sequences)
+  const int warp_id = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  // parameter vectors are either scalars, one entry per column, or (rarely) a shorter period:
+  // resolve the period once instead of three 64-bit modulos per element
+  const int Di = (int)D;
+  const int mean_p = mean_n >= D ? Di : (int)mean_n, ls_p = logstd_n >= D ? Di : (int)logstd_n,
+            mass_p = mass_n >= D ? Di : (int)mass_n;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp_id; row < chains;
        row += (int64_t)gridDim.x * 8) {
     float q0[E], qc[E], pc[E], mu[E], prec[E], ls[E], ms[E];
     // Philox blocks are 4 consecutive columns; lane owns columns c = j*32 + lane (coalesced
@@ -543,10 +551,11 @@ __global__ void __launch_bounds__(256) diag_normal_traj_kernel(
         zsh = w == 0 ? a0 : w == 1 ? a1 : w == 2 ? a2 : a3;
       }
       if (c < D) {
+        const int ci = (int)c;
         q0[j] = q[row * D + c];
-        mu[j] = mean[c % mean_n];
-        ls[j] = logstd[c % logstd_n];
-        ms[j] = mass[c % mass_n];
+        mu[j] = mean[mean_p == Di ? ci : (mean_p == 1 ? 0 : ci % mean_p)];
+        ls[j] = logstd[ls_p == Di ? ci : (ls_p == 1 ? 0 : ci % ls_p)];
+        ms[j] = mass[mass_p == Di ? ci : (mass_p == 1 ? 0 : ci % mass_p)];
         prec[j] = expf(mul(-2.f, ls[j]));                       // univariate.py:177
         const float z = noise ? noise[row * D + c] : zsh;
         pc[j] = mul(z, sqrtf(ms[j]));                           // hmc.py:22

@@ -98,7 +98,10 @@ __global__ void __launch_bounds__(256, 2) sghmc_bnn_kernel(BnnArgs a) {
   }
   __syncthreads();
 
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+  // warp index through a shuffle: provably warp-uniform, so the chain loop's exit is uniform and the
+  // shuffles inside it compile to plain SHFL instead of WARPSYNC.COLLECTIVE sequences
+  const int lane = threadIdx.x & 31, nwb = blockDim.x >> 5;
+  const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   // per-warp staging: A = weights in / noise / new weights out, B = momentum in / new momentum out.
   // Every global access of a chain's state is a coalesced, independent copy through these buffers
   // (round 1 read v element by element between dependent stores: 22 exposed global latencies).
