@@ -246,7 +246,7 @@ def _tc_split_t(t2d):
 
 class _Planes(object):
     """fp16 hi/lo operand planes of one [rows, K] matrix times a power-of-two scale: row-major
-    ``planes`` [2, rows, Kp] (forward / input-gradient products) and transposed ``planes_t``
+    ``planes`` [2, rows, Kp] (all three products of a layer) and, only with ZSB_WGRAD_T=1, transposed ``planes_t``
     [2, K, Rp] (weight-gradient product, contraction over the rows); ``scale`` = device float[4]."""
     __slots__ = ("planes", "planes_t", "scale", "rows", "K")
 
@@ -369,7 +369,7 @@ def _tag(t, amax):
 
 class _Linear(torch.autograd.Function):
     """y = relu?(h W^T + b): forward and both backward products on the tcgen05 kernel at fp32
-    accuracy (epi 0; the weight gradient uses the transposed operand planes and split-K).
+    accuracy (epi 0; the weight gradient reads the same row-major planes as MN-major operands, split-K).
     Memory passes around the GEMMs are fused (round 2): every GEMM leaves max|out| for its
     consumer's scale, ONE pass (zsb_split16_dual_f32) turns an activation / gradient into both
     operand layouts, applies the ReLU mask and accumulates the bias gradient."""
