@@ -175,3 +175,36 @@ def test_packed_statistics_one_collective_per_iteration():
             np.testing.assert_allclose(mean_t, ew.mean[0].reshape(-1), rtol=1e-5, atol=1e-6)
             np.testing.assert_allclose(var_t, var, rtol=1e-4, atol=1e-6)
     assert out[0][1] == out[1][1] == T_ + 1
+
+
+def _wmean_worker(rank, world, port, v_all, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    from zhusuan_b200 import dist
+    c0, n_local = dist.shard_chains(v_all.shape[0])
+    v = torch.tensor(v_all[c0:c0 + n_local])
+    mk = (v * v).mean().reshape(1)                   # what zsb_sgmcmc_mean_sq_f32 leaves per rank
+    dist.all_reduce_weighted_mean_(mk, v.numel())
+    out[rank] = (float(mk[0]), c0, n_local)
+    td.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_scalar_thermostat_sees_the_global_mean_kinetic_energy():
+    """sgmcmc.py:494, 504: the scalar SGNHT thermostat is driven by reduce_mean(v * v) over ALL
+    chains; with the chains sharded 7 + 6 the weighted all-reduce reproduces it on every rank."""
+    rng = np.random.RandomState(3)
+    v_all = (rng.standard_normal((13, 11)) * np.linspace(0.1, 3, 13)[:, None]).astype(np.float32)
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_wmean_worker, args=(2, port, v_all, out), nprocs=2, join=True)
+    assert (out[0][1], out[0][2], out[1][1], out[1][2]) == (0, 7, 7, 6)
+    for r in (0, 1):
+        np.testing.assert_allclose(out[r][0], float((v_all.astype(np.float64) ** 2).mean()),
+                                   rtol=1e-6)
+    # one rank: the local mean is already the global one
+    from zhusuan_b200 import dist
+    m = torch.tensor([0.25])
+    assert float(dist.all_reduce_weighted_mean_(m, 10)[0]) == 0.25

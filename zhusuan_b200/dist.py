@@ -94,6 +94,22 @@ def pack_stats(acc_sum, n_local, s1=None, s2=None):
 # The particle axis K stays local to a rank, so log_mean_exp needs no communication; the only
 # exchange is the standard gradient all-reduce of the encoder/decoder parameters (5.4 MB at config
 # 3) plus the scalar bound, packed into ONE flat buffer so there is one collective per step.
+def all_reduce_weighted_mean_(mean, n_local, group=None):
+    """In place: a LOCAL mean over ``n_local`` elements -> the mean over all ranks' elements
+    (``sum_r mean_r * n_r / sum_r n_r``, one all-reduce of two floats).  No-op on one rank.
+    Used by the scalar SGNHT thermostat, whose ``reduce_mean(v * v)`` (sgmcmc.py:494, 504)
+    runs over ALL chains of the latent."""
+    w, _ = world(group)
+    if w == 1:
+        return mean
+    buf = torch.empty(2, dtype=torch.float32, device=mean.device)
+    buf[0] = mean.reshape(-1)[0] * float(n_local)
+    buf[1] = float(n_local)
+    all_reduce_sum(buf, group)
+    mean.reshape(-1)[0] = buf[0] / buf[1]
+    return mean
+
+
 def shard_batch(n_global, group=None):
     """Contiguous partition of the data/batch axis: (first index, local size)."""
     return shard_chains(n_global, group)

@@ -346,6 +346,7 @@ class SGNHT(SGMCMC):
             for k, v in enumerate(self.vs):                # sgmcmc.py:494-496
                 lib.call("zsb_sgmcmc_mean_sq_f32", ptr(v), v.numel(),
                          ptr(self._part), ptr(self._mean_k[k]), s)
+                zdist.all_reduce_weighted_mean_(self._mean_k[k], v.numel(), self._group)
                 lib.call("zsb_sgmcmc_sgnht_alpha_f32", ptr(self._alpha1[k]),
                          ptr(self.alphas[k]), ptr(self._mean_k[k]),
                          0.5 * self.tune_rate, self.lr, s)
@@ -369,6 +370,9 @@ class SGNHT(SGMCMC):
                          self.a, int(self.second_order), self._chains,
                          self._row_len[k], self._seed_now() + k, it,
                          self._row0, ptr(self._part), ptr(self._mean_k[k]), s)
+                # chains sharded over ranks: the thermostat is driven by the mean kinetic energy
+                # of ALL chains (one 8-byte all-reduce per latent and step; no-op on one rank)
+                zdist.all_reduce_weighted_mean_(self._mean_k[k], q.numel(), self._group)
                 coef = 0.5 * self.tune_rate if self.second_order \
                     else self.tune_rate                    # sgmcmc.py:490, 506
                 lib.call("zsb_sgmcmc_sgnht_alpha_f32", ptr(self.alphas[k]),
