@@ -202,6 +202,13 @@ int zsb_linear_tc_bern_grad_planes_f32(const void* w_planes, const float* scale_
                                        const float* bias, const float* x_obs, int64_t n_x,
                                        const float* gout, void* dl_planes, float* col_sum,
                                        float* scale_out, int64_t R, int J, int K, void* stream);
+/* Input gradient of the dense layer, dh [R, K] = g W = sum_j g[r, j] * W[j, k] (tf.gradients of
+ * tf.layers.dense w.r.t. its input), with operand A = the FORWARD planes of W [J, K]
+ * (w_planes [2][J][kpad(K)], read MN-major) and B = g_planes [2][R][kpad(J)]: no W^T copy.
+ * max |dh| is folded into amax_scale[2] when amax_scale != NULL. */
+int zsb_linear_tc_dgrad_f32(const void* w_planes, const float* scale_w, const void* g_planes,
+                            const float* scale_g, int64_t R, int J, int K, float* out,
+                            float* amax_scale, void* stream);
 /* Weight gradient of the dense layer, dW [J, K] = g^T h = sum_r g[r, j] * h[r, k] (the
  * tf.gradients of tf.layers.dense w.r.t. its kernel, iwae.py:23-44), read straight from the
  * ROW-MAJOR planes h_planes [2][R][kpad(K)] and g_planes [2][R][kpad(J)]: the contraction runs

@@ -127,6 +127,35 @@ def test_linear_bernoulli_log_prob_and_grads(zs, P, Nb, K, J):
         assert np.max(np.abs(N(g) - e)) < 2e-4 * max(1.0, np.max(np.abs(e)))
 
 
+@pytest.mark.parametrize("R,K,J", [(1000, 500, 784), (77, 1, 5), (300, 130, 257), (256, 64, 128),
+                                   (5000, 40, 500)])
+def test_input_gradient_from_the_forward_weight_planes(zs, R, K, J):
+    """zsb_linear_tc_dgrad_f32: dh = g W with operand A = the forward planes of W [J, K] read
+    MN-major (contraction over W's rows; no W^T copy) and B = the planes of g, against float64
+    and against the K-major product on the planes of W^T; ragged J (TMA zero fill of the last
+    64-row box of W), odd / tiny K, K not a multiple of the 64-column box."""
+    from zhusuan_b200 import fused
+    from zhusuan_b200._lib import lib, ptr, stream
+    rng = np.random.RandomState(R + K + J)
+    W = (rng.standard_normal((J, K)) / np.sqrt(K)).astype(np.float32)
+    g = rng.standard_normal((R, J)).astype(np.float32) * 1e-2
+    tW = T(W)
+    wp, ws = fused._tc_split(tW)
+    gp, gs = fused._tc_split(T(g))
+    out = torch.full((R, K), float("nan"), device="cuda")
+    amax = torch.zeros(4, device="cuda")
+    lib.call("zsb_linear_tc_dgrad_f32", ptr(wp), ptr(ws), ptr(gp), ptr(gs), R, J, K, ptr(out),
+             ptr(amax), stream())
+    want = g.astype(np.float64) @ W.astype(np.float64)
+    scale = np.abs(g).astype(np.float64) @ np.abs(W).astype(np.float64)
+    assert np.max(np.abs(N(out) - want) / (scale + 1e-30)) < 3e-6
+    got_max = float(amax.view(torch.int32)[2:3].view(torch.float32)[0])
+    np.testing.assert_allclose(got_max, np.abs(N(out)).max(), rtol=1e-6)
+    wtp, wts = fused._tc_split(tW.t())
+    old = fused._tc_linear(0, wtp, wts, gp, gs, None, None, None, R, K, J)
+    np.testing.assert_allclose(N(out), N(old), rtol=0, atol=3e-6 * float(scale.max()))
+
+
 @pytest.mark.parametrize("R,Nb,K,J,xmax", [(700, 100, 500, 784, 1.0), (64, 64, 40, 21, 1.0),
                                             (515, 103, 96, 130, 3.5), (256, 256, 64, 64, 0.0)])
 def test_bernoulli_gradient_planes_from_the_epilogue(zs, R, Nb, K, J, xmax):

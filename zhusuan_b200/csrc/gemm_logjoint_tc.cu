@@ -33,9 +33,11 @@ __device__ __forceinline__ float bern_lp(float x, float l) {   // -sigmoid_cross
   return -(fmaxf(l, 0.f) - l * x + __logf(1.f + __expf(-fabsf(l))));
 }
 
-// MN = 1 (weight-gradient product, EPI 0 only): BOTH operands are read in their row-major plane
+// MN (bit 0: operand A, bit 1: operand B; EPI 0 only): the operand is read in a row-major plane
 // layout [contraction rows, features] -- MN-major for the tensor core (instruction-descriptor bits
-// 15 / 16) -- so dW = g^T h needs no transposed copy of either matrix.  A stage then holds, per
+// 15 / 16).  MN = 3: weight gradient dW = g^T h from the row-major planes of g and h; MN = 1: input
+// gradient dh = g W with A = the FORWARD planes of W [J, K] (no W^T copy): no product of a dense
+// layer needs a transposed copy of anything.  A stage then holds, per
 // plane, two TMA boxes of 64 contraction rows x 64 features (128-byte rows, SWIZZLE_128B): the
 // canonical MN-major tile ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in fp16 elements with
 // SBO = 1 KB (next 8 contraction rows) and LBO = 8 KB (next 64 features); one k-step of 16
@@ -127,19 +129,27 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
           const uint32_t fb = full_bar + 8 * stage;
           const uint32_t sa = smem_base + stage * GC::STAGE;
           if (leader) mbar_expect_tx(fb, 2 * GC::STAGE);
-          if (MN) {       // boxes of 64 features (c0) x 64 contraction rows (c1), 8 KB each
+          // MN-major operand: two boxes of 64 features (c0) x 64 contraction rows (c1), 8 KB each
+          if (MN & 1) {
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
               const uint32_t o = (uint32_t)b * 8192u;
               tma_load_2d_2sm(sa + o, &map_whi, fb, j0 + 64 * b, kb * 64);
               tma_load_2d_2sm(sa + GC::A_TILE + o, &map_wlo, fb, j0 + 64 * b, kb * 64);
+            }
+          } else {
+            tma_load_2d_2sm(sa, &map_whi, fb, kb * 2 * GBK, j0);
+            tma_load_2d_2sm(sa + GC::A_TILE, &map_wlo, fb, kb * 2 * GBK, j0);
+          }
+          if (MN & 2) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const uint32_t o = (uint32_t)b * 8192u;
               tma_load_2d_2sm(sa + 2 * GC::A_TILE + o, &map_hhi, fb, r0 + 64 * b, kb * 64);
               tma_load_2d_2sm(sa + 2 * GC::A_TILE + GC::B_TILE + o, &map_hlo, fb, r0 + 64 * b,
                               kb * 64);
             }
           } else {
-            tma_load_2d_2sm(sa, &map_whi, fb, kb * 2 * GBK, j0);
-            tma_load_2d_2sm(sa + GC::A_TILE, &map_wlo, fb, kb * 2 * GBK, j0);
             tma_load_2d_2sm(sa + 2 * GC::A_TILE, &map_hhi, fb, kb * 2 * GBK, r0);
             tma_load_2d_2sm(sa + 2 * GC::A_TILE + GC::B_TILE, &map_hlo, fb, kb * 2 * GBK, r0);
           }
@@ -150,7 +160,8 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      const uint32_t idesc = make_idesc_2sm_f16() | (MN ? ((1u << 15) | (1u << 16)) : 0u);
+      const uint32_t idesc = make_idesc_2sm_f16() | ((MN & 1) ? (1u << 15) : 0u) |
+                             ((MN & 2) ? (1u << 16) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -165,20 +176,21 @@ linear_tc2_kernel(const __grid_constant__ CUtensorMap map_whi,
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * GC::STAGE;
-          const uint64_t a_hi = MN ? make_smem_desc_mn(sa) : make_smem_desc<GBK>(sa);
-          const uint64_t a_lo = MN ? make_smem_desc_mn(sa + GC::A_TILE)
-                                   : make_smem_desc<GBK>(sa + GC::A_TILE);
-          const uint64_t b_hi = MN ? make_smem_desc_mn(sa + 2 * GC::A_TILE)
-                                   : make_smem_desc<GBK>(sa + 2 * GC::A_TILE);
-          const uint64_t b_lo = MN ? make_smem_desc_mn(sa + 2 * GC::A_TILE + GC::B_TILE)
-                                   : make_smem_desc<GBK>(sa + 2 * GC::A_TILE + GC::B_TILE);
+          const uint64_t a_hi = (MN & 1) ? make_smem_desc_mn(sa) : make_smem_desc<GBK>(sa);
+          const uint64_t a_lo = (MN & 1) ? make_smem_desc_mn(sa + GC::A_TILE)
+                                         : make_smem_desc<GBK>(sa + GC::A_TILE);
+          const uint64_t b_hi = (MN & 2) ? make_smem_desc_mn(sa + 2 * GC::A_TILE)
+                                         : make_smem_desc<GBK>(sa + 2 * GC::A_TILE);
+          const uint64_t b_lo = (MN & 2) ? make_smem_desc_mn(sa + 2 * GC::A_TILE + GC::B_TILE)
+                                         : make_smem_desc<GBK>(sa + 2 * GC::A_TILE + GC::B_TILE);
 #pragma unroll
           for (int k = 0; k < GBK / 8; ++k) {     // K-major: 16 halves = 32 B; MN-major: 2 KB
-            const uint64_t ko = MN ? (uint64_t)((k * 2048) >> 4) : (uint64_t)((k * 8 * 4) >> 4);
+            const uint64_t ka = (MN & 1) ? (uint64_t)((k * 2048) >> 4) : (uint64_t)((k * 8 * 4) >> 4);
+            const uint64_t kk = (MN & 2) ? (uint64_t)((k * 2048) >> 4) : (uint64_t)((k * 8 * 4) >> 4);
             const uint32_t first = ((kb - kb0) | k) != 0 ? 1u : 0u;
-            umma_f16_2sm(d_tmem, a_lo + ko, b_hi + ko, idesc, first);
-            umma_f16_2sm(d_tmem, a_hi + ko, b_lo + ko, idesc, 1u);
-            umma_f16_2sm(d_tmem, a_hi + ko, b_hi + ko, idesc, 1u);
+            umma_f16_2sm(d_tmem, a_lo + ka, b_hi + kk, idesc, first);
+            umma_f16_2sm(d_tmem, a_hi + ka, b_lo + kk, idesc, 1u);
+            umma_f16_2sm(d_tmem, a_hi + ka, b_hi + kk, idesc, 1u);
           }
           umma_commit_2sm(empty_bar + 8 * stage);
           if (++stage == GC::STAGES) { stage = 0; phase ^= 1; }
@@ -411,9 +423,12 @@ __global__ void __launch_bounds__(256) split16_dual_kernel(
   }
 }
 
-// scale[0] = power of two s with max|src| * s in [2^11, 2^12); scale[2] = running max bits
+// scale[0] = power of two s with max|src| * s in [2^11, 2^12); scale[2] = running max bits;
+// scale[1] = block ticket.  The LAST block to finish turns the maximum into scale[0] and clears
+// slots 1 and 2 again (no separate single-thread kernel; the slot must start zeroed).
 __global__ void __launch_bounds__(256) absmax2_kernel(const float* __restrict__ src, int64_t n,
                                                       float* __restrict__ scale) {
+  __shared__ float wm[8];
   float m = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -421,8 +436,24 @@ __global__ void __launch_bounds__(256) absmax2_kernel(const float* __restrict__ 
     m = (a == a && a <= 3.0e38f) ? fmaxf(m, a) : m;
   }
   m = warp_max(m);
-  if ((threadIdx.x & 31) == 0)
-    atomicMax(reinterpret_cast<unsigned int*>(scale) + 2, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bm = wm[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) bm = fmaxf(bm, wm[w]);
+    unsigned int* u = reinterpret_cast<unsigned int*>(scale);
+    atomicMax(u + 2, __float_as_uint(bm));
+    __threadfence();
+    if (atomicAdd(u + 1, 1u) == gridDim.x - 1) {
+      const float mx = __uint_as_float(atomicAdd(u + 2, 0u));
+      int e = 0;
+      if (mx > 0.f) frexpf(mx, &e);
+      scale[0] = ldexpf(1.f, 12 - e);
+      u[2] = 0u;
+      u[1] = 0u;
+    }
+  }
 }
 // EPI 3 scale, known before the GEMM runs: |g (x - sigmoid(l))| <= max|g| * (1 + max|x|).
 // absmax_slot_kernel folds max|src| into scale[slot] (uint bits); bern_grad_scale_kernel turns
@@ -564,8 +595,7 @@ int zsb_split16_pad_f32(const float* src, int64_t rows, int K, void* planes, flo
   int64_t blocks = zsb_ceil_div(n, 256 * 8);
   if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
   if (blocks < 1) blocks = 1;
-  absmax2_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n, scale);
-  pow2_scale_kernel<<<1, 32, 0, st>>>(scale);
+  absmax2_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n, scale);   // leaves scale[0]
   int64_t blocks2 = zsb_ceil_div(rows * (int64_t)Kp, 256 * 4);
   if (blocks2 > ZSB_NUM_SMS * 32) blocks2 = ZSB_NUM_SMS * 32;
   split16_pad_kernel<<<(unsigned)blocks2, 256, 0, st>>>(src, rows, K, Kp,
@@ -582,8 +612,7 @@ int zsb_split16_pad_t_f32(const float* src, int64_t R, int C, void* planes, floa
   const int64_t n = R * (int64_t)C;
   int64_t blocks = zsb_ceil_div(n, 256 * 8);
   if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
-  absmax2_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n, scale);
-  pow2_scale_kernel<<<1, 32, 0, st>>>(scale);
+  absmax2_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n, scale);   // leaves scale[0]
   int64_t tiles = ((Rp + 31) / 32) * ((C + 31) / 32);
   if (tiles > ZSB_NUM_SMS * 32) tiles = ZSB_NUM_SMS * 32;
   split16_pad_t_kernel<<<(unsigned)tiles, 256, 0, st>>>(src, R, C, Rp,
@@ -607,9 +636,10 @@ int zsb_split16_dual_f32(const float* src, const float* mask_src, int64_t R, int
     const int64_t n = R * (int64_t)K;
     int64_t blocks = zsb_ceil_div(n, 256 * 8);
     if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
-    absmax2_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n, scale);
+    absmax2_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n, scale);   // leaves scale[0]
+  } else {
+    pow2_scale_kernel<<<1, 32, 0, st>>>(scale);    // max|src| left in scale[2] by a GEMM epilogue
   }
-  pow2_scale_kernel<<<1, 32, 0, st>>>(scale);
   int64_t tiles = ((Rp + 63) / 64) * ((Kp + 63) / 64);
   if (tiles > ZSB_NUM_SMS * 16) tiles = ZSB_NUM_SMS * 16;
   split16_dual_kernel<<<(unsigned)tiles, 256, 0, st>>>(
@@ -794,11 +824,52 @@ int zsb_linear_tc_bern_grad_planes_f32(const void* w_planes, const float* scale_
   return zsb_check_launch("linear_tc_bern_grad_planes");
 }
 
+// Input gradient of a dense layer from the FORWARD weight planes:
+//   out [R, K] = sum_j g[r, j] * W[j, k]            (dh = g W, tf.gradients of tf.layers.dense)
+// w_planes [2][J][kpad(K)] = the planes of W [J, K] the forward product uses (operand A, read
+// MN-major: the contraction runs over W's rows), g_planes [2][R][kpad(J)] (operand B, K-major).
+// max |out| is folded into amax_scale[2] (may be NULL) as in zsb_linear_tc_amax_f32.
+int zsb_linear_tc_dgrad_f32(const void* w_planes, const float* scale_w, const void* g_planes,
+                            const float* scale_g, int64_t R, int J, int K, float* out,
+                            float* amax_scale, void* stream) {
+  ZSB_REQUIRE(w_planes && g_planes && scale_w && scale_g && out && R > 0 && J > 0 && K > 0,
+              "zsb_linear_tc_dgrad_f32: bad args");
+  ZSB_REQUIRE(R < (1LL << 31), "zsb_linear_tc_dgrad_f32: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kp_w = zsb_linear_tc_kpad(K), Jp = zsb_linear_tc_kpad(J);
+  const __half* wp = reinterpret_cast<const __half*>(w_planes);
+  const __half* gp = reinterpret_cast<const __half*>(g_planes);
+  CUtensorMap m_whi, m_wlo, m_hhi, m_hlo;
+  int rc;
+  if ((rc = make_map(&m_whi, wp, (uint64_t)J, (uint64_t)Kp_w, 64, GBK, 1))) return rc;
+  if ((rc = make_map(&m_wlo, wp + (int64_t)J * Kp_w, (uint64_t)J, (uint64_t)Kp_w, 64, GBK, 1)))
+    return rc;
+  if ((rc = make_map(&m_hhi, gp, (uint64_t)R, (uint64_t)Jp, BN / 2, GBK, 1))) return rc;
+  if ((rc = make_map(&m_hlo, gp + R * Jp, (uint64_t)R, (uint64_t)Jp, BN / 2, GBK, 1))) return rc;
+  const int n_blk = (K + BM - 1) / BM;
+  const int64_t n_units = ((R + BN - 1) / BN) * ((n_blk + 1) / 2);
+  int dev = 0, sms = ZSB_NUM_SMS;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t pairs = sms / 2;
+  if (n_units < pairs) pairs = n_units;
+  const unsigned grid = (unsigned)(2 * pairs);
+  const cudaError_t prep = linear_prepare<0, 1>();
+  if (prep != cudaSuccess) {
+    zsb_set_error("linear_tc_dgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(prep));
+    return ZSB_ERR_CUDA;
+  }
+  linear_tc2_kernel<0, 1><<<grid, NUM_THREADS, GC::SMEM, st>>>(
+      m_whi, m_wlo, m_hhi, m_hlo, nullptr, nullptr, 0, nullptr, out, nullptr, R, K, Jp, 0,
+      scale_w, scale_g, 1, amax_scale);
+  return zsb_check_launch("linear_tc_dgrad");
+}
+
 // Weight gradient of a dense layer WITHOUT transposed operands:
 //   out [J, K] = sum_r g[r, j] * h[r, k]            (dW = g^T h, tf.gradients of tf.layers.dense)
 // h_planes [2][R][Kp(K)], g_planes [2][R][Kp(J)]: the row-major fp16 hi/lo planes the forward /
 // input-gradient products already use (zsb_split16_pad_f32 / zsb_split16_dual_f32).  The contraction
-// runs over the rows, so both operands are MN-major for tcgen05 (see linear_tc2_kernel<0, 1>);
+// runs over the rows, so both operands are MN-major for tcgen05 (see linear_tc2_kernel<0, 3>);
 // split-K over the CTA pairs as in zsb_linear_tc_f32 (part = zsb_linear_tc_slices(J, K, R) * J * K
 // floats, or NULL for a single slice).
 int zsb_linear_tc_wgrad_f32(const void* h_planes, const float* scale_h, int K,
@@ -827,12 +898,12 @@ int zsb_linear_tc_wgrad_f32(const void* h_planes, const float* scale_h, int K,
   int64_t pairs = sms / 2;
   if (n_units * k_slices < pairs) pairs = n_units * k_slices;
   const unsigned grid = (unsigned)(2 * pairs);
-  const cudaError_t prep = linear_prepare<0, 1>();
+  const cudaError_t prep = linear_prepare<0, 3>();
   if (prep != cudaSuccess) {
     zsb_set_error("linear_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(prep));
     return ZSB_ERR_CUDA;
   }
-  linear_tc2_kernel<0, 1><<<grid, NUM_THREADS, GC::SMEM, st>>>(
+  linear_tc2_kernel<0, 3><<<grid, NUM_THREADS, GC::SMEM, st>>>(
       m_whi, m_wlo, m_hhi, m_hlo, nullptr, nullptr, 0, nullptr, k_slices > 1 ? part : out, part,
       (int64_t)J, K, Rp, 0, scale_h, scale_g, k_slices, nullptr);
   rc = zsb_check_launch("linear_tc_wgrad");

@@ -301,12 +301,24 @@ def _planes_of(h2, src, need_t):
     return pl
 
 
-def _tc_grad_input(gpl, W, R):
-    """dh [R, K] = g [R, J] @ W [J, K] on the tensor cores (+ the scale slot holding max|dh|)."""
-    wtp, wts = _tc_split(W.detach().t())
+def _tc_grad_input(gpl, W, R, wp=None, ws=None):
+    """dh [R, K] = g [R, J] @ W [J, K] on the tensor cores (+ the scale slot holding max|dh|).
+    ``wp, ws``: the forward planes of W when the caller still has them -- the product reads them
+    as an MN-major operand (zsb_linear_tc_dgrad_f32), so W^T is never formed; ZSB_WGRAD_T=1 keeps
+    the round-2 scheme (split of W^T, K-major operands) as a cross-check."""
     amax = torch.zeros(4, dtype=torch.float32, device=W.device)
-    dh = _tc_linear(0, wtp, wts, gpl.planes, gpl.scale, None, None, None, R,
-                    int(W.shape[1]), int(W.shape[0]), amax=amax)
+    if _WGRAD_T:
+        wtp, wts = _tc_split(W.detach().t())
+        dh = _tc_linear(0, wtp, wts, gpl.planes, gpl.scale, None, None, None, R,
+                        int(W.shape[1]), int(W.shape[0]), amax=amax)
+        return dh, amax
+    from ._lib import lib, ptr, stream
+    if wp is None:
+        wp, ws = _tc_split(W)
+    J, K = int(W.shape[0]), int(W.shape[1])
+    dh = torch.empty((R, K), dtype=torch.float32, device=W.device)
+    lib.call("zsb_linear_tc_dgrad_f32", ptr(wp), ptr(ws), ptr(gpl.planes), ptr(gpl.scale),
+             R, J, K, ptr(dh), ptr(amax), stream())
     return dh, amax
 
 
@@ -388,6 +400,7 @@ class _Linear(torch.autograd.Function):
                        amax=amax)
         ctx.save_for_backward(W, y if relu else None)
         ctx.hpl = hpl
+        ctx.wpl = (wp, ws)
         ctx.meta = (lead, relu, b is not None, R, K, J)
         return _tag(y.reshape(tuple(lead) + (J,)), amax)
 
@@ -405,10 +418,11 @@ class _Linear(torch.autograd.Function):
                              amax=getattr(gy, "_zsb_amax", None), col_sum=db)
         dh = None
         if need[0]:
-            dh2, amax = _tc_grad_input(gpl, W, R)
+            dh2, amax = _tc_grad_input(gpl, W, R, *(ctx.wpl or (None, None)))
             dh = _tag(dh2.reshape(tuple(lead) + (K,)), amax)
         dW = _tc_grad_weight(gpl, ctx.hpl, R) if need[1] else None
         ctx.hpl = None
+        ctx.wpl = None
         return dh, dW, db, None
 
 
@@ -466,7 +480,7 @@ class _LinearBernoulliLogProb(torch.autograd.Function):
             dlpl = _Planes(planes, None, scale, R, J)
         dh = None
         if need[0]:
-            dh2, a2 = _tc_grad_input(dlpl, W, R)
+            dh2, a2 = _tc_grad_input(dlpl, W, R, wp, ws)
             dh = _tag(dh2.reshape(tuple(lead) + (K,)), a2)
         dW = _tc_grad_weight(dlpl, hpl, R) if need[1] else None
         ctx.hpl = None
