@@ -423,10 +423,24 @@ __global__ void __launch_bounds__(256) split16_dual_kernel(
   }
 }
 
+// scale[0] = power of two s with max|src| * s in [2^11, 2^12); scale[2] = running max bits
+__global__ void __launch_bounds__(256) absmax2_kernel(const float* __restrict__ src, int64_t n,
+                                                      float* __restrict__ scale) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = fabsf(src[i]);
+    m = (a == a && a <= 3.0e38f) ? fmaxf(m, a) : m;
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0)
+    atomicMax(reinterpret_cast<unsigned int*>(scale) + 2, __float_as_uint(m));
+}
+// Ticketed variant (ZSB_ABSMAX_TICKET=1):
 // scale[0] = power of two s with max|src| * s in [2^11, 2^12); scale[2] = running max bits;
 // scale[1] = block ticket.  The LAST block to finish turns the maximum into scale[0] and clears
 // slots 1 and 2 again (no separate single-thread kernel; the slot must start zeroed).
-__global__ void __launch_bounds__(256) absmax2_kernel(const float* __restrict__ src, int64_t n,
+__global__ void __launch_bounds__(256) absmax2_ticket_kernel(const float* __restrict__ src, int64_t n,
                                                       float* __restrict__ scale) {
   __shared__ float wm[8];
   float m = 0.f;
@@ -487,6 +501,21 @@ __global__ void pow2_scale_kernel(float* __restrict__ scale) {
   if (m > 0.f) frexpf(m, &e);
   scale[0] = ldexpf(1.f, 12 - e);
   reinterpret_cast<unsigned int*>(scale)[2] = 0u;
+}
+// max pass of an operand split: leaves scale[0].  Default: max kernel + single-thread power-of-two
+// kernel; ZSB_ABSMAX_TICKET=1: one kernel whose last block converts the maximum.
+inline bool absmax_ticket() {
+  static const bool v = getenv("ZSB_ABSMAX_TICKET") && atoi(getenv("ZSB_ABSMAX_TICKET")) != 0;
+  return v;
+}
+inline void launch_absmax_scale(const float* src, int64_t n, float* scale, unsigned blocks,
+                                cudaStream_t st) {
+  if (absmax_ticket()) {
+    absmax2_ticket_kernel<<<blocks, 256, 0, st>>>(src, n, scale);
+  } else {
+    absmax2_kernel<<<blocks, 256, 0, st>>>(src, n, scale);
+    pow2_scale_kernel<<<1, 32, 0, st>>>(scale);
+  }
 }
 // src [rows, K] fp32 -> planes [2][rows][Kp] fp16 (hi, lo) of src * scale, zero padded to Kp
 __global__ void __launch_bounds__(256) split16_pad_kernel(const float* __restrict__ src,
@@ -595,7 +624,7 @@ int zsb_split16_pad_f32(const float* src, int64_t rows, int K, void* planes, flo
   int64_t blocks = zsb_ceil_div(n, 256 * 8);
   if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
   if (blocks < 1) blocks = 1;
-  absmax2_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n, scale);   // leaves scale[0]
+  launch_absmax_scale(src, n, scale, (unsigned)blocks, st);
   int64_t blocks2 = zsb_ceil_div(rows * (int64_t)Kp, 256 * 4);
   if (blocks2 > ZSB_NUM_SMS * 32) blocks2 = ZSB_NUM_SMS * 32;
   split16_pad_kernel<<<(unsigned)blocks2, 256, 0, st>>>(src, rows, K, Kp,
@@ -612,7 +641,7 @@ int zsb_split16_pad_t_f32(const float* src, int64_t R, int C, void* planes, floa
   const int64_t n = R * (int64_t)C;
   int64_t blocks = zsb_ceil_div(n, 256 * 8);
   if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
-  absmax2_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n, scale);   // leaves scale[0]
+  launch_absmax_scale(src, n, scale, (unsigned)blocks, st);
   int64_t tiles = ((Rp + 31) / 32) * ((C + 31) / 32);
   if (tiles > ZSB_NUM_SMS * 32) tiles = ZSB_NUM_SMS * 32;
   split16_pad_t_kernel<<<(unsigned)tiles, 256, 0, st>>>(src, R, C, Rp,
@@ -636,7 +665,7 @@ int zsb_split16_dual_f32(const float* src, const float* mask_src, int64_t R, int
     const int64_t n = R * (int64_t)K;
     int64_t blocks = zsb_ceil_div(n, 256 * 8);
     if (blocks > ZSB_NUM_SMS * 16) blocks = ZSB_NUM_SMS * 16;
-    absmax2_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n, scale);   // leaves scale[0]
+    launch_absmax_scale(src, n, scale, (unsigned)blocks, st);
   } else {
     pow2_scale_kernel<<<1, 32, 0, st>>>(scale);    // max|src| left in scale[2] by a GEMM epilogue
   }
