@@ -129,8 +129,6 @@ def test_linear_bernoulli_log_prob_and_grads(zs, P, Nb, K, J):
         assert np.max(np.abs(N(g) - e)) < 2e-4 * max(1.0, np.max(np.abs(e)))
 
 
-@pytest.mark.skipif(os.environ.get("ZSB_DGRAD_MN", "0") != "1",
-                    reason="zsb_linear_tc_dgrad_f32 is opt-in (ZSB_DGRAD_MN=1) until validated on a GPU")
 @pytest.mark.parametrize("R,K,J", [(1000, 500, 784), (77, 1, 5), (300, 130, 257), (256, 64, 128),
                                    (5000, 40, 500)])
 def test_input_gradient_from_the_forward_weight_planes(zs, R, K, J):

@@ -304,8 +304,8 @@ def _planes_of(h2, src, need_t):
 def _tc_grad_input(gpl, W, R, wp=None, ws=None):
     """dh [R, K] = g [R, J] @ W [J, K] on the tensor cores (+ the scale slot holding max|dh|).
     ``wp, ws``: the forward planes of W when the caller still has them -- the product reads them
-    as an MN-major operand (zsb_linear_tc_dgrad_f32, with ZSB_DGRAD_MN=1), so W^T is never formed;
-    default: split of W^T, K-major operands."""
+    as an MN-major operand (zsb_linear_tc_dgrad_f32), so W^T is never formed; ZSB_DGRAD_MN=0 (or
+    ZSB_WGRAD_T=1): split of W^T, K-major operands."""
     amax = torch.zeros(4, dtype=torch.float32, device=W.device)
     if _WGRAD_T or not _DGRAD_MN:
         wtp, wts = _tc_split(W.detach().t())
@@ -325,9 +325,9 @@ def _tc_grad_input(gpl, W, R, wp=None, ws=None):
 # ZSB_WGRAD_T=1: the weight gradient reads TRANSPOSED operand planes (the round-2 scheme, kept as a
 # cross-check); default: MN-major operands straight from the row-major planes.
 _WGRAD_T = os.environ.get("ZSB_WGRAD_T", "0") == "1"
-# ZSB_DGRAD_MN=1: the input gradient reads the forward weight planes as an MN-major operand
-# (zsb_linear_tc_dgrad_f32) instead of splitting W^T.  Opt-in until it has run on a GPU.
-_DGRAD_MN = os.environ.get("ZSB_DGRAD_MN", "0") == "1"
+# The input gradient reads the forward weight planes as an MN-major operand
+# (zsb_linear_tc_dgrad_f32) instead of splitting W^T; ZSB_DGRAD_MN=0 restores the W^T split.
+_DGRAD_MN = os.environ.get("ZSB_DGRAD_MN", "1") == "1"
 # ZSB_BERN_FUSED=1: the Bernoulli layer's backward emits d/dlogits directly as operand planes from
 # the GEMM epilogue (zsb_linear_tc_bern_grad_planes_f32, epi 3).  Correct (tests) but MEASURED SLOWER
 # than fp32 dlogits + one split pass (1.47 vs 0.75 + 0.5 ms at config 3: the longer epilogue is no
